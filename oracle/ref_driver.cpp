@@ -110,6 +110,12 @@ struct hygref_sg_args {
   uint8_t* drew_uniform;  // T                 1 if randu() was consumed at site t
   int32_t* n_pending;     // T                 (stepwise only) lag-set size after step t
   double* seconds;        // 1
+  // optional particle-system dump after step `dump_at` (stepwise only; -1 = off)
+  int64_t dump_at;
+  double* dump_logw;      // n_particles_max
+  double* dump_W;         // n_particles_max
+  uint32_t* dump_d;       // n_particles_max
+  uint32_t* dump_r;       // n_particles_max
 };
 
 int hygref_sg_run(const hygref_sg_args* a) {
@@ -184,6 +190,14 @@ int hygref_sg_run(const hygref_sg_args* a) {
       if (a->n_curr) a->n_curr[t] = static_cast<int32_t>(smc.getNParticlesCurr());
       if (a->n_pending) a->n_pending[t] = static_cast<int32_t>(oms.psiTimeIndices_.size());
       while (fin_step.size() < ti_aux.size()) fin_step.push_back(static_cast<int32_t>(t));
+      if (a->dump_at >= 0 && static_cast<uint64_t>(a->dump_at) == t) {
+        for (uint32_t n = 0; n < smc.getNParticlesCurr(); n++) {
+          if (a->dump_logw) a->dump_logw[n] = smc.getLogUnnormalisedWeightsCurr()(n);
+          if (a->dump_W) a->dump_W[n] = smc.getSelfNormalisedWeightsCurr()(n);
+          if (a->dump_d) a->dump_d[n] = smc.getParticlesCurr(n).getDistance();
+          if (a->dump_r) a->dump_r[n] = smc.getParticlesCurr(n).getRegime();
+        }
+      }
     };
     tap(0);
     for (uint64_t t = 1; t < T; t++) {

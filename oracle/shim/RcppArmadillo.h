@@ -465,9 +465,13 @@ template <class T, class U> Col<U> hyg_conv(const Mat<T>& x, Col<U>*) { return C
 template <class T, class U> Mat<U> hyg_conv(const Mat<T>& x, Mat<U>*) { return Mat<U>(x); }
 
 template <class V = colvec> V linspace(double a, double b, uword n) {
+  // Armadillo: delta = (end-start)/(N-1); x[i] = start + i*delta.  Unit-step grids (the only ones on this path)
+  // are produced with exact integer steps so that -ffast-math (reciprocal-math) cannot turn i into i - eps.
   V out(n);
+  const bool unit = (n > 1) && ((b - a) == static_cast<double>(n - 1));
+  const double delta = (n > 1) ? (b - a) / static_cast<double>(n - 1) : 0.0;
   for (uword i = 0; i < n; i++) {
-    double v = (n > 1) ? a + (b - a) * static_cast<double>(i) / static_cast<double>(n - 1) : b;
+    double v = unit ? a + static_cast<double>(i) : ((n > 1) ? a + static_cast<double>(i) * delta : b);
     out.mem[i] = static_cast<typename V::elem_type>(v);
   }
   return out;

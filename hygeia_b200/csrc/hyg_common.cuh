@@ -1,0 +1,123 @@
+// hygeia_b200/csrc/hyg_common.cuh -- device-side building blocks shared by the kernels.
+//
+// Written for sm_100a (nvcc) but deliberately limited to full-warp collectives and
+// __syncthreads so that tests/emu/ can run the same code under a CPU emulation of the
+// CUDA execution model on the GPU-less build box (test infrastructure only).
+#ifndef HYG_COMMON_CUH
+#define HYG_COMMON_CUH
+
+#include <stdint.h>
+
+#ifndef HYG_EMU
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#define HYG_INF CUDART_INF
+#else
+#include <limits>
+#define HYG_INF (std::numeric_limits<double>::infinity())
+#endif
+
+#define HYG_FULL 0xffffffffu
+#define HYG_NT 256          // threads per chain CTA (one thread per particle slot)
+#define HYG_NW (HYG_NT / 32)
+#define HYG_RMAX 8          // max number of regimes
+#define HYG_NPMAX 256       // max particles per chain
+
+namespace hyg {
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(HYG_FULL, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double t = __shfl_xor_sync(HYG_FULL, v, o);
+    v = t > v ? t : v;
+  }
+  return v;
+}
+__device__ __forceinline__ int warp_sum_int(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(HYG_FULL, v, o);
+  return v;
+}
+
+// Double-buffered cross-warp scratch: consecutive block-wide reductions need only ONE barrier each.
+struct BlockScratch {
+  double d[2][HYG_NW][16];
+  int flip;
+};
+
+// Block-wide sum of K (<= 16) per-thread values; every thread gets every total.  One __syncthreads.
+template <int K>
+__device__ __forceinline__ void block_sum(double (&v)[K], BlockScratch& sc, int& flip) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    double s = warp_sum(v[k]);
+    if (lane == 0) sc.d[flip][warp][k] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < HYG_NW; w++) s += sc.d[flip][w][k];
+    v[k] = s;
+  }
+  flip ^= 1;
+}
+__device__ __forceinline__ double block_max(double v, BlockScratch& sc, int& flip) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double s = warp_max(v);
+  if (lane == 0) sc.d[flip][warp][0] = s;
+  __syncthreads();
+  s = sc.d[flip][0][0];
+#pragma unroll
+  for (int w = 1; w < HYG_NW; w++) {
+    double t = sc.d[flip][w][0];
+    s = t > s ? t : s;
+  }
+  flip ^= 1;
+  return s;
+}
+
+// Monotone map double -> uint64 (ascending), with the thread's slot folded into the low 8 bits so that
+// keys are unique and ties (|delta| < 2^-44 relative) break towards the smaller slot under a descending sort.
+__device__ __forceinline__ unsigned long long order_key(double x, int slot) {
+  unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x));
+  b = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+  return (b & ~0xFFull) | static_cast<unsigned long long>(255 - slot);
+}
+
+// ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011), counter-based: the resampling uniform of
+// site t of chain c under seed s is a pure function of (s, c, t).  Host copy in
+// hygeia_b200/philox.py; known-answer vectors in tests/test_philox.py.
+// ---------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    const uint64_t p0 = static_cast<uint64_t>(0xD2511F53u) * c[0];
+    const uint64_t p1 = static_cast<uint64_t>(0xCD9E8D57u) * c[2];
+    const uint32_t n0 = static_cast<uint32_t>(p1 >> 32) ^ c[1] ^ k0;
+    const uint32_t n1 = static_cast<uint32_t>(p1);
+    const uint32_t n2 = static_cast<uint32_t>(p0 >> 32) ^ c[3] ^ k1;
+    const uint32_t n3 = static_cast<uint32_t>(p0);
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+#define HYG_PHILOX_TAG 0x48594745u  // "HYGE"
+__host__ __device__ __forceinline__ double philox_uniform(uint64_t seed, uint32_t chain, uint64_t t) {
+  uint32_t c[4] = {static_cast<uint32_t>(t), static_cast<uint32_t>(t >> 32), chain, HYG_PHILOX_TAG};
+  philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  const uint64_t hi = c[0] >> 5, lo = c[1] >> 6;  // 27 + 26 = 53 random bits
+  return (static_cast<double>(hi) * 67108864.0 + static_cast<double>(lo)) * (1.0 / 9007199254740992.0);
+}
+
+}  // namespace hyg
+#endif

@@ -1,0 +1,62 @@
+// hygeia_b200/csrc/hyg_dev_structs.h -- POD descriptors passed from the host side of the C ABI to the kernels.
+#ifndef HYG_DEV_STRUCTS_H
+#define HYG_DEV_STRUCTS_H
+
+#include <stdint.h>
+
+#ifndef HYG_RMAX
+#define HYG_RMAX 8
+#endif
+
+namespace hyg {
+
+// Model constants for one theta (ModelParameters of singleGroup.h:69-455 after setUnknownParameters).
+struct SgModelDev {
+  int R;            // number of regimes
+  int u;            // minimum sojourn
+  int n_particles;  // N_max (<= 256)
+  uint32_t dcap;    // table entries per regime; entry dcap-1 is the terminal (steady) value used for every d >= dcap
+  double P[HYG_RMAX][HYG_RMAX];     // P[r'][r], zero diagonal
+  double logP[HYG_RMAX][HYG_RMAX];  // log P (only used on the exact log-domain path)
+  // tab[r * dcap + (d-1)] = { c_new(d,r), lc(d,r) }:
+  //   c_new = 0 if d < u; 1 if exit flag; else rho(d,r)          (new-segment factor, singleGroup.h:584-596)
+  //   lc    = log(1 - rho(d,r)) if !exit && rho <= 1, else -inf   (continuation,      singleGroup.h:597-605)
+  const double2* tab;
+  // tabg[r * dcap + (d-1)] = d log rho(d,r) / d theta_omega_r (parameter-estimation mode only; may be null)
+  const double* tabg;
+};
+
+// One chain = one (dataset, seed) pair.
+struct SgChainDev {
+  unsigned long long T;
+  const double* logobs;   // T x R, device (output of K1)
+  const double* unif;     // T injected uniforms (device) or null -> Philox(seed, chain_id, t)
+  unsigned long long seed;
+  uint32_t chain_id;
+  double* probs;          // T x R posterior regime probabilities (device) or null
+  double* logz;           // T running log Z_t (device) or null
+  // optional step-level taps for parity tests (device, may be null)
+  int* k_kept;            // T : K of optimal resampling; -1 growth; -2 keep-largest
+  unsigned char* drew;    // T : uniform consumed at site t
+  int* n_pending;         // T : lag-set size after site t
+  int* n_curr;            // T : particle count after site t
+  int* finalised_at;      // T : step at which site t was emitted
+  short* ancestors;       // T x (n_particles - R)
+  int* status;            // [0] forced emissions (lag set full), [1] max lag-set size
+  // parameter-estimation mode
+  const double* theta0;   // D initial theta (device) or null
+  double* theta_trace;    // T x D (device) or null
+};
+
+struct SgRunDev {
+  int use_smoothing;
+  double epsilon;
+  int lcap;               // capacity of the lag set per CTA
+  double* psi_ws;         // workspace base
+  unsigned long long psi_stride;  // doubles per CTA
+  unsigned int* queue;    // atomic chain counter
+  int n_chains;
+};
+
+}  // namespace hyg
+#endif

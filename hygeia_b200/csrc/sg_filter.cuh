@@ -1,0 +1,517 @@
+// hygeia_b200/csrc/sg_filter.cuh -- K2: the single-group recursion, one CTA per chain.
+//
+// What it computes (reference = /root/reference/src/single_group/src/cpp):
+//   * discrete particle filter over (sojourn d, regime r), <= 256 support points
+//       Smc::initialise / iterate                      algorithms/Smc.h:114-286
+//       resampleCp + resample::optimalFiniteState      algorithms/Smc.h:406-450, misc/resample.h:289-409
+//       systematic resampling, ONE uniform per site    misc/resample.h:85-127
+//       sampleParticlesCp / computeWeightsCp           algorithms/Smc.h:504-574
+//       selfNormaliseWeights (running log Z_t)         algorithms/Smc.h:576-579
+//   * backward kernels of the R new-segment particles  algorithms/Smc.h:288-326
+//   * forward-only adaptive fixed-lag smoothing        algorithms/OnlineMarginalSmoothing.h:40-63,119-255
+//   * the outer loop over sites                        algorithms/OnlineCombinedInference.h:48-118
+//
+// How (B200-first, not a translation):
+//   * the emission term logObs[t][r] is read from the T x R table K1 produced (48 B per site) -- the
+//     reference re-evaluates it 1744 times per site;
+//   * transition terms come from a host-built table {c_new(d,r), log(1-rho(d,r))} that each particle
+//     carries one step ahead (entry for d+1 is gathered from the ancestor, entry for d+2 is loaded now and
+//     consumed a whole step later), so no L2 latency sits on the per-site critical path;
+//   * the R x N_prev new-segment log-sum-exps and backward kernels collapse to R class sums
+//     E[r'] = sum_{n in class r'} W_n c_new(d_n, r') because logTrans((1,r) <- (d,r')) = log c_new(d,r') + log P[r'][r]
+//     factorises: 6 block reductions instead of 3000 exp() per site (exact log-domain fallback when a class
+//     underflows);
+//   * sort = register/shuffle bitonic network (strides < 32) + 6 shared-memory exchange stages;
+//     prefix sums, the K fixed point and systematic resampling are warp scans/ballots;
+//   * the uniform of site t is Philox(seed, chain, t) or an injected per-site array.
+// All arithmetic fp64.  Rounding differs from the reference at the 1e-16 level (tree sums vs sequential
+// sums); decisions (K, ancestors) are discontinuous in the weights, so parity is stated on log Z_t and the
+// posteriors (1e-6 relative) and on the argmax regime calls, and checked step by step against the oracle.
+#ifndef HYG_SG_FILTER_CUH
+#define HYG_SG_FILTER_CUH
+
+#include "hyg_common.cuh"
+#include "hyg_dev_structs.h"
+
+namespace hyg {
+
+struct SgSmem {
+  // previous particle system, storage order (thread n owns slot n)
+  double W[HYG_NPMAX];
+  double lw[HYG_NPMAX];
+  double2 cur[HYG_NPMAX];  // {c_new(d,r), log(1-rho(d,r))}
+  double2 nxt[HYG_NPMAX];  // same for d+1
+  uint32_t d[HYG_NPMAX];
+  unsigned char r[HYG_NPMAX];
+  // resampling scratch
+  unsigned long long key[2][HYG_NPMAX];
+  double q[HYG_NPMAX];
+  double Q[HYG_NPMAX + 1];
+  unsigned short idx[HYG_NPMAX];
+  unsigned short anc[HYG_NPMAX];
+  int iscan[2][HYG_NW];
+  BlockScratch sc;
+  double lo[2][HYG_RMAX];
+};
+
+__device__ __forceinline__ bool hyg_isfinite(double x) {
+  const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x));
+  return ((b >> 52) & 0x7ffull) != 0x7ffull;
+}
+
+// #{ j in [0,L) : (j + u) / L <= c }  with the reference's floating-point expression for T_j (resample.h:95)
+__device__ __forceinline__ int sys_count(double c, double u, int L) {
+  const double Ld = static_cast<double>(L);
+  double x = c * Ld - u;
+  int j = (x < 0.0) ? -1 : (x >= Ld ? L - 1 : static_cast<int>(x));
+  while (j + 1 < L && (static_cast<double>(j + 1) + u) / Ld <= c) j++;
+  while (j >= 0 && (static_cast<double>(j) + u) / Ld > c) j--;
+  return j + 1;
+}
+
+// Descending bitonic sort of one 64-bit key per thread over the 256-thread CTA.
+__device__ __forceinline__ unsigned long long block_sort_desc(unsigned long long key, SgSmem& s, int& kbuf) {
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int k = 2; k <= HYG_NT; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      unsigned long long other;
+      if (j < 32) {
+        other = __shfl_xor_sync(HYG_FULL, key, j);
+      } else {
+        s.key[kbuf][tid] = key;
+        __syncthreads();
+        other = s.key[kbuf][tid ^ j];
+        kbuf ^= 1;
+      }
+      const bool desc_block = ((tid & k) == 0);
+      const bool lower = ((tid & j) == 0);
+      const bool take_max = (lower == desc_block);
+      const bool other_gt = other > key;
+      key = (take_max == other_gt) ? other : key;
+    }
+  }
+  return key;
+}
+
+struct SgChainState {
+  // per-thread particle (slot = threadIdx.x)
+  double lw, W;
+  double2 cur, nxt;
+  uint32_t d;
+  int r;
+};
+
+template <int RT> __device__ __forceinline__ double pick(const double (&v)[RT], int i) {
+  double o = 0.0;
+#pragma unroll
+  for (int q = 0; q < RT; q++) o = (i == q) ? v[q] : o;
+  return o;
+}
+
+template <int RT>
+__device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, const SgRunDev& run, double* psi_ws, SgSmem& s) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int R = RT;
+  const int Nmax = mdl.n_particles;
+  const uint32_t dcap = mdl.dcap;
+  const unsigned long long T = ch.T;
+  const int lcap = run.lcap;
+  int flip = 0, kbuf = 0, ibuf = 0;
+
+  // psi workspace (global, L2-resident): [2][lcap][R][256] doubles followed by lcap ints of site indices
+  double* psi[2] = {psi_ws, psi_ws + static_cast<size_t>(lcap) * R * HYG_NPMAX};
+  int* pend_t = reinterpret_cast<int*>(psi_ws + 2 * static_cast<size_t>(lcap) * R * HYG_NPMAX);
+  int n_pend = 0, n_forced = 0, max_pend = 0;
+
+  SgChainState p;
+  p.lw = -HYG_INF; p.W = 0.0; p.cur = make_double2(0.0, 0.0); p.nxt = p.cur; p.d = 0; p.r = 0;
+
+  // ---- t = 0 : Smc::initialise (Smc.h:114-188) ----
+  if (tid < R) s.lo[0][tid] = __ldg(ch.logobs + tid);
+  if (T > 1 && tid < R) s.lo[1][tid] = __ldg(ch.logobs + R + tid);
+  __syncthreads();
+  int N = R;
+  double lsum;
+  {
+    double lomax = s.lo[0][0];
+#pragma unroll
+    for (int r = 1; r < R; r++) lomax = s.lo[0][r] > lomax ? s.lo[0][r] : lomax;
+    const double lsum_prev = -log(static_cast<double>(R));  // evaluateLogInitialDensity, singleGroup.h:559-566
+    if (tid < R) {
+      p.d = 1; p.r = tid;
+      p.lw = lsum_prev + s.lo[0][tid];
+      p.cur = __ldg(mdl.tab + static_cast<size_t>(tid) * dcap + 0);
+      p.nxt = __ldg(mdl.tab + static_cast<size_t>(tid) * dcap + (dcap > 1 ? 1 : 0));
+    }
+    const double c = lsum_prev + lomax;
+    double e[1] = {(tid < N) ? exp(p.lw - c) : 0.0};
+    const double mine = e[0];
+    block_sum<1>(e, s.sc, flip);
+    lsum = c + log(e[0]);
+    p.W = mine / e[0];
+  }
+
+  for (unsigned long long t = 0; t < T; t++) {
+    const double* lo = s.lo[t & 1];
+    // emission row of site t+2 and the uniform of site t+1: issued now, consumed at the end of this step
+    const double lo_pref = (tid < R && t + 2 < T) ? __ldg(ch.logobs + (t + 2) * R + tid) : 0.0;
+    int k_kept = -1;
+    bool drew = false;
+
+    if (t > 0) {
+      // =========================== Smc::iterate (Smc.h:190-286) ===========================
+      const int N_prev = N;
+      const int N_curr = (N_prev + R > Nmax) ? Nmax : N_prev + R;
+      const int M = N_curr - R;
+      const bool capped = (N_curr < N_prev + R);
+      const double lsum_prev = lsum;
+      int anc = tid;
+
+      // ---- class sums over the previous particles (replace the R x N_prev log-sum-exps of Smc.h:562-573) ----
+      const double e_prev = (tid < N_prev) ? p.W * p.cur.x : 0.0;  // W_n * c_new(d_n, r_n)
+      const bool valid = (tid < N_prev) && (p.cur.x > 0.0) && hyg_isfinite(p.lw);
+      double red[R + 1];
+#pragma unroll
+      for (int r = 0; r < R; r++) red[r] = (p.r == r) ? e_prev : 0.0;
+      red[R] = (tid < N_prev && hyg_isfinite(p.lw)) ? 1.0 : 0.0;  // F = #finite(logw_prev), Smc.h:413
+      unsigned vmask = 0;
+#pragma unroll
+      for (int r = 0; r < R; r++) vmask |= (__any_sync(HYG_FULL, valid && p.r == r) ? 1u : 0u) << r;
+      if (lane == 0) s.iscan[ibuf][warp] = static_cast<int>(vmask);
+      block_sum<R + 1>(red, s.sc, flip);
+      vmask = 0;
+#pragma unroll
+      for (int w = 0; w < HYG_NW; w++) vmask |= static_cast<unsigned>(s.iscan[ibuf][w]);
+      ibuf ^= 1;
+      const int F = static_cast<int>(red[R] + 0.5);
+      // sumE[r] = sum_{r' != r} P[r'][r] E[r']  (linear-domain new-segment mass of regime r, relative to exp(lsum_prev))
+      unsigned slowmask = 0;
+      double my_sumE = 0.0;  // for the thread that owns new particle (1, r = tid - M)
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        double a = 0.0;
+        bool could = false;
+#pragma unroll
+        for (int rp = 0; rp < R; rp++) {
+          if (rp == r) continue;
+          a += mdl.P[rp][r] * red[rp];
+          could = could || (((vmask >> rp) & 1u) && mdl.P[rp][r] > 0.0);
+        }
+        if (!(a > 0.0) && could) slowmask |= 1u << r;
+        if (tid - M == r) my_sumE = a;
+      }
+      const double my_invE = (my_sumE > 0.0) ? 1.0 / my_sumE : 0.0;
+
+      // ---- ancestors: Smc::resampleCp (Smc.h:406-450) ----
+      bool own_weight = true;   // child keeps its ancestor's own log-weight (top-K / keep-largest / growth)
+      double resampled_lw = 0.0;
+      if (!capped) {
+        anc = tid;  // growth phase: identity (Smc.h:443-447)
+        k_kept = -1;
+      } else {
+        // sort by log-weight, descending (ties by slot); W is a monotone map of logw
+        unsigned long long key = (tid < N_prev) ? order_key(p.lw, tid) : 0ull;
+        key = block_sort_desc(key, s, kbuf);
+        const int sidx = 255 - static_cast<int>(key & 0xFFull);
+        s.idx[tid] = static_cast<unsigned short>(sidx);
+        bool keep_largest = (F <= M);
+        int K = 0;
+        double Qk = 0.0;
+        if (!keep_largest) {
+          // ---- resample::optimalFiniteState (resample.h:289-409) ----
+          const double qv = (tid < N_prev) ? s.W[sidx] : 0.0;
+          double v = qv;  // Q[p] = sum_{j >= p} q_j
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const double tt = __shfl_down_sync(HYG_FULL, v, o);
+            if (lane + o < 32) v += tt;
+          }
+          if (lane == 0) s.sc.d[flip][warp][0] = v;
+          s.q[tid] = qv;
+          __syncthreads();
+          double tail = 0.0;
+#pragma unroll
+          for (int w = HYG_NW - 1; w > 0; w--) tail += (w > warp) ? s.sc.d[flip][w][0] : 0.0;
+          flip ^= 1;
+          s.Q[tid] = v + tail;
+          if (tid == 0) s.Q[HYG_NPMAX] = 0.0;
+          __syncthreads();
+          // fixed point for K (resample.h:333-342), every warp redundantly: log q_i > -log C  <=>  q_i > Q[K]/(M-K)
+          for (;;) {
+            Qk = s.Q[K];
+            const int L = M - K;
+            if (L <= 0 || !(Qk > 0.0) || !hyg_isfinite(Qk)) { keep_largest = true; break; }  // log C not finite (:345,:366)
+            const double thr = Qk / static_cast<double>(L);
+            int cnt = 0;
+#pragma unroll
+            for (int j = 0; j < HYG_NPMAX / 32; j++) {
+              const int pp = lane + 32 * j;
+              cnt += __popc(__ballot_sync(HYG_FULL, pp >= K && pp < N_prev && s.q[pp] > thr));
+            }
+            if (cnt == 0) break;
+            K += cnt;
+          }
+        }
+        if (keep_largest) {
+          // keep the M largest by log-weight (Smc.h:432-441; resample.h:366-375)
+          __syncthreads();  // s.idx visible
+          anc = (tid < M) ? s.idx[tid] : tid;
+          k_kept = -2;
+        } else {
+          const int L = M - K;
+          const double logC = log(static_cast<double>(L)) - log(Qk);
+          resampled_lw = lsum_prev - logC;  // resample.h:361-364
+          k_kept = K;
+          drew = true;
+          // systematic resampling of L offspring among the sorted residual particles (resample.h:85-127,354-359).
+          // C_p = #{ j < L : (j+u)/L <= cumulative residual weight up to p }; forced monotone, C_last = L, so the
+          // offspring counts o_p = C_p - C_{p-1} are >= 0 and sum to L whatever the rounding of the suffix sums.
+          const double u = ch.unif ? __ldg(ch.unif + t) : philox_uniform(ch.seed, ch.chain_id, t);
+          int C = 0;
+          if (tid >= K && tid < N_prev) C = (tid == N_prev - 1) ? L : sys_count((Qk - s.Q[tid + 1]) / Qk, u, L);
+          if (tid >= N_prev) C = L;
+#pragma unroll
+          for (int dlt = 1; dlt < 32; dlt <<= 1) {
+            const int tt = __shfl_up_sync(HYG_FULL, C, dlt);
+            if (lane >= dlt) C = tt > C ? tt : C;
+          }
+          if (lane == 31) s.iscan[ibuf][warp] = C;
+          __syncthreads();
+          int before = 0;
+#pragma unroll
+          for (int w = 0; w < HYG_NW - 1; w++) before = (w < warp && s.iscan[ibuf][w] > before) ? s.iscan[ibuf][w] : before;
+          ibuf ^= 1;
+          C = before > C ? before : C;
+          int Cprev = __shfl_up_sync(HYG_FULL, C, 1);
+          if (lane == 0) Cprev = before;
+          if (tid <= K) Cprev = 0;
+          if (tid < K) s.anc[tid] = static_cast<unsigned short>(sidx);
+          if (tid >= K && tid < N_prev)
+            for (int slot = K + Cprev; slot < K + C && slot < M; slot++) s.anc[slot] = static_cast<unsigned short>(sidx);
+          __syncthreads();
+          anc = (tid < M) ? s.anc[tid] : tid;
+          own_weight = (tid < K);
+        }
+      }
+      if (ch.ancestors && tid < Nmax - R)
+        ch.ancestors[t * static_cast<unsigned long long>(Nmax - R) + tid] = (tid < M) ? static_cast<short>(anc) : static_cast<short>(-1);
+
+      // ---- propose + weight: sampleParticlesCp / computeWeightsCp (Smc.h:504-574) ----
+      SgChainState c;
+      c.lw = -HYG_INF; c.W = 0.0; c.cur = make_double2(0.0, 0.0); c.nxt = c.cur; c.d = 0; c.r = 0;
+      if (tid < M) {
+        const double base = own_weight ? s.lw[anc] : resampled_lw;
+        c.r = s.r[anc];
+        c.d = s.d[anc] + 1;
+        c.cur = s.nxt[anc];
+        const double lc = s.cur[anc].y;                 // log(1 - rho(d_prev, r)) or -inf (singleGroup.h:597-605)
+        c.lw = base + (lc + lo[c.r]);
+        const uint32_t di = (c.d + 1 <= dcap) ? c.d : dcap - 1;  // 0-based index of d+1, clamped to the terminal entry
+        c.nxt = __ldg(mdl.tab + static_cast<size_t>(c.r) * dcap + di);
+      } else if (tid < N_curr) {
+        const int r = tid - M;
+        c.r = r; c.d = 1;
+        c.cur = __ldg(mdl.tab + static_cast<size_t>(r) * dcap + 0);
+        c.nxt = __ldg(mdl.tab + static_cast<size_t>(r) * dcap + (dcap > 1 ? 1 : 0));
+        c.lw = (my_sumE > 0.0) ? lsum_prev + lo[r] + log(my_sumE) : -HYG_INF;
+      }
+      // exact log-domain path for regimes whose linear-domain sum underflowed (rare)
+      double bk_slow[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) bk_slow[r] = 0.0;
+      if (slowmask) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          if (!((slowmask >> r) & 1u)) continue;
+          const bool ok = valid && p.r != r && mdl.P[p.r][r] > 0.0;
+          const double x = ok ? p.lw + log(p.cur.x) + mdl.logP[p.r][r] : -HYG_INF;
+          const double mx = block_max(x, s.sc, flip);
+          double ex[1] = {ok ? exp(x - mx) : 0.0};
+          const double mine = ex[0];
+          block_sum<1>(ex, s.sc, flip);
+          if (tid == M + r) c.lw = lo[r] + (mx + log(ex[0]));
+          bk_slow[r] = (ex[0] > 0.0) ? mine / ex[0] : 0.0;
+        }
+      }
+
+      // ---- selfNormaliseWeights (Smc.h:576-579): shift by an upper bound instead of the exact max ----
+      {
+        double lomax = lo[0];
+#pragma unroll
+        for (int r = 1; r < R; r++) lomax = lo[r] > lomax ? lo[r] : lomax;
+        double shift = lsum_prev + lomax;
+        double ee[1] = {(tid < N_curr) ? exp(c.lw - shift) : 0.0};
+        double mine = ee[0];
+        block_sum<1>(ee, s.sc, flip);
+        if (!(ee[0] > 0.0) || !hyg_isfinite(ee[0])) {  // everything underflowed against the bound: use the exact max
+          shift = block_max((tid < N_curr) ? c.lw : -HYG_INF, s.sc, flip);
+          ee[0] = (tid < N_curr) ? exp(c.lw - shift) : 0.0;
+          mine = ee[0];
+          block_sum<1>(ee, s.sc, flip);
+        }
+        lsum = shift + log(ee[0]);
+        c.W = mine / ee[0];
+      }
+
+      // ---- fixed-lag smoothing: updatePsi (OnlineMarginalSmoothing.h:148-177) ----
+      if (run.use_smoothing && n_pend > 0) {
+        const double* pp = psi[(t + 1) & 1];   // written at step t-1
+        double* pc = psi[t & 1];
+        int kept = 0;
+        for (int i = 0; i < n_pend; i++) {
+          const double* src = pp + static_cast<size_t>(i) * R * HYG_NPMAX;
+          double own[R], val[R];
+#pragma unroll
+          for (int q = 0; q < R; q++) {
+            own[q] = (tid < N_prev) ? src[q * HYG_NPMAX + tid] : 0.0;
+            val[q] = (tid < M) ? src[q * HYG_NPMAX + anc] : 0.0;
+          }
+          // class sums G[q][r'] = sum_{n in class r'} e_n psi_q[n]; new particle (1,r): sum_{r'} P[r'][r] G[q][r'] / sumE[r]
+#pragma unroll
+          for (int q = 0; q < R; q++) {
+            double g[R];
+#pragma unroll
+            for (int rp = 0; rp < R; rp++) g[rp] = (p.r == rp) ? e_prev * own[q] : 0.0;
+            block_sum<R>(g, s.sc, flip);
+            if (tid >= M && tid < N_curr) {
+              const int r = tid - M;
+              double a = 0.0;
+#pragma unroll
+              for (int rp = 0; rp < R; rp++) a += (rp != r) ? mdl.P[rp][r] * g[rp] : 0.0;
+              val[q] = a * my_invE;
+            }
+          }
+          if (slowmask) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+              if (!((slowmask >> r) & 1u)) continue;
+              double g[R];
+#pragma unroll
+              for (int q = 0; q < R; q++) g[q] = bk_slow[r] * own[q];
+              block_sum<R>(g, s.sc, flip);
+              if (tid == M + r) {
+#pragma unroll
+                for (int q = 0; q < R; q++) val[q] = g[q];
+              }
+            }
+          }
+          // storeEstimates (OnlineMarginalSmoothing.h:197-255): emit when all R filtered variances < epsilon
+          double mv[2 * R];
+#pragma unroll
+          for (int q = 0; q < R; q++) { mv[q] = c.W * val[q]; mv[R + q] = c.W * val[q] * val[q]; }
+          block_sum<2 * R>(mv, s.sc, flip);
+          bool emit = (t == T - 1);
+          if (!emit) {
+            emit = true;
+#pragma unroll
+            for (int q = 0; q < R; q++) {
+              const double var = mv[R + q] - mv[q] * mv[q];  // sum W (x-m)^2 with sum W = 1
+              if (!(var < run.epsilon)) emit = false;
+            }
+          }
+          const int ts = pend_t[i];
+          if (emit) {
+            const double outv = pick<2 * R>(mv, tid);
+            if (tid < R && ch.probs) ch.probs[static_cast<size_t>(ts) * R + tid] = outv;
+            if (tid == 0 && ch.finalised_at) ch.finalised_at[ts] = static_cast<int>(t);
+          } else {
+            double* dst = pc + static_cast<size_t>(kept) * R * HYG_NPMAX;
+#pragma unroll
+            for (int q = 0; q < R; q++) dst[q * HYG_NPMAX + tid] = val[q];
+            __syncthreads();  // pend_t[i] has been read by every thread before slot `kept` (<= i) is overwritten
+            if (tid == 0) pend_t[kept] = ts;
+            kept++;
+          }
+        }
+        n_pend = kept;
+      }
+      p = c;
+      N = N_curr;
+    }
+
+    // ---- initialisePsi + storeEstimates for the current site (OnlineMarginalSmoothing.h:119-146,197-255) ----
+    if (run.use_smoothing) {
+      double cw[R];
+#pragma unroll
+      for (int q = 0; q < R; q++) cw[q] = (tid < N && p.r == q) ? p.W : 0.0;
+      block_sum<R>(cw, s.sc, flip);
+      double sw = 0.0;
+#pragma unroll
+      for (int q = 0; q < R; q++) sw += cw[q];
+      bool emit = (t == T - 1);
+      if (!emit) {
+        emit = true;
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+          const double m = cw[q];
+          const double var = cw[q] * (1.0 - m) * (1.0 - m) + (sw - cw[q]) * m * m;  // psi is the 0/1 regime indicator
+          if (!(var < run.epsilon)) emit = false;
+        }
+      }
+      if (!emit && n_pend >= lcap) { emit = true; n_forced++; }  // lag set full: emit the filtering estimate now (reported)
+      if (emit) {
+        const double outv = pick<R>(cw, tid);
+        if (tid < R && ch.probs) ch.probs[static_cast<size_t>(t) * R + tid] = outv;
+        if (tid == 0 && ch.finalised_at) ch.finalised_at[t] = static_cast<int>(t);
+      } else {
+        double* dst = psi[t & 1] + static_cast<size_t>(n_pend) * R * HYG_NPMAX;
+#pragma unroll
+        for (int q = 0; q < R; q++) dst[q * HYG_NPMAX + tid] = (tid < N && p.r == q) ? 1.0 : 0.0;
+        if (tid == 0) pend_t[n_pend] = static_cast<int>(t);
+        n_pend++;
+      }
+      max_pend = n_pend > max_pend ? n_pend : max_pend;
+    }
+
+    // ---- taps ----
+    if (tid == 0) {
+      if (ch.logz) ch.logz[t] = lsum;
+      if (ch.k_kept) ch.k_kept[t] = k_kept;
+      if (ch.drew) ch.drew[t] = drew ? 1 : 0;
+      if (ch.n_pending) ch.n_pending[t] = n_pend;
+      if (ch.n_curr) ch.n_curr[t] = N;
+    }
+
+    // ---- publish the particle system for the next site; stash the prefetched emission row ----
+    __syncthreads();  // all gathers of this step are done
+    s.W[tid] = p.W; s.lw[tid] = p.lw; s.cur[tid] = p.cur; s.nxt[tid] = p.nxt; s.d[tid] = p.d; s.r[tid] = static_cast<unsigned char>(p.r);
+    if (tid < R && t + 2 < T) s.lo[t & 1][tid] = lo_pref;
+    __syncthreads();
+  }
+  if (tid == 0 && ch.status) {
+    ch.status[0] = n_forced;
+    ch.status[1] = max_pend;
+  }
+  __syncthreads();
+}
+
+// Persistent launch: CTAs pull chains (pre-sorted longest first by the host) from an atomic queue.
+template <int RT>
+__device__ __forceinline__ void sg_filter_entry(const SgModelDev* mdl, const SgChainDev* chains, SgRunDev run) {
+  __shared__ SgSmem s;
+  __shared__ int s_next;
+  __shared__ SgModelDev s_mdl;
+  if (threadIdx.x == 0) s_mdl = *mdl;
+  __syncthreads();
+  double* psi_ws = run.psi_ws + static_cast<size_t>(blockIdx.x) * run.psi_stride;
+  for (;;) {
+    if (threadIdx.x == 0) s_next = static_cast<int>(atomicAdd(run.queue, 1u));
+    __syncthreads();
+    const int c = s_next;
+    __syncthreads();
+    if (c >= run.n_chains) break;
+    sg_filter_chain<RT>(s_mdl, chains[c], run, psi_ws, s);
+  }
+}
+
+#ifndef HYG_EMU
+template <int RT>
+__global__ void __launch_bounds__(HYG_NT, 1) sg_filter_kernel(const SgModelDev* mdl, const SgChainDev* chains, SgRunDev run) {
+  sg_filter_entry<RT>(mdl, chains, run);
+}
+#endif
+
+}  // namespace hyg
+#endif

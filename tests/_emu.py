@@ -1,0 +1,66 @@
+"""ctypes bindings for tests/emu/libhyg_emu.so: the repo's DEVICE code compiled for the CPU under an emulation of the
+CUDA execution model (TEST INFRASTRUCTURE -- lets the GPU-less box check kernel logic against the oracle)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+EMU_DIR = os.path.join(HERE, "emu")
+LIB = os.path.join(EMU_DIR, "libhyg_emu.so")
+
+
+def build():
+    src = [os.path.join(EMU_DIR, "emu_kernels.cpp"), os.path.join(HERE, "..", "hygeia_b200", "csrc", "hyg_tables.cpp")]
+    deps = src + [os.path.join(EMU_DIR, "cuda_emu.h")] + [
+        os.path.join(HERE, "..", "hygeia_b200", "csrc", f) for f in
+        ("sg_filter.cuh", "sg_emission.cuh", "hyg_common.cuh", "hyg_dev_structs.h", "hyg_tables.h")]
+    if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
+        return LIB
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-std=c++14", "-O2", "-fPIC", "-shared", "-I", EMU_DIR] + src + ["-o", LIB])
+    return LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Emu:
+    def __init__(self):
+        self.lib = C.CDLL(build())
+
+    def sg_filter(self, vartheta, theta, logobs, uniforms=None, seed=0, chain_id=0, n_particles=250, smoothing=True,
+                  epsilon=0.01, lcap=64, want_ancestors=False):
+        vartheta = np.ascontiguousarray(vartheta, dtype=np.float64)
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        logobs = np.ascontiguousarray(logobs, dtype=np.float64)
+        T, R = logobs.shape
+        if uniforms is not None:
+            uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
+        out = dict(probs=np.full((T, R), np.nan), logz=np.zeros(T), k_kept=np.zeros(T, np.int32), drew_uniform=np.zeros(T, np.uint8),
+                   n_pending=np.zeros(T, np.int32), n_curr=np.zeros(T, np.int32), finalised_at=np.full(T, -1, np.int32),
+                   ancestors=np.full((T, n_particles - R), -1, np.int16) if want_ancestors else None, status=np.zeros(2, np.int32))
+        rc = self.lib.hygemu_sg_filter(_p(vartheta), C.c_uint32(len(vartheta)), _p(theta), C.c_uint32(len(theta)), C.c_uint32(n_particles),
+                                       C.c_uint64(T), _p(logobs), _p(uniforms), C.c_uint64(seed), C.c_uint32(chain_id),
+                                       C.c_int(int(smoothing)), C.c_double(epsilon), C.c_int(lcap),
+                                       _p(out["probs"]), _p(out["logz"]), _p(out["k_kept"]), _p(out["drew_uniform"]), _p(out["n_pending"]),
+                                       _p(out["n_curr"]), _p(out["finalised_at"]), _p(out["ancestors"]), _p(out["status"]))
+        assert rc == 0, rc
+        return out
+
+    def sg_emission(self, alpha, beta, n_total_st, n_meth_st, nmax_table=255, nmax_smem=96, grid=3, block=64):
+        alpha = np.ascontiguousarray(alpha, dtype=np.float64)
+        beta = np.ascontiguousarray(beta, dtype=np.float64)
+        S, T = n_total_st.shape
+        pitch = (T + 7) // 8 * 8
+        nt = np.zeros((S, pitch), np.uint16); nt[:, :T] = n_total_st
+        nm = np.zeros((S, pitch), np.uint16); nm[:, :T] = n_meth_st
+        out = np.full((T, len(alpha)), np.nan)
+        rc = self.lib.hygemu_sg_emission(_p(alpha), _p(beta), C.c_int(len(alpha)), C.c_uint64(T), C.c_uint32(S), C.c_uint64(pitch),
+                                         _p(nt), _p(nm), C.c_int(nmax_table), C.c_int(nmax_smem), C.c_int(grid), C.c_int(block), _p(out))
+        assert rc == 0, rc
+        return out

@@ -1,0 +1,63 @@
+// tests/emu/emu_kernels.cpp -- TEST INFRASTRUCTURE, not product code.
+//
+// Compiles the device code of hygeia_b200/csrc/*.cuh with g++ against tests/emu/cuda_emu.h (a CPU emulation of the
+// CUDA execution model) so that `pytest -m "not gpu"` can check the KERNEL LOGIC against the oracle on the GPU-less
+// build box.  The product never links this file; on a GPU box the same device code runs through nvcc (hyg_api.cu).
+#include "cuda_emu.h"
+
+#include <vector>
+
+#include "../../hygeia_b200/csrc/hyg_tables.h"
+#include "../../hygeia_b200/csrc/sg_emission.cuh"
+#include "../../hygeia_b200/csrc/sg_filter.cuh"
+
+extern "C" {
+
+// K2 under emulation.  vartheta/theta as in the reference; logobs T x R; uniforms T or NULL (-> Philox(seed, chain_id)).
+int hygemu_sg_filter(const double* vartheta, uint32_t n_vartheta, const double* theta, uint32_t dim_theta, uint32_t n_particles,
+                     uint64_t T, const double* logobs, const double* unif, uint64_t seed, uint32_t chain_id,
+                     int use_smoothing, double epsilon, int lcap,
+                     double* probs, double* logz, int* k_kept, unsigned char* drew, int* n_pending, int* n_curr,
+                     int* finalised_at, short* ancestors, int* status) {
+  hyg::SgHostModel hm;
+  if (hm.set_known(vartheta, n_vartheta)) return -1;
+  if (hm.set_theta(theta, dim_theta, T)) return -2;
+  if (hm.R != 6) return -3;
+  hyg::SgModelDev mdl;
+  mdl.R = hm.R; mdl.u = hm.u; mdl.n_particles = static_cast<int>(n_particles); mdl.dcap = hm.dcap;
+  for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) { mdl.P[i][j] = hm.P[i][j]; mdl.logP[i][j] = hm.logP[i][j]; }
+  mdl.tab = reinterpret_cast<const double2*>(hm.tab.data());
+  mdl.tabg = hm.tabg.data();
+  hyg::SgChainDev ch;
+  std::memset(&ch, 0, sizeof(ch));
+  ch.T = T; ch.logobs = logobs; ch.unif = unif; ch.seed = seed; ch.chain_id = chain_id;
+  ch.probs = probs; ch.logz = logz; ch.k_kept = k_kept; ch.drew = drew; ch.n_pending = n_pending; ch.n_curr = n_curr;
+  ch.finalised_at = finalised_at; ch.ancestors = ancestors; ch.status = status;
+  hyg::SgRunDev run;
+  run.use_smoothing = use_smoothing; run.epsilon = epsilon; run.lcap = lcap;
+  const size_t stride = 2 * static_cast<size_t>(lcap) * hm.R * HYG_NPMAX + (lcap + 1) / 2 + 8;
+  std::vector<double> ws(stride);
+  unsigned int queue = 0;
+  run.psi_ws = ws.data(); run.psi_stride = stride; run.queue = &queue; run.n_chains = 1;
+  const hyg::SgModelDev* pm = &mdl;
+  const hyg::SgChainDev* pc = &ch;
+  emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<6>(pm, pc, run); });
+  return 0;
+}
+
+// K1 under emulation: counts uint16 [S][pitch] (site fastest), logobs T x R.
+int hygemu_sg_emission(const double* alpha, const double* beta, int R, uint64_t T, uint32_t S, uint64_t pitch,
+                       const uint16_t* n_total, const uint16_t* n_meth, int nmax_table, int nmax_smem, int grid, int block,
+                       double* logobs) {
+  if (R != 6) return -3;
+  std::vector<double> tab;
+  hyg::build_emission_table(alpha, beta, R, nmax_table, tab);
+  hyg::SgEmissionArgs a;
+  a.T = T; a.S = S; a.pitch = pitch; a.n_total = n_total; a.n_meth = n_meth; a.logobs = logobs;
+  a.table = tab.data(); a.nmax_table = nmax_table; a.nmax_smem = nmax_smem;
+  for (int r = 0; r < R; r++) { a.alpha[r] = alpha[r]; a.beta[r] = beta[r]; }
+  emu::launch(dim3(grid), dim3(block), [=]() { hyg::sg_emission_entry<6>(a); });
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,556 @@
+// hygeia_b200/csrc/hyg_api.cu -- host side of the C ABI declared in include/hygeia_b200.h.
+//
+// Owns device memory, streams and launches; the model constants are built on the host (hyg_tables.cpp) in the
+// reference's order of operations and uploaded once per theta.  No CPU fallback: without a usable device
+// hyg_create() fails and nothing computes.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/hygeia_b200.h"
+#include "hyg_tables.h"
+#include "sg_emission.cuh"
+#include "sg_filter.cuh"
+
+#define HYG_VERSION_STR "hygeia_b200 0.1.0 (sm_100a)"
+
+namespace {
+
+std::string g_create_error;
+
+struct Dataset {
+  uint64_t T = 0;
+  uint32_t S = 0;
+  uint64_t pitch = 0;
+  const uint16_t* d_nt = nullptr;
+  const uint16_t* d_nm = nullptr;
+  bool owned = false;
+  double* d_logobs = nullptr;
+};
+
+struct ChainBuf {
+  hyg_sg_chain host;  // copy of the caller's descriptor
+  uint64_t T = 0;
+  double* d_unif = nullptr;
+  uint32_t* d_pos = nullptr;
+  double* d_probs = nullptr;
+  double* d_logz = nullptr;
+  int* d_k = nullptr;
+  unsigned char* d_drew = nullptr;
+  int* d_npend = nullptr;
+  int* d_ncurr = nullptr;
+  int* d_fin = nullptr;
+  short* d_anc = nullptr;
+  int* d_status = nullptr;
+};
+
+}  // namespace
+
+struct hyg_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  hyg::SgHostModel hm;
+  bool model_set = false, theta_set = false;
+  double2* d_tab = nullptr;
+  double* d_tabg = nullptr;
+  hyg::SgModelDev* d_mdl = nullptr;
+  double* d_emtab = nullptr;
+  int nmax_table = 255;
+  std::vector<Dataset> ds;
+  std::vector<ChainBuf> chains;
+  std::vector<uint32_t> order;  // launch order (longest first) -> caller index
+  hyg::SgChainDev* d_chains = nullptr;
+  double* d_psi = nullptr;
+  size_t psi_bytes = 0;
+  unsigned int* d_queue = nullptr;
+  uint32_t n_particles_staged = 0;
+  cudaEvent_t ev_em0 = nullptr, ev_em1 = nullptr, ev_f0 = nullptr, ev_f1 = nullptr;
+  bool timed_em = false, timed_f = false;
+  uint32_t em_launches = 0, f_launches = 0;
+};
+
+namespace {
+
+int fail(hyg_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define HYG_CUDA(ctx, call)                                                                                        \
+  do {                                                                                                             \
+    cudaError_t e_ = (call);                                                                                       \
+    if (e_ != cudaSuccess) return fail((ctx), HYG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));   \
+  } while (0)
+
+template <class T> void dfree(T*& p) {
+  if (p) cudaFree(const_cast<typename std::remove_const<T>::type*>(p));
+  p = nullptr;
+}
+
+void free_chains(hyg_ctx* c) {
+  for (auto& b : c->chains) {
+    dfree(b.d_unif); dfree(b.d_pos); dfree(b.d_probs); dfree(b.d_logz); dfree(b.d_k); dfree(b.d_drew); dfree(b.d_npend);
+    dfree(b.d_ncurr); dfree(b.d_fin); dfree(b.d_anc); dfree(b.d_status);
+  }
+  c->chains.clear();
+  c->order.clear();
+  dfree(c->d_chains);
+}
+
+void free_datasets(hyg_ctx* c) {
+  for (auto& d : c->ds) {
+    if (d.owned) { dfree(d.d_nt); dfree(d.d_nm); }
+    dfree(d.d_logobs);
+  }
+  c->ds.clear();
+}
+
+__global__ void fill_positions_kernel(double* probs, const uint32_t* pos, unsigned long long T, int stride) {
+  for (unsigned long long t = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; t < T;
+       t += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
+    probs[t * stride] = pos ? static_cast<double>(pos[t]) : static_cast<double>(t);
+}
+
+template <int R> int launch_emission(hyg_ctx* c, const hyg::SgEmissionArgs& a, size_t smem) {
+  HYG_CUDA(c, cudaFuncSetAttribute(hyg::sg_emission_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  hyg::sg_emission_kernel<R><<<c->num_sms, HYG_EM_NT, smem, c->stream>>>(a);
+  HYG_CUDA(c, cudaGetLastError());
+  return HYG_OK;
+}
+
+template <int R> int launch_filter(hyg_ctx* c, const hyg::SgRunDev& run, int grid) {
+  hyg::sg_filter_kernel<R><<<grid, HYG_NT, 0, c->stream>>>(c->d_mdl, c->d_chains, run);
+  HYG_CUDA(c, cudaGetLastError());
+  return HYG_OK;
+}
+template <int R> int filter_occupancy(int* occ) {
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, hyg::sg_filter_kernel<R>, HYG_NT, 0) == cudaSuccess ? 0 : -1;
+}
+
+#define HYG_DISPATCH_R(R_, EXPR)              \
+  switch (R_) {                               \
+    case 2: { constexpr int RR = 2; EXPR; } break; \
+    case 3: { constexpr int RR = 3; EXPR; } break; \
+    case 4: { constexpr int RR = 4; EXPR; } break; \
+    case 5: { constexpr int RR = 5; EXPR; } break; \
+    case 6: { constexpr int RR = 6; EXPR; } break; \
+    case 7: { constexpr int RR = 7; EXPR; } break; \
+    case 8: { constexpr int RR = 8; EXPR; } break; \
+    default: break;                           \
+  }
+
+}  // namespace
+
+extern "C" {
+
+const char* hyg_version(void) { return HYG_VERSION_STR; }
+const char* hyg_create_error(void) { return g_create_error.c_str(); }
+const char* hyg_last_error(hyg_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* hyg_stream(hyg_ctx* ctx) { return ctx ? static_cast<void*>(ctx->stream) : nullptr; }
+
+hyg_ctx* hyg_create(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    g_create_error = std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                     " (this library has no CPU fallback)";
+    return nullptr;
+  }
+  if (device < 0 || device >= n) { g_create_error = "device index out of range"; return nullptr; }
+  if ((e = cudaSetDevice(device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return nullptr; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); return nullptr; }
+  if (prop.major < 10) {
+    g_create_error = "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + "; this build targets sm_100a only";
+    return nullptr;
+  }
+  hyg_ctx* c = new hyg_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    g_create_error = cudaGetErrorString(e);
+    delete c;
+    return nullptr;
+  }
+  cudaEventCreate(&c->ev_em0); cudaEventCreate(&c->ev_em1); cudaEventCreate(&c->ev_f0); cudaEventCreate(&c->ev_f1);
+  cudaMalloc(&c->d_mdl, sizeof(hyg::SgModelDev));
+  cudaMalloc(&c->d_queue, sizeof(unsigned int));
+  return c;
+}
+
+void hyg_destroy(hyg_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_chains(c);
+  free_datasets(c);
+  dfree(c->d_tab); dfree(c->d_tabg); dfree(c->d_mdl); dfree(c->d_emtab); dfree(c->d_psi); dfree(c->d_queue);
+  cudaEventDestroy(c->ev_em0); cudaEventDestroy(c->ev_em1); cudaEventDestroy(c->ev_f0); cudaEventDestroy(c->ev_f1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int hyg_sync(hyg_ctx* c) {
+  if (!c) return HYG_ERR_ARG;
+  HYG_CUDA(c, cudaSetDevice(c->device));
+  HYG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HYG_OK;
+}
+
+int hyg_sg_set_model(hyg_ctx* c, uint32_t R, uint32_t u, const double* alpha, const double* beta, int kappa_fixed, const double* kappa) {
+  if (!c || !alpha || !beta) return fail(c, HYG_ERR_ARG, "null argument");
+  int rc = c->hm.set_known(static_cast<int>(R), static_cast<int>(u), alpha, beta, kappa_fixed, kappa);
+  if (rc) return fail(c, rc == -2 ? HYG_ERR_UNSUPPORTED : HYG_ERR_ARG, c->hm.err);
+  c->model_set = true;
+  c->theta_set = false;
+  // emission table (misc.h:630-640 tabulated over the triangle n <= nmax_table)
+  HYG_CUDA(c, cudaSetDevice(c->device));
+  std::vector<double> tab;
+  hyg::build_emission_table(c->hm.alpha.data(), c->hm.beta.data(), c->hm.R, c->nmax_table, tab);
+  dfree(c->d_emtab);
+  HYG_CUDA(c, cudaMalloc(&c->d_emtab, tab.size() * sizeof(double)));
+  HYG_CUDA(c, cudaMemcpyAsync(c->d_emtab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  HYG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HYG_OK;
+}
+
+int hyg_sg_set_vartheta(hyg_ctx* c, const double* vt, uint32_t n) {
+  if (!c || !vt || n < 2) return fail(c, HYG_ERR_ARG, "bad vartheta");
+  const uint32_t R = static_cast<uint32_t>(vt[1]);
+  if (R < 2 || R > 8 || n < 2 * R + 3) return fail(c, HYG_ERR_ARG, "bad vartheta");
+  const int kf = vt[2 * R + 2] != 0.0;
+  if (kf && n < 3 * R + 3) return fail(c, HYG_ERR_ARG, "vartheta lacks kappa");
+  return hyg_sg_set_model(c, R, static_cast<uint32_t>(vt[0]), vt + 2, vt + 2 + R, kf, kf ? vt + 2 * R + 3 : nullptr);
+}
+
+int hyg_sg_set_theta(hyg_ctx* c, const double* theta, uint32_t dim, uint64_t t_max) {
+  if (!c || !theta) return fail(c, HYG_ERR_ARG, "null argument");
+  if (!c->model_set) return fail(c, HYG_ERR_STATE, "hyg_sg_set_model first");
+  int rc = c->hm.set_theta(theta, dim, t_max);
+  if (rc) return fail(c, HYG_ERR_ARG, c->hm.err);
+  HYG_CUDA(c, cudaSetDevice(c->device));
+  dfree(c->d_tab); dfree(c->d_tabg);
+  HYG_CUDA(c, cudaMalloc(&c->d_tab, c->hm.tab.size() * sizeof(double)));
+  HYG_CUDA(c, cudaMalloc(&c->d_tabg, c->hm.tabg.size() * sizeof(double)));
+  HYG_CUDA(c, cudaMemcpyAsync(c->d_tab, c->hm.tab.data(), c->hm.tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  HYG_CUDA(c, cudaMemcpyAsync(c->d_tabg, c->hm.tabg.data(), c->hm.tabg.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  HYG_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->theta_set = true;
+  return HYG_OK;
+}
+
+int hyg_sg_get_tables(hyg_ctx* c, double* P, double* omega, uint32_t d_max, double* rho, uint8_t* exit_status) {
+  if (!c) return HYG_ERR_ARG;
+  if (!c->theta_set) return fail(c, HYG_ERR_STATE, "hyg_sg_set_theta first");
+  const int R = c->hm.R;
+  if (P) for (int i = 0; i < R; i++) for (int j = 0; j < R; j++) P[i * R + j] = c->hm.P[i][j];
+  if (omega) for (int i = 0; i < R; i++) omega[i] = c->hm.omega[i];
+  for (int r = 0; r < R; r++)
+    for (uint32_t d = 0; d < d_max; d++) {
+      const uint32_t i = d < c->hm.dcap ? d : c->hm.dcap - 1;
+      const double cn = c->hm.tab[(static_cast<size_t>(r) * c->hm.dcap + i) * 2], lc = c->hm.tab[(static_cast<size_t>(r) * c->hm.dcap + i) * 2 + 1];
+      const bool ex = std::isinf(lc) && lc < 0 && cn == 1.0;
+      if (rho) rho[r * d_max + d] = ex ? 1.0 : (d + 1 < static_cast<uint32_t>(c->hm.u) ? 0.0 : cn);
+      if (exit_status) exit_status[r * d_max + d] = ex ? 1 : 0;
+    }
+  return HYG_OK;
+}
+
+int hyg_sg_clear(hyg_ctx* c) {
+  if (!c) return HYG_ERR_ARG;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_chains(c);
+  free_datasets(c);
+  return HYG_OK;
+}
+
+int hyg_sg_add_dataset(hyg_ctx* c, uint64_t T, uint32_t S, const uint16_t* n_total, const uint16_t* n_meth, int on_device, uint64_t pitch) {
+  if (!c || !n_total || !n_meth || T == 0 || S == 0) return fail(c, HYG_ERR_ARG, "bad data set");
+  if (!c->model_set) return fail(c, HYG_ERR_STATE, "hyg_sg_set_model first");
+  HYG_CUDA(c, cudaSetDevice(c->device));
+  Dataset d;
+  d.T = T; d.S = S;
+  if (on_device) {
+    if (pitch < T || (pitch & 1)) return fail(c, HYG_ERR_ARG, "device pitch must be even and >= T");
+    d.pitch = pitch; d.d_nt = n_total; d.d_nm = n_meth; d.owned = false;
+  } else {
+    d.pitch = (T + 7) / 8 * 8;
+    uint16_t *a = nullptr, *b = nullptr;
+    const size_t bytes = static_cast<size_t>(S) * d.pitch * sizeof(uint16_t);
+    HYG_CUDA(c, cudaMalloc(&a, bytes));
+    HYG_CUDA(c, cudaMalloc(&b, bytes));
+    if (d.pitch != T) { HYG_CUDA(c, cudaMemsetAsync(a, 0, bytes, c->stream)); HYG_CUDA(c, cudaMemsetAsync(b, 0, bytes, c->stream)); }
+    HYG_CUDA(c, cudaMemcpy2DAsync(a, d.pitch * 2, n_total, T * 2, T * 2, S, cudaMemcpyHostToDevice, c->stream));
+    HYG_CUDA(c, cudaMemcpy2DAsync(b, d.pitch * 2, n_meth, T * 2, T * 2, S, cudaMemcpyHostToDevice, c->stream));
+    d.d_nt = a; d.d_nm = b; d.owned = true;
+  }
+  HYG_CUDA(c, cudaMalloc(&d.d_logobs, static_cast<size_t>(T) * c->hm.R * sizeof(double)));
+  c->ds.push_back(d);
+  return static_cast<int>(c->ds.size()) - 1;
+}
+
+void hyg_sg_default_run_args(hyg_sg_run_args* a) {
+  if (!a) return;
+  std::memset(a, 0, sizeof(*a));
+  a->n_particles_max = 250;             // bin/estimate_parameters_and_regimes:109-115
+  a->smc_proposal_type = 1;             // :310
+  a->smc_resample_type = 2;             // :311
+  a->use_online_marginal_smoothing = 1;
+  a->epsilon = 0.01;                    // :132-138
+  a->use_online_parameter_estimation = 0;
+  a->normalise_gradients = 0;
+  a->use_adam = 1;
+  a->n_steps_without_parameter_update = 200;
+  a->learning_rate_exponent = 0.1;
+  a->learning_rate_factor = 0.01;
+  a->lag_capacity = 128;
+}
+
+int hyg_sg_set_chains(hyg_ctx* c, const hyg_sg_chain* chains, uint32_t n) {
+  if (!c || !chains || n == 0) return fail(c, HYG_ERR_ARG, "no chains");
+  if (!c->model_set) return fail(c, HYG_ERR_STATE, "hyg_sg_set_model first");
+  HYG_CUDA(c, cudaSetDevice(c->device));
+  HYG_CUDA(c, cudaStreamSynchronize(c->stream));
+  free_chains(c);
+  const int R = c->hm.R;
+  c->chains.resize(n);
+  for (uint32_t i = 0; i < n; i++) {
+    ChainBuf& b = c->chains[i];
+    b.host = chains[i];
+    if (chains[i].dataset >= c->ds.size()) return fail(c, HYG_ERR_ARG, "chain refers to an unknown data set");
+    const uint64_t T = c->ds[chains[i].dataset].T;
+    b.T = T;
+    if (chains[i].uniforms) {
+      HYG_CUDA(c, cudaMalloc(&b.d_unif, T * sizeof(double)));
+      HYG_CUDA(c, cudaMemcpyAsync(b.d_unif, chains[i].uniforms, T * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (chains[i].regime_probs) {
+      HYG_CUDA(c, cudaMalloc(&b.d_probs, T * (R + 1) * sizeof(double)));
+      if (chains[i].positions) {
+        HYG_CUDA(c, cudaMalloc(&b.d_pos, T * sizeof(uint32_t)));
+        HYG_CUDA(c, cudaMemcpyAsync(b.d_pos, chains[i].positions, T * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+      }
+    }
+    if (chains[i].logz) HYG_CUDA(c, cudaMalloc(&b.d_logz, T * sizeof(double)));
+    if (chains[i].k_kept) HYG_CUDA(c, cudaMalloc(&b.d_k, T * sizeof(int)));
+    if (chains[i].drew_uniform) HYG_CUDA(c, cudaMalloc(&b.d_drew, T));
+    if (chains[i].n_pending) HYG_CUDA(c, cudaMalloc(&b.d_npend, T * sizeof(int)));
+    if (chains[i].n_curr) HYG_CUDA(c, cudaMalloc(&b.d_ncurr, T * sizeof(int)));
+    if (chains[i].finalised_at) HYG_CUDA(c, cudaMalloc(&b.d_fin, T * sizeof(int)));
+    HYG_CUDA(c, cudaMalloc(&b.d_status, 2 * sizeof(int)));
+    HYG_CUDA(c, cudaMemsetAsync(b.d_status, 0, 2 * sizeof(int), c->stream));
+  }
+  // launch order: longest chain first (LPT), so the persistent CTAs finish together
+  c->order.resize(n);
+  std::iota(c->order.begin(), c->order.end(), 0u);
+  std::stable_sort(c->order.begin(), c->order.end(), [&](uint32_t a, uint32_t b) { return c->chains[a].T > c->chains[b].T; });
+  HYG_CUDA(c, cudaMalloc(&c->d_chains, n * sizeof(hyg::SgChainDev)));
+  c->n_particles_staged = 0;
+  return HYG_OK;
+}
+
+int hyg_sg_emission(hyg_ctx* c) {
+  if (!c) return HYG_ERR_ARG;
+  if (!c->model_set) return fail(c, HYG_ERR_STATE, "hyg_sg_set_model first");
+  if (c->ds.empty()) return fail(c, HYG_ERR_STATE, "no data sets");
+  HYG_CUDA(c, cudaSetDevice(c->device));
+  const int R = c->hm.R;
+  const size_t rows_max = static_cast<size_t>(HYG_EM_SMEM_DOUBLES) / R;
+  int nmax_smem = 0;
+  while (static_cast<size_t>(nmax_smem + 2) * (nmax_smem + 3) / 2 <= rows_max && nmax_smem + 1 <= c->nmax_table) nmax_smem++;
+  const size_t smem = static_cast<size_t>(nmax_smem + 1) * (nmax_smem + 2) / 2 * R * sizeof(double);
+  HYG_CUDA(c, cudaEventRecord(c->ev_em0, c->stream));
+  c->em_launches = 0;
+  for (auto& d : c->ds) {
+    hyg::SgEmissionArgs a;
+    a.T = d.T; a.S = d.S; a.pitch = d.pitch; a.n_total = d.d_nt; a.n_meth = d.d_nm; a.logobs = d.d_logobs;
+    a.table = c->d_emtab; a.nmax_table = c->nmax_table; a.nmax_smem = nmax_smem;
+    for (int r = 0; r < HYG_RMAX; r++) { a.alpha[r] = r < R ? c->hm.alpha[r] : 1.0; a.beta[r] = r < R ? c->hm.beta[r] : 1.0; }
+    int rc = HYG_ERR_UNSUPPORTED;
+    HYG_DISPATCH_R(R, rc = launch_emission<RR>(c, a, smem));
+    if (rc) return rc;
+    c->em_launches++;
+  }
+  HYG_CUDA(c, cudaEventRecord(c->ev_em1, c->stream));
+  c->timed_em = true;
+  return HYG_OK;
+}
+
+int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
+  if (!c || !args) return HYG_ERR_ARG;
+  if (!c->theta_set) return fail(c, HYG_ERR_STATE, "hyg_sg_set_theta first");
+  if (c->chains.empty()) return fail(c, HYG_ERR_STATE, "no chains staged");
+  if (args->smc_proposal_type != 1 || args->smc_resample_type != 2)
+    return fail(c, HYG_ERR_UNSUPPORTED, "only the change-point proposal (1) with optimal finite-state resampling (2) is implemented "
+                                        "(the only combination the reference CLI uses)");
+  const int R = c->hm.R;
+  if (args->n_particles_max > HYG_NPMAX || args->n_particles_max < static_cast<uint32_t>(2 * R))
+    return fail(c, HYG_ERR_UNSUPPORTED, "n_particles must be in [2R, 256]");
+  if (args->use_online_parameter_estimation) return fail(c, HYG_ERR_UNSUPPORTED, "online parameter estimation is not implemented yet");
+  HYG_CUDA(c, cudaSetDevice(c->device));
+  const uint32_t n = static_cast<uint32_t>(c->chains.size());
+  const uint32_t Nmax = args->n_particles_max;
+
+  // (re)allocate the ancestor taps now that N_max is known
+  for (auto& b : c->chains)
+    if (b.host.ancestors && (!b.d_anc || c->n_particles_staged != Nmax)) {
+      dfree(b.d_anc);
+      HYG_CUDA(c, cudaMalloc(&b.d_anc, b.T * (Nmax - R) * sizeof(short)));
+    }
+  c->n_particles_staged = Nmax;
+
+  // model descriptor
+  hyg::SgModelDev m;
+  m.R = R; m.u = c->hm.u; m.n_particles = static_cast<int>(Nmax); m.dcap = c->hm.dcap;
+  for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) { m.P[i][j] = c->hm.P[i][j]; m.logP[i][j] = c->hm.logP[i][j]; }
+  m.tab = c->d_tab; m.tabg = c->d_tabg;
+  HYG_CUDA(c, cudaMemcpyAsync(c->d_mdl, &m, sizeof(m), cudaMemcpyHostToDevice, c->stream));
+
+  // chain descriptors in launch order
+  std::vector<hyg::SgChainDev> cd(n);
+  for (uint32_t k = 0; k < n; k++) {
+    const ChainBuf& b = c->chains[c->order[k]];
+    hyg::SgChainDev& d = cd[k];
+    std::memset(&d, 0, sizeof(d));
+    d.T = b.T;
+    d.logobs = c->ds[b.host.dataset].d_logobs;
+    d.unif = b.d_unif; d.seed = b.host.seed; d.chain_id = b.host.chain_id;
+    d.probs = args->use_online_marginal_smoothing ? b.d_probs : nullptr;
+    d.logz = b.d_logz; d.k_kept = b.d_k; d.drew = b.d_drew; d.n_pending = b.d_npend; d.n_curr = b.d_ncurr;
+    d.finalised_at = b.d_fin; d.ancestors = b.d_anc; d.status = b.d_status;
+  }
+  HYG_CUDA(c, cudaMemcpyAsync(c->d_chains, cd.data(), n * sizeof(hyg::SgChainDev), cudaMemcpyHostToDevice, c->stream));
+  HYG_CUDA(c, cudaStreamSynchronize(c->stream));  // cd goes out of scope
+
+  int occ = 1;
+  HYG_DISPATCH_R(R, filter_occupancy<RR>(&occ));
+  if (occ < 1) occ = 1;
+  const int grid = static_cast<int>(std::min<uint64_t>(n, static_cast<uint64_t>(c->num_sms) * occ));
+
+  hyg::SgRunDev run;
+  run.use_smoothing = args->use_online_marginal_smoothing ? 1 : 0;
+  run.epsilon = args->epsilon;
+  run.lcap = args->lag_capacity ? static_cast<int>(args->lag_capacity) : 128;
+  run.psi_stride = 2ull * run.lcap * R * HYG_NPMAX + (run.lcap + 1) / 2 + 8;
+  const size_t need = run.psi_stride * sizeof(double) * grid;
+  if (need > c->psi_bytes) {
+    dfree(c->d_psi);
+    HYG_CUDA(c, cudaMalloc(&c->d_psi, need));
+    c->psi_bytes = need;
+  }
+  run.psi_ws = c->d_psi;
+  run.queue = c->d_queue;
+  run.n_chains = static_cast<int>(n);
+  HYG_CUDA(c, cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned int), c->stream));
+
+  c->f_launches = 0;
+  HYG_CUDA(c, cudaEventRecord(c->ev_f0, c->stream));
+  if (run.use_smoothing) {
+    for (auto& b : c->chains)
+      if (b.d_probs) {
+        fill_positions_kernel<<<c->num_sms, 256, 0, c->stream>>>(b.d_probs, b.d_pos, b.T, R + 1);
+        c->f_launches++;
+      }
+  }
+  int rc = HYG_ERR_UNSUPPORTED;
+  HYG_DISPATCH_R(R, rc = launch_filter<RR>(c, run, grid));
+  if (rc) return rc;
+  c->f_launches++;
+  HYG_CUDA(c, cudaEventRecord(c->ev_f1, c->stream));
+  c->timed_f = true;
+  return HYG_OK;
+}
+
+int hyg_sg_download(hyg_ctx* c, hyg_sg_chain* chains, uint32_t n) {
+  if (!c) return HYG_ERR_ARG;
+  if (n != c->chains.size()) return fail(c, HYG_ERR_ARG, "chain count differs from hyg_sg_set_chains");
+  HYG_CUDA(c, cudaSetDevice(c->device));
+  const int R = c->hm.R;
+  for (uint32_t i = 0; i < n; i++) {
+    ChainBuf& b = c->chains[i];
+    const hyg_sg_chain& h = b.host;
+    const uint64_t T = b.T;
+    if (h.regime_probs && b.d_probs) HYG_CUDA(c, cudaMemcpyAsync(h.regime_probs, b.d_probs, T * (R + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (h.logz) HYG_CUDA(c, cudaMemcpyAsync(h.logz, b.d_logz, T * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (h.k_kept) HYG_CUDA(c, cudaMemcpyAsync(h.k_kept, b.d_k, T * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (h.drew_uniform) HYG_CUDA(c, cudaMemcpyAsync(h.drew_uniform, b.d_drew, T, cudaMemcpyDeviceToHost, c->stream));
+    if (h.n_pending) HYG_CUDA(c, cudaMemcpyAsync(h.n_pending, b.d_npend, T * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (h.n_curr) HYG_CUDA(c, cudaMemcpyAsync(h.n_curr, b.d_ncurr, T * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (h.finalised_at) HYG_CUDA(c, cudaMemcpyAsync(h.finalised_at, b.d_fin, T * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (h.ancestors && b.d_anc)
+      HYG_CUDA(c, cudaMemcpyAsync(h.ancestors, b.d_anc, T * (c->n_particles_staged - R) * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
+    if (chains) HYG_CUDA(c, cudaMemcpyAsync(chains[i].status, b.d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  }
+  HYG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HYG_OK;
+}
+
+int hyg_sg_timings(hyg_ctx* c, float* ms_em, float* ms_f, uint32_t* em_launches, uint32_t* f_launches) {
+  if (!c) return HYG_ERR_ARG;
+  HYG_CUDA(c, cudaSetDevice(c->device));
+  HYG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (ms_em) { *ms_em = 0.f; if (c->timed_em) HYG_CUDA(c, cudaEventElapsedTime(ms_em, c->ev_em0, c->ev_em1)); }
+  if (ms_f) { *ms_f = 0.f; if (c->timed_f) HYG_CUDA(c, cudaEventElapsedTime(ms_f, c->ev_f0, c->ev_f1)); }
+  if (em_launches) *em_launches = c->em_launches;
+  if (f_launches) *f_launches = c->f_launches;
+  return HYG_OK;
+}
+
+int hyg_sg_get_logobs(hyg_ctx* c, uint32_t dataset, double* logobs) {
+  if (!c || !logobs || dataset >= c->ds.size()) return fail(c, HYG_ERR_ARG, "bad data set");
+  HYG_CUDA(c, cudaSetDevice(c->device));
+  const Dataset& d = c->ds[dataset];
+  HYG_CUDA(c, cudaMemcpyAsync(logobs, d.d_logobs, d.T * c->hm.R * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  HYG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return HYG_OK;
+}
+
+int hyg_sg_run_online_combined_inference(hyg_ctx* c, const double* vartheta, uint32_t n_vartheta, const double* theta_init, uint32_t dim_theta,
+                                         uint64_t T, uint32_t S, const uint32_t* positions, const uint16_t* n_total, const uint16_t* n_meth,
+                                         const hyg_sg_run_args* args, uint64_t seed, const double* uniforms,
+                                         double* regime_probs, double* theta_trace, double* logz, double* seconds) {
+  if (!c || !args) return HYG_ERR_ARG;
+  const auto t0 = std::chrono::steady_clock::now();
+  int rc;
+  if ((rc = hyg_sg_clear(c))) return rc;
+  if ((rc = hyg_sg_set_vartheta(c, vartheta, n_vartheta))) return rc;
+  if ((rc = hyg_sg_set_theta(c, theta_init, dim_theta, T))) return rc;
+  if ((rc = hyg_sg_add_dataset(c, T, S, n_total, n_meth, 0, T)) < 0) return rc;
+  hyg_sg_chain ch;
+  std::memset(&ch, 0, sizeof(ch));
+  ch.dataset = 0; ch.seed = seed; ch.chain_id = 0; ch.uniforms = uniforms; ch.positions = positions;
+  ch.regime_probs = args->use_online_marginal_smoothing ? regime_probs : nullptr;
+  ch.logz = logz; ch.theta_trace = theta_trace;
+  if ((rc = hyg_sg_set_chains(c, &ch, 1))) return rc;
+  if ((rc = hyg_sg_emission(c))) return rc;
+  if ((rc = hyg_sg_filter(c, args))) return rc;
+  if ((rc = hyg_sg_download(c, &ch, 1))) return rc;
+  if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return HYG_OK;
+}
+
+double hyg_philox_uniform(uint64_t seed, uint32_t chain_id, uint64_t t) { return hyg::philox_uniform(seed, chain_id, t); }
+
+int hyg_sg_sample_theta_prior(uint32_t dim, uint64_t seed, double* theta) {
+  if (!theta) return HYG_ERR_ARG;
+  // theta ~ N(0, I) (singleGroup.h:479-483), Box-Muller on Philox uniforms (stream tag 0xFFFFFFFF)
+  for (uint32_t i = 0; i < dim; i += 2) {
+    double u1 = hyg::philox_uniform(seed, 0xFFFFFFFFu, i), u2 = hyg::philox_uniform(seed, 0xFFFFFFFFu, i + 1);
+    if (u1 < 1e-300) u1 = 1e-300;
+    const double r = std::sqrt(-2.0 * std::log(u1)), a = 6.283185307179586476925 * u2;
+    theta[i] = r * std::cos(a);
+    if (i + 1 < dim) theta[i + 1] = r * std::sin(a);
+  }
+  return HYG_OK;
+}
+
+}  // extern "C"

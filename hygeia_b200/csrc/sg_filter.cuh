@@ -414,7 +414,7 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
           const int ts = pend_t[i];
           if (emit) {
             const double outv = pick<2 * R>(mv, tid);
-            if (tid < R && ch.probs) ch.probs[static_cast<size_t>(ts) * R + tid] = outv;
+            if (tid < R && ch.probs) ch.probs[static_cast<size_t>(ts) * (R + 1) + 1 + tid] = outv;
             if (tid == 0 && ch.finalised_at) ch.finalised_at[ts] = static_cast<int>(t);
           } else {
             double* dst = pc + static_cast<size_t>(kept) * R * HYG_NPMAX;
@@ -453,7 +453,7 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
       if (!emit && n_pend >= lcap) { emit = true; n_forced++; }  // lag set full: emit the filtering estimate now (reported)
       if (emit) {
         const double outv = pick<R>(cw, tid);
-        if (tid < R && ch.probs) ch.probs[static_cast<size_t>(t) * R + tid] = outv;
+        if (tid < R && ch.probs) ch.probs[static_cast<size_t>(t) * (R + 1) + 1 + tid] = outv;
         if (tid == 0 && ch.finalised_at) ch.finalised_at[t] = static_cast<int>(t);
       } else {
         double* dst = psi[t & 1] + static_cast<size_t>(n_pend) * R * HYG_NPMAX;

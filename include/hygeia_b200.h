@@ -1,0 +1,126 @@
+/* include/hygeia_b200.h -- C ABI of libhygeia_b200.so: the B200-native drop-in for Hygeia's inference hot path.
+ *
+ * Boundary being replaced (paths relative to /root/reference):
+ *   single-group operator   runOnlineCombinedInferenceCpp     src/single_group/src/cpp/singleGroup.cpp:76-189
+ *     (the Rcpp export the Rscript src/single_group/bin/estimate_parameters_and_regimes:303-322 calls)
+ *   its model setup          setKnownParameters/UnknownParameters  src/single_group/src/cpp/singleGroup.h:173-335
+ *   its emission term        evaluateLogObservationDensity    src/single_group/src/cpp/singleGroup.h:610-627
+ *   prior draw               sampleFromParameterPriorCpp      src/single_group/src/cpp/singleGroup.cpp:18-35
+ *
+ * Conventions: C linkage, plain pointers and sizes, caller-owned buffers, `int` status (0 = ok, < 0 = error, message via
+ * hyg_last_error).  No exceptions or exit() cross this boundary.  One context per device / host thread; contexts are
+ * independent.  There is NO CPU fallback: every entry point that computes fails with HYG_ERR_CUDA when no device is usable.
+ */
+#ifndef HYGEIA_B200_H
+#define HYGEIA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HYG_OK 0
+#define HYG_ERR_ARG (-1)
+#define HYG_ERR_UNSUPPORTED (-2)
+#define HYG_ERR_CUDA (-3)
+#define HYG_ERR_STATE (-4)
+
+typedef struct hyg_ctx hyg_ctx;
+
+/* ---- context ---------------------------------------------------------------------------------------------------- */
+hyg_ctx* hyg_create(int device);          /* NULL if the device cannot be initialised (see hyg_create_error) */
+void hyg_destroy(hyg_ctx* ctx);
+const char* hyg_last_error(hyg_ctx* ctx); /* message of the last failing call on this context */
+const char* hyg_create_error(void);       /* why the last hyg_create returned NULL */
+const char* hyg_version(void);
+void* hyg_stream(hyg_ctx* ctx);           /* the cudaStream_t every kernel of this context is launched on */
+
+/* ---- model (= vartheta and theta of the reference) -------------------------------------------------------------- */
+/* setKnownParameters (singleGroup.h:173-195): vartheta = (u, R, alpha[R], beta[R], isKappaFixed, kappa[R]) */
+int hyg_sg_set_model(hyg_ctx* ctx, uint32_t R, uint32_t u, const double* alpha, const double* beta, int kappa_fixed, const double* kappa);
+int hyg_sg_set_vartheta(hyg_ctx* ctx, const double* vartheta, uint32_t n);
+/* setUnknownParameters (singleGroup.h:197-335): theta in R^(R*R) -> P, omega and the sojourn tables, built on the host in
+ * the reference's order of operations and uploaded.  t_max bounds the table length (longest chain that will be run). */
+int hyg_sg_set_theta(hyg_ctx* ctx, const double* theta, uint32_t dim, uint64_t t_max);
+/* read back what the kernels will use: P[R*R] row-major, omega[R]; rho/exit for d = 1..d_max (each R x d_max, row-major) */
+int hyg_sg_get_tables(hyg_ctx* ctx, double* P, double* omega, uint32_t d_max, double* rho, uint8_t* exit_status);
+
+/* ---- data sets: one per chromosome / count matrix ----------------------------------------------------------------
+ * Counts are uint16 (the reference itself narrows to int16: src/two_group/run_inference_two_groups.py:246-253), layout
+ * [S][T] with the SITE index fastest.  `on_device` != 0: the pointers are device pointers with row pitch `pitch`
+ * elements (pitch even, >= T, the pad readable) and are used in place; otherwise they are host pointers (pitch = T)
+ * and are copied host -> device by this call. */
+int hyg_sg_add_dataset(hyg_ctx* ctx, uint64_t T, uint32_t S, const uint16_t* n_total, const uint16_t* n_meth, int on_device, uint64_t pitch);
+int hyg_sg_clear(hyg_ctx* ctx);           /* drop all data sets and chains */
+
+/* ---- chains: one per (data set, seed) --------------------------------------------------------------------------- */
+typedef struct hyg_sg_chain {
+  uint32_t dataset;             /* index returned by the order of hyg_sg_add_dataset calls */
+  uint64_t seed;                /* Philox key: u[t] = philox(seed, chain_id, t) ...                          */
+  uint32_t chain_id;
+  const double* uniforms;       /* ... unless T injected per-site uniforms are given (host pointer, may be NULL) */
+  const uint32_t* positions;    /* T genomic positions (host) or NULL -> 0..T-1; first column of regime_probs */
+  /* outputs, host pointers, any may be NULL */
+  double* regime_probs;         /* T x (1+R) row-major: position, p_1..p_R  (= regimeProbabilityEstimates)   */
+  double* logz;                 /* T : running log normalising constant after site t                          */
+  double* theta_trace;          /* T x D (parameter-estimation mode)                                          */
+  /* step-level taps for parity tests, host pointers, any may be NULL */
+  int32_t* k_kept;              /* T : K of optimal resampling; -1 growth phase; -2 keep-largest              */
+  uint8_t* drew_uniform;        /* T */
+  int32_t* n_pending;           /* T : lag-set size after site t                                              */
+  int32_t* n_curr;              /* T : particle count after site t                                            */
+  int32_t* finalised_at;        /* T : step at which site t was emitted                                       */
+  int16_t* ancestors;           /* T x (n_particles - R)                                                      */
+  int32_t status[2];            /* out: [0] forced emissions because the lag set was full, [1] max lag-set size */
+} hyg_sg_chain;
+
+/* Algorithm switches: same meaning as the scalar arguments of runOnlineCombinedInferenceCpp (singleGroup.cpp:83-95). */
+typedef struct hyg_sg_run_args {
+  uint32_t n_particles_max;             /* <= 256 */
+  uint32_t smc_proposal_type;           /* must be 1 (change-point model)            */
+  uint32_t smc_resample_type;           /* must be 2 (optimal finite-state)          */
+  int32_t use_online_marginal_smoothing;
+  double epsilon;
+  int32_t use_online_parameter_estimation;
+  int32_t normalise_gradients;
+  int32_t use_adam;
+  uint32_t n_steps_without_parameter_update;
+  double learning_rate_exponent;
+  double learning_rate_factor;
+  uint32_t lag_capacity;                /* pending-site capacity per chain (0 -> 128) */
+} hyg_sg_run_args;
+
+void hyg_sg_default_run_args(hyg_sg_run_args* args);
+
+/* Stage the chains (uploads injected uniforms, allocates device outputs). */
+int hyg_sg_set_chains(hyg_ctx* ctx, const hyg_sg_chain* chains, uint32_t n_chains);
+/* K1: emission tables logObs[T x R] of every data set (device resident).  Asynchronous on the context's stream. */
+int hyg_sg_emission(hyg_ctx* ctx);
+/* K2: the recursion over all staged chains (device resident).  Asynchronous on the context's stream. */
+int hyg_sg_filter(hyg_ctx* ctx, const hyg_sg_run_args* args);
+/* Device -> host copy of the outputs of every staged chain into the host pointers of hyg_sg_set_chains; synchronises. */
+int hyg_sg_download(hyg_ctx* ctx, hyg_sg_chain* chains, uint32_t n_chains);
+int hyg_sync(hyg_ctx* ctx);
+/* Device time (ms, CUDA events on the context's stream) of the last hyg_sg_emission / hyg_sg_filter; synchronises. */
+int hyg_sg_timings(hyg_ctx* ctx, float* ms_emission, float* ms_filter, uint32_t* emission_launches, uint32_t* filter_launches);
+/* Copy the emission table of data set `dataset` to the host (T x R doubles). */
+int hyg_sg_get_logobs(hyg_ctx* ctx, uint32_t dataset, double* logobs);
+
+/* The operator itself: one chain, host buffers in, host buffers out -- argument for argument runOnlineCombinedInferenceCpp
+ * (singleGroup.cpp:76-96) except that counts are uint16 [S][T] (site fastest) and the seed indexes Philox.
+ * regime_probs: T x (1+R); theta_trace: T x D (parameter mode) or NULL; seconds: wall time of the call. */
+int hyg_sg_run_online_combined_inference(hyg_ctx* ctx, const double* vartheta, uint32_t n_vartheta, const double* theta_init, uint32_t dim_theta,
+                                         uint64_t T, uint32_t S, const uint32_t* positions, const uint16_t* n_total, const uint16_t* n_meth,
+                                         const hyg_sg_run_args* args, uint64_t seed, const double* uniforms,
+                                         double* regime_probs, double* theta_trace, double* logz, double* seconds);
+
+/* sampleFromParameterPriorCpp (singleGroup.cpp:18-35): theta ~ N(0, I_D), Philox-based (host). */
+int hyg_sg_sample_theta_prior(uint32_t dim, uint64_t seed, double* theta);
+/* Host copy of the by-site uniform the kernels use. */
+double hyg_philox_uniform(uint64_t seed, uint32_t chain_id, uint64_t t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

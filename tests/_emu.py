@@ -41,7 +41,7 @@ class Emu:
         T, R = logobs.shape
         if uniforms is not None:
             uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
-        out = dict(probs=np.full((T, R), np.nan), logz=np.zeros(T), k_kept=np.zeros(T, np.int32), drew_uniform=np.zeros(T, np.uint8),
+        out = dict(probs=np.full((T, R + 1), np.nan), logz=np.zeros(T), k_kept=np.zeros(T, np.int32), drew_uniform=np.zeros(T, np.uint8),
                    n_pending=np.zeros(T, np.int32), n_curr=np.zeros(T, np.int32), finalised_at=np.full(T, -1, np.int32),
                    ancestors=np.full((T, n_particles - R), -1, np.int16) if want_ancestors else None, status=np.zeros(2, np.int32))
         rc = self.lib.hygemu_sg_filter(_p(vartheta), C.c_uint32(len(vartheta)), _p(theta), C.c_uint32(len(theta)), C.c_uint32(n_particles),
@@ -50,6 +50,7 @@ class Emu:
                                        _p(out["probs"]), _p(out["logz"]), _p(out["k_kept"]), _p(out["drew_uniform"]), _p(out["n_pending"]),
                                        _p(out["n_curr"]), _p(out["finalised_at"]), _p(out["ancestors"]), _p(out["status"]))
         assert rc == 0, rc
+        out["probs"] = out["probs"][:, 1:]
         return out
 
     def sg_emission(self, alpha, beta, n_total_st, n_meth_st, nmax_table=255, nmax_smem=96, grid=3, block=64):

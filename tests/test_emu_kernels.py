@@ -1,0 +1,82 @@
+"""Kernel LOGIC on the GPU-less box: the device code of hygeia_b200/csrc compiled under tests/emu/cuda_emu.h
+(an emulation of the CUDA execution model) against the oracle.  The GPU tests (-m gpu) are the parity tests proper."""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+
+@pytest.fixture(scope="module")
+def emu(built):
+    from _emu import Emu
+    return Emu()
+
+
+def test_emission_bit_exact(emu, oracle):
+    g = golden("sg_default_s4.npz")
+    for grid, block in ((1, 32), (3, 64)):
+        lo = emu.sg_emission(g["alpha"], g["beta"], g["n_total"], g["n_meth"], grid=grid, block=block)
+        assert np.array_equal(lo, g["ref_strict_logobs"])
+
+
+def test_emission_table_tiers(emu, oracle):
+    """Counts beyond the shared-memory rows come from the L2-resident table (still bit-exact); beyond that, device lgamma."""
+    rng = np.random.default_rng(1)
+    S, T = 3, 301  # odd T exercises the half-filled last site pair
+    n = rng.integers(0, 400, size=(S, T)).astype(np.uint16)
+    x = (rng.random((S, T)) * (n + 1)).astype(np.uint16)
+    x[0, 5] = n[0, 5] + 1  # impossible count -> -inf (misc.h:636-639)
+    from hygeia_b200 import model
+    al, be = model.beta_parameters(model.DEFAULT_MU, model.DEFAULT_SIGMA)
+    want = oracle.emission(al, be, n, x)
+    got = emu.sg_emission(al, be, n, x, nmax_table=255, nmax_smem=20, grid=2, block=64)
+    assert np.all(np.isneginf(got[5])) and np.all(np.isneginf(want[5]))
+    small = (n <= 255).all(axis=0)
+    small[5] = False
+    assert np.array_equal(got[small], want[small])
+    big = ~small
+    big[5] = False
+    assert np.allclose(got[big], want[big], rtol=1e-13)
+
+
+@pytest.mark.parametrize("case,T", [("sg_default_s4.npz", 260), ("sg_sparse_s1.npz", 250), ("sg_dense_s16.npz", 200)])
+def test_filter_matches_golden_reference(emu, case, T):
+    g = golden(case)
+    lo = g["ref_strict_logobs"][:T]
+    r = emu.sg_filter(g["vartheta"], g["theta"], lo, uniforms=g["uniforms"][:T], n_particles=int(g["n_particles"]),
+                      epsilon=float(g["epsilon"]))
+    # sites finalised before the truncation point are final-step independent
+    done = g["ref_strict_finalised_at"][:T] < T - 1
+    assert done.sum() > T // 2
+    assert np.allclose(r["logz"], g["ref_strict_logz"][:T], rtol=1e-12)
+    assert np.array_equal(r["drew_uniform"], g["ref_strict_drew_uniform"][:T])
+    assert np.array_equal(r["n_pending"][:-1], g["ref_strict_n_pending"][:T - 1])
+    want = g["ref_strict_regime_probs"][:T, 1:]
+    assert np.allclose(r["probs"][done], want[done], rtol=1e-6, atol=1e-12)
+    assert np.array_equal(r["probs"][done].argmax(1), want[done].argmax(1))
+
+
+def test_filter_step_level_vs_oracle(emu, oracle, default_model):
+    from hygeia_b200 import philox, synthetic
+    T, S = 320, 2
+    ch = synthetic.make_chain(T, S, seed=31, lam=15.0)
+    al, be = default_model["alpha_beta"]
+    lo = oracle.emission(al, be, ch["n_total"], ch["n_meth"])
+    u = philox.uniforms_by_site(4, 9, T)
+    want = oracle.run(default_model["vartheta"], default_model["theta"], u, logobs=lo)
+    got = emu.sg_filter(default_model["vartheta"], default_model["theta"], lo, uniforms=None, seed=4, chain_id=9)  # device Philox
+    assert np.array_equal(got["k_kept"], want["k_kept"])
+    assert np.array_equal(got["n_curr"], want["n_curr"])
+    assert np.array_equal(got["finalised_at"], want["finalised_at"])
+    assert np.allclose(got["logz"], want["logz"], rtol=1e-12)
+    assert np.allclose(got["probs"], want["regime_probs"][:, 1:], rtol=1e-6, atol=1e-12)
+    assert got["status"][0] == 0 and got["status"][1] == want["n_pending"].max()
+
+
+def test_filter_lag_capacity_overflow_is_reported(emu, oracle, default_model):
+    g = golden("sg_sparse_s1.npz")
+    T = 200
+    r = emu.sg_filter(g["vartheta"], g["theta"], g["ref_strict_logobs"][:T], uniforms=g["uniforms"][:T], lcap=4)
+    assert r["status"][1] <= 4
+    assert r["status"][0] > 0          # forced emissions are counted, never silent
+    assert not np.isnan(r["probs"]).any()

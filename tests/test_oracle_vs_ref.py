@@ -1,0 +1,106 @@
+"""Pin the oracle (oracle/sg_oracle.cpp) to the reference: known answers, committed golden vectors generated from the
+compiled reference (tests/golden/make_golden.py), and -- on the build box, where oracle/_ref exists -- live runs."""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+CASES = ["sg_default_s4.npz", "sg_sparse_s1.npz", "sg_dense_s16.npz", "sg_few_particles.npz"]
+
+
+def test_known_answers_beta_binomial(oracle, default_model):
+    # SURVEY.md appendix D-3, obtained from the compiled reference (strict IEEE build)
+    al, be = default_model["alpha_beta"]
+    kat = {
+        (3, 10): [-9.32240506898033, -3.69368750814891, -5.00842283620527, -1.81853454821031, -2.07824900801116, -2.39789513386705],
+        (28, 30): [-1.9413891094269, -23.9987657681863, -2.43634487097194, -15.0357587600098, -8.46979819575873, -3.43398743001897],
+        (0, 25): [-26.6532569076147, -0.812417793699673, -17.5761476314584, -3.22315238163546, -10.8498613842006, -3.25809721854992],
+    }
+    for (x, n), want in kat.items():
+        got = [oracle.log_beta_binomial(x, n, al[r], be[r]) for r in range(6)]
+        assert np.allclose(got, want, rtol=1e-13, atol=0)
+    assert all(abs(oracle.log_beta_binomial(0, 0, al[r], be[r])) < 1e-14 for r in range(6))
+    assert oracle.log_beta_binomial(5, 3, 1.0, 1.0) == -np.inf
+
+
+def test_known_answers_rho(oracle, default_model):
+    t = oracle.tables(default_model["vartheta"], default_model["theta"], 3000)
+    rho = t["rho"]
+    want0 = {1: 0, 2: 0, 3: 2.4999999999999e-05, 4: 4.97512437810924e-05, 5: 7.42574257425712e-05, 10: 1.93236714975838e-04,
+             50: 9.7165991902828e-04, 200: 2.49370277078083e-03, 1000: 4.16875522139182e-03, 3000: 4.68877072476087e-03}
+    want4 = {3: 0.01, 4: 0.0181818181818182, 5: 0.025, 10: 0.0470588235294119, 50: 0.0842105263157866, 200: 0.0956521762207093,
+             1000: 1.07763633653259e-29, 3000: 9.88990665797501e-121}
+    for d, v in want0.items():
+        assert np.isclose(rho[0, d - 1], v, rtol=1e-12, atol=0)
+    for d, v in want4.items():
+        assert np.isclose(rho[4, d - 1], v, rtol=1e-12, atol=0)
+    assert t["exit"].sum() == 0
+    assert np.allclose(t["omega"], [0.995, 0.975, 0.95, 0.925, 0.9, 0.9])
+
+
+def test_tables_match_golden(oracle):
+    g = golden("sg_tables.npz")
+    for tag in ("default", "perturbed"):
+        t = oracle.tables(g["vartheta"], g[f"{tag}_theta"], 4000)
+        assert np.array_equal(t["rho"], g[f"{tag}_rho"])          # bit-exact: same recurrence, same order
+        assert np.array_equal(t["exit"], g[f"{tag}_exit"])
+        assert np.array_equal(t["grad"], g[f"{tag}_grad"])
+        assert np.array_equal(t["P"], g[f"{tag}_P"])
+        assert np.array_equal(t["omega"], g[f"{tag}_omega"])
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_oracle_matches_golden(oracle, case):
+    g = golden(case)
+    al, be = g["alpha"], g["beta"]
+    lo = oracle.emission(al, be, g["n_total"], g["n_meth"])
+    assert np.array_equal(lo, g["ref_strict_logobs"])                      # bit-exact against the strict reference build
+    assert np.allclose(lo, g["ref_fast_logobs"], rtol=1e-12, atol=1e-12)   # -ffast-math re-association only
+    r = oracle.run(g["vartheta"], g["theta"], g["uniforms"], g["n_total"], g["n_meth"], g["positions"],
+                   n_particles=int(g["n_particles"]), epsilon=float(g["epsilon"]))
+    assert np.array_equal(r["logz"], g["ref_strict_logz"])                 # log Z_t bit-exact at every site
+    assert np.array_equal(r["drew_uniform"], g["ref_strict_drew_uniform"])
+    assert np.array_equal(r["n_pending"], g["ref_strict_n_pending"])
+    assert np.array_equal(r["finalised_at"], g["ref_strict_finalised_at"])
+    assert np.allclose(r["regime_probs"], g["ref_strict_regime_probs"], rtol=1e-10, atol=1e-14)
+    # the reference's own build flags (-O3 -ffast-math): same numbers up to re-association
+    assert np.allclose(r["logz"], g["ref_fast_logz"], rtol=1e-12)
+    assert np.allclose(r["regime_probs"], g["ref_fast_regime_probs"], rtol=1e-6, atol=1e-12)
+    assert np.array_equal(r["regime_probs"][:, 1:].argmax(1), g["ref_fast_regime_probs"][:, 1:].argmax(1))
+
+
+def test_oracle_matches_live_reference(oracle, default_model):
+    from _oracle import Ref
+    if not Ref.available("_strict"):
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    from hygeia_b200 import philox, synthetic
+    ref = Ref("_strict")
+    T, S = 900, 3
+    ch = synthetic.make_chain(T, S, seed=2024, lam=25.0)
+    u = philox.uniforms_by_site(99, 0, T)
+    a = ref.run(default_model["vartheta"], default_model["theta"], ch["n_total"], ch["n_meth"], ch["positions"], uniforms=u)
+    b = oracle.run(default_model["vartheta"], default_model["theta"], u, ch["n_total"], ch["n_meth"], ch["positions"])
+    assert np.array_equal(a["logz"], b["logz"])
+    assert np.array_equal(a["finalised_at"], b["finalised_at"])
+    assert np.allclose(a["regime_probs"], b["regime_probs"], rtol=1e-10, atol=1e-14)
+    acc = (b["regime_probs"][:, 1:].argmax(1) == ch["regimes"]).mean()
+    assert acc > 0.97
+
+
+def test_oracle_parameter_estimation_matches_live_reference(oracle, default_model):
+    from _oracle import Ref
+    if not Ref.available("_strict"):
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    from hygeia_b200 import philox, synthetic
+    ref = Ref("_strict")
+    T, S = 700, 2
+    ch = synthetic.make_chain(T, S, seed=77)
+    u = philox.uniforms_by_site(5, 0, T)
+    rng = np.random.default_rng(3)
+    theta0 = 0.5 * rng.standard_normal(36)
+    kw = dict(param_est=True, n_steps_without_update=50)
+    a = ref.run(default_model["vartheta"], theta0, ch["n_total"], ch["n_meth"], ch["positions"], uniforms=u, **kw)
+    b = oracle.run(default_model["vartheta"], theta0, u, ch["n_total"], ch["n_meth"], ch["positions"], **kw)
+    assert np.allclose(a["theta_trace"], b["theta_trace"], rtol=1e-9, atol=1e-12)
+    assert np.allclose(a["logz"], b["logz"], rtol=1e-10)
+    assert np.abs(b["theta_trace"][-1] - theta0).max() > 1e-3  # theta moved

@@ -45,7 +45,6 @@ struct SgSmem {
   unsigned char r[HYG_NPMAX];
   // resampling scratch
   unsigned long long key[2][HYG_NPMAX];
-  double q[HYG_NPMAX];
   double Q[HYG_NPMAX + 1];
   unsigned short idx[HYG_NPMAX];
   unsigned short anc[HYG_NPMAX];
@@ -229,29 +228,31 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
             if (lane + o < 32) v += tt;
           }
           if (lane == 0) s.sc.d[flip][warp][0] = v;
-          s.q[tid] = qv;
           __syncthreads();
           double tail = 0.0;
 #pragma unroll
           for (int w = HYG_NW - 1; w > 0; w--) tail += (w > warp) ? s.sc.d[flip][w][0] : 0.0;
           flip ^= 1;
-          s.Q[tid] = v + tail;
+          const double Qp = v + tail;
+          s.Q[tid] = Qp;
           if (tid == 0) s.Q[HYG_NPMAX] = 0.0;
+          // Fixed point for K (resample.h:333-342).  The reference iterates K <- K + #{i >= K : log q_i > -log C(K)},
+          // log C(K) = log(M-K) - log Q[K], from K = 0.  Along that iteration the threshold Q[K]/(M-K) only decreases, so
+          // it stops at the FIRST sorted position p whose own weight is not above its own threshold:
+          //   K* = min{ p : !(q_p (M-p) > Q[p]) }   (one parallel pass instead of up to ~N sequential ones).
+          const bool stop = (tid >= M) || (tid >= N_prev) || !(qv * static_cast<double>(M - tid) > Qp);
+          const unsigned sb = __ballot_sync(HYG_FULL, stop);
+          if (lane == 0) s.iscan[ibuf][warp] = sb ? (warp * 32 + __ffs(static_cast<int>(sb)) - 1) : HYG_NPMAX;
           __syncthreads();
-          // fixed point for K (resample.h:333-342), every warp redundantly: log q_i > -log C  <=>  q_i > Q[K]/(M-K)
-          for (;;) {
-            Qk = s.Q[K];
-            const int L = M - K;
-            if (L <= 0 || !(Qk > 0.0) || !hyg_isfinite(Qk)) { keep_largest = true; break; }  // log C not finite (:345,:366)
-            const double thr = Qk / static_cast<double>(L);
-            int cnt = 0;
+          K = HYG_NPMAX;
 #pragma unroll
-            for (int j = 0; j < HYG_NPMAX / 32; j++) {
-              const int pp = lane + 32 * j;
-              cnt += __popc(__ballot_sync(HYG_FULL, pp >= K && pp < N_prev && s.q[pp] > thr));
-            }
-            if (cnt == 0) break;
-            K += cnt;
+          for (int w = 0; w < HYG_NW; w++) K = s.iscan[ibuf][w] < K ? s.iscan[ibuf][w] : K;
+          ibuf ^= 1;
+          if (K >= M) {
+            keep_largest = true;  // log C not finite (resample.h:345,366)
+          } else {
+            Qk = s.Q[K];
+            if (!(Qk > 0.0) || !hyg_isfinite(Qk)) keep_largest = true;
           }
         }
         if (keep_largest) {

@@ -43,6 +43,7 @@ def parse():
     p.add_argument("--cpu-sites", type=int, default=1500, help="sites per chain of the bounded CPU-baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--emission-only", action="store_true", help="time K1 alone (kernel tuning aid; not a bench line)")
     return p.parse_args()
 
 
@@ -283,6 +284,15 @@ def main():
 
     # ---- device-resident leg: inputs already in HBM ----
     n_chains = stage(True)
+    if args.emission_only:
+        ms = []
+        for _ in range(3 + args.steps):
+            sess.emission(); sess.sync(); ms.append(sess.timings()["ms_emission"])
+        alg = total_T * S * 4 + total_T * R * 8
+        best = min(ms[3:]); avg = float(np.mean(ms[3:]))
+        print(json.dumps({"emission_only_ms": ms, "GBps_avg": alg / avg / 1e6, "GBps_best": alg / best / 1e6,
+                          "frac_of_6538.9": alg / avg / 1e6 / 6538.9}))
+        return
     for _ in range(max(args.warmup, 3)):
         step_device()
     barrier()

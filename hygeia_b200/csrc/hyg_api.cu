@@ -64,6 +64,8 @@ struct hyg_ctx {
   double* d_tabg = nullptr;
   hyg::SgModelDev* d_mdl = nullptr;
   double* d_emtab = nullptr;
+  hyg::SgEmissionSet* d_sets = nullptr;
+  size_t d_sets_cap = 0;
   int nmax_table = 255;
   std::vector<Dataset> ds;
   std::vector<ChainBuf> chains;
@@ -119,9 +121,9 @@ __global__ void fill_positions_kernel(double* probs, const uint32_t* pos, unsign
     probs[t * stride] = pos ? static_cast<double>(pos[t]) : static_cast<double>(t);
 }
 
-template <int R> int launch_emission(hyg_ctx* c, const hyg::SgEmissionArgs& a, size_t smem) {
+template <int R> int launch_emission(hyg_ctx* c, const hyg::SgEmissionArgs& a, size_t smem, int grid) {
   HYG_CUDA(c, cudaFuncSetAttribute(hyg::sg_emission_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  hyg::sg_emission_kernel<R><<<c->num_sms, HYG_EM_NT, smem, c->stream>>>(a);
+  hyg::sg_emission_kernel<R><<<grid, HYG_EM_NT, smem, c->stream>>>(a);
   HYG_CUDA(c, cudaGetLastError());
   return HYG_OK;
 }
@@ -192,7 +194,7 @@ void hyg_destroy(hyg_ctx* c) {
   cudaStreamSynchronize(c->stream);
   free_chains(c);
   free_datasets(c);
-  dfree(c->d_tab); dfree(c->d_tabg); dfree(c->d_mdl); dfree(c->d_emtab); dfree(c->d_psi); dfree(c->d_queue);
+  dfree(c->d_tab); dfree(c->d_tabg); dfree(c->d_mdl); dfree(c->d_emtab); dfree(c->d_sets); dfree(c->d_psi); dfree(c->d_queue);
   cudaEventDestroy(c->ev_em0); cudaEventDestroy(c->ev_em1); cudaEventDestroy(c->ev_f0); cudaEventDestroy(c->ev_f1);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -364,22 +366,36 @@ int hyg_sg_emission(hyg_ctx* c) {
   if (c->ds.empty()) return fail(c, HYG_ERR_STATE, "no data sets");
   HYG_CUDA(c, cudaSetDevice(c->device));
   const int R = c->hm.R;
-  const size_t rows_max = static_cast<size_t>(HYG_EM_SMEM_DOUBLES) / R;
+  const size_t rows_max = static_cast<size_t>(HYG_EM_SMEM_DOUBLES - 2) / R;
   int nmax_smem = 0;
   while (static_cast<size_t>(nmax_smem + 2) * (nmax_smem + 3) / 2 <= rows_max && nmax_smem + 1 <= c->nmax_table) nmax_smem++;
-  const size_t smem = static_cast<size_t>(nmax_smem + 1) * (nmax_smem + 2) / 2 * R * sizeof(double);
-  HYG_CUDA(c, cudaEventRecord(c->ev_em0, c->stream));
-  c->em_launches = 0;
-  for (auto& d : c->ds) {
-    hyg::SgEmissionArgs a;
-    a.T = d.T; a.S = d.S; a.pitch = d.pitch; a.n_total = d.d_nt; a.n_meth = d.d_nm; a.logobs = d.d_logobs;
-    a.table = c->d_emtab; a.nmax_table = c->nmax_table; a.nmax_smem = nmax_smem;
-    for (int r = 0; r < HYG_RMAX; r++) { a.alpha[r] = r < R ? c->hm.alpha[r] : 1.0; a.beta[r] = r < R ? c->hm.beta[r] : 1.0; }
-    int rc = HYG_ERR_UNSUPPORTED;
-    HYG_DISPATCH_R(R, rc = launch_emission<RR>(c, a, smem));
-    if (rc) return rc;
-    c->em_launches++;
+  const size_t smem = static_cast<size_t>(HYG_EM_SMEM_DOUBLES + 2) * sizeof(double);
+  // one persistent launch over the flattened (data set, tile of 1024 site pairs) space
+  std::vector<hyg::SgEmissionSet> sets(c->ds.size());
+  unsigned long long tiles = 0;
+  for (size_t k = 0; k < c->ds.size(); k++) {
+    const Dataset& d = c->ds[k];
+    hyg::SgEmissionSet& e = sets[k];
+    e.T = d.T; e.pitch = d.pitch; e.n_total = d.d_nt; e.n_meth = d.d_nm; e.logobs = d.d_logobs; e.tile0 = tiles; e.S = d.S; e.pad_ = 0;
+    tiles += ((d.T + 1) / 2 + HYG_EM_TILE - 1) / HYG_EM_TILE;
   }
+  if (c->d_sets_cap < sets.size()) {
+    dfree(c->d_sets);
+    HYG_CUDA(c, cudaMalloc(&c->d_sets, sets.size() * sizeof(hyg::SgEmissionSet)));
+    c->d_sets_cap = sets.size();
+  }
+  HYG_CUDA(c, cudaMemcpyAsync(c->d_sets, sets.data(), sets.size() * sizeof(hyg::SgEmissionSet), cudaMemcpyHostToDevice, c->stream));
+  HYG_CUDA(c, cudaStreamSynchronize(c->stream));  // `sets` is pageable and goes out of scope
+  hyg::SgEmissionArgs a;
+  a.sets = c->d_sets; a.n_sets = static_cast<uint32_t>(sets.size()); a.n_tiles = tiles;
+  a.table = c->d_emtab; a.nmax_table = c->nmax_table; a.nmax_smem = nmax_smem;
+  for (int r = 0; r < HYG_RMAX; r++) { a.alpha[r] = r < R ? c->hm.alpha[r] : 1.0; a.beta[r] = r < R ? c->hm.beta[r] : 1.0; }
+  const int grid = static_cast<int>(std::min<unsigned long long>(tiles, static_cast<unsigned long long>(c->num_sms)));
+  HYG_CUDA(c, cudaEventRecord(c->ev_em0, c->stream));
+  int rc = HYG_ERR_UNSUPPORTED;
+  HYG_DISPATCH_R(R, rc = launch_emission<RR>(c, a, smem, grid));
+  if (rc) return rc;
+  c->em_launches = 1;
   HYG_CUDA(c, cudaEventRecord(c->ev_em1, c->stream));
   c->timed_em = true;
   return HYG_OK;

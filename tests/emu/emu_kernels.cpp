@@ -52,11 +52,24 @@ int hygemu_sg_emission(const double* alpha, const double* beta, int R, uint64_t 
   if (R != 6) return -3;
   std::vector<double> tab;
   hyg::build_emission_table(alpha, beta, R, nmax_table, tab);
+  // split the sites into two "data sets" so the flattened tile space with several sets is exercised
+  const uint64_t T0 = (T > 2200) ? 2050 : T;  // first set ends inside a tile
+  hyg::SgEmissionSet sets[2];
+  uint32_t n_sets = (T0 < T) ? 2 : 1;
+  sets[0].T = T0; sets[0].pitch = pitch; sets[0].n_total = n_total; sets[0].n_meth = n_meth; sets[0].logobs = logobs; sets[0].tile0 = 0; sets[0].S = S;
+  unsigned long long tiles = ((T0 + 1) / 2 + HYG_EM_TILE - 1) / HYG_EM_TILE;
+  if (n_sets == 2) {
+    // second set starts at site T0 (T0 is even, so the 4-byte pair loads stay aligned)
+    sets[1].T = T - T0; sets[1].pitch = pitch; sets[1].n_total = n_total + T0; sets[1].n_meth = n_meth + T0; sets[1].logobs = logobs + T0 * R;
+    sets[1].tile0 = tiles; sets[1].S = S;
+    tiles += ((T - T0 + 1) / 2 + HYG_EM_TILE - 1) / HYG_EM_TILE;
+  }
   hyg::SgEmissionArgs a;
-  a.T = T; a.S = S; a.pitch = pitch; a.n_total = n_total; a.n_meth = n_meth; a.logobs = logobs;
+  a.sets = sets; a.n_sets = n_sets; a.n_tiles = tiles;
   a.table = tab.data(); a.nmax_table = nmax_table; a.nmax_smem = nmax_smem;
   for (int r = 0; r < R; r++) { a.alpha[r] = alpha[r]; a.beta[r] = beta[r]; }
-  emu::launch(dim3(grid), dim3(block), [=]() { hyg::sg_emission_entry<6>(a); });
+  (void)block;
+  emu::launch(dim3(grid), dim3(HYG_EM_NT), [=]() { hyg::sg_emission_entry<6>(a); });
   return 0;
 }
 

@@ -145,7 +145,6 @@ template <int R> int filter_occupancy(int* occ) {
     case 5: { constexpr int RR = 5; EXPR; } break; \
     case 6: { constexpr int RR = 6; EXPR; } break; \
     case 7: { constexpr int RR = 7; EXPR; } break; \
-    case 8: { constexpr int RR = 8; EXPR; } break; \
     default: break;                           \
   }
 
@@ -227,7 +226,7 @@ int hyg_sg_set_model(hyg_ctx* c, uint32_t R, uint32_t u, const double* alpha, co
 int hyg_sg_set_vartheta(hyg_ctx* c, const double* vt, uint32_t n) {
   if (!c || !vt || n < 2) return fail(c, HYG_ERR_ARG, "bad vartheta");
   const uint32_t R = static_cast<uint32_t>(vt[1]);
-  if (R < 2 || R > 8 || n < 2 * R + 3) return fail(c, HYG_ERR_ARG, "bad vartheta");
+  if (R < 2 || R > 7 || n < 2 * R + 3) return fail(c, HYG_ERR_ARG, "bad vartheta");
   const int kf = vt[2 * R + 2] != 0.0;
   if (kf && n < 3 * R + 3) return fail(c, HYG_ERR_ARG, "vartheta lacks kappa");
   return hyg_sg_set_model(c, R, static_cast<uint32_t>(vt[0]), vt + 2, vt + 2 + R, kf, kf ? vt + 2 * R + 3 : nullptr);

@@ -37,7 +37,7 @@ int SgHostModel::set_known(const double* vt, uint32_t n) {
   if (n < 2) { err = "vartheta too short"; return -1; }
   const int u_ = static_cast<int>(vt[0]);
   const int R_ = static_cast<int>(vt[1]);
-  if (R_ < 2 || R_ > 8) { err = "number of regimes must be in [2, 8]"; return -1; }
+  if (R_ < 2 || R_ > 7) { err = "number of regimes must be in [2, 7]"; return -1; }
   if (n < static_cast<uint32_t>(2 * R_ + 3)) { err = "vartheta too short"; return -1; }
   const int kf = vt[2 * R_ + 2] != 0.0;
   if (kf && n < static_cast<uint32_t>(3 * R_ + 3)) { err = "vartheta lacks kappa"; return -1; }
@@ -45,7 +45,7 @@ int SgHostModel::set_known(const double* vt, uint32_t n) {
 }
 
 int SgHostModel::set_known(int R_, int u_, const double* alpha_, const double* beta_, int kappa_fixed, const double* kappa_) {
-  if (R_ < 2 || R_ > 8) { err = "number of regimes must be in [2, 8]"; return -1; }
+  if (R_ < 2 || R_ > 7) { err = "number of regimes must be in [2, 7]"; return -1; }
   if (u_ < 2) { err = "u must be >= 2 (the reference indexes d-1 at d = u-1, singleGroup.h:309)"; return -1; }
   if (!kappa_fixed || !kappa_) {
     // The reference's kappa-estimation path reuses the omega index for the kappa gradient (singleGroup.h:664-668,329;

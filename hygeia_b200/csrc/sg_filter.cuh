@@ -51,6 +51,11 @@ struct SgSmem {
   int iscan[2][HYG_NW];
   BlockScratch sc;
   double lo[2][HYG_RMAX];
+  double part[2][HYG_NW][8];   // per-warp partials of the 8-wide transposed reductions (double-buffered)
+  unsigned vmask[2][HYG_NW];
+  int slow[HYG_RMAX];
+  double res_lw;               // log-weight given to resampled particles: lsum_prev - log C
+  double lsum;                 // running log Z_t
 };
 
 __device__ __forceinline__ bool hyg_isfinite(double x) {
@@ -109,15 +114,63 @@ template <int RT> __device__ __forceinline__ double pick(const double (&v)[RT], 
   return o;
 }
 
+// Transposed warp reduction of eight values per lane: 9 shuffle steps instead of 40.  On return every lane holds the
+// warp total of value index (lane >> 2) & 7.
+__device__ __forceinline__ double warp_reduce8(const double (&v)[8]) {
+  const int lane = threadIdx.x & 31;
+  double w4[4], w2[2], w1;
+  {
+    const bool hi = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const double send = hi ? v[i] : v[i + 4];
+      const double keep = hi ? v[i + 4] : v[i];
+      w4[i] = keep + __shfl_xor_sync(HYG_FULL, send, 16);
+    }
+  }
+  {
+    const bool hi = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const double send = hi ? w4[i] : w4[i + 2];
+      const double keep = hi ? w4[i + 2] : w4[i];
+      w2[i] = keep + __shfl_xor_sync(HYG_FULL, send, 8);
+    }
+  }
+  {
+    const bool hi = (lane & 4) != 0;
+    const double send = hi ? w2[0] : w2[1];
+    const double keep = hi ? w2[1] : w2[0];
+    w1 = keep + __shfl_xor_sync(HYG_FULL, send, 4);
+  }
+  w1 += __shfl_xor_sync(HYG_FULL, w1, 2);
+  w1 += __shfl_xor_sync(HYG_FULL, w1, 1);
+  return w1;
+}
+// Lanes 0,4,..,28 publish the warp totals; any warp then folds the eight rows with two loads and two shuffle steps.
+__device__ __forceinline__ void publish8(double (*part)[8], double wtot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if ((lane & 3) == 0) part[warp][lane >> 2] = wtot;
+}
+// returns in every lane the block total of value index lane & 7
+__device__ __forceinline__ double combine8(const double (*part)[8]) {
+  const int lane = threadIdx.x & 31;
+  double a = part[lane >> 3][lane & 7] + part[(lane >> 3) + 4][lane & 7];
+  a += __shfl_xor_sync(HYG_FULL, a, 8);
+  a += __shfl_xor_sync(HYG_FULL, a, 16);
+  return a;
+}
+
 template <int RT>
 __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, const SgRunDev& run, double* psi_ws, SgSmem& s) {
+  static_assert(RT <= 7, "class sums share an 8-wide reduction with the finite-weight count");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int R = RT;
   const int Nmax = mdl.n_particles;
   const uint32_t dcap = mdl.dcap;
   const unsigned long long T = ch.T;
   const int lcap = run.lcap;
-  int flip = 0, kbuf = 0, ibuf = 0;
+  int flip = 0, kbuf = 0, ibuf = 0, pbuf = 0;
 
   // psi workspace (global, L2-resident): [2][lcap][R][256] doubles followed by lcap ints of site indices
   double* psi[2] = {psi_ws, psi_ws + static_cast<size_t>(lcap) * R * HYG_NPMAX};
@@ -154,10 +207,12 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
 
   for (unsigned long long t = 0; t < T; t++) {
     const double* lo = s.lo[t & 1];
-    // emission row of site t+2 and the uniform of site t+1: issued now, consumed at the end of this step
+    // emission row of site t+2: issued now, consumed at the end of this step
     const double lo_pref = (tid < R && t + 2 < T) ? __ldg(ch.logobs + (t + 2) * R + tid) : 0.0;
     int k_kept = -1;
     bool drew = false;
+    bool emit_now = false;       // current site finalised at this step
+    double cw_lane = 0.0;        // regime mass of index lane & 7 (current site)
 
     if (t > 0) {
       // =========================== Smc::iterate (Smc.h:190-286) ===========================
@@ -170,51 +225,62 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
 
       // ---- class sums over the previous particles (replace the R x N_prev log-sum-exps of Smc.h:562-573) ----
       const double e_prev = (tid < N_prev) ? p.W * p.cur.x : 0.0;  // W_n * c_new(d_n, r_n)
-      const bool valid = (tid < N_prev) && (p.cur.x > 0.0) && hyg_isfinite(p.lw);
-      double red[R + 1];
+      const bool finite_prev = (tid < N_prev) && hyg_isfinite(p.lw);
+      const bool valid = finite_prev && (p.cur.x > 0.0);
+      {
+        double v8[8];
 #pragma unroll
-      for (int r = 0; r < R; r++) red[r] = (p.r == r) ? e_prev : 0.0;
-      red[R] = (tid < N_prev && hyg_isfinite(p.lw)) ? 1.0 : 0.0;  // F = #finite(logw_prev), Smc.h:413
-      unsigned vmask = 0;
-#pragma unroll
-      for (int r = 0; r < R; r++) vmask |= (__any_sync(HYG_FULL, valid && p.r == r) ? 1u : 0u) << r;
-      if (lane == 0) s.iscan[ibuf][warp] = static_cast<int>(vmask);
-      block_sum<R + 1>(red, s.sc, flip);
-      vmask = 0;
-#pragma unroll
-      for (int w = 0; w < HYG_NW; w++) vmask |= static_cast<unsigned>(s.iscan[ibuf][w]);
-      ibuf ^= 1;
-      const int F = static_cast<int>(red[R] + 0.5);
-      // sumE[r] = sum_{r' != r} P[r'][r] E[r']  (linear-domain new-segment mass of regime r, relative to exp(lsum_prev))
-      unsigned slowmask = 0;
-      double my_sumE = 0.0;  // for the thread that owns new particle (1, r = tid - M)
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        double a = 0.0;
-        bool could = false;
-#pragma unroll
-        for (int rp = 0; rp < R; rp++) {
-          if (rp == r) continue;
-          a += mdl.P[rp][r] * red[rp];
-          could = could || (((vmask >> rp) & 1u) && mdl.P[rp][r] > 0.0);
-        }
-        if (!(a > 0.0) && could) slowmask |= 1u << r;
-        if (tid - M == r) my_sumE = a;
+        for (int r = 0; r < 8; r++) v8[r] = (r < R && p.r == r) ? e_prev : 0.0;
+        v8[7] = finite_prev ? 1.0 : 0.0;  // F = #finite(logw_prev), Smc.h:413 (exact in fp64)
+        publish8(s.part[pbuf], warp_reduce8(v8));
+        const unsigned vm = __reduce_or_sync(HYG_FULL, valid ? (1u << p.r) : 0u);
+        if (lane == 0) s.vmask[pbuf][warp] = vm;
       }
-      const double my_invE = (my_sumE > 0.0) ? 1.0 / my_sumE : 0.0;
+      const int pA = pbuf;
+      pbuf ^= 1;
 
       // ---- ancestors: Smc::resampleCp (Smc.h:406-450) ----
       bool own_weight = true;   // child keeps its ancestor's own log-weight (top-K / keep-largest / growth)
-      double resampled_lw = 0.0;
-      if (!capped) {
-        anc = tid;  // growth phase: identity (Smc.h:443-447)
-        k_kept = -1;
-      } else {
+      int sidx = tid;
+      if (capped) {
         // sort by log-weight, descending (ties by slot); W is a monotone map of logw
         unsigned long long key = (tid < N_prev) ? order_key(p.lw, tid) : 0ull;
-        key = block_sort_desc(key, s, kbuf);
-        const int sidx = 255 - static_cast<int>(key & 0xFFull);
+        key = block_sort_desc(key, s, kbuf);   // >= 1 barrier: s.part[pA] / s.vmask[pA] are visible from here on
+        sidx = 255 - static_cast<int>(key & 0xFFull);
         s.idx[tid] = static_cast<unsigned short>(sidx);
+      } else {
+        __syncthreads();
+      }
+      const double totA = combine8(s.part[pA]);           // lane & 7 -> E[0..R-1], [7] = F
+      const int F = static_cast<int>(__shfl_sync(HYG_FULL, totA, 7) + 0.5);
+      // new-segment mass of regime r: sumE[r] = sum_{r' != r} P[r'][r] E[r'], needed by the R threads that own (1, r)
+      double my_sumE = 0.0, my_invE = 0.0;
+      {
+        const int w_lo = M >> 5, w_hi = (M + R - 1) >> 5;
+        if (warp == w_lo || warp == w_hi) {
+          const int r = tid - M;
+          const bool mine = (r >= 0 && r < R);
+          unsigned vm = 0;
+#pragma unroll
+          for (int w = 0; w < HYG_NW; w++) vm |= s.vmask[pA][w];
+          double a = 0.0;
+          bool could = false;
+#pragma unroll
+          for (int rp = 0; rp < R; rp++) {
+            const double Erp = __shfl_sync(HYG_FULL, totA, rp);
+            const double Pv = mine ? mdl.P[rp][r] : 0.0;   // zero diagonal
+            a += Pv * Erp;
+            could = could || (((vm >> rp) & 1u) && Pv > 0.0);
+          }
+          if (mine) {
+            my_sumE = a;
+            my_invE = (a > 0.0) ? 1.0 / a : 0.0;
+            s.slow[r] = (!(a > 0.0) && could) ? 1 : 0;
+          }
+        }
+      }
+      if (!capped) __syncthreads();  // growth phase has no later barrier before s.slow is read
+      if (capped) {
         bool keep_largest = (F <= M);
         int K = 0;
         double Qk = 0.0;
@@ -262,8 +328,7 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
           k_kept = -2;
         } else {
           const int L = M - K;
-          const double logC = log(static_cast<double>(L)) - log(Qk);
-          resampled_lw = lsum_prev - logC;  // resample.h:361-364
+          if (tid == 0) s.res_lw = lsum_prev - (log(static_cast<double>(L)) - log(Qk));  // lsum_prev - log C (resample.h:361-364)
           k_kept = K;
           drew = true;
           // systematic resampling of L offspring among the sorted residual particles (resample.h:85-127,354-359).
@@ -303,7 +368,7 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
       SgChainState c;
       c.lw = -HYG_INF; c.W = 0.0; c.cur = make_double2(0.0, 0.0); c.nxt = c.cur; c.d = 0; c.r = 0;
       if (tid < M) {
-        const double base = own_weight ? s.lw[anc] : resampled_lw;
+        const double base = own_weight ? s.lw[anc] : s.res_lw;
         c.r = s.r[anc];
         c.d = s.d[anc] + 1;
         c.cur = s.nxt[anc];
@@ -319,6 +384,9 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
         c.lw = (my_sumE > 0.0) ? lsum_prev + lo[r] + log(my_sumE) : -HYG_INF;
       }
       // exact log-domain path for regimes whose linear-domain sum underflowed (rare)
+      unsigned slowmask = 0;
+#pragma unroll
+      for (int r = 0; r < R; r++) slowmask |= (s.slow[r] ? 1u : 0u) << r;
       double bk_slow[R];
 #pragma unroll
       for (int r = 0; r < R; r++) bk_slow[r] = 0.0;
@@ -337,23 +405,44 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
         }
       }
 
-      // ---- selfNormaliseWeights (Smc.h:576-579): shift by an upper bound instead of the exact max ----
+      // ---- selfNormaliseWeights (Smc.h:576-579), fused with the regime masses of the new site ----
+      // shift by the bound lsum_prev + max_r logObs instead of the exact max; class sums give both the normaliser and
+      // sum_{n: r_n = q} W_n (initialisePsi + computeFilteredMean for the current site).
       {
         double lomax = lo[0];
 #pragma unroll
         for (int r = 1; r < R; r++) lomax = lo[r] > lomax ? lo[r] : lomax;
         double shift = lsum_prev + lomax;
-        double ee[1] = {(tid < N_curr) ? exp(c.lw - shift) : 0.0};
-        double mine = ee[0];
-        block_sum<1>(ee, s.sc, flip);
-        if (!(ee[0] > 0.0) || !hyg_isfinite(ee[0])) {  // everything underflowed against the bound: use the exact max
+        double mine = (tid < N_curr) ? exp(c.lw - shift) : 0.0;
+        double v8[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) v8[q] = (q < R && c.r == q) ? mine : 0.0;
+        publish8(s.part[pbuf], warp_reduce8(v8));
+        __syncthreads();
+        double tot = combine8(s.part[pbuf]);   // lane & 7 -> class sum of exp(lw - shift)
+        pbuf ^= 1;
+        double S = tot;
+        S += __shfl_xor_sync(HYG_FULL, S, 1);
+        S += __shfl_xor_sync(HYG_FULL, S, 2);
+        S += __shfl_xor_sync(HYG_FULL, S, 4);
+        if (!(S > 0.0) || !hyg_isfinite(S)) {  // everything underflowed against the bound: use the exact max
           shift = block_max((tid < N_curr) ? c.lw : -HYG_INF, s.sc, flip);
-          ee[0] = (tid < N_curr) ? exp(c.lw - shift) : 0.0;
-          mine = ee[0];
-          block_sum<1>(ee, s.sc, flip);
+          mine = (tid < N_curr) ? exp(c.lw - shift) : 0.0;
+#pragma unroll
+          for (int q = 0; q < 8; q++) v8[q] = (q < R && c.r == q) ? mine : 0.0;
+          publish8(s.part[pbuf], warp_reduce8(v8));
+          __syncthreads();
+          tot = combine8(s.part[pbuf]);
+          pbuf ^= 1;
+          S = tot;
+          S += __shfl_xor_sync(HYG_FULL, S, 1);
+          S += __shfl_xor_sync(HYG_FULL, S, 2);
+          S += __shfl_xor_sync(HYG_FULL, S, 4);
         }
-        lsum = shift + log(ee[0]);
-        c.W = mine / ee[0];
+        const double invS = 1.0 / S;
+        c.W = mine * invS;
+        cw_lane = tot * invS;
+        if (tid == 0) s.lsum = shift + log(S);   // running log Z_t; read by everybody after the end-of-step barrier
       }
 
       // ---- fixed-lag smoothing: updatePsi (OnlineMarginalSmoothing.h:148-177) ----
@@ -430,31 +519,33 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
       }
       p = c;
       N = N_curr;
+    } else {
+      // t = 0: regime masses of the initial particle system
+      double v8[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) v8[q] = (q < R && tid < N && p.r == q) ? p.W : 0.0;
+      publish8(s.part[pbuf], warp_reduce8(v8));
+      __syncthreads();
+      cw_lane = combine8(s.part[pbuf]);
+      pbuf ^= 1;
+      if (tid == 0) s.lsum = lsum;
     }
 
     // ---- initialisePsi + storeEstimates for the current site (OnlineMarginalSmoothing.h:119-146,197-255) ----
     if (run.use_smoothing) {
-      double cw[R];
-#pragma unroll
-      for (int q = 0; q < R; q++) cw[q] = (tid < N && p.r == q) ? p.W : 0.0;
-      block_sum<R>(cw, s.sc, flip);
-      double sw = 0.0;
-#pragma unroll
-      for (int q = 0; q < R; q++) sw += cw[q];
-      bool emit = (t == T - 1);
-      if (!emit) {
-        emit = true;
-#pragma unroll
-        for (int q = 0; q < R; q++) {
-          const double m = cw[q];
-          const double var = cw[q] * (1.0 - m) * (1.0 - m) + (sw - cw[q]) * m * m;  // psi is the 0/1 regime indicator
-          if (!(var < run.epsilon)) emit = false;
-        }
-      }
-      if (!emit && n_pend >= lcap) { emit = true; n_forced++; }  // lag set full: emit the filtering estimate now (reported)
-      if (emit) {
-        const double outv = pick<R>(cw, tid);
-        if (tid < R && ch.probs) ch.probs[static_cast<size_t>(t) * (R + 1) + 1 + tid] = outv;
+      // every lane holds the mass of regime (lane & 7); psi is the 0/1 regime indicator, so
+      // Var = m (1-m)^2 + (sum W - m) m^2
+      double sw = cw_lane;
+      sw += __shfl_xor_sync(HYG_FULL, sw, 1);
+      sw += __shfl_xor_sync(HYG_FULL, sw, 2);
+      sw += __shfl_xor_sync(HYG_FULL, sw, 4);
+      const double m = cw_lane;
+      const double var = m * (1.0 - m) * (1.0 - m) + (sw - m) * m * m;
+      const bool ok = ((lane & 7) >= R) || (var < run.epsilon);
+      emit_now = (t == T - 1) || __all_sync(HYG_FULL, ok);
+      if (!emit_now && n_pend >= lcap) { emit_now = true; n_forced++; }  // lag set full: emit the filtering estimate now (reported)
+      if (emit_now) {
+        if (tid < R && ch.probs) ch.probs[static_cast<size_t>(t) * (R + 1) + 1 + tid] = cw_lane;  // lanes 0..R-1 of warp 0
         if (tid == 0 && ch.finalised_at) ch.finalised_at[t] = static_cast<int>(t);
       } else {
         double* dst = psi[t & 1] + static_cast<size_t>(n_pend) * R * HYG_NPMAX;
@@ -466,6 +557,12 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
       max_pend = n_pend > max_pend ? n_pend : max_pend;
     }
 
+    // ---- publish the particle system for the next site (all gathers of this step precede the normaliser barrier) ----
+    s.W[tid] = p.W; s.lw[tid] = p.lw; s.cur[tid] = p.cur; s.nxt[tid] = p.nxt; s.d[tid] = p.d; s.r[tid] = static_cast<unsigned char>(p.r);
+    if (tid < R && t + 2 < T) s.lo[t & 1][tid] = lo_pref;
+    __syncthreads();
+    lsum = s.lsum;
+
     // ---- taps ----
     if (tid == 0) {
       if (ch.logz) ch.logz[t] = lsum;
@@ -474,12 +571,6 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
       if (ch.n_pending) ch.n_pending[t] = n_pend;
       if (ch.n_curr) ch.n_curr[t] = N;
     }
-
-    // ---- publish the particle system for the next site; stash the prefetched emission row ----
-    __syncthreads();  // all gathers of this step are done
-    s.W[tid] = p.W; s.lw[tid] = p.lw; s.cur[tid] = p.cur; s.nxt[tid] = p.nxt; s.d[tid] = p.d; s.r[tid] = static_cast<unsigned char>(p.r);
-    if (tid < R && t + 2 < T) s.lo[t & 1][tid] = lo_pref;
-    __syncthreads();
   }
   if (tid == 0 && ch.status) {
     ch.status[0] = n_forced;

@@ -277,6 +277,15 @@ inline unsigned __ballot_sync(unsigned, int pred) {
   });
   return emu::my_warp().ballot;
 }
+inline unsigned __reduce_or_sync(unsigned, unsigned v) {
+  emu::warp_rendezvous(v, [](emu::WarpState& w) {
+    unsigned b = 0;
+    unsigned n = emu::warp_width();
+    for (unsigned i = 0; i < n; i++) b |= static_cast<unsigned>(w.slot[i]);
+    w.ballot = b;
+  });
+  return emu::my_warp().ballot;
+}
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 inline int __all_sync(unsigned m, int pred) {
   unsigned n = emu::warp_width();

@@ -63,14 +63,10 @@ __device__ __forceinline__ bool hyg_isfinite(double x) {
   return ((b >> 52) & 0x7ffull) != 0x7ffull;
 }
 
-// #{ j in [0,L) : (j + u) / L <= c }  with the reference's floating-point expression for T_j (resample.h:95)
-__device__ __forceinline__ int sys_count(double c, double u, int L) {
-  const double Ld = static_cast<double>(L);
-  double x = c * Ld - u;
-  int j = (x < 0.0) ? -1 : (x >= Ld ? L - 1 : static_cast<int>(x));
-  while (j + 1 < L && (static_cast<double>(j + 1) + u) / Ld <= c) j++;
-  while (j >= 0 && (static_cast<double>(j) + u) / Ld > c) j--;
-  return j + 1;
+// #{ j in [0,L) : (j + u) / L <= c } = floor(c L - u) + 1 clamped to [0, L]  (T_j = (j+u)/L, resample.h:95); x = c L - u.
+// The closed form and the reference's compare-by-division agree unless |x - integer| is below rounding (~1e-13).
+__device__ __forceinline__ int sys_count_x(double x, int L) {
+  return (x < 0.0) ? 0 : ((x >= static_cast<double>(L)) ? L : static_cast<int>(x) + 1);
 }
 
 // Descending bitonic sort of one 64-bit key per thread over the 256-thread CTA.
@@ -336,7 +332,7 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
           // offspring counts o_p = C_p - C_{p-1} are >= 0 and sum to L whatever the rounding of the suffix sums.
           const double u = ch.unif ? __ldg(ch.unif + t) : philox_uniform(ch.seed, ch.chain_id, t);
           int C = 0;
-          if (tid >= K && tid < N_prev) C = (tid == N_prev - 1) ? L : sys_count((Qk - s.Q[tid + 1]) / Qk, u, L);
+          if (tid >= K && tid < N_prev) C = (tid == N_prev - 1) ? L : sys_count_x((Qk - s.Q[tid + 1]) * (static_cast<double>(L) / Qk) - u, L);
           if (tid >= N_prev) C = L;
 #pragma unroll
           for (int dlt = 1; dlt < 32; dlt <<= 1) {

@@ -18,7 +18,8 @@
 #endif
 
 #define HYG_FULL 0xffffffffu
-#define HYG_NT 256          // threads per chain CTA (one thread per particle slot)
+#define HYG_WORKER_WARPS 8  // warps that own particles (one slot per thread)
+#define HYG_NT 288          // threads per chain CTA: 256 particle slots + one service warp
 #define HYG_NW (HYG_NT / 32)
 #define HYG_RMAX 8          // max number of regimes
 #define HYG_NPMAX 256       // max particles per chain

@@ -54,8 +54,11 @@ struct SgSmem {
   double part[2][HYG_NW][8];   // per-warp partials of the 8-wide transposed reductions (double-buffered)
   unsigned vmask[2][HYG_NW];
   int slow[HYG_RMAX];
+  double new_lw[HYG_RMAX];     // log-weight of the new-segment particle (1, r)
+  double new_invE[HYG_RMAX];   // 1 / sumE[r]
+  double u;                    // resampling uniform of the current site
   double res_lw;               // log-weight given to resampled particles: lsum_prev - log C
-  double lsum;                 // running log Z_t
+  double lsum[2];              // running log Z_t, [t & 1]
 };
 
 __device__ __forceinline__ bool hyg_isfinite(double x) {
@@ -69,11 +72,58 @@ __device__ __forceinline__ int sys_count_x(double x, int L) {
   return (x < 0.0) ? 0 : ((x >= static_cast<double>(L)) ? L : static_cast<int>(x) + 1);
 }
 
-// Descending bitonic sort of one 64-bit key per thread over the 256-thread CTA.
-__device__ __forceinline__ unsigned long long block_sort_desc(unsigned long long key, SgSmem& s, int& kbuf) {
-  const int tid = threadIdx.x;
+#ifndef HYG_SORT_RANKMERGE
+#define HYG_SORT_RANKMERGE 0
+#endif
+#if HYG_SORT_RANKMERGE
+#define HYG_SORT_BARRIERS 2
+// Descending sort of one unique 64-bit key per worker thread (256 keys).  Each warp sorts its 32 keys with a
+// register/shuffle bitonic network (15 stages, no barrier); every key then finds its rank in the other seven sorted
+// runs by binary search in shared memory (7 independent 5-step searches) and is scattered to its final position:
+// 2 barriers instead of the 6 exchange barriers + 36 dependent stages of a full block-wide bitonic sort.
+// Returns the key of sorted position threadIdx.x.  Worker warps only.
+__device__ __forceinline__ unsigned long long block_sort_desc(unsigned long long key, SgSmem& s) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-  for (int k = 2; k <= HYG_NT; k <<= 1) {
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(HYG_FULL, key, j);
+      const bool desc_block = ((lane & k) == 0);
+      const bool lower = ((lane & j) == 0);
+      const bool take_max = (lower == desc_block);
+      const bool other_gt = other > key;
+      key = (take_max == other_gt) ? other : key;
+    }
+  }
+  s.key[0][tid] = key;   // eight descending runs of 32
+  __syncthreads();
+  int rank = lane;       // position inside the own run
+#pragma unroll
+  for (int w = 0; w < HYG_WORKER_WARPS; w++) {
+    if (w == warp) continue;
+    const unsigned long long* run = s.key[0] + 32 * w;
+    // number of keys in `run` (descending) that are greater than `key`
+    int lo = 0;
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1) lo += (run[lo + step - 1] > key) ? step : 0;
+    lo += (run[lo] > key) ? 1 : 0;   // lo <= 31 here
+    rank += lo;
+  }
+  s.key[1][rank] = key;
+  __syncthreads();
+  return s.key[1][tid];
+}
+
+#else
+#define HYG_SORT_BARRIERS 6
+// Descending bitonic sort of one 64-bit key per worker thread (256 keys): strides < 32 by warp shuffles, strides
+// 32/64/128 through shared memory (6 exchange stages, double-buffered so that each costs one barrier).
+__device__ __forceinline__ unsigned long long block_sort_desc(unsigned long long key, SgSmem& s) {
+  const int tid = threadIdx.x;
+  int kbuf = 0;
+#pragma unroll
+  for (int k = 2; k <= HYG_NPMAX; k <<= 1) {
 #pragma unroll
     for (int j = k >> 1; j > 0; j >>= 1) {
       unsigned long long other;
@@ -94,6 +144,7 @@ __device__ __forceinline__ unsigned long long block_sort_desc(unsigned long long
   }
   return key;
 }
+#endif
 
 struct SgChainState {
   // per-thread particle (slot = threadIdx.x)
@@ -157,10 +208,42 @@ __device__ __forceinline__ double combine8(const double (*part)[8]) {
   return a;
 }
 
+// Service-warp job: new-segment particles (1, r), r = lane < R.  sumE[r] = sum_{r' != r} P[r'][r] E[r'] is the linear-domain
+// mass flowing into regime r (relative to exp(lsum_prev)); its log-weight is lsum_prev + logObs_r + log(sumE[r])
+// (computeWeightsCp, Smc.h:562-573, after factorising logTrans((1,r) <- (d,r')) = log c_new(d,r') + log P[r'][r]).
+// Returns sumE[lane]; the log is taken later, in one evaluation shared with log C.
+template <int R>
+__device__ __forceinline__ double sg_service_new_segments(const SgModelDev& mdl, SgSmem& s, double totA, int pA) {
+  const int lane = threadIdx.x & 31;
+  unsigned vm = 0;
+#pragma unroll
+  for (int w = 0; w < HYG_WORKER_WARPS; w++) vm |= s.vmask[pA][w];
+  double a = 0.0;
+  bool could = false;
+#pragma unroll
+  for (int rp = 0; rp < R; rp++) {
+    const double Erp = __shfl_sync(HYG_FULL, totA, rp);
+    const double Pv = (lane < R) ? mdl.P[rp][lane] : 0.0;   // zero diagonal
+    a += Pv * Erp;
+    could = could || (((vm >> rp) & 1u) && Pv > 0.0);
+  }
+  if (lane < R) {
+    s.new_invE[lane] = (a > 0.0) ? 1.0 / a : 0.0;
+    s.slow[lane] = (!(a > 0.0) && could) ? 1 : 0;
+  }
+  return a;
+}
+
 template <int RT>
 __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, const SgRunDev& run, double* psi_ws, SgSmem& s) {
   static_assert(RT <= 7, "class sums share an 8-wide reduction with the finite-weight count");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // Warps 0..7 own the particles (one slot per thread).  Warp 8 is a SERVICE warp: it owns no particle, follows the same
+  // barrier sequence, and evaluates every scalar exp/log of the step (regime factors, new-segment weights, log C, log Z_t,
+  // the Philox draw, the emission-row prefetch) while the workers sort and scan -- so no transcendental latency chain
+  // sits on the workers' critical path.
+  const bool worker = warp < HYG_WORKER_WARPS;
+  const bool service = !worker;
   constexpr int R = RT;
   const int Nmax = mdl.n_particles;
   const uint32_t dcap = mdl.dcap;
@@ -181,7 +264,7 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
   if (T > 1 && tid < R) s.lo[1][tid] = __ldg(ch.logobs + R + tid);
   __syncthreads();
   int N = R;
-  double lsum;
+  double pend_shift = 0.0, pend_S = 1.0;   // log Z of the last completed site = pend_shift + log(pend_S)
   {
     double lomax = s.lo[0][0];
 #pragma unroll
@@ -197,14 +280,15 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
     double e[1] = {(tid < N) ? exp(p.lw - c) : 0.0};
     const double mine = e[0];
     block_sum<1>(e, s.sc, flip);
-    lsum = c + log(e[0]);
+    pend_shift = c; pend_S = e[0];
+    if (tid == 0) s.lsum[0] = c + log(e[0]);
     p.W = mine / e[0];
   }
 
   for (unsigned long long t = 0; t < T; t++) {
     const double* lo = s.lo[t & 1];
-    // emission row of site t+2: issued now, consumed at the end of this step
-    const double lo_pref = (tid < R && t + 2 < T) ? __ldg(ch.logobs + (t + 2) * R + tid) : 0.0;
+    // emission row of site t+2: issued now by the service warp, stored at the end of this step
+    const double lo_pref = (service && lane < R && t + 2 < T) ? __ldg(ch.logobs + (t + 2) * R + lane) : 0.0;
     int k_kept = -1;
     bool drew = false;
     bool emit_now = false;       // current site finalised at this step
@@ -216,14 +300,24 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
       const int N_curr = (N_prev + R > Nmax) ? Nmax : N_prev + R;
       const int M = N_curr - R;
       const bool capped = (N_curr < N_prev + R);
-      const double lsum_prev = lsum;
       int anc = tid;
+      double lomax = lo[0];
+#pragma unroll
+      for (int r = 1; r < R; r++) lomax = lo[r] > lomax ? lo[r] : lomax;
+
+      if (service) {
+        // the uniform of this site, and log Z_{t-1}: the log of last step's normaliser is evaluated now, off the
+        // workers' critical path (they read s.lsum only after the sort's barriers)
+        if (lane == 8) s.u = ch.unif ? __ldg(ch.unif + t) : philox_uniform(ch.seed, ch.chain_id, t);
+        if (lane == 0) s.lsum[(t + 1) & 1] = pend_shift + log(pend_S);
+        __syncwarp();
+      }
 
       // ---- class sums over the previous particles (replace the R x N_prev log-sum-exps of Smc.h:562-573) ----
       const double e_prev = (tid < N_prev) ? p.W * p.cur.x : 0.0;  // W_n * c_new(d_n, r_n)
       const bool finite_prev = (tid < N_prev) && hyg_isfinite(p.lw);
       const bool valid = finite_prev && (p.cur.x > 0.0);
-      {
+      if (worker) {
         double v8[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) v8[r] = (r < R && p.r == r) ? e_prev : 0.0;
@@ -236,46 +330,36 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
       pbuf ^= 1;
 
       // ---- ancestors: Smc::resampleCp (Smc.h:406-450) ----
-      bool own_weight = true;   // child keeps its ancestor's own log-weight (top-K / keep-largest / growth)
+      bool own_weight = true;   // child keeps its ancestor's own weight (top-K / keep-largest / growth)
       int sidx = tid;
+      double totA;
+      double sumE_lane = 0.0;   // service warp, lane r < R: new-segment mass of regime r
       if (capped) {
-        // sort by log-weight, descending (ties by slot); W is a monotone map of logw
-        unsigned long long key = (tid < N_prev) ? order_key(p.lw, tid) : 0ull;
-        key = block_sort_desc(key, s, kbuf);   // >= 1 barrier: s.part[pA] / s.vmask[pA] are visible from here on
-        sidx = 255 - static_cast<int>(key & 0xFFull);
-        s.idx[tid] = static_cast<unsigned short>(sidx);
+        if (worker) {
+          // sort by log-weight, descending (ties by slot); W is a monotone map of logw
+          // (dead slots get distinct tiny keys so that every key is unique)
+          unsigned long long key = (tid < N_prev) ? order_key(p.lw, tid) : static_cast<unsigned long long>(255 - tid);
+          key = block_sort_desc(key, s);   // 2 barriers; s.part[pA] / s.vmask[pA] are visible after the first
+          sidx = 255 - static_cast<int>(key & 0xFFull);
+          s.idx[tid] = static_cast<unsigned short>(sidx);
+          totA = combine8(s.part[pA]);
+        } else {
+          __syncthreads();
+          totA = combine8(s.part[pA]);
+          sumE_lane = sg_service_new_segments<R>(mdl, s, totA, pA);
+#pragma unroll
+          for (int b = 1; b < HYG_SORT_BARRIERS; b++) __syncthreads();
+        }
       } else {
         __syncthreads();
-      }
-      const double totA = combine8(s.part[pA]);           // lane & 7 -> E[0..R-1], [7] = F
-      const int F = static_cast<int>(__shfl_sync(HYG_FULL, totA, 7) + 0.5);
-      // new-segment mass of regime r: sumE[r] = sum_{r' != r} P[r'][r] E[r'], needed by the R threads that own (1, r)
-      double my_sumE = 0.0, my_invE = 0.0;
-      {
-        const int w_lo = M >> 5, w_hi = (M + R - 1) >> 5;
-        if (warp == w_lo || warp == w_hi) {
-          const int r = tid - M;
-          const bool mine = (r >= 0 && r < R);
-          unsigned vm = 0;
-#pragma unroll
-          for (int w = 0; w < HYG_NW; w++) vm |= s.vmask[pA][w];
-          double a = 0.0;
-          bool could = false;
-#pragma unroll
-          for (int rp = 0; rp < R; rp++) {
-            const double Erp = __shfl_sync(HYG_FULL, totA, rp);
-            const double Pv = mine ? mdl.P[rp][r] : 0.0;   // zero diagonal
-            a += Pv * Erp;
-            could = could || (((vm >> rp) & 1u) && Pv > 0.0);
-          }
-          if (mine) {
-            my_sumE = a;
-            my_invE = (a > 0.0) ? 1.0 / a : 0.0;
-            s.slow[r] = (!(a > 0.0) && could) ? 1 : 0;
-          }
+        totA = combine8(s.part[pA]);           // lane & 7 -> E[0..R-1], [7] = F
+        if (service) {
+          sumE_lane = sg_service_new_segments<R>(mdl, s, totA, pA);
+          if (lane < R) s.new_lw[lane] = (sumE_lane > 0.0) ? s.lsum[(t + 1) & 1] + lo[lane] + log(sumE_lane) : -HYG_INF;
         }
+        __syncthreads();                       // growth phase has no later barrier before the new-segment values are read
       }
-      if (!capped) __syncthreads();  // growth phase has no later barrier before s.slow is read
+      const int F = static_cast<int>(__shfl_sync(HYG_FULL, totA, 7) + 0.5);
       if (capped) {
         bool keep_largest = (F <= M);
         int K = 0;
@@ -296,7 +380,7 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
           for (int w = HYG_NW - 1; w > 0; w--) tail += (w > warp) ? s.sc.d[flip][w][0] : 0.0;
           flip ^= 1;
           const double Qp = v + tail;
-          s.Q[tid] = Qp;
+          if (worker) s.Q[tid] = Qp;
           if (tid == 0) s.Q[HYG_NPMAX] = 0.0;
           // Fixed point for K (resample.h:333-342).  The reference iterates K <- K + #{i >= K : log q_i > -log C(K)},
           // log C(K) = log(M-K) - log Q[K], from K = 0.  Along that iteration the threshold Q[K]/(M-K) only decreases, so
@@ -319,18 +403,27 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
         }
         if (keep_largest) {
           // keep the M largest by log-weight (Smc.h:432-441; resample.h:366-375)
-          __syncthreads();  // s.idx visible
+          if (service && lane < R) s.new_lw[lane] = (sumE_lane > 0.0) ? s.lsum[(t + 1) & 1] + lo[lane] + log(sumE_lane) : -HYG_INF;
+          __syncthreads();  // s.idx and s.new_lw visible
           anc = (tid < M) ? s.idx[tid] : tid;
           k_kept = -2;
         } else {
           const int L = M - K;
-          if (tid == 0) s.res_lw = lsum_prev - (log(static_cast<double>(L)) - log(Qk));  // lsum_prev - log C (resample.h:361-364)
+          if (service) {
+            // ONE log evaluation: lanes 0..R-1 the new-segment particles, lane 7 the weight lsum_prev - log C of a
+            // resampled particle (resample.h:361-364); consumed by the workers two barriers later
+            const double arg = (lane == 7) ? Qk / static_cast<double>(L) : sumE_lane;
+            const double lg = (arg > 0.0) ? log(arg) : -HYG_INF;
+            const double lsp = s.lsum[(t + 1) & 1];
+            if (lane < R) s.new_lw[lane] = (arg > 0.0) ? lsp + lo[lane] + lg : -HYG_INF;
+            if (lane == 7) s.res_lw = lsp + lg;
+          }
           k_kept = K;
           drew = true;
           // systematic resampling of L offspring among the sorted residual particles (resample.h:85-127,354-359).
           // C_p = #{ j < L : (j+u)/L <= cumulative residual weight up to p }; forced monotone, C_last = L, so the
           // offspring counts o_p = C_p - C_{p-1} are >= 0 and sum to L whatever the rounding of the suffix sums.
-          const double u = ch.unif ? __ldg(ch.unif + t) : philox_uniform(ch.seed, ch.chain_id, t);
+          const double u = s.u;
           int C = 0;
           if (tid >= K && tid < N_prev) C = (tid == N_prev - 1) ? L : sys_count_x((Qk - s.Q[tid + 1]) * (static_cast<double>(L) / Qk) - u, L);
           if (tid >= N_prev) C = L;
@@ -361,15 +454,15 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
         ch.ancestors[t * static_cast<unsigned long long>(Nmax - R) + tid] = (tid < M) ? static_cast<short>(anc) : static_cast<short>(-1);
 
       // ---- propose + weight: sampleParticlesCp / computeWeightsCp (Smc.h:504-574) ----
+      const double lsum_prev = s.lsum[(t + 1) & 1];
       SgChainState c;
       c.lw = -HYG_INF; c.W = 0.0; c.cur = make_double2(0.0, 0.0); c.nxt = c.cur; c.d = 0; c.r = 0;
       if (tid < M) {
-        const double base = own_weight ? s.lw[anc] : s.res_lw;
         c.r = s.r[anc];
         c.d = s.d[anc] + 1;
         c.cur = s.nxt[anc];
         const double lc = s.cur[anc].y;                 // log(1 - rho(d_prev, r)) or -inf (singleGroup.h:597-605)
-        c.lw = base + (lc + lo[c.r]);
+        c.lw = (own_weight ? s.lw[anc] : s.res_lw) + (lc + lo[c.r]);
         const uint32_t di = (c.d + 1 <= dcap) ? c.d : dcap - 1;  // 0-based index of d+1, clamped to the terminal entry
         c.nxt = __ldg(mdl.tab + static_cast<size_t>(c.r) * dcap + di);
       } else if (tid < N_curr) {
@@ -377,8 +470,9 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
         c.r = r; c.d = 1;
         c.cur = __ldg(mdl.tab + static_cast<size_t>(r) * dcap + 0);
         c.nxt = __ldg(mdl.tab + static_cast<size_t>(r) * dcap + (dcap > 1 ? 1 : 0));
-        c.lw = (my_sumE > 0.0) ? lsum_prev + lo[r] + log(my_sumE) : -HYG_INF;
+        c.lw = s.new_lw[r];
       }
+      const double my_invE = (tid >= M && tid < N_curr) ? s.new_invE[tid - M] : 0.0;
       // exact log-domain path for regimes whose linear-domain sum underflowed (rare)
       unsigned slowmask = 0;
 #pragma unroll
@@ -402,31 +496,31 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
       }
 
       // ---- selfNormaliseWeights (Smc.h:576-579), fused with the regime masses of the new site ----
-      // shift by the bound lsum_prev + max_r logObs instead of the exact max; class sums give both the normaliser and
-      // sum_{n: r_n = q} W_n (initialisePsi + computeFilteredMean for the current site).
       {
-        double lomax = lo[0];
-#pragma unroll
-        for (int r = 1; r < R; r++) lomax = lo[r] > lomax ? lo[r] : lomax;
-        double shift = lsum_prev + lomax;
-        double mine = (tid < N_curr) ? exp(c.lw - shift) : 0.0;
+        double shift = lsum_prev + lomax;   // upper bound of every logw instead of the exact max
         double v8[8];
+        c.W = (tid < N_curr) ? exp(c.lw - shift) : 0.0;
+        if (worker) {
 #pragma unroll
-        for (int q = 0; q < 8; q++) v8[q] = (q < R && c.r == q) ? mine : 0.0;
-        publish8(s.part[pbuf], warp_reduce8(v8));
+          for (int q = 0; q < 8; q++) v8[q] = (q < R && c.r == q) ? c.W : 0.0;
+          publish8(s.part[pbuf], warp_reduce8(v8));
+        }
         __syncthreads();
-        double tot = combine8(s.part[pbuf]);   // lane & 7 -> class sum of exp(lw - shift)
+        double tot = combine8(s.part[pbuf]);   // lane & 7 -> class sum of the relative weights
         pbuf ^= 1;
         double S = tot;
         S += __shfl_xor_sync(HYG_FULL, S, 1);
         S += __shfl_xor_sync(HYG_FULL, S, 2);
         S += __shfl_xor_sync(HYG_FULL, S, 4);
-        if (!(S > 0.0) || !hyg_isfinite(S)) {  // everything underflowed against the bound: use the exact max
+        if (!(S > 0.0) || !hyg_isfinite(S)) {
+          // the linear-domain weights underflowed against the bound: renormalise from the log-weights with the exact max
           shift = block_max((tid < N_curr) ? c.lw : -HYG_INF, s.sc, flip);
-          mine = (tid < N_curr) ? exp(c.lw - shift) : 0.0;
+          c.W = (tid < N_curr && c.lw > -HYG_INF) ? exp(c.lw - shift) : 0.0;
+          if (worker) {
 #pragma unroll
-          for (int q = 0; q < 8; q++) v8[q] = (q < R && c.r == q) ? mine : 0.0;
-          publish8(s.part[pbuf], warp_reduce8(v8));
+            for (int q = 0; q < 8; q++) v8[q] = (q < R && c.r == q) ? c.W : 0.0;
+            publish8(s.part[pbuf], warp_reduce8(v8));
+          }
           __syncthreads();
           tot = combine8(s.part[pbuf]);
           pbuf ^= 1;
@@ -436,9 +530,9 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
           S += __shfl_xor_sync(HYG_FULL, S, 4);
         }
         const double invS = 1.0 / S;
-        c.W = mine * invS;
+        c.W *= invS;
         cw_lane = tot * invS;
-        if (tid == 0) s.lsum = shift + log(S);   // running log Z_t; read by everybody after the end-of-step barrier
+        pend_shift = shift; pend_S = S;   // log Z_t = shift + log S is evaluated by the service warp at the next step
       }
 
       // ---- fixed-lag smoothing: updatePsi (OnlineMarginalSmoothing.h:148-177) ----
@@ -504,8 +598,10 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
             if (tid == 0 && ch.finalised_at) ch.finalised_at[ts] = static_cast<int>(t);
           } else {
             double* dst = pc + static_cast<size_t>(kept) * R * HYG_NPMAX;
+            if (worker) {
 #pragma unroll
-            for (int q = 0; q < R; q++) dst[q * HYG_NPMAX + tid] = val[q];
+              for (int q = 0; q < R; q++) dst[q * HYG_NPMAX + tid] = val[q];
+            }
             __syncthreads();  // pend_t[i] has been read by every thread before slot `kept` (<= i) is overwritten
             if (tid == 0) pend_t[kept] = ts;
             kept++;
@@ -518,13 +614,14 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
     } else {
       // t = 0: regime masses of the initial particle system
       double v8[8];
+      if (worker) {
 #pragma unroll
-      for (int q = 0; q < 8; q++) v8[q] = (q < R && tid < N && p.r == q) ? p.W : 0.0;
-      publish8(s.part[pbuf], warp_reduce8(v8));
+        for (int q = 0; q < 8; q++) v8[q] = (q < R && tid < N && p.r == q) ? p.W : 0.0;
+        publish8(s.part[pbuf], warp_reduce8(v8));
+      }
       __syncthreads();
       cw_lane = combine8(s.part[pbuf]);
       pbuf ^= 1;
-      if (tid == 0) s.lsum = lsum;
     }
 
     // ---- initialisePsi + storeEstimates for the current site (OnlineMarginalSmoothing.h:119-146,197-255) ----
@@ -545,8 +642,10 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
         if (tid == 0 && ch.finalised_at) ch.finalised_at[t] = static_cast<int>(t);
       } else {
         double* dst = psi[t & 1] + static_cast<size_t>(n_pend) * R * HYG_NPMAX;
+        if (worker) {
 #pragma unroll
-        for (int q = 0; q < R; q++) dst[q * HYG_NPMAX + tid] = (tid < N && p.r == q) ? 1.0 : 0.0;
+          for (int q = 0; q < R; q++) dst[q * HYG_NPMAX + tid] = (tid < N && p.r == q) ? 1.0 : 0.0;
+        }
         if (tid == 0) pend_t[n_pend] = static_cast<int>(t);
         n_pend++;
       }
@@ -554,14 +653,16 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
     }
 
     // ---- publish the particle system for the next site (all gathers of this step precede the normaliser barrier) ----
-    s.W[tid] = p.W; s.lw[tid] = p.lw; s.cur[tid] = p.cur; s.nxt[tid] = p.nxt; s.d[tid] = p.d; s.r[tid] = static_cast<unsigned char>(p.r);
-    if (tid < R && t + 2 < T) s.lo[t & 1][tid] = lo_pref;
+    if (worker) {
+      s.W[tid] = p.W; s.lw[tid] = p.lw; s.cur[tid] = p.cur; s.nxt[tid] = p.nxt; s.d[tid] = p.d; s.r[tid] = static_cast<unsigned char>(p.r);
+    }
+    if (service && lane < R && t + 2 < T) s.lo[t & 1][lane] = lo_pref;
     __syncthreads();
-    lsum = s.lsum;
 
     // ---- taps ----
-    if (tid == 0) {
-      if (ch.logz) ch.logz[t] = lsum;
+    if (service && lane == 0) {
+      if (ch.logz && t > 0) ch.logz[t - 1] = s.lsum[(t + 1) & 1];
+      if (ch.logz && t == T - 1) ch.logz[t] = pend_shift + log(pend_S);
       if (ch.k_kept) ch.k_kept[t] = k_kept;
       if (ch.drew) ch.drew[t] = drew ? 1 : 0;
       if (ch.n_pending) ch.n_pending[t] = n_pend;

@@ -49,6 +49,7 @@ struct ChainBuf {
   int* d_fin = nullptr;
   short* d_anc = nullptr;
   int* d_status = nullptr;
+  double* d_trace = nullptr;
 };
 
 }  // namespace
@@ -73,6 +74,9 @@ struct hyg_ctx {
   hyg::SgChainDev* d_chains = nullptr;
   double* d_psi = nullptr;
   size_t psi_bytes = 0;
+  double* d_pe = nullptr;
+  size_t pe_bytes = 0;
+  double* d_theta0 = nullptr;
   unsigned int* d_queue = nullptr;
   uint32_t n_particles_staged = 0;
   cudaEvent_t ev_em0 = nullptr, ev_em1 = nullptr, ev_f0 = nullptr, ev_f1 = nullptr;
@@ -100,7 +104,7 @@ template <class T> void dfree(T*& p) {
 void free_chains(hyg_ctx* c) {
   for (auto& b : c->chains) {
     dfree(b.d_unif); dfree(b.d_pos); dfree(b.d_probs); dfree(b.d_logz); dfree(b.d_k); dfree(b.d_drew); dfree(b.d_npend);
-    dfree(b.d_ncurr); dfree(b.d_fin); dfree(b.d_anc); dfree(b.d_status);
+    dfree(b.d_ncurr); dfree(b.d_fin); dfree(b.d_anc); dfree(b.d_status); dfree(b.d_trace);
   }
   c->chains.clear();
   c->order.clear();
@@ -128,14 +132,27 @@ template <int R> int launch_emission(hyg_ctx* c, const hyg::SgEmissionArgs& a, s
   return HYG_OK;
 }
 
-template <int R> int launch_filter(hyg_ctx* c, const hyg::SgRunDev& run, int grid) {
-  hyg::sg_filter_kernel<R><<<grid, HYG_NT, 0, c->stream>>>(c->d_mdl, c->d_chains, run);
+template <int R, bool PE> int launch_filter(hyg_ctx* c, const hyg::SgRunDev& run, int grid) {
+  const size_t smem = PE ? sizeof(hyg::SgPeSmem<R>) : 0;
+  if (PE) HYG_CUDA(c, cudaFuncSetAttribute(hyg::sg_filter_kernel<R, PE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  hyg::sg_filter_kernel<R, PE><<<grid, HYG_NT, smem, c->stream>>>(c->d_mdl, c->d_chains, run);
   HYG_CUDA(c, cudaGetLastError());
   return HYG_OK;
 }
-template <int R> int filter_occupancy(int* occ) {
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, hyg::sg_filter_kernel<R>, HYG_NT, 0) == cudaSuccess ? 0 : -1;
+template <int R, bool PE> int filter_occupancy(int* occ) {
+  const size_t smem = PE ? sizeof(hyg::SgPeSmem<R>) : 0;
+  if (PE) cudaFuncSetAttribute(hyg::sg_filter_kernel<R, PE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, hyg::sg_filter_kernel<R, PE>, HYG_NT, smem) == cudaSuccess ? 0 : -1;
 }
+#define HYG_DISPATCH_R6(R_, EXPR)             \
+  switch (R_) {                               \
+    case 2: { constexpr int RR = 2; EXPR; } break; \
+    case 3: { constexpr int RR = 3; EXPR; } break; \
+    case 4: { constexpr int RR = 4; EXPR; } break; \
+    case 5: { constexpr int RR = 5; EXPR; } break; \
+    case 6: { constexpr int RR = 6; EXPR; } break; \
+    default: break;                           \
+  }
 
 #define HYG_DISPATCH_R(R_, EXPR)              \
   switch (R_) {                               \
@@ -193,7 +210,7 @@ void hyg_destroy(hyg_ctx* c) {
   cudaStreamSynchronize(c->stream);
   free_chains(c);
   free_datasets(c);
-  dfree(c->d_tab); dfree(c->d_tabg); dfree(c->d_mdl); dfree(c->d_emtab); dfree(c->d_sets); dfree(c->d_psi); dfree(c->d_queue);
+  dfree(c->d_tab); dfree(c->d_tabg); dfree(c->d_mdl); dfree(c->d_emtab); dfree(c->d_sets); dfree(c->d_psi); dfree(c->d_pe); dfree(c->d_theta0); dfree(c->d_queue);
   cudaEventDestroy(c->ev_em0); cudaEventDestroy(c->ev_em1); cudaEventDestroy(c->ev_f0); cudaEventDestroy(c->ev_f1);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -410,7 +427,9 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
   const int R = c->hm.R;
   if (args->n_particles_max > HYG_NPMAX || args->n_particles_max < static_cast<uint32_t>(2 * R))
     return fail(c, HYG_ERR_UNSUPPORTED, "n_particles must be in [2R, 256]");
-  if (args->use_online_parameter_estimation) return fail(c, HYG_ERR_UNSUPPORTED, "online parameter estimation is not implemented yet");
+  const bool pe_mode = args->use_online_parameter_estimation != 0;
+  if (pe_mode && R > 6) return fail(c, HYG_ERR_UNSUPPORTED, "online parameter estimation supports at most 6 regimes");
+  if (pe_mode && args->n_steps_without_parameter_update == 0) return fail(c, HYG_ERR_ARG, "n_steps_without_parameter_update must be > 0");
   HYG_CUDA(c, cudaSetDevice(c->device));
   const uint32_t n = static_cast<uint32_t>(c->chains.size());
   const uint32_t Nmax = args->n_particles_max;
@@ -430,6 +449,17 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
   m.tab = c->d_tab; m.tabg = c->d_tabg;
   HYG_CUDA(c, cudaMemcpyAsync(c->d_mdl, &m, sizeof(m), cudaMemcpyHostToDevice, c->stream));
 
+  // parameter mode: initial theta on the device, theta traces, per-CTA table workspace
+  uint64_t t_max = 2;
+  for (auto& b : c->chains) t_max = std::max<uint64_t>(t_max, b.T);
+  if (pe_mode) {
+    if (!c->d_theta0) HYG_CUDA(c, cudaMalloc(&c->d_theta0, 64 * sizeof(double)));
+    HYG_CUDA(c, cudaMemcpyAsync(c->d_theta0, c->hm.theta.data(), c->hm.D * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    for (auto& b : c->chains)
+      if (b.host.theta_trace && !b.d_trace) HYG_CUDA(c, cudaMalloc(&b.d_trace, b.T * c->hm.D * sizeof(double)));
+    HYG_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+
   // chain descriptors in launch order
   std::vector<hyg::SgChainDev> cd(n);
   for (uint32_t k = 0; k < n; k++) {
@@ -442,12 +472,14 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
     d.probs = args->use_online_marginal_smoothing ? b.d_probs : nullptr;
     d.logz = b.d_logz; d.k_kept = b.d_k; d.drew = b.d_drew; d.n_pending = b.d_npend; d.n_curr = b.d_ncurr;
     d.finalised_at = b.d_fin; d.ancestors = b.d_anc; d.status = b.d_status;
+    d.theta0 = c->d_theta0; d.theta_trace = pe_mode ? b.d_trace : nullptr;
   }
   HYG_CUDA(c, cudaMemcpyAsync(c->d_chains, cd.data(), n * sizeof(hyg::SgChainDev), cudaMemcpyHostToDevice, c->stream));
   HYG_CUDA(c, cudaStreamSynchronize(c->stream));  // cd goes out of scope
 
   int occ = 1;
-  HYG_DISPATCH_R(R, filter_occupancy<RR>(&occ));
+  if (pe_mode) { HYG_DISPATCH_R6(R, (filter_occupancy<RR, true>(&occ))); }
+  else { HYG_DISPATCH_R(R, (filter_occupancy<RR, false>(&occ))); }
   if (occ < 1) occ = 1;
   const int grid = static_cast<int>(std::min<uint64_t>(n, static_cast<uint64_t>(c->num_sms) * occ));
 
@@ -465,6 +497,25 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
   run.psi_ws = c->d_psi;
   run.queue = c->d_queue;
   run.n_chains = static_cast<int>(n);
+  run.use_param_est = pe_mode ? 1 : 0;
+  run.normalise_gradients = args->normalise_gradients;
+  run.use_adam = args->use_adam;
+  run.n_steps_without_update = args->n_steps_without_parameter_update;
+  run.lr_exponent = args->learning_rate_exponent;
+  run.lr_factor = args->learning_rate_factor;
+  for (int r = 0; r < HYG_RMAX; r++) run.kappa[r] = r < R ? c->hm.kappa[r] : 1.0;
+  run.pe_ws = nullptr; run.pe_stride = 0; run.pe_dcap = 0;
+  if (pe_mode) {
+    run.pe_dcap = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(t_max + 8, 64), 65536));
+    run.pe_stride = 5ull * R * run.pe_dcap;   // tab (2) + tabg + wh + wg
+    const size_t pe_need = run.pe_stride * sizeof(double) * grid;
+    if (pe_need > c->pe_bytes) {
+      dfree(c->d_pe);
+      HYG_CUDA(c, cudaMalloc(&c->d_pe, pe_need));
+      c->pe_bytes = pe_need;
+    }
+    run.pe_ws = c->d_pe;
+  }
   HYG_CUDA(c, cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned int), c->stream));
 
   c->f_launches = 0;
@@ -477,7 +528,8 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
       }
   }
   int rc = HYG_ERR_UNSUPPORTED;
-  HYG_DISPATCH_R(R, rc = launch_filter<RR>(c, run, grid));
+  if (pe_mode) { HYG_DISPATCH_R6(R, (rc = launch_filter<RR, true>(c, run, grid))); }
+  else { HYG_DISPATCH_R(R, (rc = launch_filter<RR, false>(c, run, grid))); }
   if (rc) return rc;
   c->f_launches++;
   HYG_CUDA(c, cudaEventRecord(c->ev_f1, c->stream));
@@ -501,6 +553,7 @@ int hyg_sg_download(hyg_ctx* c, hyg_sg_chain* chains, uint32_t n) {
     if (h.n_pending) HYG_CUDA(c, cudaMemcpyAsync(h.n_pending, b.d_npend, T * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (h.n_curr) HYG_CUDA(c, cudaMemcpyAsync(h.n_curr, b.d_ncurr, T * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (h.finalised_at) HYG_CUDA(c, cudaMemcpyAsync(h.finalised_at, b.d_fin, T * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (h.theta_trace && b.d_trace) HYG_CUDA(c, cudaMemcpyAsync(h.theta_trace, b.d_trace, T * c->hm.D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (h.ancestors && b.d_anc)
       HYG_CUDA(c, cudaMemcpyAsync(h.ancestors, b.d_anc, T * (c->n_particles_staged - R) * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
     if (chains) HYG_CUDA(c, cudaMemcpyAsync(chains[i].status, b.d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));

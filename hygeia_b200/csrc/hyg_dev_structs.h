@@ -56,6 +56,17 @@ struct SgRunDev {
   unsigned long long psi_stride;  // doubles per CTA
   unsigned int* queue;    // atomic chain counter
   int n_chains;
+  // parameter-estimation mode (K3)
+  int use_param_est;
+  int normalise_gradients;
+  int use_adam;
+  unsigned int n_steps_without_update;
+  double lr_exponent;
+  double lr_factor;
+  double kappa[HYG_RMAX];
+  double* pe_ws;          // per-CTA table workspace: tab (double2) | tabg | wh | wg, each R x pe_dcap
+  unsigned long long pe_stride;   // doubles per CTA
+  uint32_t pe_dcap;
 };
 
 }  // namespace hyg

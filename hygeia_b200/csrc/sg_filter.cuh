@@ -32,6 +32,7 @@
 
 #include "hyg_common.cuh"
 #include "hyg_dev_structs.h"
+#include "sg_param.cuh"
 
 namespace hyg {
 
@@ -52,6 +53,7 @@ struct SgSmem {
   BlockScratch sc;
   double lo[2][HYG_RMAX];
   double part[2][HYG_NW][8];   // per-warp partials of the 8-wide transposed reductions (double-buffered)
+  double partG[2][HYG_NW][8];  // parameter mode: partials of Eg[r'] = sum e_n dlogrho_n
   unsigned vmask[2][HYG_NW];
   int slow[HYG_RMAX];
   double new_lw[HYG_RMAX];     // log-weight of the new-segment particle (1, r)
@@ -150,6 +152,7 @@ struct SgChainState {
   // per-thread particle (slot = threadIdx.x)
   double lw, W;
   double2 cur, nxt;
+  double gcur, gnxt;   // parameter mode: d log rho / d theta_omega for d and d+1
   uint32_t d;
   int r;
 };
@@ -234,8 +237,14 @@ __device__ __forceinline__ double sg_service_new_segments(const SgModelDev& mdl,
   return a;
 }
 
-template <int RT>
-__device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, const SgRunDev& run, double* psi_ws, SgSmem& s) {
+// plain load for tables that this kernel rewrites (parameter mode), read-only path otherwise
+template <bool PE, class T> __device__ __forceinline__ T tab_load(const T* p) {
+  if (PE) return *p;
+  return __ldg(p);
+}
+
+template <int RT, bool PE>
+__device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgRunDev& run, double* psi_ws, SgSmem& s, SgPeSmem<RT>* pe) {
   static_assert(RT <= 7, "class sums share an 8-wide reduction with the finite-weight count");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // Warps 0..7 own the particles (one slot per thread).  Warp 8 is a SERVICE warp: it owns no particle, follows the same
@@ -246,10 +255,34 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
   const bool service = !worker;
   constexpr int R = RT;
   const int Nmax = mdl.n_particles;
-  const uint32_t dcap = mdl.dcap;
+  uint32_t dcap = mdl.dcap;
   const unsigned long long T = ch.T;
   const int lcap = run.lcap;
-  int flip = 0, kbuf = 0, ibuf = 0, pbuf = 0;
+  int flip = 0, ibuf = 0, pbuf = 0;
+  constexpr int D = R * R;
+  // parameter mode: per-CTA table workspace (tables are rebuilt on the device whenever theta moves)
+  double2* pe_tab = nullptr; double* pe_tabg = nullptr; double* pe_wh = nullptr; double* pe_wg = nullptr;
+  if (PE) {
+    double* base = run.pe_ws + static_cast<size_t>(blockIdx.x) * run.pe_stride;
+    pe_tab = reinterpret_cast<double2*>(base);
+    pe_tabg = base + 2ull * R * run.pe_dcap;
+    pe_wh = pe_tabg + static_cast<size_t>(R) * run.pe_dcap;
+    pe_wg = pe_wh + static_cast<size_t>(R) * run.pe_dcap;
+    if (tid < D) {
+      pe->theta[tid] = ch.theta0[tid];
+      pe->adam_m[tid] = 0.0; pe->adam_v[tid] = 0.0; pe->grad_cur[tid] = 0.0; pe->grad_prev[tid] = 0.0;
+    }
+    if (tid < R) pe->kappa[tid] = run.kappa[tid];
+    if (tid == 0) { pe->iter = 0; mdl.tab = pe_tab; mdl.tabg = pe_tabg; }
+    for (int i = tid; i < 2 * D * HYG_PHI_PITCH; i += HYG_NT) (&pe->phi[0][0][0])[i] = 0.0;
+    __syncthreads();
+    pe_set_theta<R>(mdl, *pe);
+    uint32_t dn = run.n_steps_without_update + 12;
+    dn = dn > run.pe_dcap ? run.pe_dcap : dn;
+    pe_rebuild_tables<R>(mdl, *pe, pe_tab, pe_tabg, pe_wh, pe_wg, run.pe_dcap, dn);
+    dcap = run.pe_dcap;   // row pitch of the workspace tables; valid entries: mdl.dcap
+  }
+  const SgModelDev& cm = mdl;
 
   // psi workspace (global, L2-resident): [2][lcap][R][256] doubles followed by lcap ints of site indices
   double* psi[2] = {psi_ws, psi_ws + static_cast<size_t>(lcap) * R * HYG_NPMAX};
@@ -257,7 +290,7 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
   int n_pend = 0, n_forced = 0, max_pend = 0;
 
   SgChainState p;
-  p.lw = -HYG_INF; p.W = 0.0; p.cur = make_double2(0.0, 0.0); p.nxt = p.cur; p.d = 0; p.r = 0;
+  p.lw = -HYG_INF; p.W = 0.0; p.cur = make_double2(0.0, 0.0); p.nxt = p.cur; p.gcur = 0.0; p.gnxt = 0.0; p.d = 0; p.r = 0;
 
   // ---- t = 0 : Smc::initialise (Smc.h:114-188) ----
   if (tid < R) s.lo[0][tid] = __ldg(ch.logobs + tid);
@@ -273,8 +306,9 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
     if (tid < R) {
       p.d = 1; p.r = tid;
       p.lw = lsum_prev + s.lo[0][tid];
-      p.cur = __ldg(mdl.tab + static_cast<size_t>(tid) * dcap + 0);
-      p.nxt = __ldg(mdl.tab + static_cast<size_t>(tid) * dcap + (dcap > 1 ? 1 : 0));
+      p.cur = tab_load<PE>(mdl.tab + static_cast<size_t>(tid) * dcap + 0);
+      p.nxt = tab_load<PE>(mdl.tab + static_cast<size_t>(tid) * dcap + 1);
+      if (PE) { p.gcur = mdl.tabg[static_cast<size_t>(tid) * dcap + 0]; p.gnxt = mdl.tabg[static_cast<size_t>(tid) * dcap + 1]; }
     }
     const double c = lsum_prev + lomax;
     double e[1] = {(tid < N) ? exp(p.lw - c) : 0.0};
@@ -325,6 +359,12 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
         publish8(s.part[pbuf], warp_reduce8(v8));
         const unsigned vm = __reduce_or_sync(HYG_FULL, valid ? (1u << p.r) : 0u);
         if (lane == 0) s.vmask[pbuf][warp] = vm;
+        if (PE) {
+          pe->eprev[tid] = e_prev;
+#pragma unroll
+          for (int r = 0; r < 8; r++) v8[r] = (r < R && p.r == r) ? e_prev * p.gcur : 0.0;
+          publish8(s.partG[pbuf], warp_reduce8(v8));
+        }
       }
       const int pA = pbuf;
       pbuf ^= 1;
@@ -347,6 +387,10 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
           __syncthreads();
           totA = combine8(s.part[pA]);
           sumE_lane = sg_service_new_segments<R>(mdl, s, totA, pA);
+          if (PE) {
+            const double totG = combine8(s.partG[pA]);
+            if (lane < 8) { pe->Etot[lane] = totA; pe->Egtot[lane] = totG; }
+          }
 #pragma unroll
           for (int b = 1; b < HYG_SORT_BARRIERS; b++) __syncthreads();
         }
@@ -355,6 +399,10 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
         totA = combine8(s.part[pA]);           // lane & 7 -> E[0..R-1], [7] = F
         if (service) {
           sumE_lane = sg_service_new_segments<R>(mdl, s, totA, pA);
+          if (PE) {
+            const double totG = combine8(s.partG[pA]);
+            if (lane < 8) { pe->Etot[lane] = totA; pe->Egtot[lane] = totG; }
+          }
           if (lane < R) s.new_lw[lane] = (sumE_lane > 0.0) ? s.lsum[(t + 1) & 1] + lo[lane] + log(sumE_lane) : -HYG_INF;
         }
         __syncthreads();                       // growth phase has no later barrier before the new-segment values are read
@@ -456,20 +504,30 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
       // ---- propose + weight: sampleParticlesCp / computeWeightsCp (Smc.h:504-574) ----
       const double lsum_prev = s.lsum[(t + 1) & 1];
       SgChainState c;
-      c.lw = -HYG_INF; c.W = 0.0; c.cur = make_double2(0.0, 0.0); c.nxt = c.cur; c.d = 0; c.r = 0;
+      c.lw = -HYG_INF; c.W = 0.0; c.cur = make_double2(0.0, 0.0); c.nxt = c.cur; c.gcur = 0.0; c.gnxt = 0.0; c.d = 0; c.r = 0;
+      const uint32_t vcap = PE ? cm.dcap : dcap;   // valid table entries per regime (parameter mode: last rebuild)
+      double grad_c = 0.0;   // parameter mode: d log f / d theta_omega(r) of the continuation (singleGroup.h:679-693)
       if (tid < M) {
         c.r = s.r[anc];
         c.d = s.d[anc] + 1;
         c.cur = s.nxt[anc];
-        const double lc = s.cur[anc].y;                 // log(1 - rho(d_prev, r)) or -inf (singleGroup.h:597-605)
+        const double2 pc = s.cur[anc];
+        const double lc = pc.y;                         // log(1 - rho(d_prev, r)) or -inf (singleGroup.h:597-605)
         c.lw = (own_weight ? s.lw[anc] : s.res_lw) + (lc + lo[c.r]);
-        const uint32_t di = (c.d + 1 <= dcap) ? c.d : dcap - 1;  // 0-based index of d+1, clamped to the terminal entry
-        c.nxt = __ldg(mdl.tab + static_cast<size_t>(c.r) * dcap + di);
+        const uint32_t di = (c.d + 1 <= vcap) ? c.d : vcap - 1;  // 0-based index of d+1, clamped to the terminal entry
+        c.nxt = tab_load<PE>(mdl.tab + static_cast<size_t>(c.r) * dcap + di);
+        if (PE) {
+          c.gcur = pe->gnxt[anc];
+          c.gnxt = mdl.tabg[static_cast<size_t>(c.r) * dcap + di];
+          const double rho = pc.x;                      // c_new = rho for d >= u (0 below u)
+          grad_c = (lc > -HYG_INF && rho < 1.0) ? -pe->gcur[anc] * rho / (1.0 - rho) : 0.0;
+        }
       } else if (tid < N_curr) {
         const int r = tid - M;
         c.r = r; c.d = 1;
-        c.cur = __ldg(mdl.tab + static_cast<size_t>(r) * dcap + 0);
-        c.nxt = __ldg(mdl.tab + static_cast<size_t>(r) * dcap + (dcap > 1 ? 1 : 0));
+        c.cur = tab_load<PE>(mdl.tab + static_cast<size_t>(r) * dcap + 0);
+        c.nxt = tab_load<PE>(mdl.tab + static_cast<size_t>(r) * dcap + 1);
+        if (PE) { c.gcur = mdl.tabg[static_cast<size_t>(r) * dcap + 0]; c.gnxt = mdl.tabg[static_cast<size_t>(r) * dcap + 1]; }
         c.lw = s.new_lw[r];
       }
       const double my_invE = (tid >= M && tid < N_curr) ? s.new_invE[tid - M] : 0.0;
@@ -609,6 +667,64 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
         }
         n_pend = kept;
       }
+      // ---- K3: score recursion (OnlineParameterEstimation.h:135-158), see sg_param.cuh ----
+      if (PE) {
+        const int pb = (t + 1) & 1, cb = t & 1;   // phi buffers: [pb] was written at site t-1
+        if (tid < 8 * D) {
+          // class sums G[k][r'] = sum_{n in class r'} e_n phi_n[k]: thread = (component k, chunk of 32 previous particles)
+          const int k = tid % D, chunk = tid / D;
+          double acc[R];
+#pragma unroll
+          for (int q = 0; q < R; q++) acc[q] = 0.0;
+          for (int i = 0; i < 32; i++) {
+            const int n = chunk * 32 + i;
+            const double ev = pe->eprev[n] * pe->phi[pb][k][n];
+            const int rn = s.r[n];
+#pragma unroll
+            for (int q = 0; q < R; q++) acc[q] += (rn == q) ? ev : 0.0;
+          }
+#pragma unroll
+          for (int q = 0; q < R; q++) pe->part[chunk][k][q] = acc[q];
+        }
+        __syncthreads();
+        if (tid < D * R) {
+          const int k = tid / R, q = tid % R;
+          double a = 0.0;
+#pragma unroll
+          for (int chn = 0; chn < 8; chn++) a += pe->part[chn][k][q];
+          pe->Gs[k][q] = a;
+        }
+        __syncthreads();
+        if (tid < R * D) {
+          // new particle (1, r): phi' = sum_n bk_r[n] (phi_n + grad_n), bk_r[n] = e_n P[r_n][r] / sumE[r];
+          // grad_n = dlogrho(d_n, r_n) on the omega slot of r_n and (1[c == r] - P[r_n][c]) on the P block of r_n
+          // (singleGroup.h:657-678)
+          const int r = tid / D, k = tid % D;
+          double a = 0.0;
+          for (int rp = 0; rp < R; rp++) {
+            if (rp == r) continue;
+            double term = pe->Gs[k][rp];
+            if (k == R * (R - 1) + rp) {
+              term += pe->Egtot[rp];
+            } else if (k >= rp * (R - 1) && k < (rp + 1) * (R - 1)) {
+              const int j = k - rp * (R - 1);
+              const int col = (j < rp) ? j : j + 1;
+              term += pe->Etot[rp] * (((col == r) ? 1.0 : 0.0) - cm.P[rp][col]);
+            }
+            a += cm.P[rp][r] * term;
+          }
+          pe->phi[cb][k][M + r] = a * s.new_invE[r];
+        }
+        if (tid < M) {
+          // continuing particle: phi' = phi_anc + grad, grad touches only the omega slot of its regime
+          const int ko = R * (R - 1) + c.r;
+          for (int k = 0; k < D; k++) {
+            double v = pe->phi[pb][k][anc];
+            if (k == ko) v += grad_c;
+            pe->phi[cb][k][tid] = v;
+          }
+        }
+      }
       p = c;
       N = N_curr;
     } else {
@@ -655,9 +771,43 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
     // ---- publish the particle system for the next site (all gathers of this step precede the normaliser barrier) ----
     if (worker) {
       s.W[tid] = p.W; s.lw[tid] = p.lw; s.cur[tid] = p.cur; s.nxt[tid] = p.nxt; s.d[tid] = p.d; s.r[tid] = static_cast<unsigned char>(p.r);
+      if (PE) { pe->gcur[tid] = p.gcur; pe->gnxt[tid] = p.gnxt; }
     }
     if (service && lane < R && t + 2 < T) s.lo[t & 1][lane] = lo_pref;
     __syncthreads();
+
+    // ---- K3: parameter update every n_steps sites (OnlineParameterEstimation.h:51-61) ----
+    if (PE) {
+      if (t > 0 && (t % run.n_steps_without_update) == 0) {
+        if (tid < D) {
+          // g = sum_n W_n phi_n over the current particles (computeFilteredMean, Smc.h:340-349)
+          double g = 0.0;
+          for (int n = 0; n < N; n++) g = g + s.W[n] * pe->phi[t & 1][tid][n];
+          pe->grad_prev[tid] = pe->grad_cur[tid];
+          pe->grad_cur[tid] = g;
+        }
+        __syncthreads();
+        pe_ascent<R>(*pe, run);
+        __syncthreads();
+        pe_set_theta<R>(mdl, *pe);
+        // rebuild the sojourn tables up to the largest sojourn any particle can reach before the next rebuild
+        const double dmax = block_max((tid < N) ? static_cast<double>(p.d) : 0.0, s.sc, flip);
+        unsigned long long dn = static_cast<unsigned long long>(dmax) + run.n_steps_without_update + 4;
+        dn = dn > run.pe_dcap ? run.pe_dcap : dn;
+        pe_rebuild_tables<R>(mdl, *pe, pe_tab, pe_tabg, pe_wh, pe_wg, run.pe_dcap, static_cast<uint32_t>(dn));
+        if (worker && tid < N) {
+          const uint32_t vc = cm.dcap;
+          const uint32_t i0 = (p.d <= vc ? p.d : vc) - 1, i1 = (p.d + 1 <= vc ? p.d + 1 : vc) - 1;
+          p.cur = pe_tab[static_cast<size_t>(p.r) * dcap + i0];
+          p.nxt = pe_tab[static_cast<size_t>(p.r) * dcap + i1];
+          p.gcur = pe_tabg[static_cast<size_t>(p.r) * dcap + i0];
+          p.gnxt = pe_tabg[static_cast<size_t>(p.r) * dcap + i1];
+          s.cur[tid] = p.cur; s.nxt[tid] = p.nxt; pe->gcur[tid] = p.gcur; pe->gnxt[tid] = p.gnxt;
+        }
+        __syncthreads();
+      }
+      if (ch.theta_trace && tid < D) ch.theta_trace[t * D + tid] = pe->theta[tid];
+    }
 
     // ---- taps ----
     if (service && lane == 0) {
@@ -677,28 +827,35 @@ __device__ void sg_filter_chain(const SgModelDev& mdl, const SgChainDev& ch, con
 }
 
 // Persistent launch: CTAs pull chains (pre-sorted longest first by the host) from an atomic queue.
-template <int RT>
+#ifdef HYG_EMU
+static double hyg_pe_smem_storage[(sizeof(SgPeSmem<6>) + 7) / 8 + 8];
+#define HYG_PE_SMEM reinterpret_cast<void*>(hyg_pe_smem_storage)
+#else
+extern __shared__ __align__(16) unsigned char hyg_pe_smem_dyn[];
+#define HYG_PE_SMEM reinterpret_cast<void*>(hyg_pe_smem_dyn)
+#endif
+
+template <int RT, bool PE>
 __device__ __forceinline__ void sg_filter_entry(const SgModelDev* mdl, const SgChainDev* chains, SgRunDev run) {
   __shared__ SgSmem s;
   __shared__ int s_next;
   __shared__ SgModelDev s_mdl;
-  if (threadIdx.x == 0) s_mdl = *mdl;
-  __syncthreads();
+  SgPeSmem<RT>* pe = PE ? reinterpret_cast<SgPeSmem<RT>*>(HYG_PE_SMEM) : nullptr;
   double* psi_ws = run.psi_ws + static_cast<size_t>(blockIdx.x) * run.psi_stride;
   for (;;) {
-    if (threadIdx.x == 0) s_next = static_cast<int>(atomicAdd(run.queue, 1u));
+    if (threadIdx.x == 0) { s_next = static_cast<int>(atomicAdd(run.queue, 1u)); s_mdl = *mdl; }
     __syncthreads();
     const int c = s_next;
     __syncthreads();
     if (c >= run.n_chains) break;
-    sg_filter_chain<RT>(s_mdl, chains[c], run, psi_ws, s);
+    sg_filter_chain<RT, PE>(s_mdl, chains[c], run, psi_ws, s, pe);
   }
 }
 
 #ifndef HYG_EMU
-template <int RT>
+template <int RT, bool PE>
 __global__ void __launch_bounds__(HYG_NT, 1) sg_filter_kernel(const SgModelDev* mdl, const SgChainDev* chains, SgRunDev run) {
-  sg_filter_entry<RT>(mdl, chains, run);
+  sg_filter_entry<RT, PE>(mdl, chains, run);
 }
 #endif
 

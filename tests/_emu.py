@@ -17,11 +17,11 @@ def build():
     src = [os.path.join(EMU_DIR, "emu_kernels.cpp"), os.path.join(HERE, "..", "hygeia_b200", "csrc", "hyg_tables.cpp")]
     deps = src + [os.path.join(EMU_DIR, "cuda_emu.h")] + [
         os.path.join(HERE, "..", "hygeia_b200", "csrc", f) for f in
-        ("sg_filter.cuh", "sg_emission.cuh", "hyg_common.cuh", "hyg_dev_structs.h", "hyg_tables.h")]
+        ("sg_filter.cuh", "sg_param.cuh", "sg_emission.cuh", "hyg_common.cuh", "hyg_dev_structs.h", "hyg_tables.h")]
     if os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(d) for d in deps):
         return LIB
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    subprocess.check_call([cxx, "-std=c++14", "-O2", "-fPIC", "-shared", "-I", EMU_DIR] + src + ["-o", LIB])
+    subprocess.check_call([cxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-I", EMU_DIR] + src + ["-o", LIB])
     return LIB
 
 
@@ -34,7 +34,8 @@ class Emu:
         self.lib = C.CDLL(build())
 
     def sg_filter(self, vartheta, theta, logobs, uniforms=None, seed=0, chain_id=0, n_particles=250, smoothing=True,
-                  epsilon=0.01, lcap=64, want_ancestors=False):
+                  epsilon=0.01, lcap=64, want_ancestors=False, param_est=False, normalise=False, adam=True,
+                  n_steps_without_update=200, lr_exponent=0.1, lr_factor=0.01):
         vartheta = np.ascontiguousarray(vartheta, dtype=np.float64)
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         logobs = np.ascontiguousarray(logobs, dtype=np.float64)
@@ -43,10 +44,13 @@ class Emu:
             uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
         out = dict(probs=np.full((T, R + 1), np.nan), logz=np.zeros(T), k_kept=np.zeros(T, np.int32), drew_uniform=np.zeros(T, np.uint8),
                    n_pending=np.zeros(T, np.int32), n_curr=np.zeros(T, np.int32), finalised_at=np.full(T, -1, np.int32),
-                   ancestors=np.full((T, n_particles - R), -1, np.int16) if want_ancestors else None, status=np.zeros(2, np.int32))
+                   ancestors=np.full((T, n_particles - R), -1, np.int16) if want_ancestors else None, status=np.zeros(2, np.int32),
+                   theta_trace=np.zeros((T, len(theta))) if param_est else None)
         rc = self.lib.hygemu_sg_filter(_p(vartheta), C.c_uint32(len(vartheta)), _p(theta), C.c_uint32(len(theta)), C.c_uint32(n_particles),
                                        C.c_uint64(T), _p(logobs), _p(uniforms), C.c_uint64(seed), C.c_uint32(chain_id),
                                        C.c_int(int(smoothing)), C.c_double(epsilon), C.c_int(lcap),
+                                       C.c_int(int(param_est)), C.c_int(int(normalise)), C.c_int(int(adam)), C.c_uint32(n_steps_without_update),
+                                       C.c_double(lr_exponent), C.c_double(lr_factor), _p(out["theta_trace"]),
                                        _p(out["probs"]), _p(out["logz"]), _p(out["k_kept"]), _p(out["drew_uniform"]), _p(out["n_pending"]),
                                        _p(out["n_curr"]), _p(out["finalised_at"]), _p(out["ancestors"]), _p(out["status"]))
         assert rc == 0, rc

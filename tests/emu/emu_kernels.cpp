@@ -17,6 +17,7 @@ extern "C" {
 int hygemu_sg_filter(const double* vartheta, uint32_t n_vartheta, const double* theta, uint32_t dim_theta, uint32_t n_particles,
                      uint64_t T, const double* logobs, const double* unif, uint64_t seed, uint32_t chain_id,
                      int use_smoothing, double epsilon, int lcap,
+                     int use_param_est, int normalise, int use_adam, uint32_t n_steps, double lr_exponent, double lr_factor, double* theta_trace,
                      double* probs, double* logz, int* k_kept, unsigned char* drew, int* n_pending, int* n_curr,
                      int* finalised_at, short* ancestors, int* status) {
   hyg::SgHostModel hm;
@@ -39,9 +40,18 @@ int hygemu_sg_filter(const double* vartheta, uint32_t n_vartheta, const double* 
   std::vector<double> ws(stride);
   unsigned int queue = 0;
   run.psi_ws = ws.data(); run.psi_stride = stride; run.queue = &queue; run.n_chains = 1;
+  run.use_param_est = use_param_est; run.normalise_gradients = normalise; run.use_adam = use_adam; run.n_steps_without_update = n_steps;
+  run.lr_exponent = lr_exponent; run.lr_factor = lr_factor;
+  for (int r = 0; r < HYG_RMAX; r++) run.kappa[r] = r < hm.R ? hm.kappa[r] : 1.0;
+  run.pe_dcap = static_cast<uint32_t>(T + 8 < 64 ? 64 : T + 8);
+  run.pe_stride = 5ull * hm.R * run.pe_dcap;
+  std::vector<double> pews(use_param_est ? run.pe_stride : 1);
+  run.pe_ws = pews.data();
+  ch.theta0 = theta; ch.theta_trace = theta_trace;
   const hyg::SgModelDev* pm = &mdl;
   const hyg::SgChainDev* pc = &ch;
-  emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<6>(pm, pc, run); });
+  if (use_param_est) emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<6, true>(pm, pc, run); });
+  else emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<6, false>(pm, pc, run); });
   return 0;
 }
 

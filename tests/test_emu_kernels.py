@@ -80,3 +80,22 @@ def test_filter_lag_capacity_overflow_is_reported(emu, oracle, default_model):
     assert r["status"][1] <= 4
     assert r["status"][0] > 0          # forced emissions are counted, never silent
     assert not np.isnan(r["probs"]).any()
+
+
+def test_parameter_estimation_under_emulation(emu, oracle, default_model):
+    """K3 (score recursion + ADAM + on-device table rebuild) against the oracle, which is pinned to the reference."""
+    from hygeia_b200 import model, philox, synthetic
+    T, S = 330, 2
+    ch = synthetic.make_chain(T, S, seed=77)
+    al, be = default_model["alpha_beta"]
+    lo = oracle.emission(al, be, ch["n_total"], ch["n_meth"])
+    u = philox.uniforms_by_site(1, 0, T)
+    theta0 = model.default_theta() + 0.2 * np.random.default_rng(3).standard_normal(36)
+    for kw in (dict(adam=True), dict(adam=False, normalise=True, lr_factor=0.05)):
+        want = oracle.run(default_model["vartheta"], theta0, u, logobs=lo, param_est=True, n_steps_without_update=50, **kw)
+        got = emu.sg_filter(default_model["vartheta"], theta0, lo, uniforms=u, param_est=True, n_steps_without_update=50, **kw)
+        assert np.abs(want["theta_trace"][-1] - theta0).max() > 1e-3           # theta moved
+        assert np.allclose(got["theta_trace"], want["theta_trace"], rtol=1e-9, atol=1e-12)
+        assert np.allclose(got["logz"], want["logz"], rtol=1e-12)
+        assert np.array_equal(got["k_kept"], want["k_kept"])
+        assert np.allclose(got["probs"], want["regime_probs"][:, 1:], rtol=1e-6, atol=1e-12)

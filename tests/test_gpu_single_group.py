@@ -215,3 +215,36 @@ def test_error_behaviour(sess, default_model):
     v = default_model["vartheta"].copy(); v[14] = 0.0          # is_kappa_fixed = FALSE
     with pytest.raises(HygeiaError):
         sess.set_vartheta(v[:15])
+
+
+def test_parameter_estimation_parity(sess, oracle, default_model):
+    """K3 on the device (--estimate_parameters): theta trace, log Z_t and posteriors against the oracle.  Device libm differs
+    from glibc by ulps in the table rebuild, hence 1e-6 (north_star tolerance) instead of bit-level agreement."""
+    from hygeia_b200 import model, philox, synthetic
+    from hygeia_b200.single_group import make_run_args
+    T, S = 3000, 3
+    ch = synthetic.make_chain(T, S, seed=4242)
+    u = philox.uniforms_by_site(9, 0, T)
+    theta0 = model.default_theta() + 0.2 * np.random.default_rng(11).standard_normal(36)
+    want = oracle.run(default_model["vartheta"], theta0, u, ch["n_total"], ch["n_meth"], ch["positions"], param_est=True)
+    sess.clear()
+    sess.set_vartheta(default_model["vartheta"])
+    sess.set_theta(theta0, T)
+    ds = sess.add_dataset(ch["n_total"], ch["n_meth"])
+    out = dict(regime_probs=np.full((T, 7), np.nan), logz=np.zeros(T), theta_trace=np.zeros((T, 36)), k_kept=np.zeros(T, np.int32))
+    sess.set_chains([dict(dataset=ds, seed=9, chain_id=0, positions=ch["positions"], **out)])
+    sess.emission()
+    sess.filter(make_run_args(use_online_parameter_estimation=True))
+    sess.download()
+    assert np.abs(want["theta_trace"][-1] - theta0).max() > 0.05                     # 15 ADAM steps moved theta
+    assert np.allclose(out["theta_trace"], want["theta_trace"], rtol=RTOL, atol=1e-9)
+    assert np.array_equal(out["theta_trace"][0], theta0)
+    assert np.allclose(out["logz"], want["logz"], rtol=RTOL)
+    assert np.allclose(out["regime_probs"], want["regime_probs"], rtol=1e-5, atol=1e-9)
+    assert (out["k_kept"] == want["k_kept"]).mean() > 0.999
+    # the operator mirror returns thetaEstimates exactly like runOnlineCombinedInferenceCpp
+    from hygeia_b200.single_group import run_online_combined_inference
+    r = run_online_combined_inference(default_model["vartheta"], theta0, ch["positions"], ch["n_total"], ch["n_meth"],
+                                      use_online_parameter_estimation=True, rng_seed=9)
+    assert r["thetaEstimates"].shape == (T, 36)
+    assert np.allclose(r["thetaEstimates"], want["theta_trace"], rtol=RTOL, atol=1e-9)

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -79,6 +80,8 @@ struct hyg_ctx {
   double* d_theta0 = nullptr;
   unsigned int* d_queue = nullptr;
   uint32_t n_particles_staged = 0;
+  std::multimap<size_t, void*> pool_free_blocks;
+  std::map<void*, size_t> pool_live;
   cudaEvent_t ev_em0 = nullptr, ev_em1 = nullptr, ev_f0 = nullptr, ev_f1 = nullptr;
   bool timed_em = false, timed_f = false;
   uint32_t em_launches = 0, f_launches = 0;
@@ -101,10 +104,54 @@ template <class T> void dfree(T*& p) {
   p = nullptr;
 }
 
+// Per-context caching allocator for the per-sweep buffers (counts, emission tables, posteriors): a whole-genome sweep
+// stages ~10 GB in ~150 buffers, and cudaMalloc/cudaFree of those dominated the end-to-end time of repeated sweeps.
+// Freed blocks are kept and reused for requests of the same size; hyg_destroy releases them.
+cudaError_t pool_alloc(hyg_ctx* c, void** p, size_t bytes);
+template <class T> void pool_free(hyg_ctx* c, T*& p);
+
+cudaError_t pool_alloc(hyg_ctx* c, void** p, size_t bytes) {
+  if (bytes == 0) bytes = 8;
+  auto it = c->pool_free_blocks.find(bytes);
+  if (it != c->pool_free_blocks.end()) {
+    *p = it->second;
+    c->pool_free_blocks.erase(it);
+    c->pool_live[*p] = bytes;
+    return cudaSuccess;
+  }
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e != cudaSuccess) {
+    // out of memory: drop the cache and retry once
+    for (auto& kv : c->pool_free_blocks) cudaFree(kv.second);
+    c->pool_free_blocks.clear();
+    cudaGetLastError();
+    e = cudaMalloc(p, bytes);
+  }
+  if (e == cudaSuccess) c->pool_live[*p] = bytes;
+  return e;
+}
+template <class T> void pool_free(hyg_ctx* c, T*& p) {
+  if (!p) return;
+  void* q = const_cast<void*>(static_cast<const void*>(p));
+  auto it = c->pool_live.find(q);
+  if (it != c->pool_live.end()) {
+    c->pool_free_blocks.insert({it->second, q});
+    c->pool_live.erase(it);
+  } else {
+    cudaFree(q);
+  }
+  p = nullptr;
+}
+void pool_release(hyg_ctx* c) {
+  for (auto& kv : c->pool_free_blocks) cudaFree(kv.second);
+  c->pool_free_blocks.clear();
+}
+
 void free_chains(hyg_ctx* c) {
   for (auto& b : c->chains) {
-    dfree(b.d_unif); dfree(b.d_pos); dfree(b.d_probs); dfree(b.d_logz); dfree(b.d_k); dfree(b.d_drew); dfree(b.d_npend);
-    dfree(b.d_ncurr); dfree(b.d_fin); dfree(b.d_anc); dfree(b.d_status); dfree(b.d_trace);
+    pool_free(c, b.d_unif); pool_free(c, b.d_pos); pool_free(c, b.d_probs); pool_free(c, b.d_logz); pool_free(c, b.d_k);
+    pool_free(c, b.d_drew); pool_free(c, b.d_npend); pool_free(c, b.d_ncurr); pool_free(c, b.d_fin); pool_free(c, b.d_anc);
+    pool_free(c, b.d_status); pool_free(c, b.d_trace);
   }
   c->chains.clear();
   c->order.clear();
@@ -113,8 +160,8 @@ void free_chains(hyg_ctx* c) {
 
 void free_datasets(hyg_ctx* c) {
   for (auto& d : c->ds) {
-    if (d.owned) { dfree(d.d_nt); dfree(d.d_nm); }
-    dfree(d.d_logobs);
+    if (d.owned) { pool_free(c, d.d_nt); pool_free(c, d.d_nm); }
+    pool_free(c, d.d_logobs);
   }
   c->ds.clear();
 }
@@ -210,6 +257,7 @@ void hyg_destroy(hyg_ctx* c) {
   cudaStreamSynchronize(c->stream);
   free_chains(c);
   free_datasets(c);
+  pool_release(c);
   dfree(c->d_tab); dfree(c->d_tabg); dfree(c->d_mdl); dfree(c->d_emtab); dfree(c->d_sets); dfree(c->d_psi); dfree(c->d_pe); dfree(c->d_theta0); dfree(c->d_queue);
   cudaEventDestroy(c->ev_em0); cudaEventDestroy(c->ev_em1); cudaEventDestroy(c->ev_f0); cudaEventDestroy(c->ev_f1);
   cudaStreamDestroy(c->stream);
@@ -304,14 +352,17 @@ int hyg_sg_add_dataset(hyg_ctx* c, uint64_t T, uint32_t S, const uint16_t* n_tot
     d.pitch = (T + 7) / 8 * 8;
     uint16_t *a = nullptr, *b = nullptr;
     const size_t bytes = static_cast<size_t>(S) * d.pitch * sizeof(uint16_t);
-    HYG_CUDA(c, cudaMalloc(&a, bytes));
-    HYG_CUDA(c, cudaMalloc(&b, bytes));
-    if (d.pitch != T) { HYG_CUDA(c, cudaMemsetAsync(a, 0, bytes, c->stream)); HYG_CUDA(c, cudaMemsetAsync(b, 0, bytes, c->stream)); }
+    HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&a), bytes));
+    HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b), bytes));
+    if (d.pitch != T) {  // zero only the pad columns (the kernels read whole site pairs)
+      HYG_CUDA(c, cudaMemset2DAsync(a + T, d.pitch * 2, 0, (d.pitch - T) * 2, S, c->stream));
+      HYG_CUDA(c, cudaMemset2DAsync(b + T, d.pitch * 2, 0, (d.pitch - T) * 2, S, c->stream));
+    }
     HYG_CUDA(c, cudaMemcpy2DAsync(a, d.pitch * 2, n_total, T * 2, T * 2, S, cudaMemcpyHostToDevice, c->stream));
     HYG_CUDA(c, cudaMemcpy2DAsync(b, d.pitch * 2, n_meth, T * 2, T * 2, S, cudaMemcpyHostToDevice, c->stream));
     d.d_nt = a; d.d_nm = b; d.owned = true;
   }
-  HYG_CUDA(c, cudaMalloc(&d.d_logobs, static_cast<size_t>(T) * c->hm.R * sizeof(double)));
+  HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&d.d_logobs), static_cast<size_t>(T) * c->hm.R * sizeof(double)));
   c->ds.push_back(d);
   return static_cast<int>(c->ds.size()) - 1;
 }
@@ -348,23 +399,23 @@ int hyg_sg_set_chains(hyg_ctx* c, const hyg_sg_chain* chains, uint32_t n) {
     const uint64_t T = c->ds[chains[i].dataset].T;
     b.T = T;
     if (chains[i].uniforms) {
-      HYG_CUDA(c, cudaMalloc(&b.d_unif, T * sizeof(double)));
+      HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_unif), T * sizeof(double)));
       HYG_CUDA(c, cudaMemcpyAsync(b.d_unif, chains[i].uniforms, T * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     }
     if (chains[i].regime_probs) {
-      HYG_CUDA(c, cudaMalloc(&b.d_probs, T * (R + 1) * sizeof(double)));
+      HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_probs), T * (R + 1) * sizeof(double)));
       if (chains[i].positions) {
-        HYG_CUDA(c, cudaMalloc(&b.d_pos, T * sizeof(uint32_t)));
+        HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_pos), T * sizeof(uint32_t)));
         HYG_CUDA(c, cudaMemcpyAsync(b.d_pos, chains[i].positions, T * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
       }
     }
-    if (chains[i].logz) HYG_CUDA(c, cudaMalloc(&b.d_logz, T * sizeof(double)));
-    if (chains[i].k_kept) HYG_CUDA(c, cudaMalloc(&b.d_k, T * sizeof(int)));
-    if (chains[i].drew_uniform) HYG_CUDA(c, cudaMalloc(&b.d_drew, T));
-    if (chains[i].n_pending) HYG_CUDA(c, cudaMalloc(&b.d_npend, T * sizeof(int)));
-    if (chains[i].n_curr) HYG_CUDA(c, cudaMalloc(&b.d_ncurr, T * sizeof(int)));
-    if (chains[i].finalised_at) HYG_CUDA(c, cudaMalloc(&b.d_fin, T * sizeof(int)));
-    HYG_CUDA(c, cudaMalloc(&b.d_status, 2 * sizeof(int)));
+    if (chains[i].logz) HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_logz), T * sizeof(double)));
+    if (chains[i].k_kept) HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_k), T * sizeof(int)));
+    if (chains[i].drew_uniform) HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_drew), T));
+    if (chains[i].n_pending) HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_npend), T * sizeof(int)));
+    if (chains[i].n_curr) HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_ncurr), T * sizeof(int)));
+    if (chains[i].finalised_at) HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_fin), T * sizeof(int)));
+    HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_status), 2 * sizeof(int)));
     HYG_CUDA(c, cudaMemsetAsync(b.d_status, 0, 2 * sizeof(int), c->stream));
   }
   // launch order: longest chain first (LPT), so the persistent CTAs finish together
@@ -437,8 +488,8 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
   // (re)allocate the ancestor taps now that N_max is known
   for (auto& b : c->chains)
     if (b.host.ancestors && (!b.d_anc || c->n_particles_staged != Nmax)) {
-      dfree(b.d_anc);
-      HYG_CUDA(c, cudaMalloc(&b.d_anc, b.T * (Nmax - R) * sizeof(short)));
+      pool_free(c, b.d_anc);
+      HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_anc), b.T * (Nmax - R) * sizeof(short)));
     }
   c->n_particles_staged = Nmax;
 
@@ -456,7 +507,7 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
     if (!c->d_theta0) HYG_CUDA(c, cudaMalloc(&c->d_theta0, 64 * sizeof(double)));
     HYG_CUDA(c, cudaMemcpyAsync(c->d_theta0, c->hm.theta.data(), c->hm.D * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     for (auto& b : c->chains)
-      if (b.host.theta_trace && !b.d_trace) HYG_CUDA(c, cudaMalloc(&b.d_trace, b.T * c->hm.D * sizeof(double)));
+      if (b.host.theta_trace && !b.d_trace) HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_trace), b.T * c->hm.D * sizeof(double)));
     HYG_CUDA(c, cudaStreamSynchronize(c->stream));
   }
 

@@ -14,6 +14,7 @@ SYMBOLS = [
     "hyg_sg_add_dataset", "hyg_sg_clear", "hyg_sg_default_run_args", "hyg_sg_set_chains",
     "hyg_sg_emission", "hyg_sg_filter", "hyg_sg_download", "hyg_sync", "hyg_sg_timings", "hyg_sg_get_logobs",
     "hyg_sg_run_online_combined_inference", "hyg_sg_sample_theta_prior", "hyg_philox_uniform",
+    "hyg_tg_set_model", "hyg_tg_run", "hyg_tg_hazard_table",
 ]
 
 
@@ -34,6 +35,23 @@ class HygRunArgs(C.Structure):
         ("use_online_parameter_estimation", C.c_int32), ("normalise_gradients", C.c_int32), ("use_adam", C.c_int32),
         ("n_steps_without_parameter_update", C.c_uint32), ("learning_rate_exponent", C.c_double),
         ("learning_rate_factor", C.c_double), ("lag_capacity", C.c_uint32),
+    ]
+
+
+class HygTgModel(C.Structure):
+    _fields_ = [
+        ("R", C.c_uint32), ("minimum_duration", C.c_uint32), ("num_resampled", C.c_uint32), ("num_backward", C.c_uint32),
+        ("log_p_control", C.c_void_p), ("omega_control", C.c_void_p), ("omega_case", C.c_void_p),
+        ("kappa_control", C.c_void_p), ("kappa_case", C.c_void_p),
+        ("merge_prob", C.c_double), ("split_prob", C.c_double),
+        ("rho_control", C.c_void_p), ("rho_case", C.c_void_p), ("d_max", C.c_uint32),
+    ]
+
+
+class HygTgChain(C.Structure):
+    _fields_ = [
+        ("control_dataset", C.c_uint32), ("case_dataset", C.c_uint32), ("seed", C.c_uint64), ("chain_id", C.c_uint32),
+        ("trajectories", C.c_void_p), ("log_normalizing_constant", C.c_void_p), ("taps", C.c_void_p),
     ]
 
 
@@ -76,6 +94,9 @@ def load():
         C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
         C.POINTER(HygRunArgs), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
     lib.hyg_sg_sample_theta_prior.argtypes = [C.c_uint32, C.c_uint64, C.c_void_p]
+    lib.hyg_tg_set_model.argtypes = [C.c_void_p, C.POINTER(HygTgModel), C.c_uint64]
+    lib.hyg_tg_run.argtypes = [C.c_void_p, C.POINTER(HygTgChain), C.c_uint32, C.POINTER(C.c_float)]
+    lib.hyg_tg_hazard_table.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.hyg_philox_uniform.restype = C.c_double
     lib.hyg_philox_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64]
     _lib = lib

@@ -19,6 +19,7 @@
 #include "hyg_tables.h"
 #include "sg_emission.cuh"
 #include "sg_filter.cuh"
+#include "hyg_tg.cuh"
 
 #define HYG_VERSION_STR "hygeia_b200 0.1.0 (sm_100a)"
 
@@ -85,6 +86,11 @@ struct hyg_ctx {
   cudaEvent_t ev_em0 = nullptr, ev_em1 = nullptr, ev_f0 = nullptr, ev_f1 = nullptr;
   bool timed_em = false, timed_f = false;
   uint32_t em_launches = 0, f_launches = 0;
+  // two-group
+  bool tg_set = false;
+  hyg::TgModelDev tg_host;
+  hyg::TgModelDev* d_tg_mdl = nullptr;
+  double* d_tg_rho = nullptr;   // [2][R][dmax + 1]
 };
 
 namespace {
@@ -258,7 +264,7 @@ void hyg_destroy(hyg_ctx* c) {
   free_chains(c);
   free_datasets(c);
   pool_release(c);
-  dfree(c->d_tab); dfree(c->d_tabg); dfree(c->d_mdl); dfree(c->d_emtab); dfree(c->d_sets); dfree(c->d_psi); dfree(c->d_pe); dfree(c->d_theta0); dfree(c->d_queue);
+  dfree(c->d_tab); dfree(c->d_tabg); dfree(c->d_mdl); dfree(c->d_emtab); dfree(c->d_sets); dfree(c->d_psi); dfree(c->d_pe); dfree(c->d_theta0); dfree(c->d_queue); dfree(c->d_tg_mdl); dfree(c->d_tg_rho);
   cudaEventDestroy(c->ev_em0); cudaEventDestroy(c->ev_em1); cudaEventDestroy(c->ev_f0); cudaEventDestroy(c->ev_f1);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -655,6 +661,170 @@ int hyg_sg_run_online_combined_inference(hyg_ctx* c, const double* vartheta, uin
   if ((rc = hyg_sg_download(c, &ch, 1))) return rc;
   if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return HYG_OK;
+}
+
+
+// ---- two-group path ------------------------------------------------------------------------------------------------
+
+int hyg_tg_hazard_table(const double* omega, const double* kappa, uint32_t R, uint32_t u, uint32_t d_max, double* rho) {
+  if (!omega || !kappa || !rho || R < 1 || R > HYG_RMAX || d_max < u) return HYG_ERR_ARG;
+  std::vector<double> t;
+  hyg::build_hazard_table(omega, kappa, static_cast<int>(R), static_cast<int>(u), d_max, t);
+  std::memcpy(rho, t.data(), t.size() * sizeof(double));
+  return HYG_OK;
+}
+
+int hyg_tg_set_model(hyg_ctx* c, const hyg_tg_model* m, uint64_t t_max) {
+  if (!c || !m) return HYG_ERR_ARG;
+  if (m->R < 2 || m->R > HYG_RMAX) return fail(c, HYG_ERR_UNSUPPORTED, "two-group: R must be in 2..8");
+  if (m->minimum_duration < 1) return fail(c, HYG_ERR_ARG, "two-group: minimum_duration must be >= 1");
+  if (m->num_resampled < 1 || m->num_resampled > HYG_TG_MMAX) return fail(c, HYG_ERR_UNSUPPORTED, "two-group: num_resampled must be in 1..64");
+  if (m->num_backward < 1 || m->num_backward > HYG_TG_BMAX) return fail(c, HYG_ERR_UNSUPPORTED, "two-group: num_backward must be in 1..32");
+  const uint32_t R = m->R;
+  if (static_cast<size_t>(m->num_resampled) * (2 * R + R * R) > HYG_TG_NPMAX)
+    return fail(c, HYG_ERR_UNSUPPORTED, "two-group: num_resampled * (2R + R^2) exceeds the 2432 particle slots");
+  if (!m->log_p_control) return fail(c, HYG_ERR_ARG, "two-group: log_p_control is required");
+  if (!(m->merge_prob > 0.0 && m->merge_prob < 1.0 && m->split_prob > 0.0 && m->split_prob < 1.0))
+    return fail(c, HYG_ERR_ARG, "two-group: merge_prob and split_prob must be in (0,1)");
+  HYG_CUDA(c, cudaSetDevice(c->device));
+  hyg::TgModelDev& h = c->tg_host;
+  std::memset(&h, 0, sizeof(h));
+  h.R = static_cast<int>(R); h.u = static_cast<int>(m->minimum_duration); h.M = static_cast<int>(m->num_resampled); h.B = static_cast<int>(m->num_backward);
+  // tf.nn.softmax of the log-probabilities with a -inf diagonal (case_control_regime_model.py:90-95), in log space
+  for (uint32_t i = 0; i < R; i++) {
+    double mx = -HUGE_VAL;
+    for (uint32_t j = 0; j < R; j++) if (j != i) mx = std::max(mx, m->log_p_control[i * R + j]);
+    if (!std::isfinite(mx)) return fail(c, HYG_ERR_ARG, "two-group: a row of log_p_control has no finite off-diagonal entry");
+    double sm = 0.0;
+    for (uint32_t j = 0; j < R; j++) if (j != i) sm += std::exp(m->log_p_control[i * R + j] - mx);
+    const double lz = mx + std::log(sm);
+    for (uint32_t j = 0; j < R; j++) h.logP[i][j] = (j == i) ? -HUGE_VAL : m->log_p_control[i * R + j] - lz;
+  }
+  // rows = previous indicator (0 = split, 1 = merged); run_inference_two_groups.py:163-167
+  h.logPm[0][0] = std::log(1.0 - m->merge_prob); h.logPm[0][1] = std::log(m->merge_prob);
+  h.logPm[1][0] = std::log(m->split_prob);       h.logPm[1][1] = std::log(1.0 - m->split_prob);
+  std::vector<double> rho_c, rho_k;
+  uint32_t dmax;
+  if (m->rho_control && m->rho_case) {
+    dmax = m->d_max;
+    if (dmax < m->minimum_duration) return fail(c, HYG_ERR_ARG, "two-group: d_max of the supplied hazard tables is below minimum_duration");
+    rho_c.assign(m->rho_control, m->rho_control + static_cast<size_t>(R) * (dmax + 1));
+    rho_k.assign(m->rho_case, m->rho_case + static_cast<size_t>(R) * (dmax + 1));
+  } else {
+    if (!m->omega_control || !m->omega_case) return fail(c, HYG_ERR_ARG, "two-group: omega_control / omega_case (or hazard tables) are required");
+    for (uint32_t r = 0; r < R; r++)
+      if (!(m->omega_control[r] > 0.0 && m->omega_control[r] < 1.0 && m->omega_case[r] > 0.0 && m->omega_case[r] < 1.0))
+        return fail(c, HYG_ERR_ARG, "two-group: omega must be in (0,1)");
+    const double two[HYG_RMAX] = {2, 2, 2, 2, 2, 2, 2, 2};
+    // sojourn times beyond d_max reuse the last entry (the hazard of a negative binomial is flat by then)
+    dmax = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(t_max, m->minimum_duration + 1), 4096));
+    hyg::build_hazard_table(m->omega_control, m->kappa_control ? m->kappa_control : two, h.R, h.u, dmax, rho_c);
+    hyg::build_hazard_table(m->omega_case, m->kappa_case ? m->kappa_case : two, h.R, h.u, dmax, rho_k);
+  }
+  h.dmax = dmax;
+  const size_t n = static_cast<size_t>(R) * (dmax + 1);
+  dfree(c->d_tg_rho);
+  HYG_CUDA(c, cudaMalloc(&c->d_tg_rho, 2 * n * sizeof(double)));
+  HYG_CUDA(c, cudaMemcpy(c->d_tg_rho, rho_c.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  HYG_CUDA(c, cudaMemcpy(c->d_tg_rho + n, rho_k.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  h.rho_c = c->d_tg_rho; h.rho_k = c->d_tg_rho + n;
+  if (!c->d_tg_mdl) HYG_CUDA(c, cudaMalloc(&c->d_tg_mdl, sizeof(hyg::TgModelDev)));
+  HYG_CUDA(c, cudaMemcpy(c->d_tg_mdl, &h, sizeof(h), cudaMemcpyHostToDevice));
+  c->tg_set = true;
+  return HYG_OK;
+}
+
+int hyg_tg_run(hyg_ctx* c, const hyg_tg_chain* chains, uint32_t n, float* ms_device) {
+  if (!c || (!chains && n)) return HYG_ERR_ARG;
+  if (!c->tg_set) return fail(c, HYG_ERR_STATE, "hyg_tg_set_model first");
+  if (n == 0) return HYG_OK;
+  HYG_CUDA(c, cudaSetDevice(c->device));
+  const int R = c->tg_host.R, B = c->tg_host.B, M = c->tg_host.M;
+  if (R != c->hm.R) return fail(c, HYG_ERR_STATE, "two-group: R differs from the emission model (hyg_sg_set_model)");
+  uint64_t t_max = 0;
+  for (uint32_t k = 0; k < n; k++) {
+    const hyg_tg_chain& ch = chains[k];
+    if (ch.control_dataset >= c->ds.size() || ch.case_dataset >= c->ds.size()) return fail(c, HYG_ERR_ARG, "two-group: data-set index out of range");
+    const Dataset& a = c->ds[ch.control_dataset];
+    const Dataset& b = c->ds[ch.case_dataset];
+    if (a.T != b.T) return fail(c, HYG_ERR_ARG, "two-group: control and case data sets differ in length");
+    if (!a.d_logobs || !b.d_logobs) return fail(c, HYG_ERR_STATE, "two-group: emission tables missing");
+    if (a.T == 0) return fail(c, HYG_ERR_ARG, "two-group: empty data set");
+    if (!ch.trajectories || !ch.log_normalizing_constant) return fail(c, HYG_ERR_ARG, "two-group: output pointers are required");
+    t_max = std::max<uint64_t>(t_max, a.T);
+  }
+  if (!c->timed_em) return fail(c, HYG_ERR_STATE, "hyg_sg_emission first");
+  // longest chain first (one CTA per chain, dynamic queue)
+  std::vector<uint32_t> order(n);
+  std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return c->ds[chains[x].control_dataset].T > c->ds[chains[y].control_dataset].T; });
+  std::vector<hyg::TgChainDev> dev(n);
+  std::vector<int*> d_traj(n, nullptr), d_taps(n, nullptr);
+  double* d_ln = nullptr;
+  hyg::TgChainDev* d_chains = nullptr;
+  unsigned char* d_ws = nullptr;
+  int rc = HYG_OK;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto cleanup = [&]() {
+    for (auto& p : d_traj) pool_free(c, p);
+    for (auto& p : d_taps) pool_free(c, p);
+    pool_free(c, d_ln); pool_free(c, d_chains); pool_free(c, d_ws);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+  };
+#define HYG_TG_CUDA(call)                                                                       \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) { cleanup(); return fail(c, HYG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } \
+  } while (0)
+  HYG_TG_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_ln), n * sizeof(double)));
+  for (uint32_t i = 0; i < n; i++) {
+    const uint32_t k = order[i];
+    const hyg_tg_chain& ch = chains[k];
+    const uint64_t T = c->ds[ch.control_dataset].T;
+    HYG_TG_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_traj[k]), T * B * 5 * sizeof(int)));
+    if (ch.taps) HYG_TG_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_taps[k]), T * 3 * sizeof(int)));
+    hyg::TgChainDev& d = dev[i];
+    d.T = T; d.lo_c = c->ds[ch.control_dataset].d_logobs; d.lo_k = c->ds[ch.case_dataset].d_logobs;
+    d.seed = ch.seed; d.chain = ch.chain_id; d.traj = d_traj[k]; d.log_norm = d_ln + k; d.taps = d_taps[k];
+  }
+  hyg::TgRunDev run;
+  run.t_max = t_max;
+  run.anc_pitch = static_cast<unsigned long long>(std::max(M, R * R));
+  run.ws_stride = (sizeof(hyg::TgStepRec) * t_max + sizeof(hyg::TgAncRec) * t_max * run.anc_pitch + 255) & ~static_cast<size_t>(255);
+  run.n_chains = static_cast<int>(n);
+  run.queue = c->d_queue;
+  // one CTA per SM; fewer when the per-CTA ancestor history would not fit in what is free
+  size_t free_b = 0, total_b = 0;
+  HYG_TG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  int grid = static_cast<int>(std::min<uint32_t>(n, static_cast<uint32_t>(c->num_sms)));
+  const size_t fit = static_cast<size_t>(0.8 * static_cast<double>(free_b)) / run.ws_stride;
+  if (fit < 1) { cleanup(); return fail(c, HYG_ERR_CUDA, "two-group: not enough device memory for one chain's ancestor history"); }
+  grid = static_cast<int>(std::min<size_t>(static_cast<size_t>(grid), fit));
+  HYG_TG_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_ws), run.ws_stride * grid));
+  run.ws = d_ws;
+  HYG_TG_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_chains), n * sizeof(hyg::TgChainDev)));
+  HYG_TG_CUDA(cudaMemcpyAsync(d_chains, dev.data(), n * sizeof(hyg::TgChainDev), cudaMemcpyHostToDevice, c->stream));
+  HYG_TG_CUDA(cudaMemsetAsync(c->d_queue, 0, sizeof(unsigned int), c->stream));
+  HYG_TG_CUDA(cudaFuncSetAttribute(hyg::tg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(hyg::TgSmem))));
+  HYG_TG_CUDA(cudaEventCreate(&e0));
+  HYG_TG_CUDA(cudaEventCreate(&e1));
+  HYG_TG_CUDA(cudaEventRecord(e0, c->stream));
+  hyg::tg_kernel<<<grid, HYG_TG_NT, sizeof(hyg::TgSmem), c->stream>>>(c->d_tg_mdl, d_chains, run);
+  HYG_TG_CUDA(cudaGetLastError());
+  HYG_TG_CUDA(cudaEventRecord(e1, c->stream));
+  for (uint32_t k = 0; k < n; k++) {
+    const hyg_tg_chain& ch = chains[k];
+    const uint64_t T = c->ds[ch.control_dataset].T;
+    HYG_TG_CUDA(cudaMemcpyAsync(ch.trajectories, d_traj[k], T * B * 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    HYG_TG_CUDA(cudaMemcpyAsync(ch.log_normalizing_constant, d_ln + k, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (ch.taps) HYG_TG_CUDA(cudaMemcpyAsync(ch.taps, d_taps[k], T * 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  }
+  HYG_TG_CUDA(cudaStreamSynchronize(c->stream));
+  if (ms_device) HYG_TG_CUDA(cudaEventElapsedTime(ms_device, e0, e1));
+#undef HYG_TG_CUDA
+  cleanup();
+  return rc;
 }
 
 double hyg_philox_uniform(uint64_t seed, uint32_t chain_id, uint64_t t) { return hyg::philox_uniform(seed, chain_id, t); }

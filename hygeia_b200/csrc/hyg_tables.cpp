@@ -144,4 +144,25 @@ int SgHostModel::set_theta(const double* th, uint32_t dim, uint64_t t_max) {
   return 0;
 }
 
+
+void build_hazard_table(const double* omega, const double* kappa, int R, int u, uint32_t d_max, std::vector<double>& rho) {
+  // Backward recurrence of the inverse hazard g(k) = P(X >= k) / pmf(k):  g(k) = 1 + omega (k + kappa)/(k + 1) g(k+1), with
+  // g(inf) = 1/(1 - omega); started far enough beyond d_max that the start-up error (contracted by ~omega per step) is
+  // below 1e-18.  No lgamma, no underflow, no cancellation.
+  rho.assign(static_cast<size_t>(R) * (d_max + 1), 0.0);
+  for (int r = 0; r < R; r++) {
+    const double om = omega[r], ka = kappa[r];
+    const long long n_extra = static_cast<long long>(std::min(std::ceil(-41.5 / std::log(om)), 5e7));
+    double g = 1.0 / (1.0 - om);
+    const long long kmax = static_cast<long long>(d_max) - u;
+    for (long long k = kmax + n_extra - 1; k >= 0; k--) {
+      g = 1.0 + (om * (static_cast<double>(k) + ka) / (static_cast<double>(k) + 1.0)) * g;
+      if (k <= kmax) {
+        const double v = 1.0 / g;
+        rho[static_cast<size_t>(r) * (d_max + 1) + static_cast<size_t>(k + u)] = std::isfinite(v) ? v : 0.1;
+      }
+    }
+  }
+}
+
 }  // namespace hyg

@@ -1,0 +1,588 @@
+// hygeia_b200/csrc/hyg_tg.cuh -- K4/K5: the two-group (case/control) particle filter and backward simulation.
+//
+// Reference (/root/reference/src/two_group, TensorFlow 2.3 / TFP 0.11 -- not runnable here; see oracle/tg_oracle.py for
+// the restatement this kernel is checked against and for the documented differences):
+//   filter step                 hygeia/filter_and_smoother_algorithm.py:176-288
+//   first step / padding        hygeia/filter_and_smoother_algorithm.py:141-172,334-365
+//   backward simulation         hygeia/filter_and_smoother_algorithm.py:368-446, hygeia/smoothing_functions.py:46-59
+//   transition densities        hygeia/case_control_regime_model.py:80-193, hygeia/case_control_distributions.py:138-151,246-291
+//   the 2R + R^2 proposals      hygeia/case_control_proposal_mappings.py:11-134,175-207
+//   optimal finite-state + systematic resampling   hygeia/resampling_functions.py:7-69
+//   emission                    hygeia/case_control_regime_model.py:197-231  (= two K1 tables: control and case)
+//
+// B200 design: one 256-thread CTA per chain (chromosome x batch x seed); the <= 2400 particles of a site live in shared
+// memory; the emission term is the sum of two T x R tables produced by K1 (the reference evaluates 2400 x S beta-binomial
+// densities per site); only the FINITE-weight particles (typically 300-600) are compacted and sorted (shared-memory
+// bitonic network sized to the next power of two) for the optimal finite-state selection of the <= 50 ancestors.
+// The reference keeps the whole filter history (T x 2400 weights and states, 16 GB+ of RAM per task) for the backward
+// pass; here each site stores only its <= 50 ancestors (~1.4 KB) in HBM and the backward pass RECOMPUTES the children.
+// All arithmetic fp64; draws are Philox(seed, chain, site).
+#ifndef HYG_TG_CUH
+#define HYG_TG_CUH
+
+#include "hyg_common.cuh"
+
+#define HYG_TG_NT 256
+#define HYG_TG_NW (HYG_TG_NT / 32)
+#define HYG_TG_NPMAX 2432     // >= M * (2R + R^2) for M = 50, R = 6, multiple of 256... (2400)
+#define HYG_TG_MMAX 64        // max resampled ancestors
+#define HYG_TG_BMAX 32        // max backward trajectories
+#define HYG_TG_SORTMAX 4096
+#define HYG_TAG_FILTER 0x46494C54u
+#define HYG_TAG_BACKWARD 0x42414B57u
+#define HYG_TAG_PHANTOM 0x5048414Eu
+
+namespace hyg {
+
+struct TgModelDev {
+  int R, u, M, B;
+  uint32_t dmax;                 // hazard tables hold d = 0..dmax per regime (row pitch dmax + 1)
+  double logP[HYG_RMAX][HYG_RMAX];   // control regime transitions (log, -inf diagonal)
+  double logPm[2][2];            // merged-indicator transitions (log), rows = previous
+  const double* rho_c;           // [R][dmax+1]
+  const double* rho_k;           // [R][dmax+1]
+};
+
+struct TgState {   // one particle
+  int m, dc, rc, dk, rk;
+};
+
+struct TgAncRec {  // per-ancestor record kept for the backward pass (HBM)
+  int dc, dk;
+  unsigned char m, rc, rk, pad;
+  double w_prev;     // unnormalised log-weight of the ancestor
+  double logW_prev;  // normalised log-weight
+};
+struct TgStepRec {   // per-site header
+  int n_anc;         // M'
+  int mode;          // 0: F <= M (plain), 1: optimal, 2: unbiased (log c infinite)
+  double log_c;
+  double lse;        // logsumexp of the previous unnormalised weights
+};
+
+struct TgChainDev {
+  unsigned long long T;
+  const double* lo_c;   // T x R
+  const double* lo_k;   // T x R
+  unsigned long long seed;
+  uint32_t chain;
+  // outputs (device)
+  int* traj;            // T x B x 5 : m, dc, rc, dk, rk
+  double* log_norm;     // 1
+  int* taps;            // optional T x 3 : n_particles, K, n_finite
+};
+
+struct TgRunDev {
+  unsigned char* ws;               // per-CTA workspace: T_max step headers + T_max * anc_pitch ancestor records
+  unsigned long long ws_stride;    // bytes per CTA
+  unsigned long long t_max;
+  unsigned long long anc_pitch;    // ancestor records per site (>= M and >= the R^2 particles of the first site)
+  unsigned int* queue;
+  int n_chains;
+};
+
+__host__ __device__ __forceinline__ double tg_uniform(uint64_t seed, uint32_t chain, uint32_t tag, uint64_t index) {
+  uint32_t c[4] = {static_cast<uint32_t>(index), static_cast<uint32_t>(index >> 32), chain, tag};
+  philox4x32_10(c, static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+  const uint64_t hi = c[0] >> 5, lo = c[1] >> 6;
+  return (static_cast<double>(hi) * 67108864.0 + static_cast<double>(lo)) * (1.0 / 9007199254740992.0);
+}
+
+// log transition density of `n` given `p` (case_control_regime_model.py:97-193; case_control_distributions.py:138-151,246-291)
+__device__ __forceinline__ double tg_log_trans(const TgModelDev& md, const TgState& p, const TgState& n, bool step0) {
+  const int R = md.R, u = md.u;
+  // merged indicator
+  double lm;
+  if (step0) lm = (n.m == 1) ? 0.0 : -HYG_INF;
+  else if ((p.dk < p.dc ? p.dk : p.dc) >= u) lm = md.logPm[p.m][n.m];
+  else lm = (n.m == p.m) ? 0.0 : -HYG_INF;
+  if (lm == -HYG_INF) return -HYG_INF;
+  // control
+  const uint32_t pitch = md.dmax + 1;
+  const double rho_c = step0 ? 1.0 : md.rho_c[p.rc * pitch + (static_cast<uint32_t>(p.dc) < md.dmax ? p.dc : md.dmax)];
+  double lc;
+  if (n.dc == 1) lc = log(rho_c) + md.logP[p.rc][n.rc];
+  else lc = (n.dc == p.dc + 1 && n.rc == p.rc) ? log(1.0 - rho_c) : -HYG_INF;
+  if (!(lc > -HYG_INF)) return -HYG_INF;
+  // case, first matching rule
+  double lk;
+  if (n.m == 1) {
+    lk = (n.rc == n.rk && n.dc == n.dk) ? 0.0 : -HYG_INF;
+  } else if (p.m == 1 && n.dc != 1) {
+    lk = (n.rk != n.rc && n.dk == 1) ? -log(static_cast<double>(R - 1)) : -HYG_INF;
+  } else {
+    const bool allowed = (n.rk != n.rc) && (n.rk != p.rk);
+    const double unif = allowed ? -log(static_cast<double>(R) - ((n.rc == p.rk) ? 1.0 : 2.0)) : -HYG_INF;
+    if (n.rc == p.rk && p.m == 0) {
+      lk = (n.dk == 1) ? unif : -HYG_INF;
+    } else {
+      const double rho_k = step0 ? 1.0 : md.rho_k[p.rk * pitch + (static_cast<uint32_t>(p.dk) < md.dmax ? p.dk : md.dmax)];
+      if (n.dk == 1) lk = log(rho_k) + unif;
+      else lk = (n.dk == p.dk + 1 && n.rk == p.rk) ? log(1.0 - rho_k) : -HYG_INF;
+    }
+  }
+  const double out = lm + lc + lk;
+  return (out == out) ? out : -HYG_INF;
+}
+
+// proposal q (0 .. 2R + R^2 - 1) of ancestor a (case_control_proposal_mappings.py:11-134)
+__device__ __forceinline__ TgState tg_propose(int R, const TgState& a, int q) {
+  TgState n;
+  if (q == 0) {
+    n.m = a.m; n.dc = a.dc + 1; n.rc = a.rc; n.dk = a.dk + 1; n.rk = a.rk;
+  } else if (q < R) {                       // control jumps, skipping the case regime
+    n.m = 0; n.dc = 1; n.rc = (q <= a.rk) ? q - 1 : q; n.dk = a.dk + 1; n.rk = a.rk;
+  } else if (q < 2 * R - 1) {               // case jumps, skipping the control regime
+    n.m = 0; n.dc = a.dc + 1; n.rc = a.rc; n.dk = 1; n.rk = (q < R + a.rc) ? q - R : q - R + 1;
+  } else if (q == 2 * R - 1) {              // merge (durations 0 = impossible state if already merged)
+    const int dm = (a.m == 0) ? a.dc + 1 : 0;
+    n.m = 1; n.dc = dm; n.rc = a.rc; n.dk = dm; n.rk = a.rc;
+  } else {                                  // both change: control regime i, case regime j
+    const int ij = q - 2 * R, i = ij / R, j = ij % R;
+    n.m = (i == j) ? 1 : 0; n.dc = 1; n.rc = i; n.dk = 1; n.rk = j;
+  }
+  return n;
+}
+
+struct TgSmem {
+  // particles of the current site
+  double w[HYG_TG_NPMAX];
+  int dc[HYG_TG_NPMAX], dk[HYG_TG_NPMAX];
+  unsigned char m[HYG_TG_NPMAX], rc[HYG_TG_NPMAX], rk[HYG_TG_NPMAX];
+  // sorting / resampling scratch
+  unsigned long long key[HYG_TG_SORTMAX];   // exact order-preserving image of the normalised log-weight
+  unsigned short sidx[HYG_TG_SORTMAX];      // particle index travelling with the key
+  double e[HYG_TG_SORTMAX];        // exp(normalised log-weight) in sorted order, then cumulative sums
+  // ancestors
+  TgState anc[HYG_TG_MMAX];
+  double anc_w[HYG_TG_MMAX], anc_logW[HYG_TG_MMAX];
+  int parents[HYG_TG_MMAX];
+  // backward trajectories
+  TgState nxt[HYG_TG_BMAX];
+  int pick[HYG_TG_BMAX];
+  double red[2][HYG_TG_NW][4];
+  int ired[2][HYG_TG_NW];
+  double bc[8];
+  int ibc[8];
+  TgModelDev mdl;
+};
+
+__device__ __forceinline__ double tg_block_sum(double v, TgSmem& s, int& flip) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  if (lane == 0) s.red[flip][warp][0] = v;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < HYG_TG_NW; w++) t += s.red[flip][w][0];
+  flip ^= 1;
+  return t;
+}
+__device__ __forceinline__ double tg_block_max(double v, TgSmem& s, int& flip) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_max(v);
+  if (lane == 0) s.red[flip][warp][0] = v;
+  __syncthreads();
+  double t = s.red[flip][0][0];
+#pragma unroll
+  for (int w = 1; w < HYG_TG_NW; w++) t = s.red[flip][w][0] > t ? s.red[flip][w][0] : t;
+  flip ^= 1;
+  return t;
+}
+// block-wide exclusive prefix sum of one int per thread; returns the exclusive prefix, total in `total`
+__device__ __forceinline__ int tg_block_excl_scan(int v, int& total, TgSmem& s, int& flip) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(HYG_FULL, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) s.ired[flip][warp] = inc;
+  __syncthreads();
+  int off = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < HYG_TG_NW; w++) { const int x = s.ired[flip][w]; if (w < warp) off += x; tot += x; }
+  flip ^= 1;
+  total = tot;
+  return off + inc - v;
+}
+
+// in-place bitonic sort of (s.key, s.sidx)[0..n), n a power of two, all threads of the CTA: descending in the key, ties by
+// ascending particle index (= a stable descending sort of the weights in particle order)
+__device__ __forceinline__ void tg_sort_desc(TgSmem& s, int n) {
+  for (int k = 2; k <= n; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n; i += HYG_TG_NT) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = s.key[i], b = s.key[l];
+          const unsigned short ia = s.sidx[i], ib = s.sidx[l];
+          const bool desc = ((i & k) == 0);
+          const bool a_after_b = (a < b) || (a == b && ia > ib);   // a belongs after b in the final order
+          if (a_after_b == desc) { s.key[i] = b; s.key[l] = a; s.sidx[i] = ib; s.sidx[l] = ia; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---- one chain: filter over all sites, then backward simulation ----
+__device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, unsigned char* ws) {
+  const TgModelDev& md = s.mdl;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int R = md.R, M = md.M, B = md.B, I = 2 * R + R * R;
+  const unsigned long long T = ch.T;
+  int flip = 0;
+  TgStepRec* steps = reinterpret_cast<TgStepRec*>(ws);
+  TgAncRec* ancs = reinterpret_cast<TgAncRec*>(ws + sizeof(TgStepRec) * run.t_max);
+
+  // ---- first site (filter_and_smoother_algorithm.py:141-172; case_control_regime_model.py:233-244) ----
+  int n_part = R * R;
+  {
+    const int r_ph = static_cast<int>(tg_uniform(ch.seed, ch.chain, HYG_TAG_PHANTOM, 0) * R);
+    TgState ph; ph.m = 1; ph.dc = 0; ph.rc = r_ph; ph.dk = 0; ph.rk = r_ph;
+    for (int c = tid; c < n_part; c += HYG_TG_NT) {
+      TgState n; n.rc = c / R; n.rk = c % R; n.m = (n.rc == n.rk) ? 1 : 0; n.dc = 1; n.dk = 1;
+      const double lt = tg_log_trans(md, ph, n, true);
+      s.w[c] = (lt > -HYG_INF) ? lt + ch.lo_c[n.rc] + ch.lo_k[n.rk] : -HYG_INF;
+      s.m[c] = n.m; s.dc[c] = 1; s.rc[c] = n.rc; s.dk[c] = 1; s.rk[c] = n.rk;
+    }
+    if (tid == 0) { steps[0].n_anc = 0; steps[0].mode = 0; steps[0].log_c = 0.0; steps[0].lse = 0.0; }
+    __syncthreads();
+    if (ch.taps && tid == 0) {
+      int nf = 0;
+      for (int c = 0; c < n_part; c++) nf += (s.w[c] > -HYG_INF);
+      ch.taps[0] = n_part; ch.taps[1] = -1; ch.taps[2] = nf;
+    }
+  }
+
+  // ---- filter (filter_and_smoother_algorithm.py:176-288) ----
+  for (unsigned long long t = 1; t < T; t++) {
+    // log-sum-exp of the previous weights and the number of finite ones
+    double mx = -HYG_INF;
+    int nf = 0;
+    for (int c = tid; c < n_part; c += HYG_TG_NT) { const double v = s.w[c]; mx = v > mx ? v : mx; nf += (v > -HYG_INF); }
+    mx = tg_block_max(mx, s, flip);
+    double se = 0.0;
+    for (int c = tid; c < n_part; c += HYG_TG_NT) { const double v = s.w[c]; se += (v > -HYG_INF) ? exp(v - mx) : 0.0; }
+    se = tg_block_sum(se, s, flip);
+    const double lse = mx + log(se);
+    // compact the finite particles (in index order) into s.key
+    int F;
+    const int per = (n_part + HYG_TG_NT - 1) / HYG_TG_NT;   // contiguous chunk per thread keeps index order
+    const int c0 = tid * per, c1 = (c0 + per < n_part) ? c0 + per : n_part;
+    nf = 0;
+    for (int c = c0; c < c1; c++) nf += (s.w[c] > -HYG_INF);
+    int pos = tg_block_excl_scan(nf, F, s, flip);
+    for (int c = c0; c < c1; c++)
+      if (s.w[c] > -HYG_INF) {
+        // order-preserving key of the normalised log-weight; the particle index travels beside it (stable ties)
+        unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(s.w[c] - lse));
+        b = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+        s.key[pos] = b;
+        s.sidx[pos++] = static_cast<unsigned short>(c);
+      }
+    __syncthreads();
+    int Mp, mode = 0, K = -1;
+    double log_c = 0.0;
+    if (F <= M) {
+      Mp = F;
+      for (int a = tid; a < Mp; a += HYG_TG_NT) s.parents[a] = static_cast<int>(s.sidx[a]);
+      __syncthreads();
+    } else {
+      // ---- OptimalFiniteState (resampling_functions.py:7-52) over the finite particles ----
+      Mp = M;
+      int n_sort = 64;
+      while (n_sort < F) n_sort <<= 1;
+      for (int i = F + tid; i < n_sort; i += HYG_TG_NT) { s.key[i] = 0ull; s.sidx[i] = 0xFFFFu; }
+      __syncthreads();
+      tg_sort_desc(s, n_sort);
+      // e[p] = exp(sorted normalised log-weight); reverse cumulative sums rcs[p] = sum_{i >= p} e[i]
+      for (int p = tid; p < n_sort; p += HYG_TG_NT) {
+        double v = 0.0;
+        if (p < F) v = exp(s.w[s.sidx[p]] - lse);
+        s.e[p] = v;
+      }
+      __syncthreads();
+      // sequential-in-chunks suffix sums (warp 0 walks from the end; F <= 2400 -> at most 75 chunks)
+      if (tid < 32) {
+        double carry = 0.0;
+        for (int base = ((F - 1) / 32) * 32; base >= 0; base -= 32) {
+          const int p = base + lane;
+          double v = (p < F) ? s.e[p] : 0.0;
+          double inc = v;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const double tt = __shfl_down_sync(HYG_FULL, inc, o);
+            if (lane + o < 32) inc += tt;
+          }
+          const double suf = inc + carry;
+          // the reverse cumulative sum is only needed at positions <= M (K < M): anc_w doubles as rcs[0..M]
+          if (p <= M && p < F) s.anc_w[p] = suf;
+          carry += __shfl_sync(HYG_FULL, inc, 0);
+        }
+        // fixed point with the reference's loop structure: (a, b, log_c) <- (k_new, a, log_c(a)) while a != b, a < n, a < M
+        int a = 0, b = -1;
+        double lc = -1.0;
+        while (a != b && a < F && a < M) {
+          const double lcn = log(static_cast<double>(M - a)) - log(s.anc_w[a]);
+          int cnt = 0;
+          for (int base = a; base < F && base < a + 96; base += 32) {   // counts beyond M do not change the outcome
+            const int p = base + lane;
+            const bool gt = (p < F) && (lcn + (s.w[s.sidx[p < F ? p : 0]] - lse) > 0.0);
+            cnt += __popc(__ballot_sync(HYG_FULL, gt));
+          }
+          b = a; a = a + cnt; lc = lcn;
+        }
+        int Kf = b;
+        if (!(Kf < F)) { Kf = F; lc = -HYG_INF; }
+        if (lane == 0) { s.ibc[0] = Kf; s.bc[0] = lc; }
+      }
+      __syncthreads();
+      K = s.ibc[0];
+      log_c = s.bc[0];
+      if (log_c - log_c != 0.0) {
+        // log c infinite: multinomial ancestors by inverse CDF over the particle-order weights, unbiased weights
+        mode = 2;
+        // cumulative sums over the particles in index order (s.e reused)
+        for (int c = tid; c < n_part; c += HYG_TG_NT) s.e[c] = (s.w[c] > -HYG_INF) ? exp(s.w[c] - lse) : 0.0;
+        __syncthreads();
+        if (tid == 0) { double acc = 0.0; for (int c = 0; c < n_part; c++) { acc += s.e[c]; s.e[c] = acc; } }
+        __syncthreads();
+        for (int a = tid; a < M; a += HYG_TG_NT) {
+          const double uu = tg_uniform(ch.seed, ch.chain, HYG_TAG_FILTER, (static_cast<uint64_t>(a + 1) << 32) + t) * s.e[n_part - 1];
+          int lo = 0, hi = n_part - 1;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.e[mid] < uu) lo = mid + 1; else hi = mid; }
+          s.parents[a] = lo;
+        }
+        log_c = 0.0;
+        __syncthreads();
+      } else {
+        mode = 1;
+        const int L = M - K;
+        // kept particles
+        for (int a = tid; a < K; a += HYG_TG_NT) s.parents[a] = static_cast<int>(s.sidx[a]);
+        // residual: cumulative sums of e[K..F) in sorted order (single warp, chunked), normalised by their total
+        if (tid < 32 && L > 0) {
+          double carry = 0.0;
+          for (int base = K; base < F; base += 32) {
+            const int p = base + lane;
+            double inc = (p < F) ? s.e[p] : 0.0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const double tt = __shfl_up_sync(HYG_FULL, inc, o);
+              if (lane >= o) inc += tt;
+            }
+            if (p < F) s.e[p] = inc + carry;
+            carry += __shfl_sync(HYG_FULL, inc, 31);
+          }
+        }
+        __syncthreads();
+        if (L > 0) {
+          const double tot = s.e[F - 1];
+          const double u = tg_uniform(ch.seed, ch.chain, HYG_TAG_FILTER, t);
+          for (int j = tid; j < L; j += HYG_TG_NT) {
+            // first residual position i with T_j <= Q_i, T_j = (j + u) / L  (resampling_functions.py:56-69); 0 if none
+            const double Tj = (static_cast<double>(j) + u) / static_cast<double>(L) * tot;
+            int lo = K, hi = F;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.e[mid] < Tj) lo = mid + 1; else hi = mid; }
+            const int ps = (lo < F) ? lo : K;
+            s.parents[K + j] = static_cast<int>(s.sidx[ps]);
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // ---- gather the ancestors, record them for the backward pass ----
+    for (int a = tid; a < Mp; a += HYG_TG_NT) {
+      const int c = s.parents[a];
+      TgState st; st.m = s.m[c]; st.dc = s.dc[c]; st.rc = s.rc[c]; st.dk = s.dk[c]; st.rk = s.rk[c];
+      s.anc[a] = st;
+      s.anc_w[a] = s.w[c];
+      s.anc_logW[a] = s.w[c] - lse;
+      TgAncRec rec; rec.dc = st.dc; rec.dk = st.dk; rec.m = static_cast<unsigned char>(st.m); rec.rc = static_cast<unsigned char>(st.rc);
+      rec.rk = static_cast<unsigned char>(st.rk); rec.pad = 0; rec.w_prev = s.anc_w[a]; rec.logW_prev = s.anc_logW[a];
+      ancs[t * run.anc_pitch + a] = rec;
+    }
+    if (tid == 0) { steps[t].n_anc = Mp; steps[t].mode = mode; steps[t].log_c = log_c; steps[t].lse = lse; }
+    __syncthreads();
+    // ---- propose the 48 children of every ancestor and weight them (proposal-major order) ----
+    const double* loc = ch.lo_c + t * R;
+    const double* lok = ch.lo_k + t * R;
+    const int n_new = I * Mp;
+    int nfin = 0;
+    for (int c = tid; c < n_new; c += HYG_TG_NT) {
+      const int q = c / Mp, a = c % Mp;
+      const TgState pa = s.anc[a];
+      const TgState n = tg_propose(R, pa, q);
+      const double lt = tg_log_trans(md, pa, n, false);
+      double wn = -HYG_INF;
+      if (lt > -HYG_INF) {
+        const double lg = lt + loc[n.rc] + lok[n.rk];
+        if (mode == 0) wn = s.anc_w[a] + lg;
+        else if (mode == 2) wn = -log(static_cast<double>(M)) + lse + lg;
+        else { const double adj = log_c + s.anc_logW[a]; wn = s.anc_w[a] + lg - (adj < 0.0 ? adj : 0.0); }
+      }
+      nfin += (wn > -HYG_INF);
+      s.w[c] = wn; s.m[c] = static_cast<unsigned char>(n.m); s.dc[c] = n.dc; s.rc[c] = static_cast<unsigned char>(n.rc);
+      s.dk[c] = n.dk; s.rk[c] = static_cast<unsigned char>(n.rk);
+    }
+    n_part = n_new;
+    __syncthreads();
+    if (ch.taps) {
+      const double tot = tg_block_sum(static_cast<double>(nfin), s, flip);
+      if (tid == 0) { ch.taps[t * 3] = n_part; ch.taps[t * 3 + 1] = K; ch.taps[t * 3 + 2] = static_cast<int>(tot + 0.5); }
+    }
+  }
+
+  // ---- log normalising constant ----
+  {
+    double mx = -HYG_INF;
+    for (int c = tid; c < n_part; c += HYG_TG_NT) mx = s.w[c] > mx ? s.w[c] : mx;
+    mx = tg_block_max(mx, s, flip);
+    double se = 0.0;
+    for (int c = tid; c < n_part; c += HYG_TG_NT) se += (s.w[c] > -HYG_INF) ? exp(s.w[c] - mx) : 0.0;
+    se = tg_block_sum(se, s, flip);
+    if (tid == 0 && ch.log_norm) *ch.log_norm = mx + log(se);
+  }
+
+  // ---- backward simulation (filter_and_smoother_algorithm.py:368-446) ----
+  // the particles of site T-1 are still in shared memory; earlier sites are recomputed from their ancestor records
+  for (long long t = static_cast<long long>(T) - 1; t >= 0; t--) {
+    if (t < static_cast<long long>(T) - 1) {
+      if (t == 0) {
+        n_part = R * R;
+        const int r_ph = static_cast<int>(tg_uniform(ch.seed, ch.chain, HYG_TAG_PHANTOM, 0) * R);
+        TgState ph; ph.m = 1; ph.dc = 0; ph.rc = r_ph; ph.dk = 0; ph.rk = r_ph;
+        for (int c = tid; c < n_part; c += HYG_TG_NT) {
+          TgState n; n.rc = c / R; n.rk = c % R; n.m = (n.rc == n.rk) ? 1 : 0; n.dc = 1; n.dk = 1;
+          const double lt = tg_log_trans(md, ph, n, true);
+          s.w[c] = (lt > -HYG_INF) ? lt + ch.lo_c[n.rc] + ch.lo_k[n.rk] : -HYG_INF;
+          s.m[c] = n.m; s.dc[c] = 1; s.rc[c] = n.rc; s.dk[c] = 1; s.rk[c] = n.rk;
+        }
+      } else {
+        const TgStepRec hd = steps[t];
+        const int Mp = hd.n_anc;
+        for (int a = tid; a < Mp; a += HYG_TG_NT) {
+          const TgAncRec rec = ancs[t * run.anc_pitch + a];
+          TgState st; st.m = rec.m; st.dc = rec.dc; st.rc = rec.rc; st.dk = rec.dk; st.rk = rec.rk;
+          s.anc[a] = st; s.anc_w[a] = rec.w_prev; s.anc_logW[a] = rec.logW_prev;
+        }
+        __syncthreads();
+        const double* loc = ch.lo_c + t * R;
+        const double* lok = ch.lo_k + t * R;
+        n_part = I * Mp;
+        for (int c = tid; c < n_part; c += HYG_TG_NT) {
+          const int q = c / Mp, a = c % Mp;
+          const TgState pa = s.anc[a];
+          const TgState n = tg_propose(R, pa, q);
+          const double lt = tg_log_trans(md, pa, n, false);
+          double wn = -HYG_INF;
+          if (lt > -HYG_INF) {
+            const double lg = lt + loc[n.rc] + lok[n.rk];
+            if (hd.mode == 0) wn = s.anc_w[a] + lg;
+            else if (hd.mode == 2) wn = -log(static_cast<double>(M)) + hd.lse + lg;
+            else { const double adj = hd.log_c + s.anc_logW[a]; wn = s.anc_w[a] + lg - (adj < 0.0 ? adj : 0.0); }
+          }
+          s.w[c] = wn; s.m[c] = static_cast<unsigned char>(n.m); s.dc[c] = n.dc; s.rc[c] = static_cast<unsigned char>(n.rc);
+          s.dk[c] = n.dk; s.rk[c] = static_cast<unsigned char>(n.rk);
+        }
+      }
+      __syncthreads();
+    }
+    // one categorical draw per trajectory: logits_i = w_t[i] (+ log f(x_{t+1}^j | x_t^i)), inverse CDF in particle order
+    const bool last = (t == static_cast<long long>(T) - 1);
+    for (int j = 0; j < B; j++) {
+      TgState nx;
+      if (!last) nx = s.nxt[j];
+      double mx = -HYG_INF;
+      for (int c = tid; c < n_part; c += HYG_TG_NT) {
+        double lg = s.w[c];
+        if (!last && lg > -HYG_INF) {
+          TgState pc; pc.m = s.m[c]; pc.dc = s.dc[c]; pc.rc = s.rc[c]; pc.dk = s.dk[c]; pc.rk = s.rk[c];
+          const double lt = tg_log_trans(md, pc, nx, false);
+          lg = (lt > -HYG_INF) ? lg + lt : -HYG_INF;
+        }
+        s.e[c] = lg;
+        mx = lg > mx ? lg : mx;
+      }
+      mx = tg_block_max(mx, s, flip);
+      // cumulative probabilities in particle order: per-thread contiguous chunks + block scan of chunk totals
+      const int per = (n_part + HYG_TG_NT - 1) / HYG_TG_NT;
+      const int c0 = tid * per, c1 = (c0 + per < n_part) ? c0 + per : n_part;
+      double loc_sum = 0.0;
+      for (int c = c0; c < c1; c++) { const double p = (s.e[c] > -HYG_INF) ? exp(s.e[c] - mx) : 0.0; loc_sum += p; s.e[c] = loc_sum; }
+      // exclusive scan of loc_sum over threads (warp scan + cross-warp)
+      double inc = loc_sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double tt = __shfl_up_sync(HYG_FULL, inc, o);
+        if (lane >= o) inc += tt;
+      }
+      if (lane == 31) s.red[flip][tid >> 5][1] = inc;
+      __syncthreads();
+      double off = 0.0, tot = 0.0;
+#pragma unroll
+      for (int w = 0; w < HYG_TG_NW; w++) { const double x = s.red[flip][w][1]; if (w < (tid >> 5)) off += x; tot += x; }
+      flip ^= 1;
+      const double excl = off + inc - loc_sum;
+      const double target = tg_uniform(ch.seed, ch.chain, HYG_TAG_BACKWARD, (static_cast<uint64_t>(j) << 32) + static_cast<uint64_t>(t)) * tot;
+      // the first particle whose cumulative probability reaches the target lives in exactly one thread's chunk
+      if (c0 < c1) {
+        const double hi_c = excl + loc_sum;
+        const bool mine = (excl < target || (tid == 0 && target <= 0.0)) && (target <= hi_c);
+        if (mine) {
+          int pickc = c1 - 1;
+          for (int c = c0; c < c1; c++) if (excl + s.e[c] >= target) { pickc = c; break; }
+          s.pick[j] = pickc;
+        }
+      }
+      if (tid == 0 && !(tot > 0.0)) s.pick[j] = 0;
+      __syncthreads();
+    }
+    // record the sampled states; they become x_{t+1} of the next (earlier) site
+    for (int j = tid; j < B; j += HYG_TG_NT) {
+      const int c = s.pick[j];
+      TgState st; st.m = s.m[c]; st.dc = s.dc[c]; st.rc = s.rc[c]; st.dk = s.dk[c]; st.rk = s.rk[c];
+      s.nxt[j] = st;
+      int* o = ch.traj + (static_cast<size_t>(t) * B + j) * 5;
+      o[0] = st.m; o[1] = st.dc; o[2] = st.rc; o[3] = st.dk; o[4] = st.rk;
+    }
+    __syncthreads();
+  }
+}
+
+#ifdef HYG_EMU
+static unsigned char hyg_tg_smem_storage[sizeof(TgSmem) + 64];
+#define HYG_TG_SMEM hyg_tg_smem_storage
+#else
+extern __shared__ __align__(16) unsigned char hyg_tg_smem_dyn[];
+#define HYG_TG_SMEM hyg_tg_smem_dyn
+#endif
+
+__device__ __forceinline__ void tg_entry(const TgModelDev* mdl, const TgChainDev* chains, TgRunDev run) {
+  TgSmem& s = *reinterpret_cast<TgSmem*>(HYG_TG_SMEM);
+  __shared__ int s_next;
+  if (threadIdx.x == 0) s.mdl = *mdl;
+  __syncthreads();
+  unsigned char* ws = run.ws + static_cast<size_t>(blockIdx.x) * run.ws_stride;
+  for (;;) {
+    if (threadIdx.x == 0) s_next = static_cast<int>(atomicAdd(run.queue, 1u));
+    __syncthreads();
+    const int c = s_next;
+    __syncthreads();
+    if (c >= run.n_chains) break;
+    tg_chain(chains[c], run, s, ws);
+  }
+}
+
+#ifndef HYG_EMU
+__global__ void __launch_bounds__(HYG_TG_NT, 1) tg_kernel(const TgModelDev* mdl, const TgChainDev* chains, TgRunDev run) {
+  tg_entry(mdl, chains, run);
+}
+#endif
+
+}  // namespace hyg
+#endif

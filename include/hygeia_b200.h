@@ -115,6 +115,46 @@ int hyg_sg_run_online_combined_inference(hyg_ctx* ctx, const double* vartheta, u
                                          const hyg_sg_run_args* args, uint64_t seed, const double* uniforms,
                                          double* regime_probs, double* theta_trace, double* logz, double* seconds);
 
+/* ---- two-group (case/control) path -------------------------------------------------------------------------------
+ * Boundary being replaced: hygeia/filter_and_smoother_algorithm.py::run as called by `hygeia infer`
+ * (src/two_group/run_inference_two_groups.py:261-276; parameters :110-167, outputs :233-240,294-322).
+ * Emission tables come from K1: add the control and the case count matrices as two data sets (hyg_sg_add_dataset, after
+ * hyg_sg_set_model has fixed alpha/beta) and call hyg_sg_emission. */
+typedef struct hyg_tg_model {
+  uint32_t R;                      /* regimes                                                                    */
+  uint32_t minimum_duration;       /* u (flag --minimum_duration, default 3)                                     */
+  uint32_t num_resampled;          /* M ancestors kept per site (--num_resampled_particles, default 50; <= 64)   */
+  uint32_t num_backward;           /* backward trajectories (--num_samples_backward, default 25; <= 32)          */
+  const double* log_p_control;     /* R x R row-major log transition matrix of the control regimes (diagonal ignored) */
+  const double* omega_control;     /* R                                                                          */
+  const double* omega_case;        /* R (the CLI uses 0.8 for every regime)                                      */
+  const double* kappa_control;     /* R (2.0)                                                                    */
+  const double* kappa_case;        /* R (2.0)                                                                    */
+  double merge_prob;               /* P(split -> merged), 0.1                                                    */
+  double split_prob;               /* P(merged -> split), 0.01                                                   */
+  /* optional precomputed hazards rho[r][d], d = 0..d_max, row pitch d_max + 1 (NULL -> computed here in fp64)   */
+  const double* rho_control;
+  const double* rho_case;
+  uint32_t d_max;
+} hyg_tg_model;
+
+typedef struct hyg_tg_chain {
+  uint32_t control_dataset;        /* data-set indices (hyg_sg_add_dataset order); both must have the same T     */
+  uint32_t case_dataset;
+  uint64_t seed;
+  uint32_t chain_id;
+  /* outputs, host pointers */
+  int32_t* trajectories;           /* T x B x 5 : merged, d_control, r_control, d_case, r_case                   */
+  double* log_normalizing_constant;/* 1                                                                          */
+  int32_t* taps;                   /* optional T x 3 : particles proposed, K, finite-weight particles            */
+} hyg_tg_chain;
+
+int hyg_tg_set_model(hyg_ctx* ctx, const hyg_tg_model* model, uint64_t t_max);
+/* K4/K5 over all chains: particle filter then backward simulation; synchronous (results are in the host buffers on return). */
+int hyg_tg_run(hyg_ctx* ctx, const hyg_tg_chain* chains, uint32_t n_chains, float* ms_device);
+/* host copy of the hazard table the kernels use: rho[R][d_max + 1] */
+int hyg_tg_hazard_table(const double* omega, const double* kappa, uint32_t R, uint32_t u, uint32_t d_max, double* rho);
+
 /* sampleFromParameterPriorCpp (singleGroup.cpp:18-35): theta ~ N(0, I_D), Philox-based (host). */
 int hyg_sg_sample_theta_prior(uint32_t dim, uint64_t seed, double* theta);
 /* Host copy of the by-site uniform the kernels use. */

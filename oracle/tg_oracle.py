@@ -16,7 +16,7 @@ installed here (no network); it ships no tests or golden vectors for this path. 
 algorithm from the reference's own call sites.  Deliberate, documented differences from the reference's arithmetic:
   * everything is fp64 (the reference evaluates the model in fp32 with fp64 weights);
   * TFP's NegativeBinomial log_prob / log_survival_function are replaced by an fp64 evaluation of the same hazard
-    rho(d) = pmf(d-u) / P(X >= d-u);
+    rho(d) = pmf(d-u) / P(X >= d-u) (see hazard_table; the reference's "0.1 where not finite" fp32 artefact is not reproduced);
   * random draws (the systematic-resampling uniform of each filter step, the categorical draws of the backward pass and
     the phantom initial regime) come from Philox keyed by (seed, chain) and indexed by site, and categorical sampling is
     inverse-CDF in particle order -- TensorFlow's own stream cannot be reproduced.
@@ -27,7 +27,6 @@ import os
 import sys
 
 import numpy as np
-from scipy.special import gammaln
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
@@ -66,23 +65,22 @@ def control_params_from_theta(theta, R):
 
 def hazard_table(omega, kappa, u, d_max):
     """rho[r][d] for d = 0..d_max: pmf(d-u) / P(X >= d-u), X ~ NB(kappa, omega) (case_control_regime_model.py:111-168);
-    0 below u; 0.1 where not finite."""
+    0 below u.  Evaluated by the backward recurrence of the inverse hazard g(k) = P(X >= k) / pmf(k):
+        g(k) = 1 + pmf(k+1)/pmf(k) * g(k+1) = 1 + omega (k + kappa)/(k + 1) * g(k+1),   g(inf) = 1/(1 - omega),
+    started far enough beyond d_max that the start-up error (contracted by ~omega per step) is below 1e-18.  It never
+    leaves the finite range, so the reference's "0.1 where not finite" branch (an fp32 underflow of TFP's survival function
+    at sojourns of several hundred sites) is not reproduced."""
     R = len(omega)
     rho = np.zeros((R, d_max + 1))
     for r in range(R):
         om, ka = float(omega[r]), float(kappa[r])
-        k = np.arange(0, d_max + 400)
-        logpmf = gammaln(k + ka) - gammaln(ka) - gammaln(k + 1.0) + ka * np.log1p(-om) + k * np.log(om)
-        pmf = np.exp(logpmf)
-        # tail sums from the far end (stable); the truncated remainder is bounded by a geometric tail
-        tail = np.cumsum(pmf[::-1])[::-1]
-        rem = pmf[-1] * om / max(1.0 - om, 1e-300)
-        sf = tail + rem
-        with np.errstate(divide="ignore", invalid="ignore"):
-            hz = pmf / sf
-        for d in range(u, d_max + 1):
-            v = hz[d - u]
-            rho[r, d] = v if np.isfinite(v) else 0.1
+        n_extra = int(min(np.ceil(-41.5 / np.log(om)), 5e7))
+        g = 1.0 / (1.0 - om)
+        for k in range(d_max - u + n_extra - 1, -1, -1):
+            g = 1.0 + (om * (k + ka) / (k + 1.0)) * g
+            if k <= d_max - u:
+                v = 1.0 / g
+                rho[r, k + u] = v if np.isfinite(v) else 0.1
     return rho
 
 

@@ -5,11 +5,13 @@
 // build box.  The product never links this file; on a GPU box the same device code runs through nvcc (hyg_api.cu).
 #include "cuda_emu.h"
 
+#include <algorithm>
 #include <vector>
 
 #include "../../hygeia_b200/csrc/hyg_tables.h"
 #include "../../hygeia_b200/csrc/sg_emission.cuh"
 #include "../../hygeia_b200/csrc/sg_filter.cuh"
+#include "../../hygeia_b200/csrc/hyg_tg.cuh"
 
 extern "C" {
 
@@ -80,6 +82,31 @@ int hygemu_sg_emission(const double* alpha, const double* beta, int R, uint64_t 
   for (int r = 0; r < R; r++) { a.alpha[r] = alpha[r]; a.beta[r] = beta[r]; }
   (void)block;
   emu::launch(dim3(grid), dim3(HYG_EM_NT), [=]() { hyg::sg_emission_entry<6>(a); });
+  return 0;
+}
+
+// K4/K5 under emulation: two-group filter + backward simulation of one chain.
+int hygemu_tg_run(int R, int u, int M, int B, const double* logP /*R x R*/, const double* logPm /*2 x 2*/, const double* rho_c,
+                  const double* rho_k, uint32_t dmax, uint64_t T, const double* lo_c, const double* lo_k, uint64_t seed, uint32_t chain,
+                  int* traj, double* log_norm, int* taps) {
+  hyg::TgModelDev mdl;
+  std::memset(&mdl, 0, sizeof(mdl));
+  mdl.R = R; mdl.u = u; mdl.M = M; mdl.B = B; mdl.dmax = dmax;
+  for (int i = 0; i < R; i++) for (int j = 0; j < R; j++) mdl.logP[i][j] = logP[i * R + j];
+  for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) mdl.logPm[i][j] = logPm[i * 2 + j];
+  mdl.rho_c = rho_c; mdl.rho_k = rho_k;
+  hyg::TgChainDev ch;
+  ch.T = T; ch.lo_c = lo_c; ch.lo_k = lo_k; ch.seed = seed; ch.chain = chain; ch.traj = traj; ch.log_norm = log_norm; ch.taps = taps;
+  hyg::TgRunDev run;
+  run.t_max = T;
+  run.anc_pitch = std::max(M, R * R);
+  run.ws_stride = sizeof(hyg::TgStepRec) * T + sizeof(hyg::TgAncRec) * T * run.anc_pitch;
+  std::vector<unsigned char> ws(run.ws_stride);
+  unsigned int queue = 0;
+  run.ws = ws.data(); run.queue = &queue; run.n_chains = 1;
+  const hyg::TgModelDev* pm = &mdl;
+  const hyg::TgChainDev* pc = &ch;
+  emu::launch(dim3(1), dim3(HYG_TG_NT), [=]() { hyg::tg_entry(pm, pc, run); });
   return 0;
 }
 

@@ -211,6 +211,8 @@ __device__ __forceinline__ double combine8(const double (*part)[8]) {
   return a;
 }
 
+#define HYG_LINEAR_FLOOR 1e-250
+
 // Service-warp job: new-segment particles (1, r), r = lane < R.  sumE[r] = sum_{r' != r} P[r'][r] E[r'] is the linear-domain
 // mass flowing into regime r (relative to exp(lsum_prev)); its log-weight is lsum_prev + logObs_r + log(sumE[r])
 // (computeWeightsCp, Smc.h:562-573, after factorising logTrans((1,r) <- (d,r')) = log c_new(d,r') + log P[r'][r]).
@@ -231,8 +233,11 @@ __device__ __forceinline__ double sg_service_new_segments(const SgModelDev& mdl,
     could = could || (((vm >> rp) & 1u) && Pv > 0.0);
   }
   if (lane < R) {
-    s.new_invE[lane] = (a > 0.0) ? 1.0 / a : 0.0;
-    s.slow[lane] = (!(a > 0.0) && could) ? 1 : 0;
+    // Below HYG_LINEAR_FLOOR the linear-domain sum is made of subnormal terms (or 1/a overflows): such regimes take the
+    // exact log-domain path, like the ones whose sum underflowed to zero.
+    const bool lin = a > HYG_LINEAR_FLOOR;
+    s.new_invE[lane] = lin ? 1.0 / a : 0.0;
+    s.slow[lane] = (!lin && could) ? 1 : 0;
   }
   return a;
 }
@@ -714,6 +719,31 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
             a += cm.P[rp][r] * term;
           }
           pe->phi[cb][k][M + r] = a * s.new_invE[r];
+        }
+        if (slowmask) {
+          // regimes on the log-domain path: phi' = sum_n bk_r[n] (phi_n + grad_n) with the per-particle normalised kernel
+          __syncthreads();
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            if (!((slowmask >> r) & 1u)) continue;
+            for (int k = 0; k < D; k++) {
+              double v[1] = {0.0};
+              if (bk_slow[r] > 0.0) {
+                const int rn = p.r;
+                double g = pe->phi[pb][k][tid];
+                if (k == R * (R - 1) + rn) {
+                  g += p.gcur;
+                } else if (k >= rn * (R - 1) && k < (rn + 1) * (R - 1)) {
+                  const int j = k - rn * (R - 1);
+                  const int col = (j < rn) ? j : j + 1;
+                  g += ((col == r) ? 1.0 : 0.0) - cm.P[rn][col];
+                }
+                v[0] = bk_slow[r] * g;
+              }
+              block_sum<1>(v, s.sc, flip);
+              if (tid == 0) pe->phi[cb][k][M + r] = v[0];
+            }
+          }
         }
         if (tid < M) {
           // continuing particle: phi' = phi_anc + grad, grad touches only the omega slot of its regime

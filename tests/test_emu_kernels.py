@@ -99,3 +99,24 @@ def test_parameter_estimation_under_emulation(emu, oracle, default_model):
         assert np.allclose(got["logz"], want["logz"], rtol=1e-12)
         assert np.array_equal(got["k_kept"], want["k_kept"])
         assert np.allclose(got["probs"], want["regime_probs"][:, 1:], rtol=1e-6, atol=1e-12)
+
+
+def test_parameter_estimation_underflow_regime(emu, oracle, default_model):
+    """Informative data (32 samples): all but one regime class underflow in the linear domain around site 2865, where the
+    new-segment particles must take the log-domain path -- in the weights AND in the score recursion (regression: phi
+    became 0 * inf = NaN).  Components of the score that are mathematically zero are rounding noise in both
+    implementations and ADAM turns that noise into steps of up to lr * |noise| / 1e-8, hence the absolute tolerance."""
+    from hygeia_b200 import model, philox, synthetic
+    T, S = 3100, 32
+    ch = synthetic.make_chain(T, S, seed=7)
+    al, be = default_model["alpha_beta"]
+    lo = oracle.emission(al, be, ch["n_total"], ch["n_meth"])
+    u = philox.uniforms_by_site(1, 0, T)
+    theta0 = model.default_theta()
+    want = oracle.run(default_model["vartheta"], theta0, u, logobs=lo, param_est=True)
+    got = emu.sg_filter(default_model["vartheta"], theta0, lo, uniforms=u, param_est=True, lcap=128)
+    assert np.isfinite(got["theta_trace"]).all() and np.isfinite(got["logz"]).all()
+    assert np.abs(got["theta_trace"] - want["theta_trace"]).max() < 1e-6
+    assert np.allclose(got["logz"], want["logz"], rtol=1e-9)
+    assert (got["k_kept"] == want["k_kept"]).mean() > 0.999
+    assert got["status"][0] == 0      # no forced emissions: the lag set never filled up

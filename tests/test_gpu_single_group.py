@@ -248,3 +248,37 @@ def test_parameter_estimation_parity(sess, oracle, default_model):
                                       use_online_parameter_estimation=True, rng_seed=9)
     assert r["thetaEstimates"].shape == (T, 36)
     assert np.allclose(r["thetaEstimates"], want["theta_trace"], rtol=RTOL, atol=1e-9)
+
+
+def test_informative_data_underflow_regime(sess, oracle, default_model):
+    """32 samples per site: regime classes underflow in the linear domain (site ~2865 of this chain); filtering and
+    parameter estimation must stay finite and on the oracle (regression: 0 * inf in the score recursion, which also
+    filled the lag set and slowed the chain down 50x)."""
+    from hygeia_b200 import model, philox, synthetic
+    from hygeia_b200.single_group import make_run_args
+    T, S = 5000, 32
+    ch = synthetic.make_chain(T, S, seed=7)
+    u = philox.uniforms_by_site(1, 0, T)
+    theta0 = model.default_theta()
+    for pe in (False, True):
+        want = oracle.run(default_model["vartheta"], theta0, u, ch["n_total"], ch["n_meth"], ch["positions"], param_est=pe)
+        sess.clear()
+        sess.set_vartheta(default_model["vartheta"])
+        sess.set_theta(theta0, T)
+        ds = sess.add_dataset(ch["n_total"], ch["n_meth"])
+        out = dict(regime_probs=np.full((T, 7), np.nan), logz=np.zeros(T), k_kept=np.zeros(T, np.int32))
+        if pe:
+            out["theta_trace"] = np.zeros((T, 36))
+        sess.set_chains([dict(dataset=ds, seed=1, chain_id=0, positions=ch["positions"], **out)])
+        sess.emission()
+        sess.filter(make_run_args(use_online_parameter_estimation=pe))
+        status = sess.download()
+        assert status[0][0] == 0                                   # no forced emissions
+        assert np.isfinite(out["logz"]).all() and np.isfinite(out["regime_probs"]).all()
+        assert np.allclose(out["logz"], want["logz"], rtol=RTOL)
+        assert np.allclose(out["regime_probs"], want["regime_probs"], rtol=1e-5, atol=1e-9)
+        assert (out["k_kept"] == want["k_kept"]).mean() > 0.999
+        if pe:
+            assert np.isfinite(out["theta_trace"]).all()
+            # ADAM amplifies rounding noise in score components that are mathematically zero (see the emulation test)
+            assert np.abs(out["theta_trace"] - want["theta_trace"]).max() < 2e-6

@@ -1,7 +1,7 @@
 // hygeia_b200/csrc/hyg_tg.cuh -- K4/K5: the two-group (case/control) particle filter and backward simulation.
 //
-// Reference (/root/reference/src/two_group, TensorFlow 2.3 / TFP 0.11 -- not runnable here; see oracle/tg_oracle.py for
-// the restatement this kernel is checked against and for the documented differences):
+// Reference (/root/reference/src/two_group, TensorFlow 2.3 / TFP 0.11 -- not runnable here; DESIGN.md section 2 describes
+// the restatement this kernel is checked against and the documented differences):
 //   filter step                 hygeia/filter_and_smoother_algorithm.py:176-288
 //   first step / padding        hygeia/filter_and_smoother_algorithm.py:141-172,334-365
 //   backward simulation         hygeia/filter_and_smoother_algorithm.py:368-446, hygeia/smoothing_functions.py:46-59

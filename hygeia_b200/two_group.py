@@ -157,6 +157,8 @@ def infer(n_total_reads_control, n_methylated_reads_control, n_total_reads_case,
     if device not in _sessions:
         _sessions[device] = TwoGroupSession(device)
     s = _sessions[device]
+    mu = [float(x) for x in mu]          # absl's DEFINE_list hands over strings
+    sigma = [float(x) for x in sigma]
     R = len(mu)
     mats = []
     for a in (n_total_reads_control, n_methylated_reads_control, n_total_reads_case, n_methylated_reads_case):

@@ -52,6 +52,8 @@ struct ChainBuf {
   short* d_anc = nullptr;
   int* d_status = nullptr;
   double* d_trace = nullptr;
+  double* d_seginc = nullptr;   // segmented execution: log Z increment of every segment
+  uint32_t n_seg = 1, seginc_cap = 0;
 };
 
 }  // namespace
@@ -80,6 +82,11 @@ struct hyg_ctx {
   size_t pe_bytes = 0;
   double* d_theta0 = nullptr;
   unsigned int* d_queue = nullptr;
+  size_t d_chains_cap = 0;
+  uint64_t seg_sites = 0, seg_halo_left = 5000, seg_halo_right = 5000;   // hyg_sg_set_segmentation (0 = whole chains)
+  hyg::SgLogzFix* d_fix = nullptr;
+  size_t d_fix_cap = 0;
+  uint32_t n_units_last = 0;
   uint32_t n_particles_staged = 0;
   std::multimap<size_t, void*> pool_free_blocks;
   std::map<void*, size_t> pool_live;
@@ -157,11 +164,10 @@ void free_chains(hyg_ctx* c) {
   for (auto& b : c->chains) {
     pool_free(c, b.d_unif); pool_free(c, b.d_pos); pool_free(c, b.d_probs); pool_free(c, b.d_logz); pool_free(c, b.d_k);
     pool_free(c, b.d_drew); pool_free(c, b.d_npend); pool_free(c, b.d_ncurr); pool_free(c, b.d_fin); pool_free(c, b.d_anc);
-    pool_free(c, b.d_status); pool_free(c, b.d_trace);
+    pool_free(c, b.d_status); pool_free(c, b.d_trace); pool_free(c, b.d_seginc);
   }
   c->chains.clear();
   c->order.clear();
-  dfree(c->d_chains);
 }
 
 void free_datasets(hyg_ctx* c) {
@@ -176,6 +182,23 @@ __global__ void fill_positions_kernel(double* probs, const uint32_t* pos, unsign
   for (unsigned long long t = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; t < T;
        t += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
     probs[t * stride] = pos ? static_cast<double>(pos[t]) : static_cast<double>(t);
+}
+
+// Segmented execution: shift the rows of segment j >= 1 by the log Z accumulated over the segments before it.
+__global__ void sg_logz_fix_kernel(const hyg::SgLogzFix* units, unsigned int n_units) {
+  __shared__ double s_off;
+  for (unsigned int k = blockIdx.x; k < n_units; k += gridDim.x) {
+    const hyg::SgLogzFix f = units[k];
+    if (threadIdx.x == 0) {
+      double off = 0.0;
+      for (unsigned int i = 0; i < f.j; i++) off += f.seg_inc[i];
+      s_off = off;
+    }
+    __syncthreads();
+    const double off = s_off;
+    for (unsigned long long t = threadIdx.x; t < f.len; t += blockDim.x) f.logz[t] += off;
+    __syncthreads();
+  }
 }
 
 template <int R> int launch_emission(hyg_ctx* c, const hyg::SgEmissionArgs& a, size_t smem, int grid) {
@@ -264,7 +287,7 @@ void hyg_destroy(hyg_ctx* c) {
   free_chains(c);
   free_datasets(c);
   pool_release(c);
-  dfree(c->d_tab); dfree(c->d_tabg); dfree(c->d_mdl); dfree(c->d_emtab); dfree(c->d_sets); dfree(c->d_psi); dfree(c->d_pe); dfree(c->d_theta0); dfree(c->d_queue); dfree(c->d_tg_mdl); dfree(c->d_tg_rho);
+  dfree(c->d_tab); dfree(c->d_tabg); dfree(c->d_mdl); dfree(c->d_emtab); dfree(c->d_sets); dfree(c->d_psi); dfree(c->d_pe); dfree(c->d_theta0); dfree(c->d_queue); dfree(c->d_chains); dfree(c->d_fix); dfree(c->d_tg_mdl); dfree(c->d_tg_rho);
   cudaEventDestroy(c->ev_em0); cudaEventDestroy(c->ev_em1); cudaEventDestroy(c->ev_f0); cudaEventDestroy(c->ev_f1);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -390,6 +413,21 @@ void hyg_sg_default_run_args(hyg_sg_run_args* a) {
   a->lag_capacity = 128;
 }
 
+int hyg_sg_set_segmentation(hyg_ctx* c, uint64_t segment_sites, uint64_t halo_left, uint64_t halo_right) {
+  if (!c) return HYG_ERR_ARG;
+  if (segment_sites > 0 && segment_sites < 16) return fail(c, HYG_ERR_ARG, "segment_sites must be 0 (whole chains) or >= 16");
+  c->seg_sites = segment_sites;
+  c->seg_halo_left = halo_left;
+  c->seg_halo_right = halo_right;
+  return HYG_OK;
+}
+
+int hyg_sg_filter_units(hyg_ctx* c, uint32_t* n_units) {
+  if (!c || !n_units) return HYG_ERR_ARG;
+  *n_units = c->n_units_last;
+  return HYG_OK;
+}
+
 int hyg_sg_set_chains(hyg_ctx* c, const hyg_sg_chain* chains, uint32_t n) {
   if (!c || !chains || n == 0) return fail(c, HYG_ERR_ARG, "no chains");
   if (!c->model_set) return fail(c, HYG_ERR_STATE, "hyg_sg_set_model first");
@@ -421,14 +459,12 @@ int hyg_sg_set_chains(hyg_ctx* c, const hyg_sg_chain* chains, uint32_t n) {
     if (chains[i].n_pending) HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_npend), T * sizeof(int)));
     if (chains[i].n_curr) HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_ncurr), T * sizeof(int)));
     if (chains[i].finalised_at) HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_fin), T * sizeof(int)));
-    HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_status), 2 * sizeof(int)));
-    HYG_CUDA(c, cudaMemsetAsync(b.d_status, 0, 2 * sizeof(int), c->stream));
+    HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_status), 4 * sizeof(int)));
   }
   // launch order: longest chain first (LPT), so the persistent CTAs finish together
   c->order.resize(n);
   std::iota(c->order.begin(), c->order.end(), 0u);
   std::stable_sort(c->order.begin(), c->order.end(), [&](uint32_t a, uint32_t b) { return c->chains[a].T > c->chains[b].T; });
-  HYG_CUDA(c, cudaMalloc(&c->d_chains, n * sizeof(hyg::SgChainDev)));
   c->n_particles_staged = 0;
   return HYG_OK;
 }
@@ -517,28 +553,80 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
     HYG_CUDA(c, cudaStreamSynchronize(c->stream));
   }
 
-  // chain descriptors in launch order
-  std::vector<hyg::SgChainDev> cd(n);
+  // chain descriptors in launch order.  Whole-chain execution: one descriptor per chain.  Segmented execution
+  // (hyg_sg_set_segmentation; not in parameter mode, where theta evolves along the chain): every chain is cut into
+  // near-equal segments of <= seg_sites owned sites; a segment starts seg_halo_left sites early from the R-particle initial
+  // system (the filter forgets it) and may run up to seg_halo_right sites past its end until its last owned site settles.
+  const bool segmented = c->seg_sites > 0 && !pe_mode;
+  std::vector<hyg::SgChainDev> cd;
+  std::vector<hyg::SgLogzFix> fix;
+  for (auto& b : c->chains) {
+    b.n_seg = segmented ? static_cast<uint32_t>((b.T + c->seg_sites - 1) / c->seg_sites) : 1u;
+    if (b.n_seg < 1) b.n_seg = 1;
+    HYG_CUDA(c, cudaMemsetAsync(b.d_status, 0, 4 * sizeof(int), c->stream));
+    if (b.n_seg > 1 && b.seginc_cap < b.n_seg) {
+      pool_free(c, b.d_seginc);
+      HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_seginc), b.n_seg * sizeof(double)));
+      b.seginc_cap = b.n_seg;
+    }
+  }
   for (uint32_t k = 0; k < n; k++) {
     const ChainBuf& b = c->chains[c->order[k]];
-    hyg::SgChainDev& d = cd[k];
-    std::memset(&d, 0, sizeof(d));
-    d.T = b.T;
-    d.logobs = c->ds[b.host.dataset].d_logobs;
-    d.unif = b.d_unif; d.seed = b.host.seed; d.chain_id = b.host.chain_id;
-    d.probs = args->use_online_marginal_smoothing ? b.d_probs : nullptr;
-    d.logz = b.d_logz; d.k_kept = b.d_k; d.drew = b.d_drew; d.n_pending = b.d_npend; d.n_curr = b.d_ncurr;
-    d.finalised_at = b.d_fin; d.ancestors = b.d_anc; d.status = b.d_status;
-    d.theta0 = c->d_theta0; d.theta_trace = pe_mode ? b.d_trace : nullptr;
+    const uint64_t seg_len = (b.T + b.n_seg - 1) / b.n_seg;
+    for (uint32_t j = 0; j < b.n_seg; j++) {
+      const uint64_t t0 = j * seg_len, t1 = std::min<uint64_t>(b.T, t0 + seg_len);
+      if (t0 >= t1) break;
+      const bool last = (t1 == b.T);
+      const uint64_t a = (b.n_seg == 1 || t0 < c->seg_halo_left) ? 0 : t0 - c->seg_halo_left;
+      const uint64_t e = last ? b.T : std::min<uint64_t>(b.T, t1 + c->seg_halo_right);
+      hyg::SgChainDev d;
+      std::memset(&d, 0, sizeof(d));
+      d.T = e - a;
+      d.t_off = a; d.own_lo = t0 - a; d.own_hi = t1 - a; d.last_segment = (e == b.T) ? 1 : 0;
+      d.logobs = c->ds[b.host.dataset].d_logobs + a * R;
+      d.unif = b.d_unif ? b.d_unif + a : nullptr; d.seed = b.host.seed; d.chain_id = b.host.chain_id;
+      d.probs = (args->use_online_marginal_smoothing && b.d_probs) ? b.d_probs + a * (R + 1) : nullptr;
+      d.logz = b.d_logz ? b.d_logz + a : nullptr;
+      d.k_kept = b.d_k ? b.d_k + a : nullptr; d.drew = b.d_drew ? b.d_drew + a : nullptr;
+      d.n_pending = b.d_npend ? b.d_npend + a : nullptr; d.n_curr = b.d_ncurr ? b.d_ncurr + a : nullptr;
+      d.finalised_at = b.d_fin ? b.d_fin + a : nullptr;
+      d.ancestors = b.d_anc ? b.d_anc + a * (Nmax - R) : nullptr;
+      d.status = b.d_status;
+      d.theta0 = c->d_theta0; d.theta_trace = pe_mode ? b.d_trace : nullptr;
+      d.seg_inc = (b.n_seg > 1) ? b.d_seginc + j : nullptr;
+      cd.push_back(d);
+      if (j > 0 && b.d_logz) {
+        hyg::SgLogzFix f;
+        f.logz = b.d_logz + t0; f.seg_inc = b.d_seginc; f.len = t1 - t0; f.j = j; f.pad_ = 0;
+        fix.push_back(f);
+      }
+    }
   }
-  HYG_CUDA(c, cudaMemcpyAsync(c->d_chains, cd.data(), n * sizeof(hyg::SgChainDev), cudaMemcpyHostToDevice, c->stream));
-  HYG_CUDA(c, cudaStreamSynchronize(c->stream));  // cd goes out of scope
+  // longest first (LPT) over all segments of all chains
+  std::stable_sort(cd.begin(), cd.end(), [](const hyg::SgChainDev& x, const hyg::SgChainDev& y) { return x.T > y.T; });
+  const uint32_t n_units = static_cast<uint32_t>(cd.size());
+  if (c->d_chains_cap < n_units) {
+    dfree(c->d_chains);
+    HYG_CUDA(c, cudaMalloc(&c->d_chains, n_units * sizeof(hyg::SgChainDev)));
+    c->d_chains_cap = n_units;
+  }
+  HYG_CUDA(c, cudaMemcpyAsync(c->d_chains, cd.data(), n_units * sizeof(hyg::SgChainDev), cudaMemcpyHostToDevice, c->stream));
+  if (!fix.empty()) {
+    if (c->d_fix_cap < fix.size()) {
+      dfree(c->d_fix);
+      HYG_CUDA(c, cudaMalloc(&c->d_fix, fix.size() * sizeof(hyg::SgLogzFix)));
+      c->d_fix_cap = fix.size();
+    }
+    HYG_CUDA(c, cudaMemcpyAsync(c->d_fix, fix.data(), fix.size() * sizeof(hyg::SgLogzFix), cudaMemcpyHostToDevice, c->stream));
+  }
+  HYG_CUDA(c, cudaStreamSynchronize(c->stream));  // cd / fix are pageable
+  c->n_units_last = n_units;
 
   int occ = 1;
   if (pe_mode) { HYG_DISPATCH_R6(R, (filter_occupancy<RR, true>(&occ))); }
   else { HYG_DISPATCH_R(R, (filter_occupancy<RR, false>(&occ))); }
   if (occ < 1) occ = 1;
-  const int grid = static_cast<int>(std::min<uint64_t>(n, static_cast<uint64_t>(c->num_sms) * occ));
+  const int grid = static_cast<int>(std::min<uint64_t>(n_units, static_cast<uint64_t>(c->num_sms) * occ));
 
   hyg::SgRunDev run;
   run.use_smoothing = args->use_online_marginal_smoothing ? 1 : 0;
@@ -553,7 +641,7 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
   }
   run.psi_ws = c->d_psi;
   run.queue = c->d_queue;
-  run.n_chains = static_cast<int>(n);
+  run.n_chains = static_cast<int>(n_units);
   run.use_param_est = pe_mode ? 1 : 0;
   run.normalise_gradients = args->normalise_gradients;
   run.use_adam = args->use_adam;
@@ -589,6 +677,11 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
   else { HYG_DISPATCH_R(R, (rc = launch_filter<RR, false>(c, run, grid))); }
   if (rc) return rc;
   c->f_launches++;
+  if (!fix.empty()) {
+    sg_logz_fix_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(c->d_fix, static_cast<unsigned int>(fix.size()));
+    HYG_CUDA(c, cudaGetLastError());
+    c->f_launches++;
+  }
   HYG_CUDA(c, cudaEventRecord(c->ev_f1, c->stream));
   c->timed_f = true;
   return HYG_OK;
@@ -613,7 +706,7 @@ int hyg_sg_download(hyg_ctx* c, hyg_sg_chain* chains, uint32_t n) {
     if (h.theta_trace && b.d_trace) HYG_CUDA(c, cudaMemcpyAsync(h.theta_trace, b.d_trace, T * c->hm.D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (h.ancestors && b.d_anc)
       HYG_CUDA(c, cudaMemcpyAsync(h.ancestors, b.d_anc, T * (c->n_particles_staged - R) * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
-    if (chains) HYG_CUDA(c, cudaMemcpyAsync(chains[i].status, b.d_status, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (chains) HYG_CUDA(c, cudaMemcpyAsync(chains[i].status, b.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   }
   HYG_CUDA(c, cudaStreamSynchronize(c->stream));
   return HYG_OK;

@@ -42,10 +42,29 @@ struct SgChainDev {
   int* n_curr;            // T : particle count after site t
   int* finalised_at;      // T : step at which site t was emitted
   short* ancestors;       // T x (n_particles - R)
-  int* status;            // [0] forced emissions (lag set full), [1] max lag-set size
+  int* status;            // accumulated over the chain's segments: [0] forced emissions (lag set full), [1] max lag-set size,
+                          // [2] owned sites emitted by force at the end of a segment's right halo, [3] sites stepped through
+  // Segmented execution (hyg_sg_set_segmentation): this descriptor covers the sites [t_off, t_off + T) of its chain -- every
+  // pointer above is already offset to local site 0 -- and OWNS the local sites [own_lo, own_hi): rows outside that range are
+  // warm-up (left halo: the filter forgets its initial condition) or run-out (right halo: until every owned site is finalised)
+  // and are not written.  Whole-chain execution: t_off = 0, own_lo = 0, own_hi = T, last_segment = 1.
+  unsigned long long t_off;
+  unsigned long long own_lo, own_hi;
+  int last_segment;       // T-1 is the end of the chain (the reference's forced finalisation there is genuine)
+  double* seg_inc;        // out: log Z_{own_hi-1} - log Z_{own_lo-1} (device) or null
   // parameter-estimation mode
   const double* theta0;   // D initial theta (device) or null
   double* theta_trace;    // T x D (device) or null
+};
+
+// Segmented execution: one unit per segment j >= 1 of a chain with a logz output.  The segment's rows hold log Z relative to
+// the site before the segment; the fix-up adds seg_inc[0] + ... + seg_inc[j-1] (summed in that order).
+struct SgLogzFix {
+  double* logz;            // first owned row of the segment
+  const double* seg_inc;   // the chain's per-segment increments
+  unsigned long long len;  // owned rows
+  unsigned int j;          // segment index
+  unsigned int pad_;
 };
 
 struct SgRunDev {

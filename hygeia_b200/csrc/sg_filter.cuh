@@ -293,6 +293,12 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
   double* psi[2] = {psi_ws, psi_ws + static_cast<size_t>(lcap) * R * HYG_NPMAX};
   int* pend_t = reinterpret_cast<int*>(psi_ws + 2 * static_cast<size_t>(lcap) * R * HYG_NPMAX);
   int n_pend = 0, n_forced = 0, max_pend = 0;
+  // segmented execution: local sites [own_lo, own_hi) are written, the rest is warm-up / run-out (hyg_dev_structs.h)
+  const unsigned long long own_lo = ch.own_lo, own_hi = ch.own_hi, t_off = ch.t_off;
+  const bool last_seg = ch.last_segment != 0;
+  int n_halo_forced = 0;
+  int n_steps = 0;
+  double lz_base = 0.0;   // log Z (local) of site own_lo - 1: owned rows of logz are written relative to it
 
   SgChainState p;
   p.lw = -HYG_INF; p.W = 0.0; p.cur = make_double2(0.0, 0.0); p.nxt = p.cur; p.gcur = 0.0; p.gnxt = 0.0; p.d = 0; p.r = 0;
@@ -331,6 +337,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
     int k_kept = -1;
     bool drew = false;
     bool emit_now = false;       // current site finalised at this step
+    const bool own_t = (t >= own_lo) && (t < own_hi);
     double cw_lane = 0.0;        // regime mass of index lane & 7 (current site)
 
     if (t > 0) {
@@ -347,7 +354,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       if (service) {
         // the uniform of this site, and log Z_{t-1}: the log of last step's normaliser is evaluated now, off the
         // workers' critical path (they read s.lsum only after the sort's barriers)
-        if (lane == 8) s.u = ch.unif ? __ldg(ch.unif + t) : philox_uniform(ch.seed, ch.chain_id, t);
+        if (lane == 8) s.u = ch.unif ? __ldg(ch.unif + t) : philox_uniform(ch.seed, ch.chain_id, t + t_off);
         if (lane == 0) s.lsum[(t + 1) & 1] = pend_shift + log(pend_S);
         __syncwarp();
       }
@@ -503,7 +510,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           own_weight = (tid < K);
         }
       }
-      if (ch.ancestors && tid < Nmax - R)
+      if (ch.ancestors && own_t && tid < Nmax - R)
         ch.ancestors[t * static_cast<unsigned long long>(Nmax - R) + tid] = (tid < M) ? static_cast<short>(anc) : static_cast<short>(-1);
 
       // ---- propose + weight: sampleParticlesCp / computeWeightsCp (Smc.h:504-574) ----
@@ -645,20 +652,22 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
 #pragma unroll
           for (int q = 0; q < R; q++) { mv[q] = c.W * val[q]; mv[R + q] = c.W * val[q] * val[q]; }
           block_sum<2 * R>(mv, s.sc, flip);
-          bool emit = (t == T - 1);
-          if (!emit) {
-            emit = true;
+          bool settled = true;
 #pragma unroll
-            for (int q = 0; q < R; q++) {
-              const double var = mv[R + q] - mv[q] * mv[q];  // sum W (x-m)^2 with sum W = 1
-              if (!(var < run.epsilon)) emit = false;
-            }
+          for (int q = 0; q < R; q++) {
+            const double var = mv[R + q] - mv[q] * mv[q];  // sum W (x-m)^2 with sum W = 1
+            if (!(var < run.epsilon)) settled = false;
           }
+          const bool emit = settled || (t == T - 1);
           const int ts = pend_t[i];
           if (emit) {
-            const double outv = pick<2 * R>(mv, tid);
-            if (tid < R && ch.probs) ch.probs[static_cast<size_t>(ts) * (R + 1) + 1 + tid] = outv;
-            if (tid == 0 && ch.finalised_at) ch.finalised_at[ts] = static_cast<int>(t);
+            const bool own_s = (static_cast<unsigned long long>(ts) >= own_lo) && (static_cast<unsigned long long>(ts) < own_hi);
+            if (own_s) {
+              const double outv = pick<2 * R>(mv, tid);
+              if (tid < R && ch.probs) ch.probs[static_cast<size_t>(ts) * (R + 1) + 1 + tid] = outv;
+              if (tid == 0 && ch.finalised_at) ch.finalised_at[ts] = static_cast<int>(t + t_off);
+              if (!settled && !last_seg) n_halo_forced++;   // the segment's right halo ended before this site settled
+            }
           } else {
             double* dst = pc + static_cast<size_t>(kept) * R * HYG_NPMAX;
             if (worker) {
@@ -781,11 +790,15 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       const double m = cw_lane;
       const double var = m * (1.0 - m) * (1.0 - m) + (sw - m) * m * m;
       const bool ok = ((lane & 7) >= R) || (var < run.epsilon);
-      emit_now = (t == T - 1) || __all_sync(HYG_FULL, ok);
-      if (!emit_now && n_pend >= lcap) { emit_now = true; n_forced++; }  // lag set full: emit the filtering estimate now (reported)
+      const bool settled = __all_sync(HYG_FULL, ok);
+      emit_now = (t == T - 1) || settled;
+      if (!emit_now && n_pend >= lcap) { emit_now = true; n_forced += own_t ? 1 : 0; }  // lag set full: emit the filtering estimate now (reported)
       if (emit_now) {
-        if (tid < R && ch.probs) ch.probs[static_cast<size_t>(t) * (R + 1) + 1 + tid] = cw_lane;  // lanes 0..R-1 of warp 0
-        if (tid == 0 && ch.finalised_at) ch.finalised_at[t] = static_cast<int>(t);
+        if (own_t) {
+          if (tid < R && ch.probs) ch.probs[static_cast<size_t>(t) * (R + 1) + 1 + tid] = cw_lane;  // lanes 0..R-1 of warp 0
+          if (tid == 0 && ch.finalised_at) ch.finalised_at[t] = static_cast<int>(t + t_off);
+          if (t == T - 1 && !settled && !last_seg) n_halo_forced++;
+        }
       } else {
         double* dst = psi[t & 1] + static_cast<size_t>(n_pend) * R * HYG_NPMAX;
         if (worker) {
@@ -805,6 +818,12 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
     }
     if (service && lane < R && t + 2 < T) s.lo[t & 1][lane] = lo_pref;
     __syncthreads();
+    // segmented execution: stop as soon as the owned range is stepped through and none of its sites is still pending
+    // (the lag set is ordered by site, oldest first)
+    bool exit_now = false;
+    if (!PE && t + 1 >= own_hi && t + 1 < T) exit_now = (n_pend == 0) || (static_cast<unsigned long long>(pend_t[0]) >= own_hi);
+    const bool last_step = (t == T - 1) || exit_now;
+    n_steps++;
 
     // ---- K3: parameter update every n_steps sites (OnlineParameterEstimation.h:51-61) ----
     if (PE) {
@@ -841,17 +860,33 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
 
     // ---- taps ----
     if (service && lane == 0) {
-      if (ch.logz && t > 0) ch.logz[t - 1] = s.lsum[(t + 1) & 1];
-      if (ch.logz && t == T - 1) ch.logz[t] = pend_shift + log(pend_S);
-      if (ch.k_kept) ch.k_kept[t] = k_kept;
-      if (ch.drew) ch.drew[t] = drew ? 1 : 0;
-      if (ch.n_pending) ch.n_pending[t] = n_pend;
-      if (ch.n_curr) ch.n_curr[t] = N;
+      if (t > 0) {
+        const double lz_prev = s.lsum[(t + 1) & 1];   // log Z (local) of site t-1
+        if (t == own_lo) lz_base = lz_prev;
+        if (t - 1 >= own_lo && t - 1 < own_hi) {
+          if (ch.logz) ch.logz[t - 1] = lz_prev - lz_base;
+          if (t == own_hi && ch.seg_inc) *ch.seg_inc = lz_prev - lz_base;
+        }
+      }
+      if (last_step && own_t) {
+        const double lz = pend_shift + log(pend_S) - lz_base;
+        if (ch.logz) ch.logz[t] = lz;
+        if (t + 1 == own_hi && ch.seg_inc) *ch.seg_inc = lz;
+      }
+      if (own_t) {
+        if (ch.k_kept) ch.k_kept[t] = k_kept;
+        if (ch.drew) ch.drew[t] = drew ? 1 : 0;
+        if (ch.n_pending) ch.n_pending[t] = n_pend;
+        if (ch.n_curr) ch.n_curr[t] = N;
+      }
     }
+    if (exit_now) break;
   }
   if (tid == 0 && ch.status) {
-    ch.status[0] = n_forced;
-    ch.status[1] = max_pend;
+    atomicAdd(ch.status + 0, n_forced);
+    atomicMax(ch.status + 1, max_pend);
+    atomicAdd(ch.status + 2, n_halo_forced);
+    atomicAdd(ch.status + 3, n_steps);
   }
   __syncthreads();
 }

@@ -128,6 +128,16 @@ class Session:
         self._chains = arr
         self._check(self.lib.hyg_sg_set_chains(self.ctx, arr, n), "hyg_sg_set_chains")
 
+    def set_segmentation(self, segment_sites=0, halo_left=5000, halo_right=5000):
+        """Throughput mode: cut every chain into concurrent segments of <= segment_sites sites (0 = whole chains, the
+        reference's sequential run).  See hyg_sg_set_segmentation in include/hygeia_b200.h."""
+        self._check(self.lib.hyg_sg_set_segmentation(self.ctx, int(segment_sites), int(halo_left), int(halo_right)), "hyg_sg_set_segmentation")
+
+    def filter_units(self):
+        n = C.c_uint32(0)
+        self._check(self.lib.hyg_sg_filter_units(self.ctx, C.byref(n)), "hyg_sg_filter_units")
+        return n.value
+
     def emission(self):
         self._check(self.lib.hyg_sg_emission(self.ctx), "hyg_sg_emission")
 
@@ -137,7 +147,7 @@ class Session:
 
     def download(self):
         self._check(self.lib.hyg_sg_download(self.ctx, self._chains, len(self._chains)), "hyg_sg_download")
-        return [(c.status[0], c.status[1]) for c in self._chains]
+        return [tuple(c.status) for c in self._chains]
 
     def sync(self):
         self._check(self.lib.hyg_sync(self.ctx), "hyg_sync")

@@ -72,7 +72,9 @@ typedef struct hyg_sg_chain {
   int32_t* n_curr;              /* T : particle count after site t                                            */
   int32_t* finalised_at;        /* T : step at which site t was emitted                                       */
   int16_t* ancestors;           /* T x (n_particles - R)                                                      */
-  int32_t status[2];            /* out: [0] forced emissions because the lag set was full, [1] max lag-set size */
+  int32_t status[4];            /* out: [0] forced emissions because the lag set was full, [1] max lag-set size,
+                                        [2] owned sites emitted by force at the end of a segment's right halo (segmented
+                                        execution only), [3] sites stepped through, halos included                      */
 } hyg_sg_chain;
 
 /* Algorithm switches: same meaning as the scalar arguments of runOnlineCombinedInferenceCpp (singleGroup.cpp:83-95). */
@@ -92,6 +94,19 @@ typedef struct hyg_sg_run_args {
 } hyg_sg_run_args;
 
 void hyg_sg_default_run_args(hyg_sg_run_args* args);
+
+/* Segmented execution of the recursion (throughput mode).  segment_sites = 0 (default): every chain is one sequential run from
+ * its first to its last site, exactly as OnlineCombinedInference::run (OnlineCombinedInference.h:48-118).  segment_sites > 0:
+ * every chain is cut into near-equal segments of at most segment_sites sites which run concurrently; a segment starts
+ * halo_left sites early from the R-particle initial system (Smc::initialise) -- the filter forgets its initial condition -- and
+ * runs up to halo_right sites past its end, until its last site has been finalised by the fixed-lag smoother.  Uniforms stay
+ * indexed by the site, and log Z_t is stitched from the per-segment increments.  The reference uses the same device for its
+ * two-group path (segment_size 100000, buffer_size 5000: src/two_group/run_inference_two_groups.py:64-72,195-218).  Deviation
+ * from the whole-chain run with the default halos: <= 3e-10 on the posteriors, 0 differing regime calls, <= 4e-8 absolute on
+ * log Z increments (tools/segment_study.py; GPU tests).  Ignored in parameter-estimation mode (theta evolves along the chain). */
+int hyg_sg_set_segmentation(hyg_ctx* ctx, uint64_t segment_sites, uint64_t halo_left, uint64_t halo_right);
+/* Number of (chain, segment) units the last hyg_sg_filter launched. */
+int hyg_sg_filter_units(hyg_ctx* ctx, uint32_t* n_units);
 
 /* Stage the chains (uploads injected uniforms, allocates device outputs). */
 int hyg_sg_set_chains(hyg_ctx* ctx, const hyg_sg_chain* chains, uint32_t n_chains);

@@ -311,6 +311,7 @@ inline double __longlong_as_double(long long l) { double d; std::memcpy(&d, &l, 
 inline unsigned __umulhi(unsigned a, unsigned b) { return static_cast<unsigned>((static_cast<uint64_t>(a) * b) >> 32); }
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T atomicAdd(T* p, T v) { T old = *p; *p = old + v; return old; }
+template <class T> inline T atomicMax(T* p, T v) { T old = *p; *p = old > v ? old : v; return old; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 
 struct double2 { double x, y; };

@@ -120,3 +120,45 @@ def test_parameter_estimation_underflow_regime(emu, oracle, default_model):
     assert np.allclose(got["logz"], want["logz"], rtol=1e-9)
     assert (got["k_kept"] == want["k_kept"]).mean() > 0.999
     assert got["status"][0] == 0      # no forced emissions: the lag set never filled up
+
+
+@pytest.mark.parametrize("S,lam", [(1, 10.0), (4, 30.0)])
+def test_filter_segment_view_mechanics(emu, oracle, default_model, S, lam):
+    """Segmented execution (hyg_sg_set_segmentation): a descriptor that covers sites [t_off, t_off + T) and owns a
+    sub-range must reproduce, on the owned rows, the plain algorithm run on that slice -- global Philox counters, log Z
+    relative to the site before the owned range, early exit once no owned site is pending, unowned rows untouched."""
+    from hygeia_b200 import philox, synthetic
+    T_full, a, lo_, hi_ = 700, 100, 150, 450            # slice starts at global site 100, owns global sites [250, 550)
+    ch = synthetic.make_chain(T_full, S, seed=77, lam=lam)
+    al, be = default_model["alpha_beta"]
+    lo = oracle.emission(al, be, ch["n_total"], ch["n_meth"])
+    u = philox.uniforms_by_site(5, 2, T_full)
+    want = oracle.run(default_model["vartheta"], default_model["theta"], u[a:], logobs=lo[a:])
+    got = emu.sg_filter(default_model["vartheta"], default_model["theta"], lo[a:], uniforms=None, seed=5, chain_id=2,
+                        t_off=a, own=(lo_, hi_), last_segment=False)
+    steps = int(got["status"][3])
+    assert hi_ <= steps < T_full - a, "the run must stop early, after the owned range"
+    own = slice(lo_, hi_)
+    assert (want["finalised_at"][own] < steps).all() and got["status"][2] == 0
+    assert np.array_equal(got["finalised_at"][own], want["finalised_at"][own] + a)
+    assert np.array_equal(got["k_kept"][own], want["k_kept"][own])
+    assert np.array_equal(got["drew_uniform"][own], want["drew_uniform"][own])
+    assert np.allclose(got["probs"][own], want["regime_probs"][own, 1:], rtol=1e-9, atol=1e-13)
+    assert np.allclose(got["logz"][own], want["logz"][own] - want["logz"][lo_ - 1], rtol=0, atol=1e-9)
+    assert abs(got["seg_inc"][0] - (want["logz"][hi_ - 1] - want["logz"][lo_ - 1])) < 1e-9
+    # nothing outside the owned range is written
+    assert np.isnan(got["probs"][:lo_]).all() and np.isnan(got["probs"][hi_:]).all()
+    assert (got["finalised_at"][:lo_] == -1).all() and (got["finalised_at"][hi_:] == -1).all()
+    assert (got["logz"][:lo_] == 0).all() and (got["logz"][hi_:] == 0).all()
+
+
+def test_filter_segment_right_halo_forced_is_counted(emu, oracle, default_model):
+    """If the right halo ends while owned sites are still pending they are emitted by force and counted in status[2]."""
+    g = golden("sg_sparse_s1.npz")
+    lo = g["ref_strict_logobs"]
+    pend = g["ref_strict_n_pending"]
+    t = int(np.argmax(pend[100:400] >= 2)) + 100          # a step with >= 2 pending sites
+    r = emu.sg_filter(g["vartheta"], g["theta"], lo[:t + 1], uniforms=g["uniforms"][:t + 1], own=(0, t + 1), last_segment=False)
+    assert r["status"][2] == pend[t] and r["status"][3] == t + 1
+    r = emu.sg_filter(g["vartheta"], g["theta"], lo[:t + 1], uniforms=g["uniforms"][:t + 1])
+    assert r["status"][2] == 0

@@ -282,3 +282,82 @@ def test_informative_data_underflow_regime(sess, oracle, default_model):
             assert np.isfinite(out["theta_trace"]).all()
             # ADAM amplifies rounding noise in score components that are mathematically zero (see the emulation test)
             assert np.abs(out["theta_trace"] - want["theta_trace"]).max() < 2e-6
+
+
+# ---- segmented execution (throughput mode, hyg_sg_set_segmentation) ------------------------------------------------
+def _run_two_modes(sess, default_model, chains, segment_sites, halo_left, halo_right, seeds=(3,)):
+    """chains: list of synthetic chains.  Returns (whole, segmented): lists of output dicts, one per (chain, seed)."""
+    from hygeia_b200.single_group import make_run_args
+    res = []
+    for seg in (0, segment_sites):
+        sess.clear()
+        sess.set_segmentation(seg, halo_left, halo_right)
+        sess.set_vartheta(default_model["vartheta"])
+        sess.set_theta(default_model["theta"], max(c["n_total"].shape[1] for c in chains))
+        specs, outs = [], []
+        for ci, ch in enumerate(chains):
+            ds = sess.add_dataset(ch["n_total"], ch["n_meth"])
+            T = ch["n_total"].shape[1]
+            for sd in seeds:
+                o = dict(regime_probs=np.full((T, 7), np.nan), logz=np.full(T, np.nan), k_kept=np.full(T, -9, np.int32),
+                         finalised_at=np.full(T, -1, np.int32), n_curr=np.zeros(T, np.int32))
+                outs.append(o)
+                specs.append(dict(dataset=ds, seed=sd, chain_id=ci, positions=ch["positions"], **o))
+        sess.set_chains(specs)
+        sess.emission()
+        sess.filter(make_run_args())
+        st = sess.download()
+        for o, s_ in zip(outs, st):
+            o["status"] = s_
+        res.append((outs, sess.filter_units(), sess.timings()["ms_filter"]))
+    sess.set_segmentation(0)
+    return res
+
+
+@pytest.mark.parametrize("S,lam,T", [(4, 30.0, 60000), (1, 10.0, 40000), (32, 30.0, 30000)])
+def test_segmented_matches_whole_chain(sess, oracle, default_model, S, lam, T):
+    """Throughput mode against the sequential whole-chain run (itself pinned to the reference by the tests above):
+    posteriors and log Z within the north_star tolerance (observed: 1e-10), regime calls identical, every site written
+    exactly once, no site forced at a segment end."""
+    from hygeia_b200 import synthetic
+    chains = [synthetic.make_chain(T, S, seed=90 + S, lam=lam), synthetic.make_chain(T // 3 + 17, S, seed=91 + S, lam=lam)]
+    (whole, nu_w, _), (seg, nu_s, _) = _run_two_modes(sess, default_model, chains, segment_sites=8000, halo_left=3000, halo_right=3000,
+                                                      seeds=(3, 4))
+    assert nu_w == 4 and nu_s == 2 * (-(-T // 8000) + -(-(T // 3 + 17) // 8000))
+    for w, s_ in zip(whole, seg):
+        Tn = w["logz"].shape[0]
+        assert np.isfinite(s_["regime_probs"]).all() and np.isfinite(s_["logz"]).all()
+        assert np.array_equal(s_["regime_probs"][:, 0], w["regime_probs"][:, 0])
+        assert np.abs(s_["regime_probs"][:, 1:] - w["regime_probs"][:, 1:]).max() < 1e-8
+        assert np.array_equal(s_["regime_probs"][:, 1:].argmax(1), w["regime_probs"][:, 1:].argmax(1))
+        assert np.allclose(s_["logz"], w["logz"], rtol=1e-9, atol=0)
+        assert np.array_equal(s_["finalised_at"], w["finalised_at"])
+        assert (s_["k_kept"][8000:] == w["k_kept"][8000:]).mean() > 0.999
+        assert s_["status"][0] == 0 and s_["status"][2] == 0
+        assert Tn <= w["status"][3] == Tn and Tn < s_["status"][3] < 1.5 * Tn
+
+
+def test_segmented_single_segment_is_the_whole_chain(sess, default_model):
+    """segment_sites >= T: one segment, no halo -> bit-identical to the default mode."""
+    from hygeia_b200 import synthetic
+    ch = synthetic.make_chain(5000, 2, seed=12)
+    (whole, _, _), (seg, nu, _) = _run_two_modes(sess, default_model, [ch], segment_sites=5000, halo_left=100, halo_right=100)
+    assert nu == 1
+    for k in ("regime_probs", "logz", "k_kept", "finalised_at"):
+        assert np.array_equal(whole[0][k], seg[0][k])
+
+
+def test_segmented_vs_oracle_and_short_halo_detected(sess, oracle, default_model):
+    """Against the CPU oracle directly, and: a deliberately short right halo on sparse data must be REPORTED (status[2])."""
+    from hygeia_b200 import philox, synthetic
+    T = 20000
+    ch = synthetic.make_chain(T, 1, seed=5, lam=10.0)
+    u = philox.uniforms_by_site(3, 0, T)
+    want = oracle.run(default_model["vartheta"], default_model["theta"], u, ch["n_total"], ch["n_meth"], ch["positions"])
+    (_, _, _), (seg, _, _) = _run_two_modes(sess, default_model, [ch], segment_sites=2500, halo_left=2500, halo_right=2500)
+    assert np.abs(seg[0]["regime_probs"] - want["regime_probs"]).max() < 1e-8
+    assert np.allclose(seg[0]["logz"], want["logz"], rtol=1e-9)
+    assert seg[0]["status"][2] == 0
+    (_, _, _), (short, _, _) = _run_two_modes(sess, default_model, [ch], segment_sites=2500, halo_left=2500, halo_right=2)
+    pending_at_cuts = sum(int(want["n_pending"][t - 1 + 2]) > 0 for t in range(2500, T, 2500))
+    assert pending_at_cuts > 0 and short[0]["status"][2] > 0

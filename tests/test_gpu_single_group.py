@@ -359,5 +359,6 @@ def test_segmented_vs_oracle_and_short_halo_detected(sess, oracle, default_model
     assert np.allclose(seg[0]["logz"], want["logz"], rtol=1e-9)
     assert seg[0]["status"][2] == 0
     (_, _, _), (short, _, _) = _run_two_modes(sess, default_model, [ch], segment_sites=2500, halo_left=2500, halo_right=2)
-    pending_at_cuts = sum(int(want["n_pending"][t - 1 + 2]) > 0 for t in range(2500, T, 2500))
-    assert pending_at_cuts > 0 and short[0]["status"][2] > 0
+    fa = want["finalised_at"]   # a segment [t0, t1) with halo_right = 2 ends at step t1 + 1: later finalisations are forced there
+    expected = sum(int((fa[t1 - 2500:t1] > t1 + 1).sum()) for t1 in range(2500, T, 2500))
+    assert expected > 10 and short[0]["status"][2] == expected

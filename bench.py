@@ -44,6 +44,11 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--emission-only", action="store_true", help="time K1 alone (kernel tuning aid; not a bench line)")
+    p.add_argument("--segment-sites", type=int, default=-1,
+                   help="K2 execution: -1 = segmented, size chosen by the library (default); 0 = whole chains (the reference's "
+                        "sequential run); N = segments of <= N sites")
+    p.add_argument("--halo", type=int, default=5000, help="left/right halo of a segment (sites)")
+    p.add_argument("--no-mode-check", action="store_true", help="skip the full-size comparison of segmented vs whole-chain results")
     return p.parse_args()
 
 
@@ -249,6 +254,8 @@ def main():
 
     sess = Session(local)
     run_args = make_run_args()
+    seg_request = Session.SEGMENT_AUTO if args.segment_sites < 0 else args.segment_sites
+    sess.set_segmentation(seg_request, args.halo, args.halo)
 
     def stage(device_resident):
         sess.clear()
@@ -305,6 +312,10 @@ def main():
         barrier()
         wall = time.perf_counter() - t0
     launches = tm["emission_launches"] + tm["filter_launches"]
+    n_units, seg_sites, workers = sess.filter_units(with_segment_sites=True)
+    st = sess.download()   # also brings the per-chain status words back (outside the timed region)
+    stepped = int(sum(x[3] for x in st))
+    forced_halo = int(sum(x[2] for x in st)); forced_lag = int(sum(x[0] for x in st))
     dev_s = sum(ev_ms) / 1000.0
     t_all = torch.tensor([dev_s, wall], dtype=torch.float64, device=dev)
     if world > 1:
@@ -325,20 +336,25 @@ def main():
     # log-densities and writes the R posterior probabilities and log Z_t.  It is a sequential recursion (one CTA per chain, 250
     # particles), bound by per-site latency, not by HBM -- the fraction below says how far from HBM it is, the
     # us/site figure is the number to optimise.
-    k2_alg = total_T * n_seeds * (R * 8 + R * 8 + 8)   # + the running log-evidence
+    k2_alg = total_T * n_seeds * (R * 8 + R * 8 + 8)   # + the running log-evidence (owned rows only: halo steps are overhead)
     k2_ms = float(np.mean(f_ms))
     k2_ach = k2_alg / (k2_ms / 1000.0) / 1e9
     # DRAM bytes per site measured by ncu --set full (profiles/r01_ncu_full_k1_k2_details.txt, 3M-site capture), scaled
     K2_DRAM_B_PER_SITE_CHAIN, K1_DRAM_B_PER_SITE = 129.3, 176.4
-    roofline = {"bound": "hbm", "kernel": "sg_filter_kernel<6,0> (K2: particle filter + fixed-lag smoother), 1 launch per step, one CTA per chain",
+    roofline = {"bound": "hbm", "kernel": "sg_filter_kernel<6,0> (K2: particle filter + fixed-lag smoother), 1 persistent launch per step, "
+                                          "one CTA per (chain, segment) unit",
                 "share_of_step": k2_ms / (k2_ms + float(np.mean(em_ms))),
                 "achieved": k2_ach, "peak": peak, "unit": "GB/s", "frac": k2_ach / peak, "peak_source": peak_source,
                 "algorithmic_bytes_per_launch": k2_alg, "ms_per_launch": k2_ms,
                 "traffic": K2_DRAM_B_PER_SITE_CHAIN * total_T * n_seeds,
                 "traffic_source": "ncu dram__bytes_read+write of a 3M-site capture, per site-chain, scaled to this launch",
-                "latency_bound": {"chains": n_chains, "sms": 148, "longest_chain_sites": longest,
-                                  "us_per_site_longest_chain": 1000.0 * k2_ms / longest,
-                                  "note": "step time = the longest chromosome's chain; HBM is idle, see DESIGN.md section 6"}}
+                "latency_bound": {"chains": n_chains, "units": n_units, "segment_sites": seg_sites, "halo_sites": args.halo if seg_sites else 0,
+                                  "resident_ctas": workers, "sms": 148, "longest_chain_sites": longest,
+                                  "sites_stepped_incl_halos": stepped, "halo_overhead": stepped / float(total_T * n_seeds) - 1.0,
+                                  "us_per_site_per_cta": 1000.0 * k2_ms * workers / max(stepped, 1),
+                                  "sites_forced_at_segment_end": forced_halo, "sites_forced_lag_set_full": forced_lag,
+                                  "note": "a strictly sequential recursion per unit: the bound is per-site latency x units in flight, "
+                                          "HBM is idle; see DESIGN.md section 4 (K2) and 6"}}
     # K1, the HBM-streaming kernel north_star sets the roofline target for
     alg_bytes = total_T * S * 2 * 2 + total_T * R * 8
     ach = alg_bytes / (float(np.mean(em_ms)) / 1000.0) / 1e9
@@ -380,6 +396,33 @@ def main():
         e2e["regime_call_accuracy_vs_simulated_truth_last_chromosome"] = acc
         e2e["non_finite_posterior_rows"] = int(sum(int((~np.isfinite(o["probs"].numpy())).any(1).sum()) for c in chroms for o in c["out"]))
 
+    # ---- full-size parity of the two execution modes: segmented (timed above) vs the sequential whole-chain run ----
+    mode_check = None
+    if e2e is not None and seg_sites and not args.no_mode_check:
+        seg_out = [[(o["probs"].numpy().copy(), o["logz"].numpy().copy()) for o in c["out"]] for c in chroms[-3:]]
+        sess.set_segmentation(0, args.halo, args.halo)
+        sub = chroms[-3:]   # the three shortest chromosomes, every seed: whole-chain runs of 0.4-0.75 M sites
+        sess.clear(); sess.set_vartheta(vartheta); sess.set_theta(theta, max(c["T"] for c in chroms))
+        specs = []
+        for ci, c in enumerate(sub):
+            ds = sess.add_dataset_ptr(c["T"], S, c["h_nt"].data_ptr(), c["h_nm"].data_ptr(), False, c["T"])
+            for k, sd in enumerate(seeds):
+                specs.append(dict(dataset=ds, seed=sd, chain_id=len(chroms) - 3 + ci, positions=c["h_pos"].data_ptr(),
+                                  regime_probs=c["out"][k]["probs"].data_ptr(), logz=c["out"][k]["logz"].data_ptr()))
+        sess.set_chains(specs); sess.emission(); sess.filter(run_args); sess.download()
+        whole_ms = sess.timings()["ms_filter"]
+        dp = dz = 0.0; calls = 0; rows = 0
+        for c, so in zip(sub, seg_out):
+            for o, (sp, sz) in zip(c["out"], so):
+                wp, wz = o["probs"].numpy(), o["logz"].numpy()
+                dp = max(dp, float(np.abs(sp[:, 1:] - wp[:, 1:]).max()))
+                dz = max(dz, float((np.abs(sz - wz) / np.abs(wz)).max()))
+                calls += int((sp[:, 1:].argmax(1) != wp[:, 1:].argmax(1)).sum()); rows += wp.shape[0]
+        mode_check = {"compared": f"segmented vs whole-chain execution on the 3 shortest chromosomes x {n_seeds} seeds ({rows} site rows)",
+                      "max_abs_posterior_diff": dp, "max_rel_logz_diff": dz, "differing_regime_calls": calls, "tolerance": 1e-6,
+                      "whole_chain_us_per_site": 1000.0 * whole_ms / max(c["T"] for c in sub)}
+        sess.set_segmentation(seg_request, args.halo, args.halo)
+
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -393,10 +436,12 @@ def main():
                 "config": {"workload": f"single_group whole-genome synthetic (~{args.total_sites // 1_000_000}M CpGs in 22 chromosomes), "
                                        f"{S} samples, {n_seeds} seeds per GPU ({n_seeds * world} seeds total), 250 particles, u=3",
                            "sites": total_T, "samples": S, "seeds": n_seeds * world, "chains_per_gpu": n_chains,
+                           "k2_execution": (f"segmented: {n_units} units of <= {seg_sites} sites + {args.halo}-site halos, all resident CTAs busy"
+                                            if seg_sites else "whole chains (sequential per chromosome x seed)"),
                            "l2": "inputs (3.6 GB counts + 1.3 GB emission table per GPU) exceed the 126 MB L2; no flush needed",
                            "parallelism": f"seeds sharded over {world} GPU(s), no data-path collective"},
                 "gpu_launches": int(launches) * args.steps, "clocks": clk.summary(), "roofline": roofline, "roofline_emission": roofline_emission,
-                "e2e": e2e, "cpu_baseline": cpu}
+                "e2e": e2e, "mode_check": mode_check, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libhygeia_b200.so")
+LIB_PATH = os.environ.get("HYGEIA_B200_LIB") or os.path.join(HERE, "csrc", "libhygeia_b200.so")   # override: kernel-variant experiments
 
 # every symbol include/hygeia_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
@@ -86,7 +86,7 @@ def load():
     lib.hyg_sg_default_run_args.argtypes = [C.POINTER(HygRunArgs)]
     lib.hyg_sg_set_chains.argtypes = [C.c_void_p, C.POINTER(HygChain), C.c_uint32]
     lib.hyg_sg_set_segmentation.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]
-    lib.hyg_sg_filter_units.argtypes = [C.c_void_p, C.POINTER(C.c_uint32)]
+    lib.hyg_sg_filter_units.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)]
     lib.hyg_sg_emission.argtypes = [C.c_void_p]
     lib.hyg_sg_filter.argtypes = [C.c_void_p, C.POINTER(HygRunArgs)]
     lib.hyg_sg_download.argtypes = [C.c_void_p, C.POINTER(HygChain), C.c_uint32]

@@ -12,6 +12,8 @@
 #include <cstring>
 #include <map>
 #include <numeric>
+#include <queue>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -87,6 +89,8 @@ struct hyg_ctx {
   hyg::SgLogzFix* d_fix = nullptr;
   size_t d_fix_cap = 0;
   uint32_t n_units_last = 0;
+  uint64_t seg_sites_last = 0;
+  uint32_t grid_last = 0;
   uint32_t n_particles_staged = 0;
   std::multimap<size_t, void*> pool_free_blocks;
   std::map<void*, size_t> pool_live;
@@ -199,6 +203,31 @@ __global__ void sg_logz_fix_kernel(const hyg::SgLogzFix* units, unsigned int n_u
     for (unsigned long long t = threadIdx.x; t < f.len; t += blockDim.x) f.logz[t] += off;
     __syncthreads();
   }
+}
+
+// Segment size for HYG_SEGMENT_AUTO: the candidate (multiples of halo_left / 2) whose units, handed longest-first to `workers`
+// persistent CTAs, finish earliest.  Cost of a unit = its sites + the left halo it has to step through first.
+uint64_t choose_segment_sites(const std::vector<uint64_t>& chain_T, uint64_t halo_left, int workers) {
+  uint64_t longest = 0;
+  for (uint64_t T : chain_T) longest = std::max(longest, T);
+  if (workers < 1) workers = 1;
+  const uint64_t step = std::max<uint64_t>(halo_left, 256);
+  uint64_t best_seg = 0, best_span = longest;   // whole chains: the longest chain bounds the launch
+  if (chain_T.size() >= static_cast<size_t>(workers) * 4) return 0;   // enough independent chains already
+  for (uint64_t seg = 2 * step; seg < longest + step; seg += step / 2) {
+    std::vector<uint64_t> units;
+    for (uint64_t T : chain_T) {
+      const uint64_t ns = (T + seg - 1) / seg, len = (T + ns - 1) / ns;
+      for (uint64_t j = 0; j < ns && j * len < T; j++) units.push_back(std::min(len, T - j * len) + (j ? halo_left : 0));
+    }
+    std::sort(units.begin(), units.end(), std::greater<uint64_t>());
+    std::priority_queue<uint64_t, std::vector<uint64_t>, std::greater<uint64_t>> load;
+    for (int w = 0; w < workers; w++) load.push(0);
+    uint64_t span = 0;
+    for (uint64_t u : units) { uint64_t l = load.top() + u; load.pop(); load.push(l); span = std::max(span, l); }
+    if (span < best_span) { best_span = span; best_seg = seg; }
+  }
+  return best_seg;
 }
 
 template <int R> int launch_emission(hyg_ctx* c, const hyg::SgEmissionArgs& a, size_t smem, int grid) {
@@ -415,16 +444,18 @@ void hyg_sg_default_run_args(hyg_sg_run_args* a) {
 
 int hyg_sg_set_segmentation(hyg_ctx* c, uint64_t segment_sites, uint64_t halo_left, uint64_t halo_right) {
   if (!c) return HYG_ERR_ARG;
-  if (segment_sites > 0 && segment_sites < 16) return fail(c, HYG_ERR_ARG, "segment_sites must be 0 (whole chains) or >= 16");
+  if (segment_sites != HYG_SEGMENT_AUTO && segment_sites > 0 && segment_sites < 16) return fail(c, HYG_ERR_ARG, "segment_sites must be 0 (whole chains) or >= 16");
   c->seg_sites = segment_sites;
   c->seg_halo_left = halo_left;
   c->seg_halo_right = halo_right;
   return HYG_OK;
 }
 
-int hyg_sg_filter_units(hyg_ctx* c, uint32_t* n_units) {
-  if (!c || !n_units) return HYG_ERR_ARG;
-  *n_units = c->n_units_last;
+int hyg_sg_filter_units(hyg_ctx* c, uint32_t* n_units, uint64_t* segment_sites, uint32_t* resident_ctas) {
+  if (!c) return HYG_ERR_ARG;
+  if (n_units) *n_units = c->n_units_last;
+  if (resident_ctas) *resident_ctas = c->grid_last;
+  if (segment_sites) *segment_sites = c->seg_sites_last;
   return HYG_OK;
 }
 
@@ -553,15 +584,28 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
     HYG_CUDA(c, cudaStreamSynchronize(c->stream));
   }
 
+  int occ = 1;
+  if (pe_mode) { HYG_DISPATCH_R6(R, (filter_occupancy<RR, true>(&occ))); }
+  else { HYG_DISPATCH_R(R, (filter_occupancy<RR, false>(&occ))); }
+  if (occ < 1) occ = 1;
+  const int workers = c->num_sms * occ;
+  uint64_t seg_sites = pe_mode ? 0 : c->seg_sites;
+  if (seg_sites == HYG_SEGMENT_AUTO) {
+    std::vector<uint64_t> lens;
+    for (auto& b : c->chains) lens.push_back(b.T);
+    seg_sites = choose_segment_sites(lens, c->seg_halo_left, workers);
+  }
+  c->seg_sites_last = seg_sites;
+
   // chain descriptors in launch order.  Whole-chain execution: one descriptor per chain.  Segmented execution
   // (hyg_sg_set_segmentation; not in parameter mode, where theta evolves along the chain): every chain is cut into
   // near-equal segments of <= seg_sites owned sites; a segment starts seg_halo_left sites early from the R-particle initial
   // system (the filter forgets it) and may run up to seg_halo_right sites past its end until its last owned site settles.
-  const bool segmented = c->seg_sites > 0 && !pe_mode;
+  const bool segmented = seg_sites > 0;
   std::vector<hyg::SgChainDev> cd;
   std::vector<hyg::SgLogzFix> fix;
   for (auto& b : c->chains) {
-    b.n_seg = segmented ? static_cast<uint32_t>((b.T + c->seg_sites - 1) / c->seg_sites) : 1u;
+    b.n_seg = segmented ? static_cast<uint32_t>((b.T + seg_sites - 1) / seg_sites) : 1u;
     if (b.n_seg < 1) b.n_seg = 1;
     HYG_CUDA(c, cudaMemsetAsync(b.d_status, 0, 4 * sizeof(int), c->stream));
     if (b.n_seg > 1 && b.seginc_cap < b.n_seg) {
@@ -621,12 +665,8 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
   }
   HYG_CUDA(c, cudaStreamSynchronize(c->stream));  // cd / fix are pageable
   c->n_units_last = n_units;
-
-  int occ = 1;
-  if (pe_mode) { HYG_DISPATCH_R6(R, (filter_occupancy<RR, true>(&occ))); }
-  else { HYG_DISPATCH_R(R, (filter_occupancy<RR, false>(&occ))); }
-  if (occ < 1) occ = 1;
-  const int grid = static_cast<int>(std::min<uint64_t>(n_units, static_cast<uint64_t>(c->num_sms) * occ));
+  const int grid = static_cast<int>(std::min<uint64_t>(n_units, static_cast<uint64_t>(workers)));
+  c->grid_last = static_cast<uint32_t>(grid);
 
   hyg::SgRunDev run;
   run.use_smoothing = args->use_online_marginal_smoothing ? 1 : 0;

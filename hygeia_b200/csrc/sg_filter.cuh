@@ -917,9 +917,12 @@ __device__ __forceinline__ void sg_filter_entry(const SgModelDev* mdl, const SgC
   }
 }
 
+#ifndef HYG_K2_MIN_CTAS
+#define HYG_K2_MIN_CTAS 2   // resident CTAs per SM the register budget is held to (K2 is latency-bound: a second chain fills idle issue slots)
+#endif
 #ifndef HYG_EMU
 template <int RT, bool PE>
-__global__ void __launch_bounds__(HYG_NT, 1) sg_filter_kernel(const SgModelDev* mdl, const SgChainDev* chains, SgRunDev run) {
+__global__ void __launch_bounds__(HYG_NT, PE ? 1 : HYG_K2_MIN_CTAS) sg_filter_kernel(const SgModelDev* mdl, const SgChainDev* chains, SgRunDev run) {
   sg_filter_entry<RT, PE>(mdl, chains, run);
 }
 #endif

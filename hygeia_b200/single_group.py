@@ -128,15 +128,18 @@ class Session:
         self._chains = arr
         self._check(self.lib.hyg_sg_set_chains(self.ctx, arr, n), "hyg_sg_set_chains")
 
+    SEGMENT_AUTO = 0xFFFFFFFFFFFFFFFF
+
     def set_segmentation(self, segment_sites=0, halo_left=5000, halo_right=5000):
         """Throughput mode: cut every chain into concurrent segments of <= segment_sites sites (0 = whole chains, the
         reference's sequential run).  See hyg_sg_set_segmentation in include/hygeia_b200.h."""
         self._check(self.lib.hyg_sg_set_segmentation(self.ctx, int(segment_sites), int(halo_left), int(halo_right)), "hyg_sg_set_segmentation")
 
-    def filter_units(self):
-        n = C.c_uint32(0)
-        self._check(self.lib.hyg_sg_filter_units(self.ctx, C.byref(n)), "hyg_sg_filter_units")
-        return n.value
+    def filter_units(self, with_segment_sites=False):
+        """Units of the last filter launch; with_segment_sites: (units, segment size used, persistent CTAs)."""
+        n, seg, g = C.c_uint32(0), C.c_uint64(0), C.c_uint32(0)
+        self._check(self.lib.hyg_sg_filter_units(self.ctx, C.byref(n), C.byref(seg), C.byref(g)), "hyg_sg_filter_units")
+        return (n.value, seg.value, g.value) if with_segment_sites else n.value
 
     def emission(self):
         self._check(self.lib.hyg_sg_emission(self.ctx), "hyg_sg_emission")

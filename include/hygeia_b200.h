@@ -104,9 +104,11 @@ void hyg_sg_default_run_args(hyg_sg_run_args* args);
  * two-group path (segment_size 100000, buffer_size 5000: src/two_group/run_inference_two_groups.py:64-72,195-218).  Deviation
  * from the whole-chain run with the default halos: <= 3e-10 on the posteriors, 0 differing regime calls, <= 4e-8 absolute on
  * log Z increments (tools/segment_study.py; GPU tests).  Ignored in parameter-estimation mode (theta evolves along the chain). */
+#define HYG_SEGMENT_AUTO UINT64_MAX  /* segment size chosen per launch so that the resident CTAs of the device finish together */
 int hyg_sg_set_segmentation(hyg_ctx* ctx, uint64_t segment_sites, uint64_t halo_left, uint64_t halo_right);
-/* Number of (chain, segment) units the last hyg_sg_filter launched. */
-int hyg_sg_filter_units(hyg_ctx* ctx, uint32_t* n_units);
+/* Number of (chain, segment) units the last hyg_sg_filter launched, the segment size it used (0 = whole chains) and the
+ * number of persistent CTAs that shared the units (any pointer may be NULL). */
+int hyg_sg_filter_units(hyg_ctx* ctx, uint32_t* n_units, uint64_t* segment_sites, uint32_t* resident_ctas);
 
 /* Stage the chains (uploads injected uniforms, allocates device outputs). */
 int hyg_sg_set_chains(hyg_ctx* ctx, const hyg_sg_chain* chains, uint32_t n_chains);

@@ -389,7 +389,9 @@ def main():
         e2e_s = float(te[0])
         e2e = {"value": units_per_step * world * args.e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": 1000.0 * e2e_s / args.e2e_steps, "steps": args.e2e_steps,
-               "api": "hygeia_b200.single_group.Session: add_dataset(host) -> set_chains -> emission -> filter -> download"}
+               "api": "hygeia_b200.single_group.Session: add_dataset(pinned host) -> set_chains -> emission -> filter -> download; "
+                      "posterior rows are written by K2 straight into the pinned host buffers (counted in d2h_bytes_per_step), "
+                      "log Z is staged in HBM and copied"}
         # sanity on the downloaded results of the last step
         p = chroms[-1]["out"][0]["probs"].numpy()
         acc = float((p[:, 1:].argmax(1) == chroms[-1]["regimes"]).mean())

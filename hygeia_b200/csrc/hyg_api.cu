@@ -45,6 +45,7 @@ struct ChainBuf {
   double* d_unif = nullptr;
   uint32_t* d_pos = nullptr;
   double* d_probs = nullptr;
+  bool probs_mapped = false;   // d_probs aliases the caller's pinned host buffer: rows stream out of K2, nothing to download
   double* d_logz = nullptr;
   int* d_k = nullptr;
   unsigned char* d_drew = nullptr;
@@ -88,6 +89,7 @@ struct hyg_ctx {
   uint64_t seg_sites = 0, seg_halo_left = 5000, seg_halo_right = 5000;   // hyg_sg_set_segmentation (0 = whole chains)
   hyg::SgLogzFix* d_fix = nullptr;
   size_t d_fix_cap = 0;
+  bool zero_copy_out = true;
   uint32_t n_units_last = 0;
   uint64_t seg_sites_last = 0;
   uint32_t grid_last = 0;
@@ -166,6 +168,7 @@ void pool_release(hyg_ctx* c) {
 
 void free_chains(hyg_ctx* c) {
   for (auto& b : c->chains) {
+    if (b.probs_mapped) b.d_probs = nullptr;
     pool_free(c, b.d_unif); pool_free(c, b.d_pos); pool_free(c, b.d_probs); pool_free(c, b.d_logz); pool_free(c, b.d_k);
     pool_free(c, b.d_drew); pool_free(c, b.d_npend); pool_free(c, b.d_ncurr); pool_free(c, b.d_fin); pool_free(c, b.d_anc);
     pool_free(c, b.d_status); pool_free(c, b.d_trace); pool_free(c, b.d_seginc);
@@ -180,12 +183,6 @@ void free_datasets(hyg_ctx* c) {
     pool_free(c, d.d_logobs);
   }
   c->ds.clear();
-}
-
-__global__ void fill_positions_kernel(double* probs, const uint32_t* pos, unsigned long long T, int stride) {
-  for (unsigned long long t = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; t < T;
-       t += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
-    probs[t * stride] = pos ? static_cast<double>(pos[t]) : static_cast<double>(t);
 }
 
 // Segmented execution: shift the rows of segment j >= 1 by the log Z accumulated over the segments before it.
@@ -451,6 +448,12 @@ int hyg_sg_set_segmentation(hyg_ctx* c, uint64_t segment_sites, uint64_t halo_le
   return HYG_OK;
 }
 
+int hyg_sg_set_zero_copy_outputs(hyg_ctx* c, int enable) {
+  if (!c) return HYG_ERR_ARG;
+  c->zero_copy_out = enable != 0;
+  return HYG_OK;
+}
+
 int hyg_sg_filter_units(hyg_ctx* c, uint32_t* n_units, uint64_t* segment_sites, uint32_t* resident_ctas) {
   if (!c) return HYG_ERR_ARG;
   if (n_units) *n_units = c->n_units_last;
@@ -478,7 +481,17 @@ int hyg_sg_set_chains(hyg_ctx* c, const hyg_sg_chain* chains, uint32_t n) {
       HYG_CUDA(c, cudaMemcpyAsync(b.d_unif, chains[i].uniforms, T * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     }
     if (chains[i].regime_probs) {
-      HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_probs), T * (R + 1) * sizeof(double)));
+      // pinned (page-locked) caller memory is addressable from the device: K2 then writes every finalised row straight into
+      // it (56 contiguous bytes per row, posted writes over PCIe at ~3 GB/s of the link's ~55) and there is no D2H stage
+      cudaPointerAttributes pa;
+      std::memset(&pa, 0, sizeof(pa));
+      if (c->zero_copy_out && cudaPointerGetAttributes(&pa, chains[i].regime_probs) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
+        b.d_probs = static_cast<double*>(pa.devicePointer);
+        b.probs_mapped = true;
+      } else {
+        cudaGetLastError();
+        HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_probs), T * (R + 1) * sizeof(double)));
+      }
       if (chains[i].positions) {
         HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_pos), T * sizeof(uint32_t)));
         HYG_CUDA(c, cudaMemcpyAsync(b.d_pos, chains[i].positions, T * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
@@ -630,6 +643,7 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
       d.logobs = c->ds[b.host.dataset].d_logobs + a * R;
       d.unif = b.d_unif ? b.d_unif + a : nullptr; d.seed = b.host.seed; d.chain_id = b.host.chain_id;
       d.probs = (args->use_online_marginal_smoothing && b.d_probs) ? b.d_probs + a * (R + 1) : nullptr;
+      d.pos = b.d_pos ? b.d_pos + a : nullptr;
       d.logz = b.d_logz ? b.d_logz + a : nullptr;
       d.k_kept = b.d_k ? b.d_k + a : nullptr; d.drew = b.d_drew ? b.d_drew + a : nullptr;
       d.n_pending = b.d_npend ? b.d_npend + a : nullptr; d.n_curr = b.d_ncurr ? b.d_ncurr + a : nullptr;
@@ -705,13 +719,6 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
 
   c->f_launches = 0;
   HYG_CUDA(c, cudaEventRecord(c->ev_f0, c->stream));
-  if (run.use_smoothing) {
-    for (auto& b : c->chains)
-      if (b.d_probs) {
-        fill_positions_kernel<<<c->num_sms, 256, 0, c->stream>>>(b.d_probs, b.d_pos, b.T, R + 1);
-        c->f_launches++;
-      }
-  }
   int rc = HYG_ERR_UNSUPPORTED;
   if (pe_mode) { HYG_DISPATCH_R6(R, (rc = launch_filter<RR, true>(c, run, grid))); }
   else { HYG_DISPATCH_R(R, (rc = launch_filter<RR, false>(c, run, grid))); }
@@ -736,7 +743,7 @@ int hyg_sg_download(hyg_ctx* c, hyg_sg_chain* chains, uint32_t n) {
     ChainBuf& b = c->chains[i];
     const hyg_sg_chain& h = b.host;
     const uint64_t T = b.T;
-    if (h.regime_probs && b.d_probs) HYG_CUDA(c, cudaMemcpyAsync(h.regime_probs, b.d_probs, T * (R + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (h.regime_probs && b.d_probs && !b.probs_mapped) HYG_CUDA(c, cudaMemcpyAsync(h.regime_probs, b.d_probs, T * (R + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (h.logz) HYG_CUDA(c, cudaMemcpyAsync(h.logz, b.d_logz, T * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (h.k_kept) HYG_CUDA(c, cudaMemcpyAsync(h.k_kept, b.d_k, T * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (h.drew_uniform) HYG_CUDA(c, cudaMemcpyAsync(h.drew_uniform, b.d_drew, T, cudaMemcpyDeviceToHost, c->stream));

@@ -33,7 +33,9 @@ struct SgChainDev {
   const double* unif;     // T injected uniforms (device) or null -> Philox(seed, chain_id, t)
   unsigned long long seed;
   uint32_t chain_id;
-  double* probs;          // T x (1+R) rows (position, p_1..p_R): the kernel writes columns 1..R (device) or null
+  double* probs;          // T x (1+R) rows (position, p_1..p_R), written whole -- device memory, or pinned host memory mapped
+                          // into the device address space (the rows then stream to the host as sites are finalised) -- or null
+  const uint32_t* pos;    // T genomic positions (device) or null -> global site index
   double* logz;           // T running log Z_t (device) or null
   // optional step-level taps for parity tests (device, may be null)
   int* k_kept;            // T : K of optimal resampling; -1 growth; -2 keep-largest

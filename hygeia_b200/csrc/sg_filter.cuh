@@ -330,10 +330,14 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
     p.W = mine / e[0];
   }
 
+  double pos_nxt = (tid == 0) ? (ch.pos ? static_cast<double>(__ldg(ch.pos)) : static_cast<double>(t_off)) : 0.0;
   for (unsigned long long t = 0; t < T; t++) {
     const double* lo = s.lo[t & 1];
     // emission row of site t+2: issued now by the service warp, stored at the end of this step
     const double lo_pref = (service && lane < R && t + 2 < T) ? __ldg(ch.logobs + (t + 2) * R + lane) : 0.0;
+    // genomic position of the next site, loaded a step ahead by the thread that writes column 0 of the posterior rows
+    const double pos_cur = pos_nxt;
+    if (tid == 0 && t + 1 < T) pos_nxt = ch.pos ? static_cast<double>(__ldg(ch.pos + t + 1)) : static_cast<double>(t + 1 + t_off);
     int k_kept = -1;
     bool drew = false;
     bool emit_now = false;       // current site finalised at this step
@@ -663,8 +667,12 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           if (emit) {
             const bool own_s = (static_cast<unsigned long long>(ts) >= own_lo) && (static_cast<unsigned long long>(ts) < own_hi);
             if (own_s) {
-              const double outv = pick<2 * R>(mv, tid);
-              if (tid < R && ch.probs) ch.probs[static_cast<size_t>(ts) * (R + 1) + 1 + tid] = outv;
+              // whole row (position, p_1..p_R) in one store instruction: 56 contiguous bytes, also when the row goes to mapped host memory
+              if (tid <= R && ch.probs) {
+                const double outv = (tid == 0) ? (ch.pos ? static_cast<double>(ch.pos[ts]) : static_cast<double>(static_cast<unsigned long long>(ts) + t_off))
+                                               : pick<2 * R>(mv, tid - 1);
+                ch.probs[static_cast<size_t>(ts) * (R + 1) + tid] = outv;
+              }
               if (tid == 0 && ch.finalised_at) ch.finalised_at[ts] = static_cast<int>(t + t_off);
               if (!settled && !last_seg) n_halo_forced++;   // the segment's right halo ended before this site settled
             }
@@ -795,7 +803,10 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       if (!emit_now && n_pend >= lcap) { emit_now = true; n_forced += own_t ? 1 : 0; }  // lag set full: emit the filtering estimate now (reported)
       if (emit_now) {
         if (own_t) {
-          if (tid < R && ch.probs) ch.probs[static_cast<size_t>(t) * (R + 1) + 1 + tid] = cw_lane;  // lanes 0..R-1 of warp 0
+          if (warp == 0 && ch.probs) {
+            const double left = __shfl_up_sync(HYG_FULL, cw_lane, 1);   // lane j >= 1: mass of regime j-1
+            if (lane <= R) ch.probs[static_cast<size_t>(t) * (R + 1) + lane] = (lane == 0) ? pos_cur : left;
+          }
           if (tid == 0 && ch.finalised_at) ch.finalised_at[t] = static_cast<int>(t + t_off);
           if (t == T - 1 && !settled && !last_seg) n_halo_forced++;
         }

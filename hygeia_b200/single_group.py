@@ -135,6 +135,10 @@ class Session:
         reference's sequential run).  See hyg_sg_set_segmentation in include/hygeia_b200.h."""
         self._check(self.lib.hyg_sg_set_segmentation(self.ctx, int(segment_sites), int(halo_left), int(halo_right)), "hyg_sg_set_segmentation")
 
+    def set_zero_copy_outputs(self, enable=True):
+        """Pinned ``regime_probs`` buffers are written by the kernel directly (no D2H stage); False forces staging."""
+        self._check(self.lib.hyg_sg_set_zero_copy_outputs(self.ctx, int(bool(enable))), "hyg_sg_set_zero_copy_outputs")
+
     def filter_units(self, with_segment_sites=False):
         """Units of the last filter launch; with_segment_sites: (units, segment size used, persistent CTAs)."""
         n, seg, g = C.c_uint32(0), C.c_uint64(0), C.c_uint32(0)

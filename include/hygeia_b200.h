@@ -62,7 +62,9 @@ typedef struct hyg_sg_chain {
   const double* uniforms;       /* ... unless T injected per-site uniforms are given (host pointer, may be NULL) */
   const uint32_t* positions;    /* T genomic positions (host) or NULL -> 0..T-1; first column of regime_probs */
   /* outputs, host pointers, any may be NULL */
-  double* regime_probs;         /* T x (1+R) row-major: position, p_1..p_R  (= regimeProbabilityEstimates)   */
+  double* regime_probs;         /* T x (1+R) row-major: position, p_1..p_R  (= regimeProbabilityEstimates).  If this is
+                                   pinned (page-locked) memory the kernel writes the rows straight into it as sites are
+                                   finalised and hyg_sg_download only synchronises; pageable memory is staged + copied */
   double* logz;                 /* T : running log normalising constant after site t                          */
   double* theta_trace;          /* T x D (parameter-estimation mode)                                          */
   /* step-level taps for parity tests, host pointers, any may be NULL */
@@ -106,6 +108,8 @@ void hyg_sg_default_run_args(hyg_sg_run_args* args);
  * log Z increments (tools/segment_study.py; GPU tests).  Ignored in parameter-estimation mode (theta evolves along the chain). */
 #define HYG_SEGMENT_AUTO UINT64_MAX  /* segment size chosen per launch so that the resident CTAs of the device finish together */
 int hyg_sg_set_segmentation(hyg_ctx* ctx, uint64_t segment_sites, uint64_t halo_left, uint64_t halo_right);
+/* Pinned regime_probs buffers are written by the kernel directly (default on); 0 forces device staging + a D2H copy. */
+int hyg_sg_set_zero_copy_outputs(hyg_ctx* ctx, int enable);
 /* Number of (chain, segment) units the last hyg_sg_filter launched, the segment size it used (0 = whole chains) and the
  * number of persistent CTAs that shared the units (any pointer may be NULL). */
 int hyg_sg_filter_units(hyg_ctx* ctx, uint32_t* n_units, uint64_t* segment_sites, uint32_t* resident_ctas);

@@ -362,3 +362,35 @@ def test_segmented_vs_oracle_and_short_halo_detected(sess, oracle, default_model
     fa = want["finalised_at"]   # a segment [t0, t1) with halo_right = 2 ends at step t1 + 1: later finalisations are forced there
     expected = sum(int((fa[t1 - 2500:t1] > t1 + 1).sum()) for t1 in range(2500, T, 2500))
     assert expected > 10 and short[0]["status"][2] == expected
+
+
+def test_pinned_outputs_are_written_by_the_kernel(sess, default_model):
+    """regime_probs in pinned host memory: K2 streams the rows into it (no staging, no D2H); results identical to the staged
+    path (pageable buffers), in whole-chain and in segmented execution."""
+    import torch
+    from hygeia_b200 import synthetic
+    from hygeia_b200.single_group import make_run_args
+    T = 30000
+    ch = synthetic.make_chain(T, 4, seed=21)
+    res = {}
+    for seg in (0, 6000):
+        for pinned in (False, True):
+            sess.clear()
+            sess.set_segmentation(seg, 3000, 3000)
+            sess.set_vartheta(default_model["vartheta"]); sess.set_theta(default_model["theta"], T)
+            ds = sess.add_dataset(ch["n_total"], ch["n_meth"])
+            if pinned:
+                tp = torch.full((T, 7), float("nan"), dtype=torch.float64).pin_memory()
+                probs, ptr = tp.numpy(), tp.data_ptr()
+            else:
+                probs = np.full((T, 7), np.nan); ptr = probs
+            logz = np.zeros(T)
+            sess.set_chains([dict(dataset=ds, seed=2, chain_id=0, positions=ch["positions"], regime_probs=ptr, logz=logz)])
+            sess.emission(); sess.filter(make_run_args()); sess.download()
+            assert np.isfinite(probs).all()
+            res[(seg, pinned)] = (probs.copy(), logz.copy())
+    sess.set_segmentation(0)
+    for seg in (0, 6000):
+        assert np.array_equal(res[(seg, True)][0], res[(seg, False)][0])
+        assert np.array_equal(res[(seg, True)][1], res[(seg, False)][1])
+    assert np.array_equal(res[(0, True)][0][:, 0], ch["positions"].astype(np.float64))

@@ -248,6 +248,102 @@ template <bool PE, class T> __device__ __forceinline__ T tab_load(const T* p) {
   return __ldg(p);
 }
 
+// Lag-set update of one site: psi of every pending site is propagated to the new particle system and sites whose R filtered
+// variances dropped below epsilon are emitted (OnlineMarginalSmoothing.h:148-255).  Returns the number of sites still pending.
+template <int R> struct SgLagArgs {
+  const double* pp;   // psi written at step t-1
+  double* pc;         // psi of step t
+  int* pend_t;
+  int n_pend, N_prev, M, N_curr, anc, pr;
+  double e_prev, cW, my_invE;
+  unsigned slowmask;
+  double bk_slow[R];
+  unsigned long long t, T, own_lo, own_hi, t_off;
+  bool last_seg, worker;
+  double epsilon;
+};
+
+template <int R>
+__device__ __noinline__ int sg_lag_update(const SgLagArgs<R>& a, const SgModelDev& mdl, const SgChainDev& ch, SgSmem& s, int& flip, int& n_halo_forced) {
+  const int tid = threadIdx.x;
+  const int N_prev = a.N_prev, M = a.M, N_curr = a.N_curr, anc = a.anc;
+  int kept = 0;
+  for (int i = 0; i < a.n_pend; i++) {
+    const double* src = a.pp + static_cast<size_t>(i) * R * HYG_NPMAX;
+    double own[R], val[R];
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      own[q] = (tid < N_prev) ? src[q * HYG_NPMAX + tid] : 0.0;
+      val[q] = (tid < M) ? src[q * HYG_NPMAX + anc] : 0.0;
+    }
+    // class sums G[q][r'] = sum_{n in class r'} e_n psi_q[n]; new particle (1,r): sum_{r'} P[r'][r] G[q][r'] / sumE[r]
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      double g[R];
+#pragma unroll
+      for (int rp = 0; rp < R; rp++) g[rp] = (a.pr == rp) ? a.e_prev * own[q] : 0.0;
+      block_sum<R>(g, s.sc, flip);
+      if (tid >= M && tid < N_curr) {
+        const int r = tid - M;
+        double acc = 0.0;
+#pragma unroll
+        for (int rp = 0; rp < R; rp++) acc += (rp != r) ? mdl.P[rp][r] * g[rp] : 0.0;
+        val[q] = acc * a.my_invE;
+      }
+    }
+    if (a.slowmask) {
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        if (!((a.slowmask >> r) & 1u)) continue;
+        double g[R];
+#pragma unroll
+        for (int q = 0; q < R; q++) g[q] = a.bk_slow[r] * own[q];
+        block_sum<R>(g, s.sc, flip);
+        if (tid == M + r) {
+#pragma unroll
+          for (int q = 0; q < R; q++) val[q] = g[q];
+        }
+      }
+    }
+    // storeEstimates (OnlineMarginalSmoothing.h:197-255): emit when all R filtered variances < epsilon
+    double mv[2 * R];
+#pragma unroll
+    for (int q = 0; q < R; q++) { mv[q] = a.cW * val[q]; mv[R + q] = a.cW * val[q] * val[q]; }
+    block_sum<2 * R>(mv, s.sc, flip);
+    bool settled = true;
+#pragma unroll
+    for (int q = 0; q < R; q++) {
+      const double var = mv[R + q] - mv[q] * mv[q];  // sum W (x-m)^2 with sum W = 1
+      if (!(var < a.epsilon)) settled = false;
+    }
+    const bool emit = settled || (a.t == a.T - 1);
+    const int ts = a.pend_t[i];
+    if (emit) {
+      const bool own_s = (static_cast<unsigned long long>(ts) >= a.own_lo) && (static_cast<unsigned long long>(ts) < a.own_hi);
+      if (own_s) {
+        // whole row (position, p_1..p_R) in one store instruction: 56 contiguous bytes, also when the row goes to mapped host memory
+        if (tid <= R && ch.probs) {
+          const double outv = (tid == 0) ? (ch.pos ? static_cast<double>(ch.pos[ts]) : static_cast<double>(static_cast<unsigned long long>(ts) + a.t_off))
+                                         : pick<2 * R>(mv, tid - 1);
+          ch.probs[static_cast<size_t>(ts) * (R + 1) + tid] = outv;
+        }
+        if (tid == 0 && ch.finalised_at) ch.finalised_at[ts] = static_cast<int>(a.t + a.t_off);
+        if (!settled && !a.last_seg) n_halo_forced++;   // the segment's right halo ended before this site settled
+      }
+    } else {
+      double* dst = a.pc + static_cast<size_t>(kept) * R * HYG_NPMAX;
+      if (a.worker) {
+#pragma unroll
+        for (int q = 0; q < R; q++) dst[q * HYG_NPMAX + tid] = val[q];
+      }
+      __syncthreads();  // pend_t[i] has been read by every thread before slot `kept` (<= i) is overwritten
+      if (tid == 0) a.pend_t[kept] = ts;
+      kept++;
+    }
+  }
+  return kept;
+}
+
 template <int RT, bool PE>
 __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgRunDev& run, double* psi_ws, SgSmem& s, SgPeSmem<RT>* pe) {
   static_assert(RT <= 7, "class sums share an 8-wide reduction with the finite-weight count");
@@ -611,83 +707,17 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
 
       // ---- fixed-lag smoothing: updatePsi (OnlineMarginalSmoothing.h:148-177) ----
       if (run.use_smoothing && n_pend > 0) {
-        const double* pp = psi[(t + 1) & 1];   // written at step t-1
-        double* pc = psi[t & 1];
-        int kept = 0;
-        for (int i = 0; i < n_pend; i++) {
-          const double* src = pp + static_cast<size_t>(i) * R * HYG_NPMAX;
-          double own[R], val[R];
+        // out of line: the lag set is empty at most sites of informative data, and its 30 live doubles per thread would
+        // otherwise set the register budget (and the spills) of the whole recursion
+        SgLagArgs<R> la;
+        la.pp = psi[(t + 1) & 1]; la.pc = psi[t & 1]; la.pend_t = pend_t; la.n_pend = n_pend;
+        la.N_prev = N_prev; la.M = M; la.N_curr = N_curr; la.anc = anc; la.pr = p.r;
+        la.e_prev = e_prev; la.cW = c.W; la.my_invE = my_invE; la.slowmask = slowmask;
 #pragma unroll
-          for (int q = 0; q < R; q++) {
-            own[q] = (tid < N_prev) ? src[q * HYG_NPMAX + tid] : 0.0;
-            val[q] = (tid < M) ? src[q * HYG_NPMAX + anc] : 0.0;
-          }
-          // class sums G[q][r'] = sum_{n in class r'} e_n psi_q[n]; new particle (1,r): sum_{r'} P[r'][r] G[q][r'] / sumE[r]
-#pragma unroll
-          for (int q = 0; q < R; q++) {
-            double g[R];
-#pragma unroll
-            for (int rp = 0; rp < R; rp++) g[rp] = (p.r == rp) ? e_prev * own[q] : 0.0;
-            block_sum<R>(g, s.sc, flip);
-            if (tid >= M && tid < N_curr) {
-              const int r = tid - M;
-              double a = 0.0;
-#pragma unroll
-              for (int rp = 0; rp < R; rp++) a += (rp != r) ? mdl.P[rp][r] * g[rp] : 0.0;
-              val[q] = a * my_invE;
-            }
-          }
-          if (slowmask) {
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-              if (!((slowmask >> r) & 1u)) continue;
-              double g[R];
-#pragma unroll
-              for (int q = 0; q < R; q++) g[q] = bk_slow[r] * own[q];
-              block_sum<R>(g, s.sc, flip);
-              if (tid == M + r) {
-#pragma unroll
-                for (int q = 0; q < R; q++) val[q] = g[q];
-              }
-            }
-          }
-          // storeEstimates (OnlineMarginalSmoothing.h:197-255): emit when all R filtered variances < epsilon
-          double mv[2 * R];
-#pragma unroll
-          for (int q = 0; q < R; q++) { mv[q] = c.W * val[q]; mv[R + q] = c.W * val[q] * val[q]; }
-          block_sum<2 * R>(mv, s.sc, flip);
-          bool settled = true;
-#pragma unroll
-          for (int q = 0; q < R; q++) {
-            const double var = mv[R + q] - mv[q] * mv[q];  // sum W (x-m)^2 with sum W = 1
-            if (!(var < run.epsilon)) settled = false;
-          }
-          const bool emit = settled || (t == T - 1);
-          const int ts = pend_t[i];
-          if (emit) {
-            const bool own_s = (static_cast<unsigned long long>(ts) >= own_lo) && (static_cast<unsigned long long>(ts) < own_hi);
-            if (own_s) {
-              // whole row (position, p_1..p_R) in one store instruction: 56 contiguous bytes, also when the row goes to mapped host memory
-              if (tid <= R && ch.probs) {
-                const double outv = (tid == 0) ? (ch.pos ? static_cast<double>(ch.pos[ts]) : static_cast<double>(static_cast<unsigned long long>(ts) + t_off))
-                                               : pick<2 * R>(mv, tid - 1);
-                ch.probs[static_cast<size_t>(ts) * (R + 1) + tid] = outv;
-              }
-              if (tid == 0 && ch.finalised_at) ch.finalised_at[ts] = static_cast<int>(t + t_off);
-              if (!settled && !last_seg) n_halo_forced++;   // the segment's right halo ended before this site settled
-            }
-          } else {
-            double* dst = pc + static_cast<size_t>(kept) * R * HYG_NPMAX;
-            if (worker) {
-#pragma unroll
-              for (int q = 0; q < R; q++) dst[q * HYG_NPMAX + tid] = val[q];
-            }
-            __syncthreads();  // pend_t[i] has been read by every thread before slot `kept` (<= i) is overwritten
-            if (tid == 0) pend_t[kept] = ts;
-            kept++;
-          }
-        }
-        n_pend = kept;
+        for (int r = 0; r < R; r++) la.bk_slow[r] = bk_slow[r];
+        la.t = t; la.T = T; la.own_lo = own_lo; la.own_hi = own_hi; la.t_off = t_off; la.last_seg = last_seg; la.worker = worker;
+        la.epsilon = run.epsilon;
+        n_pend = sg_lag_update<R>(la, mdl, ch, s, flip, n_halo_forced);
       }
       // ---- K3: score recursion (OnlineParameterEstimation.h:135-158), see sg_param.cuh ----
       if (PE) {
@@ -916,6 +946,7 @@ __device__ __forceinline__ void sg_filter_entry(const SgModelDev* mdl, const SgC
   __shared__ SgSmem s;
   __shared__ int s_next;
   __shared__ SgModelDev s_mdl;
+  __shared__ SgChainDev s_ch;
   SgPeSmem<RT>* pe = PE ? reinterpret_cast<SgPeSmem<RT>*>(HYG_PE_SMEM) : nullptr;
   double* psi_ws = run.psi_ws + static_cast<size_t>(blockIdx.x) * run.psi_stride;
   for (;;) {
@@ -924,7 +955,11 @@ __device__ __forceinline__ void sg_filter_entry(const SgModelDev* mdl, const SgC
     const int c = s_next;
     __syncthreads();
     if (c >= run.n_chains) break;
-    sg_filter_chain<RT, PE>(s_mdl, chains[c], run, psi_ws, s, pe);
+    // the descriptor lives in shared memory: its dozen pointers are re-read where they are used (after a barrier the compiler
+    // must reload them) instead of occupying two registers each for the whole recursion
+    if (threadIdx.x == 0) s_ch = chains[c];
+    __syncthreads();
+    sg_filter_chain<RT, PE>(s_mdl, s_ch, run, psi_ws, s, pe);
   }
 }
 

@@ -332,22 +332,24 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_source = "MEASURED_PEAKS.json hbm_gbs (burst copy figure)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     longest = max(c["T"] for c in chroms)
-    # K2, the dominant kernel (99.9 % of the step in profiles/r01_launches_4M.csv): per site and chain it reads the R emission
+    # K2, the dominant kernel (99.7 % of the step in profiles/r01_launches_4M_segmented.csv): per site and chain it reads the R emission
     # log-densities and writes the R posterior probabilities and log Z_t.  It is a sequential recursion (one CTA per chain, 250
     # particles), bound by per-site latency, not by HBM -- the fraction below says how far from HBM it is, the
     # us/site figure is the number to optimise.
     k2_alg = total_T * n_seeds * (R * 8 + R * 8 + 8)   # + the running log-evidence (owned rows only: halo steps are overhead)
     k2_ms = float(np.mean(f_ms))
     k2_ach = k2_alg / (k2_ms / 1000.0) / 1e9
-    # DRAM bytes per site measured by ncu --set full (profiles/r01_ncu_full_k1_k2_details.txt, 3M-site capture), scaled
-    K2_DRAM_B_PER_SITE_CHAIN, K1_DRAM_B_PER_SITE = 129.3, 176.4
+    # DRAM bytes per site measured by ncu --set full (profiles/r01_k2_final_details.txt, r01_k1_final_details.txt: 4M-site
+    # capture, 2 seeds; K2 332.4 MB for 8M owned site-chains -- the posterior rows go to pinned host memory, not to DRAM), scaled
+    K2_DRAM_B_PER_SITE_CHAIN, K1_DRAM_B_PER_SITE = 41.5, 176.2
     roofline = {"bound": "hbm", "kernel": "sg_filter_kernel<6,0> (K2: particle filter + fixed-lag smoother), 1 persistent launch per step, "
                                           "one CTA per (chain, segment) unit",
                 "share_of_step": k2_ms / (k2_ms + float(np.mean(em_ms))),
                 "achieved": k2_ach, "peak": peak, "unit": "GB/s", "frac": k2_ach / peak, "peak_source": peak_source,
                 "algorithmic_bytes_per_launch": k2_alg, "ms_per_launch": k2_ms,
                 "traffic": K2_DRAM_B_PER_SITE_CHAIN * total_T * n_seeds,
-                "traffic_source": "ncu dram__bytes_read+write of a 3M-site capture, per site-chain, scaled to this launch",
+                "traffic_source": "ncu dram__bytes_read+write of a 4M-site capture, per owned site-chain, scaled to this launch "
+                                  "(posterior rows leave over PCIe into pinned host memory and are not DRAM traffic)",
                 "latency_bound": {"chains": n_chains, "units": n_units, "segment_sites": seg_sites, "halo_sites": args.halo if seg_sites else 0,
                                   "resident_ctas": workers, "sms": 148, "longest_chain_sites": longest,
                                   "sites_stepped_incl_halos": stepped, "halo_overhead": stepped / float(total_T * n_seeds) - 1.0,
@@ -363,7 +365,7 @@ def main():
                          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_source,
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": float(np.mean(em_ms)),
                          "traffic": K1_DRAM_B_PER_SITE * total_T,
-                         "traffic_source": "ncu dram__bytes_read+write of a 3M-site capture, per site, scaled to this launch",
+                         "traffic_source": "ncu dram__bytes_read+write of a 4M-site capture, per site, scaled to this launch",
                          "limiter": "shared-memory wavefronts of the fp64 table look-ups (L1 pipe 94 % busy, 59 % of wavefronts are bank conflicts)"}
 
     # ---- end-to-end leg: host (pinned) buffers in, host buffers out, through the public API ----

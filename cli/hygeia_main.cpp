@@ -153,7 +153,9 @@ int cmd_single_group(int argc, char** argv) {
                                        "regime_probabilities_csv_file", "theta_trace_csv_file", "omega_csv_file", "kappa_csv_file", "p_csv_file",
                                        "theta_file", "is_kappa_fixed", "n_particles", "estimate_regime_probabilities", "estimate_parameters",
                                        "epsilon", "normalise_gradients", "use_adam", "n_steps_without_parameter_update", "learning_rate_exponent",
-                                       "learning_rate_factor", "root_dir", "randomise_rng_seed", "rng_seed"};
+                                       "learning_rate_factor", "root_dir", "randomise_rng_seed", "rng_seed",
+                                       // extensions (absent from the reference CLI; defaults reproduce it)
+                                       "segment_sites", "segment_halo"};
   const std::set<std::string> flags = {"estimate_regime_probabilities", "estimate_parameters"};
   const Args a = parse_args(argc, argv, 2, known, flags);
 
@@ -196,6 +198,12 @@ int cmd_single_group(int argc, char** argv) {
   const double lr_fac = get_double(a, "learning_rate_factor", 0.01);
   const bool randomise = get_bool(a, "randomise_rng_seed", true);
   const long rng_seed = get_int(a, "rng_seed", -73);
+  // throughput mode of the regimes pass: cut the chromosome into concurrent segments (0 = one sequential run, the reference's
+  // behaviour; "auto" = size chosen for the device).  Ignored with --estimate_parameters (theta evolves along the chain).
+  const std::string seg_s = a.str("segment_sites", "0");
+  const uint64_t segment_sites = (seg_s == "auto") ? HYG_SEGMENT_AUTO : static_cast<uint64_t>(std::stoull(seg_s));
+  const long segment_halo = get_int(a, "segment_halo", 5000);
+  if (segment_halo < 0) throw Error("--segment_halo must be >= 0");
   if (!is_kappa_fixed) throw Error("--is_kappa_fixed FALSE is not supported (the reference's kappa-gradient path is broken: SURVEY.md C-7)");
 
   const std::string f_meth = a.str("n_methylated_reads_csv_file", ""), f_pos = a.str("genomic_positions_csv_file", ""),
@@ -278,6 +286,8 @@ int cmd_single_group(int argc, char** argv) {
   ra.n_steps_without_parameter_update = static_cast<uint32_t>(n_steps);
   ra.learning_rate_exponent = lr_exp;
   ra.learning_rate_factor = lr_fac;
+  ctx.check(hyg_sg_set_segmentation(ctx.c, segment_sites, static_cast<uint64_t>(segment_halo), static_cast<uint64_t>(segment_halo)),
+            "hyg_sg_set_segmentation");
   std::vector<double> probs(est_regimes ? T * (1 + R) : 0), trace(est_params ? T * D : 0);
   double seconds = 0.0;
   ctx.check(hyg_sg_run_online_combined_inference(ctx.c, vartheta.data(), static_cast<uint32_t>(vartheta.size()), theta.data(), static_cast<uint32_t>(D), T,

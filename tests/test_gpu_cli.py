@@ -163,3 +163,25 @@ def test_infer_cli_matches_mirror(tmp_path):
     r = run("infer", "--mu", MU, "--sigma", SIGMA, "--chrom", 21, "--single_group_dir", sg, "--data_dir", d, "--results_dir", tmp_path / "x",
             "--seed", 4, "--batch", 7, "--segment_size", 100, "--buffer_size", 20)
     assert "Batch index is too large" in r.stdout
+
+
+def test_estimate_regimes_cli_segmented_extension(tmp_path):
+    """--segment_sites (an extension; default 0 = the reference's sequential run): same regimes file to the printed digits."""
+    from hygeia_b200 import synthetic
+    T, S = 24000, 2
+    ch = synthetic.make_chain(T, S, seed=33)
+    _write_single_group_inputs(tmp_path, ch)
+    outs = []
+    for k, extra in enumerate(([], ["--segment_sites", 5000, "--segment_halo", 2500], ["--segment_sites", "auto"])):
+        out = tmp_path / f"regimes_{k}.csv.gz"
+        run("estimate_parameters_and_regimes", "--mu", MU, "--sigma", SIGMA, "--u", 3,
+            "--n_methylated_reads_csv_file", tmp_path / "n_methylated_reads_1.txt.gz", "--genomic_positions_csv_file", tmp_path / "positions_1.txt.gz",
+            "--n_total_reads_csv_file", tmp_path / "n_total_reads_1.txt.gz", "--regime_probabilities_csv_file", out,
+            "--estimate_regime_probabilities", "--randomise_rng_seed", "FALSE", "--rng_seed", 5, *extra)
+        _, rows = read_csv(out)
+        outs.append(np.array([[float(x) for x in r] for r in rows]))
+    assert outs[0].shape == (T - 1, 7)
+    for o in outs[1:]:
+        assert np.array_equal(o[:, 0], outs[0][:, 0])
+        assert np.abs(o[:, 1:] - outs[0][:, 1:]).max() < 1e-8
+        assert np.array_equal(o[:, 1:].argmax(1), outs[0][:, 1:].argmax(1))

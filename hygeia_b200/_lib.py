@@ -16,6 +16,7 @@ SYMBOLS = [
     "hyg_sg_emission", "hyg_sg_filter", "hyg_sg_download", "hyg_sync", "hyg_sg_timings", "hyg_sg_get_logobs",
     "hyg_sg_run_online_combined_inference", "hyg_sg_sample_theta_prior", "hyg_philox_uniform",
     "hyg_tg_set_model", "hyg_tg_run", "hyg_tg_hazard_table",
+    "hyg_tg_site_statistics", "hyg_fdr_procedure", "hyg_weighted_fdr_procedure",
 ]
 
 
@@ -101,6 +102,12 @@ def load():
     lib.hyg_tg_set_model.argtypes = [C.c_void_p, C.POINTER(HygTgModel), C.c_uint64]
     lib.hyg_tg_run.argtypes = [C.c_void_p, C.POINTER(HygTgChain), C.c_uint32, C.POINTER(C.c_float)]
     lib.hyg_tg_hazard_table.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.hyg_tg_site_statistics.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+    lib.hyg_fdr_procedure.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_double, C.POINTER(C.c_uint64), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double)]
+    lib.hyg_weighted_fdr_procedure.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p,
+                                               C.POINTER(C.c_uint64), C.c_void_p, C.POINTER(C.c_double)]
     lib.hyg_philox_uniform.restype = C.c_double
     lib.hyg_philox_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64]
     _lib = lib

@@ -22,6 +22,13 @@
 #include "sg_emission.cuh"
 #include "sg_filter.cuh"
 #include "hyg_tg.cuh"
+#include "hyg_dmp.cuh"
+
+#include <thrust/count.h>
+#include <thrust/device_ptr.h>
+#include <thrust/execution_policy.h>
+#include <thrust/scan.h>
+#include <thrust/sort.h>
 
 #define HYG_VERSION_STR "hygeia_b200 0.1.0 (sm_100a)"
 
@@ -968,6 +975,145 @@ int hyg_tg_run(hyg_ctx* c, const hyg_tg_chain* chains, uint32_t n, float* ms_dev
 }
 
 double hyg_philox_uniform(uint64_t seed, uint32_t chain_id, uint64_t t) { return hyg::philox_uniform(seed, chain_id, t); }
+
+// ---- DMP calling: per-site statistics of the aggregated trajectories (K6) and the two FDR procedures ------------------------
+
+int hyg_tg_site_statistics(hyg_ctx* c, uint64_t T, uint32_t P, uint32_t R, const int8_t* merged, const int8_t* control_regimes,
+                           const int8_t* case_regimes, int on_device, double* split_prob, double* null_stat, double* control_freq,
+                           double* case_freq, double* pair_stat, float* ms_device) {
+  if (!c || !merged || !control_regimes || !case_regimes || !split_prob || !null_stat) return fail(c, HYG_ERR_ARG, "null argument");
+  if (T == 0 || P == 0 || R == 0 || R > 8) return fail(c, HYG_ERR_ARG, "need T > 0, P > 0, 1 <= R <= 8");
+  const size_t smem = 3 * ((static_cast<size_t>(HYG_DMP_TILE) * P + 15) / 16 * 16);
+  if (smem > 227 * 1024) return fail(c, HYG_ERR_UNSUPPORTED, "more than 605 particles per site do not fit the shared-memory tile");
+  HYG_CUDA(c, cudaSetDevice(c->device));
+  const size_t nb = static_cast<size_t>(T) * P;
+  const int8_t* d_in[3] = {merged, control_regimes, case_regimes};
+  int8_t* own_in[3] = {nullptr, nullptr, nullptr};
+  double *d_split = nullptr, *d_null = nullptr, *d_cf = nullptr, *d_kf = nullptr, *d_pair = nullptr;
+  auto cleanup = [&]() {
+    for (auto& p : own_in) pool_free(c, p);
+    pool_free(c, d_split); pool_free(c, d_null); pool_free(c, d_cf); pool_free(c, d_kf); pool_free(c, d_pair);
+  };
+#define HYG_DMP_CUDA(call)                                                                                          \
+  do {                                                                                                              \
+    cudaError_t e_ = (call);                                                                                        \
+    if (e_ != cudaSuccess) { cleanup(); return fail(c, HYG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } \
+  } while (0)
+  if (!on_device) {
+    for (int k = 0; k < 3; k++) {
+      HYG_DMP_CUDA(pool_alloc(c, reinterpret_cast<void**>(&own_in[k]), nb + 16));
+      HYG_DMP_CUDA(cudaMemcpyAsync(own_in[k], d_in[k], nb, cudaMemcpyHostToDevice, c->stream));
+      d_in[k] = own_in[k];
+    }
+  }
+  // outputs: device pointers when the inputs are device resident, else staged
+  double* o_split = split_prob; double* o_null = null_stat; double* o_cf = control_freq; double* o_kf = case_freq; double* o_pair = pair_stat;
+  if (!on_device) {
+    HYG_DMP_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_split), T * sizeof(double))); o_split = d_split;
+    HYG_DMP_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_null), T * sizeof(double))); o_null = d_null;
+    if (control_freq) { HYG_DMP_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_cf), T * R * sizeof(double))); o_cf = d_cf; }
+    if (case_freq) { HYG_DMP_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_kf), T * R * sizeof(double))); o_kf = d_kf; }
+    if (pair_stat) { HYG_DMP_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_pair), T * R * R * sizeof(double))); o_pair = d_pair; }
+  }
+  hyg::DmpArgs a;
+  a.T = T; a.P = P; a.R = R; a.merged = reinterpret_cast<const signed char*>(d_in[0]);
+  a.control = reinterpret_cast<const signed char*>(d_in[1]); a.cse = reinterpret_cast<const signed char*>(d_in[2]);
+  a.split_prob = o_split; a.null_stat = o_null; a.control_freq = o_cf; a.case_freq = o_kf; a.pair_stat = o_pair;
+  a.n_tiles = (T + HYG_DMP_TILE - 1) / HYG_DMP_TILE;
+  HYG_DMP_CUDA(cudaFuncSetAttribute(hyg::dmp_site_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hyg::dmp_site_stats_kernel, HYG_DMP_TILE, smem);
+  if (occ < 1) occ = 1;
+  const int grid = static_cast<int>(std::min<unsigned long long>(a.n_tiles, static_cast<unsigned long long>(c->num_sms) * occ));
+  HYG_DMP_CUDA(cudaEventRecord(c->ev_em0, c->stream));
+  hyg::dmp_site_stats_kernel<<<grid, HYG_DMP_TILE, smem, c->stream>>>(a);
+  HYG_DMP_CUDA(cudaGetLastError());
+  HYG_DMP_CUDA(cudaEventRecord(c->ev_em1, c->stream));
+  if (!on_device) {
+    HYG_DMP_CUDA(cudaMemcpyAsync(split_prob, d_split, T * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HYG_DMP_CUDA(cudaMemcpyAsync(null_stat, d_null, T * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (control_freq) HYG_DMP_CUDA(cudaMemcpyAsync(control_freq, d_cf, T * R * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (case_freq) HYG_DMP_CUDA(cudaMemcpyAsync(case_freq, d_kf, T * R * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (pair_stat) HYG_DMP_CUDA(cudaMemcpyAsync(pair_stat, d_pair, T * R * R * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  }
+  HYG_DMP_CUDA(cudaStreamSynchronize(c->stream));
+  if (ms_device) HYG_DMP_CUDA(cudaEventElapsedTime(ms_device, c->ev_em0, c->ev_em1));
+  c->timed_em = false;
+  cleanup();
+  return HYG_OK;
+}
+
+int hyg_fdr_procedure(hyg_ctx* c, uint64_t n, const double* test_statistics, double fdr_threshold, uint64_t* k, double* Qk, double* threshold) {
+  if (!c || !test_statistics || !k || !Qk || !threshold || n == 0) return fail(c, HYG_ERR_ARG, "null argument / empty input");
+  HYG_CUDA(c, cudaSetDevice(c->device));
+  double *d_t = nullptr, *d_q = nullptr;
+  auto cleanup = [&]() { pool_free(c, d_t); pool_free(c, d_q); };
+  HYG_DMP_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_t), n * sizeof(double)));
+  HYG_DMP_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_q), n * sizeof(double)));
+  HYG_DMP_CUDA(cudaMemcpyAsync(d_t, test_statistics, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  try {
+    auto pol = thrust::cuda::par.on(c->stream);
+    thrust::device_ptr<double> t(d_t), q(d_q);
+    thrust::sort(pol, t, t + n);                                   // np.sort (multiple_testing.py:4)
+    thrust::inclusive_scan(pol, t, t + n, q);                      // np.cumsum
+    hyg::dmp_running_mean_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(d_q, d_q, n);
+    const uint64_t s = static_cast<uint64_t>(thrust::count_if(pol, q, q + n, [fdr_threshold] __device__(double v) { return v <= fdr_threshold; }));
+    double first = 0.0;
+    HYG_DMP_CUDA(cudaMemcpyAsync(&first, d_t, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HYG_DMP_CUDA(cudaStreamSynchronize(c->stream));
+    if (fdr_threshold < first) {                                   // :8-9
+      *k = 0; *Qk = 0.0; *threshold = 0.0;
+    } else {
+      // s >= 1 here (Qs[0] = sorted[0] <= fdr_threshold)
+      HYG_DMP_CUDA(cudaMemcpyAsync(Qk, d_q + (s - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      if (s == n) *threshold = 1.01;                               // :10-11
+      else HYG_DMP_CUDA(cudaMemcpyAsync(threshold, d_t + s, sizeof(double), cudaMemcpyDeviceToHost, c->stream));   // :12
+      HYG_DMP_CUDA(cudaStreamSynchronize(c->stream));
+      *k = s;
+    }
+  } catch (const std::exception& e) {
+    cleanup();
+    return fail(c, HYG_ERR_CUDA, std::string("thrust: ") + e.what());
+  }
+  cleanup();
+  return HYG_OK;
+}
+
+int hyg_weighted_fdr_procedure(hyg_ctx* c, uint64_t n, const double* test_statistics, double fdr_threshold, const double* weights_false_positives,
+                               const double* weights_false_negatives, uint64_t* n_selected, uint64_t* indices, double* Nk) {
+  if (!c || !test_statistics || !weights_false_positives || !weights_false_negatives || !n_selected || !indices || !Nk || n == 0)
+    return fail(c, HYG_ERR_ARG, "null argument / empty input");
+  HYG_CUDA(c, cudaSetDevice(c->device));
+  double *d_t = nullptr, *d_fp = nullptr, *d_fn = nullptr, *d_rank = nullptr, *d_ex = nullptr, *d_sum = nullptr;
+  unsigned long long* d_idx = nullptr;
+  auto cleanup = [&]() { pool_free(c, d_t); pool_free(c, d_fp); pool_free(c, d_fn); pool_free(c, d_rank); pool_free(c, d_ex); pool_free(c, d_sum); pool_free(c, d_idx); };
+  for (double** p : {&d_t, &d_fp, &d_fn, &d_rank, &d_ex, &d_sum}) HYG_DMP_CUDA(pool_alloc(c, reinterpret_cast<void**>(p), n * sizeof(double)));
+  HYG_DMP_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_idx), n * sizeof(unsigned long long)));
+  HYG_DMP_CUDA(cudaMemcpyAsync(d_t, test_statistics, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  HYG_DMP_CUDA(cudaMemcpyAsync(d_fp, weights_false_positives, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  HYG_DMP_CUDA(cudaMemcpyAsync(d_fn, weights_false_negatives, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  try {
+    auto pol = thrust::cuda::par.on(c->stream);
+    hyg::dmp_weighted_rank_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(d_t, d_fp, d_fn, fdr_threshold, d_rank, d_ex, d_idx, n);
+    thrust::device_ptr<double> rank(d_rank), ex(d_ex), sum(d_sum);
+    thrust::device_ptr<unsigned long long> idx(d_idx);
+    // np.argsort(ranking) (:15); ties keep the smaller index first (numpy's default sort leaves tie order unspecified)
+    thrust::stable_sort_by_key(pol, rank, rank + n, thrust::make_zip_iterator(thrust::make_tuple(idx, ex)));
+    thrust::inclusive_scan(pol, ex, ex + n, sum);                  // Nsums (:18)
+    const uint64_t s = static_cast<uint64_t>(thrust::count_if(pol, sum, sum + n, [] __device__(double v) { return v <= 0.0; }));   // :19
+    *n_selected = s;
+    if (s > 0) HYG_DMP_CUDA(cudaMemcpyAsync(indices, d_idx, s * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    // Nsums[s-1]; for s = 0 Python's index -1 is the last element (:20)
+    HYG_DMP_CUDA(cudaMemcpyAsync(Nk, d_sum + (s > 0 ? s - 1 : n - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    HYG_DMP_CUDA(cudaStreamSynchronize(c->stream));
+  } catch (const std::exception& e) {
+    cleanup();
+    return fail(c, HYG_ERR_CUDA, std::string("thrust: ") + e.what());
+  }
+  cleanup();
+  return HYG_OK;
+}
+#undef HYG_DMP_CUDA
 
 int hyg_sg_sample_theta_prior(uint32_t dim, uint64_t seed, double* theta) {
   if (!theta) return HYG_ERR_ARG;

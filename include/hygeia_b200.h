@@ -176,6 +176,26 @@ int hyg_tg_run(hyg_ctx* ctx, const hyg_tg_chain* chains, uint32_t n_chains, floa
 /* host copy of the hazard table the kernels use: rho[R][d_max + 1] */
 int hyg_tg_hazard_table(const double* omega, const double* kappa, uint32_t R, uint32_t u, uint32_t d_max, double* rho);
 
+/* ---- DMP calling -------------------------------------------------------------------------
+ * Boundary being replaced: the reductions of `hygeia aggregate` and `hygeia get_dmps`
+ * (src/two_group/aggregate_results.py:125-147,181; src/two_group/get_dmps.py:63-76,111-126) and the two procedures of
+ * src/two_group/multiple_testing.py.  Inputs of hyg_tg_site_statistics are the aggregated trajectory matrices the reference
+ * writes as merge_states_/control_regimes_/case_regimes_chrom_<chrom>.csv.gz: int8 [T][P], site-major, P = seeds x backward
+ * trajectories.  Outputs (fp64, bit-identical to the NumPy expressions): split_prob[T] = mean(merged == 0);
+ * null_stat[T] = 1 - #(control != case) / P; control_freq / case_freq [T][R] = bincount / P (may be NULL);
+ * pair_stat[T][R][R] = 1 - #(control == i and case == j) / P (--test_regime_combinations; may be NULL).
+ * on_device != 0: every pointer is a device pointer (inputs readable 16 bytes past their end) and nothing is copied. */
+int hyg_tg_site_statistics(hyg_ctx* ctx, uint64_t T, uint32_t P, uint32_t R, const int8_t* merged, const int8_t* control_regimes,
+                           const int8_t* case_regimes, int on_device, double* split_prob, double* null_stat, double* control_freq,
+                           double* case_freq, double* pair_stat, float* ms_device);
+/* FDR_procedure(test_statistics, fdr_threshold) -> (k, Qk, threshold)  (multiple_testing.py:3-12); host pointers */
+int hyg_fdr_procedure(hyg_ctx* ctx, uint64_t n, const double* test_statistics, double fdr_threshold, uint64_t* k, double* Qk, double* threshold);
+/* weighted_FDR_procedure(test_statistics, fdr_threshold, weights_false_positives, weights_false_negatives)
+ * -> (ranking_indices[:s], Nsums[s-1])  (multiple_testing.py:13-22); `indices` has room for n entries; ties in the ranking
+ * keep the smaller index first (NumPy leaves their order unspecified) */
+int hyg_weighted_fdr_procedure(hyg_ctx* ctx, uint64_t n, const double* test_statistics, double fdr_threshold, const double* weights_false_positives,
+                               const double* weights_false_negatives, uint64_t* n_selected, uint64_t* indices, double* Nk);
+
 /* sampleFromParameterPriorCpp (singleGroup.cpp:18-35): theta ~ N(0, I_D), Philox-based (host). */
 int hyg_sg_sample_theta_prior(uint32_t dim, uint64_t seed, double* theta);
 /* Host copy of the by-site uniform the kernels use. */

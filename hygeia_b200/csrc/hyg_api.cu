@@ -983,8 +983,8 @@ int hyg_tg_site_statistics(hyg_ctx* c, uint64_t T, uint32_t P, uint32_t R, const
                            double* case_freq, double* pair_stat, float* ms_device) {
   if (!c || !merged || !control_regimes || !case_regimes || !split_prob || !null_stat) return fail(c, HYG_ERR_ARG, "null argument");
   if (T == 0 || P == 0 || R == 0 || R > 8) return fail(c, HYG_ERR_ARG, "need T > 0, P > 0, 1 <= R <= 8");
-  const size_t smem = 3 * ((static_cast<size_t>(HYG_DMP_TILE) * P + 15) / 16 * 16);
-  if (smem > 227 * 1024) return fail(c, HYG_ERR_UNSUPPORTED, "more than 605 particles per site do not fit the shared-memory tile");
+  const size_t smem = 16 + 3 * ((static_cast<size_t>(HYG_DMP_TILE) * P + 15) / 16 * 16) + (static_cast<size_t>(P) + 2) * sizeof(double);
+  if (smem > 227 * 1024) return fail(c, HYG_ERR_UNSUPPORTED, "more than 590 particles per site do not fit the shared-memory tile");
   HYG_CUDA(c, cudaSetDevice(c->device));
   const size_t nb = static_cast<size_t>(T) * P;
   const int8_t* d_in[3] = {merged, control_regimes, case_regimes};
@@ -1022,11 +1022,11 @@ int hyg_tg_site_statistics(hyg_ctx* c, uint64_t T, uint32_t P, uint32_t R, const
   a.n_tiles = (T + HYG_DMP_TILE - 1) / HYG_DMP_TILE;
   HYG_DMP_CUDA(cudaFuncSetAttribute(hyg::dmp_site_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hyg::dmp_site_stats_kernel, HYG_DMP_TILE, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hyg::dmp_site_stats_kernel, HYG_DMP_NT, smem);
   if (occ < 1) occ = 1;
   const int grid = static_cast<int>(std::min<unsigned long long>(a.n_tiles, static_cast<unsigned long long>(c->num_sms) * occ));
   HYG_DMP_CUDA(cudaEventRecord(c->ev_em0, c->stream));
-  hyg::dmp_site_stats_kernel<<<grid, HYG_DMP_TILE, smem, c->stream>>>(a);
+  hyg::dmp_site_stats_kernel<<<grid, HYG_DMP_NT, smem, c->stream>>>(a);
   HYG_DMP_CUDA(cudaGetLastError());
   HYG_DMP_CUDA(cudaEventRecord(c->ev_em1, c->stream));
   if (!on_device) {

@@ -12,8 +12,8 @@
 //
 // B200 mapping: a streaming byte kernel, bound by HBM (3 P bytes in, 16 + 16 R bytes out per site).  Persistent CTAs take
 // tiles of 128 consecutive sites; the tile's rows are contiguous in memory, so the three [128][P] byte blocks are staged in
-// shared memory with coalesced 16-byte loads; then one thread per site walks its rows with 4-byte shared-memory loads and
-// counts with byte-sliced 64-bit accumulators (one 8-bit field per regime, flushed every 252 particles).
+// shared memory by TMA bulk copies (cp.async.bulk + mbarrier, one issuing thread); then four threads per site walk its rows
+// with 4-byte shared-memory loads, transpose 32 particles at a time into bit planes and count every regime with one LOP3 + POPC.
 #ifndef HYG_DMP_CUH
 #define HYG_DMP_CUH
 
@@ -23,8 +23,9 @@
 #include <cuda_runtime.h>
 #endif
 
-#define HYG_DMP_TILE 128   // sites per tile = threads per CTA
-#define HYG_DMP_FLUSH 252  // particles between flushes of the 8-bit count fields (multiple of 4, <= 255)
+#define HYG_DMP_TILE 128      // sites per tile
+#define HYG_DMP_LANES 4       // threads per site (each walks every 4th word of the site's rows)
+#define HYG_DMP_NT (HYG_DMP_TILE * HYG_DMP_LANES)
 
 namespace hyg {
 
@@ -43,102 +44,197 @@ struct DmpArgs {
   unsigned long long n_tiles;
 };
 
-__device__ __forceinline__ void dmp_count_particle(unsigned c, unsigned k, unsigned long long& cc, unsigned long long& kc, int& ne) {
-  cc += 1ull << ((c & 7u) * 8u);
-  kc += 1ull << ((k & 7u) * 8u);
-  ne += (c != k) ? 1 : 0;
+// Bit planes of up to 32 particles: bit j of plane k = bit k of the regime of particle j.  A regime count is then ONE
+// three-input logic op (LOP3) + POPC per 32 particles.
+struct DmpPlanes {
+  unsigned c0, c1, c2, k0, k1, k2, m;
+  __device__ __forceinline__ void clear() { c0 = c1 = c2 = k0 = k1 = k2 = m = 0u; }
+  // bit k of every byte of w, moved to bit j of that byte: one funnel shift + one AND (the OR into the plane fuses with it)
+  template <int k, int j> __device__ __forceinline__ static unsigned plane(unsigned w) {
+    return ((j >= k) ? (w << (j >= k ? j - k : 0)) : (w >> (k > j ? k - j : 0))) & (0x01010101u << j);
+  }
+  // add the four particles of one word of each matrix at bit positions j, 8 + j, 16 + j, 24 + j (j is a compile-time constant)
+  template <int j> __device__ __forceinline__ void add(unsigned mw, unsigned cw, unsigned kw) {
+    m |= plane<0, j>(mw);
+    c0 |= plane<0, j>(cw); c1 |= plane<1, j>(cw); c2 |= plane<2, j>(cw);
+    k0 |= plane<0, j>(kw); k1 |= plane<1, j>(kw); k2 |= plane<2, j>(kw);
+  }
+  template <int r> __device__ __forceinline__ static int count(unsigned p0, unsigned p1, unsigned p2) {
+    return __popc(((r & 1) ? p0 : ~p0) & ((r & 2) ? p1 : ~p1) & ((r & 4) ? p2 : ~p2));
+  }
+  // counts of regimes 0..7 (positions that hold no particle count as regime 0: the caller subtracts them)
+  __device__ __forceinline__ void flush(int (&cc)[8], int (&kc)[8], int& msum, int& ne) {
+    cc[0] += count<0>(c0, c1, c2); cc[1] += count<1>(c0, c1, c2); cc[2] += count<2>(c0, c1, c2); cc[3] += count<3>(c0, c1, c2);
+    cc[4] += count<4>(c0, c1, c2); cc[5] += count<5>(c0, c1, c2); cc[6] += count<6>(c0, c1, c2); cc[7] += count<7>(c0, c1, c2);
+    kc[0] += count<0>(k0, k1, k2); kc[1] += count<1>(k0, k1, k2); kc[2] += count<2>(k0, k1, k2); kc[3] += count<3>(k0, k1, k2);
+    kc[4] += count<4>(k0, k1, k2); kc[5] += count<5>(k0, k1, k2); kc[6] += count<6>(k0, k1, k2); kc[7] += count<7>(k0, k1, k2);
+    msum += __popc(m);
+    ne += __popc((c0 ^ k0) | (c1 ^ k1) | (c2 ^ k2));
+    clear();
+  }
+};
+
+// Stage `bytes` from global to shared memory (dst, src 16-byte aligned).  Device: one thread issues TMA bulk copies
+// (cp.async.bulk) that complete on an mbarrier every thread then waits on; `phase` is the barrier's parity for this use.
+__device__ __forceinline__ void dmp_stage3(unsigned char* d0, unsigned char* d1, unsigned char* d2, const signed char* s0, const signed char* s1,
+                                           const signed char* s2, size_t bytes, unsigned long long* mbar, unsigned phase) {
+  const size_t vec = bytes / 16 * 16;
+#ifdef HYG_EMU
+  (void)mbar; (void)phase;
+  for (size_t i = threadIdx.x; i < vec; i += blockDim.x) { d0[i] = static_cast<unsigned char>(s0[i]); d1[i] = static_cast<unsigned char>(s1[i]); d2[i] = static_cast<unsigned char>(s2[i]); }
+#else
+  const uint32_t bar = static_cast<uint32_t>(__cvta_generic_to_shared(mbar));
+  if (threadIdx.x == 0 && vec > 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(static_cast<uint32_t>(3 * vec)) : "memory");
+    const uint32_t CH = 32768;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      unsigned char* d = (a == 0) ? d0 : ((a == 1) ? d1 : d2);
+      const signed char* g = (a == 0) ? s0 : ((a == 1) ? s1 : s2);
+      for (size_t off = 0; off < vec; off += CH) {
+        const uint32_t n = static_cast<uint32_t>((vec - off < CH) ? vec - off : CH);
+        const uint32_t da = static_cast<uint32_t>(__cvta_generic_to_shared(d + off));
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(da), "l"(g + off), "r"(n),
+                     "r"(bar)
+                     : "memory");
+      }
+    }
+  }
+#endif
+  // the last tile may end inside a 16-byte vector
+  for (size_t i = vec + threadIdx.x; i < bytes; i += blockDim.x) {
+    d0[i] = static_cast<unsigned char>(s0[i]); d1[i] = static_cast<unsigned char>(s1[i]); d2[i] = static_cast<unsigned char>(s2[i]);
+  }
+#ifndef HYG_EMU
+  if (vec > 0) {
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(phase)
+          : "memory");
+    }
+  }
+#endif
+  __syncthreads();
 }
 
 __device__ __forceinline__ void dmp_site_stats_entry(const DmpArgs& a, unsigned char* sm) {
   const int tid = threadIdx.x;
+  const int site = tid / HYG_DMP_LANES, q = tid % HYG_DMP_LANES;
   const unsigned P = a.P;
   const size_t tile_bytes = static_cast<size_t>(HYG_DMP_TILE) * P;
   const size_t arr_pitch = (tile_bytes + 15) / 16 * 16;
-  unsigned char* sm_m = sm;
-  unsigned char* sm_c = sm + arr_pitch;
-  unsigned char* sm_k = sm + 2 * arr_pitch;
+  unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sm);
+  unsigned char* sm_m = sm + 16;
+  unsigned char* sm_c = sm_m + arr_pitch;
+  unsigned char* sm_k = sm_c + arr_pitch;
+#ifndef HYG_EMU
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(mbar))));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+#endif
+  // quot[i] = i / P for i = 0..P: every output is one of these IEEE quotients (the reference divides counts by P)
+  double* quot = reinterpret_cast<double*>(sm_k + arr_pitch);
+  for (unsigned i = tid; i <= P; i += HYG_DMP_NT) quot[i] = static_cast<double>(i) / static_cast<double>(P);
+  __syncthreads();
+  unsigned phase = 0;
   for (unsigned long long tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
     const unsigned long long t0 = tile * HYG_DMP_TILE;
     const unsigned nt = static_cast<unsigned>((a.T - t0 < HYG_DMP_TILE) ? (a.T - t0) : HYG_DMP_TILE);
     const size_t bytes = static_cast<size_t>(nt) * P;
     const size_t goff = static_cast<size_t>(t0) * P;   // multiple of 16: HYG_DMP_TILE = 8 x 16
-    // ---- stage the three byte blocks (coalesced 16-byte loads; the tail of the last tile byte by byte) ----
+    dmp_stage3(sm_m, sm_c, sm_k, a.merged + goff, a.control + goff, a.cse + goff, bytes, mbar, phase);
+    if (bytes >= 16) phase ^= 1u;
+    int cnt_c[8], cnt_k[8];
 #pragma unroll
-    for (int arr = 0; arr < 3; arr++) {
-      const signed char* g = (arr == 0 ? a.merged : (arr == 1 ? a.control : a.cse)) + goff;
-      unsigned char* d = (arr == 0 ? sm_m : (arr == 1 ? sm_c : sm_k));
-      const size_t nvec = bytes / 16;
-      const uint4* gv = reinterpret_cast<const uint4*>(g);
-      uint4* dv = reinterpret_cast<uint4*>(d);
-      for (size_t i = tid; i < nvec; i += HYG_DMP_TILE) dv[i] = gv[i];
-      for (size_t i = nvec * 16 + tid; i < bytes; i += HYG_DMP_TILE) d[i] = static_cast<unsigned char>(g[i]);
-    }
-    __syncthreads();
-    if (static_cast<unsigned>(tid) < nt) {
-      const unsigned char* rm = sm_m + static_cast<size_t>(tid) * P;
-      const unsigned char* rc = sm_c + static_cast<size_t>(tid) * P;
-      const unsigned char* rk = sm_k + static_cast<size_t>(tid) * P;
-      int cnt_c[8], cnt_k[8], pair[64];
+    for (int r = 0; r < 8; r++) { cnt_c[r] = 0; cnt_k[r] = 0; }
+    int msum = 0, ne = 0;
+    const bool active = static_cast<unsigned>(site) < nt;
+    if (active) {
+      const unsigned char* rm = sm_m + static_cast<size_t>(site) * P;
+      const unsigned char* rc = sm_c + static_cast<size_t>(site) * P;
+      const unsigned char* rk = sm_k + static_cast<size_t>(site) * P;
+      if ((P & 3u) == 0u) {   // rows are 4-byte aligned: one shared-memory word = four particles
+        const unsigned nw = P / 4;
+        DmpPlanes pl;
+        pl.clear();
+        const unsigned* wm = reinterpret_cast<const unsigned*>(rm);
+        const unsigned* wc = reinterpret_cast<const unsigned*>(rc);
+        const unsigned* wk = reinterpret_cast<const unsigned*>(rk);
+        int mine = 0, groups = 0;
+        // this lane's words are q, q + 4, q + 8, ...; eight of them (32 particles) fill the planes
+#define HYG_DMP_ADD(J)                                                       \
+  {                                                                          \
+    const unsigned w = w0 + (J) * HYG_DMP_LANES;                             \
+    if (w < nw) { pl.add<J>(wm[w], wc[w], wk[w]); mine += 4; }               \
+  }
+        for (unsigned w0 = q; w0 < nw; w0 += 8 * HYG_DMP_LANES) {
+          HYG_DMP_ADD(0) HYG_DMP_ADD(1) HYG_DMP_ADD(2) HYG_DMP_ADD(3) HYG_DMP_ADD(4) HYG_DMP_ADD(5) HYG_DMP_ADD(6) HYG_DMP_ADD(7)
+          pl.flush(cnt_c, cnt_k, msum, ne);
+          groups++;
+        }
+#undef HYG_DMP_ADD
+        // bit positions that held no particle were counted as regime 0 (each flush covers 32 positions)
+        const int pad = groups * 32 - mine;
+        cnt_c[0] -= pad; cnt_k[0] -= pad;
+      } else {                // ragged rows: byte by byte
+        for (unsigned p = q; p < P; p += HYG_DMP_LANES) {
+          const unsigned c = rc[p] & 7u, k = rk[p] & 7u;
+          msum += rm[p] & 1u;
+          ne += (c != k) ? 1 : 0;
 #pragma unroll
-      for (int r = 0; r < 8; r++) { cnt_c[r] = 0; cnt_k[r] = 0; }
-      int msum = 0, ne = 0;
-      const bool want_pairs = a.pair_stat != nullptr;
-      if (want_pairs)
-        for (int i = 0; i < 64; i++) pair[i] = 0;
-      for (unsigned p0 = 0; p0 < P; p0 += HYG_DMP_FLUSH) {
-        const unsigned p1 = (p0 + HYG_DMP_FLUSH < P) ? p0 + HYG_DMP_FLUSH : P;
-        unsigned long long cc = 0ull, kc = 0ull;
-        unsigned p = p0;
-        if ((P & 3u) == 0u) {   // rows are 4-byte aligned: one shared-memory word = four particles
-          for (; p + 4 <= p1; p += 4) {
-            const unsigned mw = *reinterpret_cast<const unsigned*>(rm + p);
-            const unsigned cw = *reinterpret_cast<const unsigned*>(rc + p);
-            const unsigned kw = *reinterpret_cast<const unsigned*>(rk + p);
-            msum += static_cast<int>((mw & 0xFFu) + ((mw >> 8) & 0xFFu) + ((mw >> 16) & 0xFFu) + (mw >> 24));
-            dmp_count_particle(cw & 0xFFu, kw & 0xFFu, cc, kc, ne);
-            dmp_count_particle((cw >> 8) & 0xFFu, (kw >> 8) & 0xFFu, cc, kc, ne);
-            dmp_count_particle((cw >> 16) & 0xFFu, (kw >> 16) & 0xFFu, cc, kc, ne);
-            dmp_count_particle(cw >> 24, kw >> 24, cc, kc, ne);
-          }
+          for (int r = 0; r < 8; r++) { cnt_c[r] += (c == static_cast<unsigned>(r)) ? 1 : 0; cnt_k[r] += (k == static_cast<unsigned>(r)) ? 1 : 0; }
         }
-        for (; p < p1; p++) {
-          msum += rm[p];
-          dmp_count_particle(rc[p], rk[p], cc, kc, ne);
-        }
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-          cnt_c[r] += static_cast<int>((cc >> (8 * r)) & 0xFFull);
-          cnt_k[r] += static_cast<int>((kc >> (8 * r)) & 0xFFull);
-        }
-        if (want_pairs)
-          for (unsigned q = p0; q < p1; q++) pair[(rc[q] & 7u) * 8u + (rk[q] & 7u)]++;
       }
-      const unsigned long long t = t0 + tid;
+    }
+    // ---- combine the HYG_DMP_LANES partial counts of a site (adjacent lanes of one warp) ----
+#pragma unroll
+    for (int o = 1; o < HYG_DMP_LANES; o <<= 1) {
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        cnt_c[r] += __shfl_xor_sync(0xffffffffu, cnt_c[r], o);
+        cnt_k[r] += __shfl_xor_sync(0xffffffffu, cnt_k[r], o);
+      }
+      msum += __shfl_xor_sync(0xffffffffu, msum, o);
+      ne += __shfl_xor_sync(0xffffffffu, ne, o);
+    }
+    if (active) {
+      const unsigned long long t = t0 + site;
       const double dP = static_cast<double>(P);
-      a.split_prob[t] = static_cast<double>(static_cast<int>(P) - msum) / dP;       // np.mean(merged == 0, axis = 1)
-      a.null_stat[t] = 1.0 - static_cast<double>(ne) / dP;                            // 1. - np.sum(control != case) / P
-      if (a.control_freq) {
-#pragma unroll
-        for (unsigned r = 0; r < 8; r++)
-          if (r < a.R) a.control_freq[t * a.R + r] = static_cast<double>(cnt_c[r]) / dP;   // np.bincount(row) / row.shape[0]
+      if (q == 0) {
+        a.split_prob[t] = quot[static_cast<int>(P) - msum];       // np.mean(merged == 0, axis = 1)
+        a.null_stat[t] = 1.0 - quot[ne];                           // 1. - np.sum(control != case) / P
       }
-      if (a.case_freq) {
+      // lane q writes regimes q and q + 4 of both frequency rows: np.bincount(row) / row.shape[0]
 #pragma unroll
-        for (unsigned r = 0; r < 8; r++)
-          if (r < a.R) a.case_freq[t * a.R + r] = static_cast<double>(cnt_k[r]) / dP;
+      for (int r = 0; r < 8; r++) {
+        if ((r % HYG_DMP_LANES) == q && static_cast<unsigned>(r) < a.R) {
+          if (a.control_freq) a.control_freq[t * a.R + r] = quot[cnt_c[r]];
+          if (a.case_freq) a.case_freq[t * a.R + r] = quot[cnt_k[r]];
+        }
       }
-      if (want_pairs)
+      if (a.pair_stat && q == 0) {   // --test_regime_combinations: R x R table per site, built in local memory
+        const unsigned char* rc = sm_c + static_cast<size_t>(site) * P;
+        const unsigned char* rk = sm_k + static_cast<size_t>(site) * P;
+        int pair[64];
+        for (int i = 0; i < 64; i++) pair[i] = 0;
+        for (unsigned p = 0; p < P; p++) pair[(rc[p] & 7u) * 8u + (rk[p] & 7u)]++;
         for (unsigned i = 0; i < a.R; i++)
-          for (unsigned j = 0; j < a.R; j++)
-            a.pair_stat[(t * a.R + i) * a.R + j] = 1.0 - static_cast<double>(pair[i * 8 + j]) / dP;
+          for (unsigned jj = 0; jj < a.R; jj++) a.pair_stat[(t * a.R + i) * a.R + jj] = 1.0 - static_cast<double>(pair[i * 8 + jj]) / dP;
+      }
     }
-    __syncthreads();
+    __syncthreads();   // every row has been read before the next tile's copies land
   }
 }
 
 #ifndef HYG_EMU
 extern __shared__ __align__(16) unsigned char hyg_dmp_smem[];
-__global__ void __launch_bounds__(HYG_DMP_TILE) dmp_site_stats_kernel(DmpArgs a) { dmp_site_stats_entry(a, hyg_dmp_smem); }
+__global__ void __launch_bounds__(HYG_DMP_NT) dmp_site_stats_kernel(DmpArgs a) { dmp_site_stats_entry(a, hyg_dmp_smem); }
 
 // ---- FDR procedures (multiple_testing.py) : element-wise pieces; sorts and scans are thrust calls in hyg_api.cu ----
 // Qs[i] = 1 / (i + 1) * cumsum[i]   (multiple_testing.py:5-6: 1./np.linspace(1, n, n) * np.cumsum(sorted))

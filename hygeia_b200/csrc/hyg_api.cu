@@ -871,10 +871,16 @@ int hyg_tg_set_model(hyg_ctx* c, const hyg_tg_model* m, uint64_t t_max) {
   h.dmax = dmax;
   const size_t n = static_cast<size_t>(R) * (dmax + 1);
   dfree(c->d_tg_rho);
-  HYG_CUDA(c, cudaMalloc(&c->d_tg_rho, 2 * n * sizeof(double)));
-  HYG_CUDA(c, cudaMemcpy(c->d_tg_rho, rho_c.data(), n * sizeof(double), cudaMemcpyHostToDevice));
-  HYG_CUDA(c, cudaMemcpy(c->d_tg_rho + n, rho_k.data(), n * sizeof(double), cudaMemcpyHostToDevice));
-  h.rho_c = c->d_tg_rho; h.rho_k = c->d_tg_rho + n;
+  // the kernels only ever need log rho and log(1 - rho): taken here with libm (as the oracle does), two per entry
+  std::vector<double> lr(4 * n);
+  for (size_t i = 0; i < n; i++) {
+    lr[2 * i] = std::log(rho_c[i]); lr[2 * i + 1] = std::log(1.0 - rho_c[i]);
+    lr[2 * n + 2 * i] = std::log(rho_k[i]); lr[2 * n + 2 * i + 1] = std::log(1.0 - rho_k[i]);
+  }
+  HYG_CUDA(c, cudaMalloc(&c->d_tg_rho, 4 * n * sizeof(double)));
+  HYG_CUDA(c, cudaMemcpy(c->d_tg_rho, lr.data(), 4 * n * sizeof(double), cudaMemcpyHostToDevice));
+  h.lrho_c = reinterpret_cast<const double2*>(c->d_tg_rho); h.lrho_k = reinterpret_cast<const double2*>(c->d_tg_rho + 2 * n);
+  h.nl_rm1 = -std::log(static_cast<double>(R) - 1.0); h.nl_rm2 = -std::log(static_cast<double>(R) - 2.0);
   if (!c->d_tg_mdl) HYG_CUDA(c, cudaMalloc(&c->d_tg_mdl, sizeof(hyg::TgModelDev)));
   HYG_CUDA(c, cudaMemcpy(c->d_tg_mdl, &h, sizeof(h), cudaMemcpyHostToDevice));
   c->tg_set = true;

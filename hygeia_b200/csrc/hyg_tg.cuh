@@ -39,8 +39,10 @@ struct TgModelDev {
   uint32_t dmax;                 // hazard tables hold d = 0..dmax per regime (row pitch dmax + 1)
   double logP[HYG_RMAX][HYG_RMAX];   // control regime transitions (log, -inf diagonal)
   double logPm[2][2];            // merged-indicator transitions (log), rows = previous
-  const double* rho_c;           // [R][dmax+1]
-  const double* rho_k;           // [R][dmax+1]
+  // hazards as host-built logs (libm, like the oracle): {log rho(d, r), log(1 - rho(d, r))}, [R][dmax+1]
+  const double2* lrho_c;
+  const double2* lrho_k;
+  double nl_rm1, nl_rm2;         // -log(R - 1), -log(R - 2)
 };
 
 struct TgState {   // one particle
@@ -90,7 +92,7 @@ __host__ __device__ __forceinline__ double tg_uniform(uint64_t seed, uint32_t ch
 
 // log transition density of `n` given `p` (case_control_regime_model.py:97-193; case_control_distributions.py:138-151,246-291)
 __device__ __forceinline__ double tg_log_trans(const TgModelDev& md, const TgState& p, const TgState& n, bool step0) {
-  const int R = md.R, u = md.u;
+  const int u = md.u;
   // merged indicator
   double lm;
   if (step0) lm = (n.m == 1) ? 0.0 : -HYG_INF;
@@ -99,26 +101,26 @@ __device__ __forceinline__ double tg_log_trans(const TgModelDev& md, const TgSta
   if (lm == -HYG_INF) return -HYG_INF;
   // control
   const uint32_t pitch = md.dmax + 1;
-  const double rho_c = step0 ? 1.0 : md.rho_c[p.rc * pitch + (static_cast<uint32_t>(p.dc) < md.dmax ? p.dc : md.dmax)];
+  const double2 lr_c = step0 ? make_double2(0.0, -HYG_INF) : md.lrho_c[p.rc * pitch + (static_cast<uint32_t>(p.dc) < md.dmax ? p.dc : md.dmax)];
   double lc;
-  if (n.dc == 1) lc = log(rho_c) + md.logP[p.rc][n.rc];
-  else lc = (n.dc == p.dc + 1 && n.rc == p.rc) ? log(1.0 - rho_c) : -HYG_INF;
+  if (n.dc == 1) lc = lr_c.x + md.logP[p.rc][n.rc];
+  else lc = (n.dc == p.dc + 1 && n.rc == p.rc) ? lr_c.y : -HYG_INF;
   if (!(lc > -HYG_INF)) return -HYG_INF;
   // case, first matching rule
   double lk;
   if (n.m == 1) {
     lk = (n.rc == n.rk && n.dc == n.dk) ? 0.0 : -HYG_INF;
   } else if (p.m == 1 && n.dc != 1) {
-    lk = (n.rk != n.rc && n.dk == 1) ? -log(static_cast<double>(R - 1)) : -HYG_INF;
+    lk = (n.rk != n.rc && n.dk == 1) ? md.nl_rm1 : -HYG_INF;
   } else {
     const bool allowed = (n.rk != n.rc) && (n.rk != p.rk);
-    const double unif = allowed ? -log(static_cast<double>(R) - ((n.rc == p.rk) ? 1.0 : 2.0)) : -HYG_INF;
+    const double unif = allowed ? ((n.rc == p.rk) ? md.nl_rm1 : md.nl_rm2) : -HYG_INF;
     if (n.rc == p.rk && p.m == 0) {
       lk = (n.dk == 1) ? unif : -HYG_INF;
     } else {
-      const double rho_k = step0 ? 1.0 : md.rho_k[p.rk * pitch + (static_cast<uint32_t>(p.dk) < md.dmax ? p.dk : md.dmax)];
-      if (n.dk == 1) lk = log(rho_k) + unif;
-      else lk = (n.dk == p.dk + 1 && n.rk == p.rk) ? log(1.0 - rho_k) : -HYG_INF;
+      const double2 lr_k = step0 ? make_double2(0.0, -HYG_INF) : md.lrho_k[p.rk * pitch + (static_cast<uint32_t>(p.dk) < md.dmax ? p.dk : md.dmax)];
+      if (n.dk == 1) lk = lr_k.x + unif;
+      else lk = (n.dk == p.dk + 1 && n.rk == p.rk) ? lr_k.y : -HYG_INF;
     }
   }
   const double out = lm + lc + lk;

@@ -491,7 +491,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           // sort by log-weight, descending (ties by slot); W is a monotone map of logw
           // (dead slots get distinct tiny keys so that every key is unique)
           unsigned long long key = (tid < N_prev) ? order_key(p.lw, tid) : static_cast<unsigned long long>(255 - tid);
-          key = block_sort_desc(key, s);   // 2 barriers; s.part[pA] / s.vmask[pA] are visible after the first
+          key = block_sort_desc(key, s);   // s.part[pA] / s.vmask[pA] are visible after its first barrier
           sidx = 255 - static_cast<int>(key & 0xFFull);
           s.idx[tid] = static_cast<unsigned short>(sidx);
           totA = combine8(s.part[pA]);

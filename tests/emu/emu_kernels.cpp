@@ -97,7 +97,14 @@ int hygemu_tg_run(int R, int u, int M, int B, const double* logP /*R x R*/, cons
   mdl.R = R; mdl.u = u; mdl.M = M; mdl.B = B; mdl.dmax = dmax;
   for (int i = 0; i < R; i++) for (int j = 0; j < R; j++) mdl.logP[i][j] = logP[i * R + j];
   for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++) mdl.logPm[i][j] = logPm[i * 2 + j];
-  mdl.rho_c = rho_c; mdl.rho_k = rho_k;
+  const size_t nrho = static_cast<size_t>(R) * (dmax + 1);
+  std::vector<double2> lrc(nrho), lrk(nrho);
+  for (size_t i = 0; i < nrho; i++) {
+    lrc[i] = make_double2(std::log(rho_c[i]), std::log(1.0 - rho_c[i]));
+    lrk[i] = make_double2(std::log(rho_k[i]), std::log(1.0 - rho_k[i]));
+  }
+  mdl.lrho_c = lrc.data(); mdl.lrho_k = lrk.data();
+  mdl.nl_rm1 = -std::log(static_cast<double>(R) - 1.0); mdl.nl_rm2 = -std::log(static_cast<double>(R) - 2.0);
   hyg::TgChainDev ch;
   ch.T = T; ch.lo_c = lo_c; ch.lo_k = lo_k; ch.seed = seed; ch.chain = chain; ch.traj = traj; ch.log_norm = log_norm; ch.taps = taps;
   hyg::TgRunDev run;

@@ -357,7 +357,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
   constexpr int R = RT;
   const int Nmax = mdl.n_particles;
   uint32_t dcap = mdl.dcap;
-  const unsigned long long T = ch.T;
+  const unsigned int T = static_cast<unsigned int>(ch.T);   // sites of this unit (< 2^32): 32-bit counters in the hot loop
   const int lcap = run.lcap;
   int flip = 0, ibuf = 0, pbuf = 0;
   constexpr int D = R * R;
@@ -390,7 +390,8 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
   int* pend_t = reinterpret_cast<int*>(psi_ws + 2 * static_cast<size_t>(lcap) * R * HYG_NPMAX);
   int n_pend = 0, n_forced = 0, max_pend = 0;
   // segmented execution: local sites [own_lo, own_hi) are written, the rest is warm-up / run-out (hyg_dev_structs.h)
-  const unsigned long long own_lo = ch.own_lo, own_hi = ch.own_hi, t_off = ch.t_off;
+  const unsigned int own_lo = static_cast<unsigned int>(ch.own_lo), own_hi = static_cast<unsigned int>(ch.own_hi);
+  const unsigned long long t_off = ch.t_off;
   const bool last_seg = ch.last_segment != 0;
   int n_halo_forced = 0;
   int n_steps = 0;
@@ -427,13 +428,13 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
   }
 
   double pos_nxt = (tid == 0) ? (ch.pos ? static_cast<double>(__ldg(ch.pos)) : static_cast<double>(t_off)) : 0.0;
-  for (unsigned long long t = 0; t < T; t++) {
+  for (unsigned int t = 0; t < T; t++) {
     const double* lo = s.lo[t & 1];
     // emission row of site t+2: issued now by the service warp, stored at the end of this step
-    const double lo_pref = (service && lane < R && t + 2 < T) ? __ldg(ch.logobs + (t + 2) * R + lane) : 0.0;
+    const double lo_pref = (service && lane < R && t + 2 < T) ? __ldg(ch.logobs + static_cast<size_t>(t + 2) * R + lane) : 0.0;
     // genomic position of the next site, loaded a step ahead by the thread that writes column 0 of the posterior rows
     const double pos_cur = pos_nxt;
-    if (tid == 0 && t + 1 < T) pos_nxt = ch.pos ? static_cast<double>(__ldg(ch.pos + t + 1)) : static_cast<double>(t + 1 + t_off);
+    if (tid == 0 && t + 1 < T) pos_nxt = ch.pos ? static_cast<double>(__ldg(ch.pos + t + 1)) : static_cast<double>(static_cast<unsigned long long>(t) + 1ull + t_off);
     int k_kept = -1;
     bool drew = false;
     bool emit_now = false;       // current site finalised at this step
@@ -611,7 +612,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
         }
       }
       if (ch.ancestors && own_t && tid < Nmax - R)
-        ch.ancestors[t * static_cast<unsigned long long>(Nmax - R) + tid] = (tid < M) ? static_cast<short>(anc) : static_cast<short>(-1);
+        ch.ancestors[static_cast<unsigned long long>(t) * static_cast<unsigned long long>(Nmax - R) + tid] = (tid < M) ? static_cast<short>(anc) : static_cast<short>(-1);
 
       // ---- propose + weight: sampleParticlesCp / computeWeightsCp (Smc.h:504-574) ----
       const double lsum_prev = s.lsum[(t + 1) & 1];
@@ -862,7 +863,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
     // segmented execution: stop as soon as the owned range is stepped through and none of its sites is still pending
     // (the lag set is ordered by site, oldest first)
     bool exit_now = false;
-    if (!PE && t + 1 >= own_hi && t + 1 < T) exit_now = (n_pend == 0) || (static_cast<unsigned long long>(pend_t[0]) >= own_hi);
+    if (!PE && t + 1 >= own_hi && t + 1 < T) exit_now = (n_pend == 0) || (static_cast<unsigned int>(pend_t[0]) >= own_hi);
     const bool last_step = (t == T - 1) || exit_now;
     n_steps++;
 
@@ -896,7 +897,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
         }
         __syncthreads();
       }
-      if (ch.theta_trace && tid < D) ch.theta_trace[t * D + tid] = pe->theta[tid];
+      if (ch.theta_trace && tid < D) ch.theta_trace[static_cast<size_t>(t) * D + tid] = pe->theta[tid];
     }
 
     // ---- taps ----

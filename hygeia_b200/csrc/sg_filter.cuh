@@ -56,6 +56,8 @@ struct SgSmem {
   double partG[2][HYG_NW][8];  // parameter mode: partials of Eg[r'] = sum e_n dlogrho_n
   unsigned vmask[2][HYG_NW];
   int slow[HYG_RMAX];
+  unsigned slowmask;           // bit r: regime r takes the log-domain path at this site
+  double lomax[2];             // max_r logObs(t, r), [t & 1] (published by the service warp with the prefetched row)
   double new_lw[HYG_RMAX];     // log-weight of the new-segment particle (1, r)
   double new_invE[HYG_RMAX];   // 1 / sumE[r]
   double u;                    // resampling uniform of the current site
@@ -239,6 +241,8 @@ __device__ __forceinline__ double sg_service_new_segments(const SgModelDev& mdl,
     s.new_invE[lane] = lin ? 1.0 / a : 0.0;
     s.slow[lane] = (!lin && could) ? 1 : 0;
   }
+  const unsigned smask = __ballot_sync(HYG_FULL, (lane < R) && !(a > HYG_LINEAR_FLOOR) && could);
+  if (lane == 0) s.slowmask = smask;
   return a;
 }
 
@@ -404,6 +408,12 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
   if (tid < R) s.lo[0][tid] = __ldg(ch.logobs + tid);
   if (T > 1 && tid < R) s.lo[1][tid] = __ldg(ch.logobs + R + tid);
   __syncthreads();
+  if (tid < 2 && static_cast<unsigned int>(tid) < T) {
+    double m = s.lo[tid][0];
+#pragma unroll
+    for (int r = 1; r < R; r++) m = s.lo[tid][r] > m ? s.lo[tid][r] : m;
+    s.lomax[tid] = m;
+  }
   int N = R;
   double pend_shift = 0.0, pend_S = 1.0;   // log Z of the last completed site = pend_shift + log(pend_S)
   {
@@ -448,9 +458,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       const int M = N_curr - R;
       const bool capped = (N_curr < N_prev + R);
       int anc = tid;
-      double lomax = lo[0];
-#pragma unroll
-      for (int r = 1; r < R; r++) lomax = lo[r] > lomax ? lo[r] : lomax;
+      const double lomax = s.lomax[t & 1];
 
       if (service) {
         // the uniform of this site, and log Z_{t-1}: the log of last step's normaliser is evaluated now, off the
@@ -645,9 +653,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       }
       const double my_invE = (tid >= M && tid < N_curr) ? s.new_invE[tid - M] : 0.0;
       // exact log-domain path for regimes whose linear-domain sum underflowed (rare)
-      unsigned slowmask = 0;
-#pragma unroll
-      for (int r = 0; r < R; r++) slowmask |= (s.slow[r] ? 1u : 0u) << r;
+      const unsigned slowmask = s.slowmask;
       double bk_slow[R];
 #pragma unroll
       for (int r = 0; r < R; r++) bk_slow[r] = 0.0;
@@ -858,7 +864,13 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       s.W[tid] = p.W; s.lw[tid] = p.lw; s.cur[tid] = p.cur; s.nxt[tid] = p.nxt; s.d[tid] = p.d; s.r[tid] = static_cast<unsigned char>(p.r);
       if (PE) { pe->gcur[tid] = p.gcur; pe->gnxt[tid] = p.gnxt; }
     }
-    if (service && lane < R && t + 2 < T) s.lo[t & 1][lane] = lo_pref;
+    if (service && t + 2 < T) {
+      if (lane < R) s.lo[t & 1][lane] = lo_pref;
+      double mx = (lane < R) ? lo_pref : -HYG_INF;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) { const double tt = __shfl_xor_sync(HYG_FULL, mx, o); mx = tt > mx ? tt : mx; }
+      if (lane == 0) s.lomax[t & 1] = mx;
+    }
     __syncthreads();
     // segmented execution: stop as soon as the owned range is stepped through and none of its sites is still pending
     // (the lag set is ordered by site, oldest first)

@@ -199,6 +199,43 @@ __device__ __forceinline__ double warp_reduce8(const double (&v)[8]) {
   w1 += __shfl_xor_sync(HYG_FULL, w1, 1);
   return w1;
 }
+// The same reduction for the one-hot input v[i] = (i == r ? e : 0), i < 7, v[7] = x7 (r < 7): the first exchange stage needs
+// only the class index relative to the half the lane sends / keeps, so the eight values are never materialised.  Bit-identical
+// to warp_reduce8 on that input (same additions in the same order).
+__device__ __forceinline__ double warp_reduce_onehot(double e, int r, double x7) {
+  const int lane = threadIdx.x & 31;
+  double w4[4], w2[2], w1;
+  {
+    const bool hi = (lane & 16) != 0;
+    const int rs = hi ? r : r - 4;   // index (0..3) of the non-zero among the four values this lane sends
+    const int rk = hi ? r - 4 : r;   // ... and among the four it keeps
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      double send = (rs == i) ? e : 0.0;
+      double keep = (rk == i) ? e : 0.0;
+      if (i == 3) { send = hi ? send : x7; keep = hi ? x7 : keep; }   // v[7] travels with the upper four
+      w4[i] = keep + __shfl_xor_sync(HYG_FULL, send, 16);
+    }
+  }
+  {
+    const bool hi = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const double send = hi ? w4[i] : w4[i + 2];
+      const double keep = hi ? w4[i + 2] : w4[i];
+      w2[i] = keep + __shfl_xor_sync(HYG_FULL, send, 8);
+    }
+  }
+  {
+    const bool hi = (lane & 4) != 0;
+    const double send = hi ? w2[0] : w2[1];
+    const double keep = hi ? w2[1] : w2[0];
+    w1 = keep + __shfl_xor_sync(HYG_FULL, send, 4);
+  }
+  w1 += __shfl_xor_sync(HYG_FULL, w1, 2);
+  w1 += __shfl_xor_sync(HYG_FULL, w1, 1);
+  return w1;
+}
 // Lanes 0,4,..,28 publish the warp totals; any warp then folds the eight rows with two loads and two shuffle steps.
 __device__ __forceinline__ void publish8(double (*part)[8], double wtot) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -473,18 +510,13 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       const bool finite_prev = (tid < N_prev) && hyg_isfinite(p.lw);
       const bool valid = finite_prev && (p.cur.x > 0.0);
       if (worker) {
-        double v8[8];
-#pragma unroll
-        for (int r = 0; r < 8; r++) v8[r] = (r < R && p.r == r) ? e_prev : 0.0;
-        v8[7] = finite_prev ? 1.0 : 0.0;  // F = #finite(logw_prev), Smc.h:413 (exact in fp64)
-        publish8(s.part[pbuf], warp_reduce8(v8));
+        // class sums of e_prev; slot 7: F = #finite(logw_prev), Smc.h:413 (exact in fp64).  e_prev is 0 beyond N_prev.
+        publish8(s.part[pbuf], warp_reduce_onehot(e_prev, p.r, finite_prev ? 1.0 : 0.0));
         const unsigned vm = __reduce_or_sync(HYG_FULL, valid ? (1u << p.r) : 0u);
         if (lane == 0) s.vmask[pbuf][warp] = vm;
         if (PE) {
           pe->eprev[tid] = e_prev;
-#pragma unroll
-          for (int r = 0; r < 8; r++) v8[r] = (r < R && p.r == r) ? e_prev * p.gcur : 0.0;
-          publish8(s.partG[pbuf], warp_reduce8(v8));
+          publish8(s.partG[pbuf], warp_reduce_onehot(e_prev * p.gcur, p.r, 0.0));
         }
       }
       const int pA = pbuf;
@@ -559,9 +591,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           const unsigned sb = __ballot_sync(HYG_FULL, stop);
           if (lane == 0) s.iscan[ibuf][warp] = sb ? (warp * 32 + __ffs(static_cast<int>(sb)) - 1) : HYG_NPMAX;
           __syncthreads();
-          K = HYG_NPMAX;
-#pragma unroll
-          for (int w = 0; w < HYG_NW; w++) K = s.iscan[ibuf][w] < K ? s.iscan[ibuf][w] : K;
+          K = __reduce_min_sync(HYG_FULL, (lane < HYG_NW) ? s.iscan[ibuf][lane] : HYG_NPMAX);   // one load + one warp reduction
           ibuf ^= 1;
           if (K >= M) {
             keep_largest = true;  // log C not finite (resample.h:345,366)
@@ -603,9 +633,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           }
           if (lane == 31) s.iscan[ibuf][warp] = C;
           __syncthreads();
-          int before = 0;
-#pragma unroll
-          for (int w = 0; w < HYG_NW - 1; w++) before = (w < warp && s.iscan[ibuf][w] > before) ? s.iscan[ibuf][w] : before;
+          int before = __reduce_max_sync(HYG_FULL, (lane < warp && lane < HYG_NW - 1) ? s.iscan[ibuf][lane] : 0);
           ibuf ^= 1;
           C = before > C ? before : C;
           int Cprev = __shfl_up_sync(HYG_FULL, C, 1);
@@ -675,13 +703,8 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       // ---- selfNormaliseWeights (Smc.h:576-579), fused with the regime masses of the new site ----
       {
         double shift = lsum_prev + lomax;   // upper bound of every logw instead of the exact max
-        double v8[8];
         c.W = (tid < N_curr) ? exp(c.lw - shift) : 0.0;
-        if (worker) {
-#pragma unroll
-          for (int q = 0; q < 8; q++) v8[q] = (q < R && c.r == q) ? c.W : 0.0;
-          publish8(s.part[pbuf], warp_reduce8(v8));
-        }
+        if (worker) publish8(s.part[pbuf], warp_reduce_onehot(c.W, c.r, 0.0));   // c.W is 0 beyond N_curr
         __syncthreads();
         double tot = combine8(s.part[pbuf]);   // lane & 7 -> class sum of the relative weights
         pbuf ^= 1;
@@ -693,11 +716,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           // the linear-domain weights underflowed against the bound: renormalise from the log-weights with the exact max
           shift = block_max((tid < N_curr) ? c.lw : -HYG_INF, s.sc, flip);
           c.W = (tid < N_curr && c.lw > -HYG_INF) ? exp(c.lw - shift) : 0.0;
-          if (worker) {
-#pragma unroll
-            for (int q = 0; q < 8; q++) v8[q] = (q < R && c.r == q) ? c.W : 0.0;
-            publish8(s.part[pbuf], warp_reduce8(v8));
-          }
+          if (worker) publish8(s.part[pbuf], warp_reduce_onehot(c.W, c.r, 0.0));
           __syncthreads();
           tot = combine8(s.part[pbuf]);
           pbuf ^= 1;

@@ -286,6 +286,15 @@ inline unsigned __reduce_or_sync(unsigned, unsigned v) {
   });
   return emu::my_warp().ballot;
 }
+inline int __reduce_max_sync(unsigned, int v) {
+  emu::warp_rendezvous(static_cast<uint64_t>(static_cast<int64_t>(v)), [](emu::WarpState& w) {
+    int64_t b = INT64_MIN;
+    unsigned n = emu::warp_width();
+    for (unsigned i = 0; i < n; i++) b = static_cast<int64_t>(w.slot[i]) > b ? static_cast<int64_t>(w.slot[i]) : b;
+    w.result[0] = static_cast<uint64_t>(b);
+  });
+  return static_cast<int>(static_cast<int64_t>(emu::my_warp().result[0]));
+}
 inline int __reduce_min_sync(unsigned, int v) {
   emu::warp_rendezvous(static_cast<uint64_t>(static_cast<int64_t>(v)), [](emu::WarpState& w) {
     int64_t b = INT64_MAX;

@@ -578,7 +578,8 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           __syncthreads();
           double tail = 0.0;
 #pragma unroll
-          for (int w = HYG_NW - 1; w > 0; w--) tail += (w > warp) ? s.sc.d[flip][w][0] : 0.0;
+          for (int w = HYG_NW - 1; w > 0; w--)
+            if (w > warp) tail += s.sc.d[flip][w][0];   // warp-uniform predicate: the additions of the warps below are skipped
           flip ^= 1;
           const double Qp = v + tail;
           if (worker) s.Q[tid] = Qp;

@@ -26,6 +26,15 @@
 
 namespace hyg {
 
+// bar.sync id, count: a barrier among `count` threads (whole warps) of the CTA; id 1..15 (0 is __syncthreads)
+__device__ __forceinline__ void named_barrier(int id, int count) {
+#ifdef HYG_EMU
+  hyg_emu_named_barrier(id, static_cast<unsigned>(count));
+#else
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(HYG_FULL, v, o);

@@ -45,7 +45,7 @@ struct SgSmem {
   uint32_t d[HYG_NPMAX];
   unsigned char r[HYG_NPMAX];
   // resampling scratch
-  unsigned long long key[2][HYG_NPMAX];
+  unsigned long long key[6][HYG_NPMAX];   // one exchange buffer per cross-warp sort stage (no reuse inside a site)
   double Q[HYG_NPMAX + 1];
   unsigned short idx[HYG_NPMAX];
   unsigned short anc[HYG_NPMAX];
@@ -120,11 +120,13 @@ __device__ __forceinline__ unsigned long long block_sort_desc(unsigned long long
 }
 
 #else
-#define HYG_SORT_BARRIERS 6
+#define HYG_SORT_BARRIERS 1
 // Descending bitonic sort of one 64-bit key per worker thread (256 keys): strides < 32 by warp shuffles, strides
-// 32/64/128 through shared memory (6 exchange stages, double-buffered so that each costs one barrier).
+// 32/64/128 through shared memory (6 exchange stages, each with its own buffer).  The first exchange is a full block barrier
+// (it also publishes the class sums to every warp, service warp included); in the other five a warp only needs its partner
+// warp's keys, so they are 64-thread named barriers: id = 1 + 4 log2(stride / 32) + pair index, always the same two warps per id.
 __device__ __forceinline__ unsigned long long block_sort_desc(unsigned long long key, SgSmem& s) {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5;
   int kbuf = 0;
 #pragma unroll
   for (int k = 2; k <= HYG_NPMAX; k <<= 1) {
@@ -135,9 +137,16 @@ __device__ __forceinline__ unsigned long long block_sort_desc(unsigned long long
         other = __shfl_xor_sync(HYG_FULL, key, j);
       } else {
         s.key[kbuf][tid] = key;
-        __syncthreads();
+        if (kbuf == 0) {
+          __syncthreads();
+        } else {
+          // pair index: the warp number with the bit of the partner stride removed
+          const int jw = j >> 5;   // 1, 2, 4
+          const int pair = (warp & (jw - 1)) | ((warp & ~(2 * jw - 1)) >> 1);
+          named_barrier(1 + 4 * (jw == 1 ? 0 : (jw == 2 ? 1 : 2)) + pair, 64);
+        }
         other = s.key[kbuf][tid ^ j];
-        kbuf ^= 1;
+        kbuf++;
       }
       const bool desc_block = ((tid & k) == 0);
       const bool lower = ((tid & j) == 0);

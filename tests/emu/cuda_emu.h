@@ -64,9 +64,15 @@ struct Fiber {
   std::vector<char> stack;
   bool done = false;
   unsigned tid = 0;
-  // parked at: 0 none, 1 block barrier, 2 warp collective
+  // parked at: 0 none, 1 block barrier, 2 warp collective, 3 named barrier `bar_id`
   int parked = 0;
+  int bar_id = 0;
   unsigned long long gen = 0;
+};
+
+struct NamedBarrier {   // bar.sync id, count
+  unsigned long long gen = 0;
+  unsigned arrived = 0;
 };
 
 struct WarpState {
@@ -82,6 +88,7 @@ struct BlockState {
   std::vector<WarpState> warps;
   unsigned long long gen = 0;
   unsigned arrived = 0;
+  NamedBarrier named[16];
   unsigned live = 0;
   unsigned nthreads = 0;
   void* sched_sp = nullptr;
@@ -127,6 +134,24 @@ inline void block_barrier() {
   }
   f.parked = 1;
   while (b->gen == my) yield_to_sched();
+  f.parked = 0;
+}
+
+// bar.sync id, count: the first `count` threads to arrive are released together
+inline void named_barrier(int id, unsigned count) {
+  BlockState* b = cur_block();
+  Fiber& f = b->fibers[b->current];
+  NamedBarrier& nb = b->named[id];
+  unsigned long long my = nb.gen;
+  nb.arrived++;
+  if (nb.arrived == count) {
+    nb.arrived = 0;
+    nb.gen++;
+    return;
+  }
+  f.parked = 3;
+  f.bar_id = id;
+  while (nb.gen == my) yield_to_sched();
   f.parked = 0;
 }
 
@@ -198,12 +223,13 @@ template <class K> void launch(dim3 grid, dim3 block, K kernel_body) {
             if (f.done) continue;
             if (f.parked == 1 && f.gen == bs.gen) continue;                 // still waiting on block barrier
             if (f.parked == 2 && f.gen == bs.warps[w].gen) continue;       // still waiting on warp collective
+            if (f.parked == 3 && f.gen == bs.named[f.bar_id].gen) continue; // still waiting on a named barrier
             // remember generations so the skip tests above are valid
             bs.current = static_cast<int>(w * 32 + l);
             threadIdx = emu_dim3(f.tid);
             hyg_emu_ctx_switch(&bs.sched_sp, f.sp);
             // after it yields, snapshot what it is waiting for
-            if (!f.done) f.gen = (f.parked == 1) ? bs.gen : (f.parked == 2 ? bs.warps[w].gen : 0);
+            if (!f.done) f.gen = (f.parked == 1) ? bs.gen : (f.parked == 2 ? bs.warps[w].gen : (f.parked == 3 ? bs.named[f.bar_id].gen : 0));
             progressed = true;
             any = true;
           }
@@ -215,6 +241,7 @@ template <class K> void launch(dim3 grid, dim3 block, K kernel_body) {
             if (f.done) continue;
             if (f.parked == 1 && f.gen == bs.gen) continue;
             if (f.parked == 2 && f.gen == bs.warps[w].gen) continue;
+            if (f.parked == 3 && f.gen == bs.named[f.bar_id].gen) continue;
             runnable = true;
           }
           progressed = runnable;
@@ -239,6 +266,7 @@ template <class K> void launch(dim3 grid, dim3 block, K kernel_body) {
 // CUDA intrinsics used by the kernels
 // ---------------------------------------------------------------------------
 inline void __syncthreads() { emu::block_barrier(); }
+inline void hyg_emu_named_barrier(int id, unsigned count) { emu::named_barrier(id, count); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_rendezvous(0, [](emu::WarpState&) {}); }
 inline void __threadfence() {}
 inline void __threadfence_block() {}

@@ -48,6 +48,8 @@ def parse():
                    help="K2 execution: -1 = segmented, size chosen by the library (default); 0 = whole chains (the reference's "
                         "sequential run); N = segments of <= N sites")
     p.add_argument("--halo", type=int, default=5000, help="left/right halo of a segment (sites)")
+    p.add_argument("--no-e2e-pipeline", dest="e2e_pipeline", action="store_false",
+                   help="end-to-end leg with ONE session (copies not overlapped with the recursion)")
     p.add_argument("--no-mode-check", action="store_true", help="skip the full-size comparison of segmented vs whole-chain results")
     return p.parse_args()
 
@@ -257,20 +259,24 @@ def main():
     seg_request = Session.SEGMENT_AUTO if args.segment_sites < 0 else args.segment_sites
     sess.set_segmentation(seg_request, args.halo, args.halo)
 
-    def stage(device_resident):
-        sess.clear()
-        sess.set_vartheta(vartheta)
-        sess.set_theta(theta, max(c["T"] for c in chroms))
+    def stage(device_resident, ses=None, which=None):
+        """Stage the chromosomes `which` (indices into chroms; default all) on session `ses` (default the main one)."""
+        ses = ses or sess
+        which = range(len(chroms)) if which is None else which
+        ses.clear()
+        ses.set_vartheta(vartheta)
+        ses.set_theta(theta, max(c["T"] for c in chroms))
         specs = []
-        for ci, c in enumerate(chroms):
+        for ci in which:
+            c = chroms[ci]
             if device_resident:
-                ds = sess.add_dataset_ptr(c["T"], S, c["n_total"].data_ptr(), c["n_meth"].data_ptr(), True, c["pitch"])
+                ds = ses.add_dataset_ptr(c["T"], S, c["n_total"].data_ptr(), c["n_meth"].data_ptr(), True, c["pitch"])
             else:
-                ds = sess.add_dataset_ptr(c["T"], S, c["h_nt"].data_ptr(), c["h_nm"].data_ptr(), False, c["T"])
+                ds = ses.add_dataset_ptr(c["T"], S, c["h_nt"].data_ptr(), c["h_nm"].data_ptr(), False, c["T"])
             for k, sd in enumerate(seeds):
                 specs.append(dict(dataset=ds, seed=sd, chain_id=ci, positions=c["h_pos"].data_ptr(),
                                   regime_probs=c["out"][k]["probs"].data_ptr(), logz=c["out"][k]["logz"].data_ptr()))
-        sess.set_chains(specs)
+        ses.set_chains(specs)
         return len(specs)
 
     def barrier():
@@ -373,11 +379,23 @@ def main():
     if not args.no_e2e:
         h2d = sum(2 * S * c["T"] * 2 + c["T"] * 4 * n_seeds for c in chroms)
         d2h = sum((c["T"] * (1 + R) * 8 + c["T"] * 8) * n_seeds for c in chroms)
+        # Two contexts (two streams) take half of the chromosomes each, so that the host -> device copy of the second half and
+        # the device -> host copy of the first half's log Z overlap the recursion of the other half.
+        order = sorted(range(len(chroms)), key=lambda i: -chroms[i]["T"])
+        halves = [order[0::2], order[1::2]] if args.e2e_pipeline else [list(range(len(chroms)))]
+        sessions = [sess]
+        if len(halves) > 1:
+            s2 = Session(local)
+            s2.set_segmentation(seg_request, args.halo, args.halo)
+            sessions.append(s2)
+
         def step_e2e():
-            stage(False)
-            sess.emission()
-            sess.filter(run_args)
-            sess.download()
+            for ses, which in zip(sessions, halves):
+                stage(False, ses, which)
+                ses.emission()
+                ses.filter(run_args)
+            for ses in sessions:
+                ses.download()
         step_e2e()
         barrier()
         t0 = time.perf_counter()
@@ -391,7 +409,9 @@ def main():
         e2e_s = float(te[0])
         e2e = {"value": units_per_step * world * args.e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": 1000.0 * e2e_s / args.e2e_steps, "steps": args.e2e_steps,
-               "api": "hygeia_b200.single_group.Session: add_dataset(pinned host) -> set_chains -> emission -> filter -> download; "
+               "api": "hygeia_b200.single_group.Session: add_dataset(pinned host) -> set_chains -> emission -> filter -> download"
+                      + (", two Sessions (contexts) with half of the chromosomes each so that copies overlap the other half's recursion; "
+                         if len(halves) > 1 else "; ") +
                       "posterior rows are written by K2 straight into the pinned host buffers (counted in d2h_bytes_per_step), "
                       "log Z is staged in HBM and copied"}
         # sanity on the downloaded results of the last step

@@ -487,10 +487,13 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
   for (unsigned int t = 0; t < T; t++) {
     const double* lo = s.lo[t & 1];
     // emission row of site t+2: issued now by the service warp, stored at the end of this step
-    const double lo_pref = (service && lane < R && t + 2 < T) ? __ldg(ch.logobs + static_cast<size_t>(t + 2) * R + lane) : 0.0;
+    double lo_pref = 0.0;
+    if (service) {   // warp-uniform: the eight worker warps skip the address arithmetic
+      if (lane < R && t + 2 < T) lo_pref = __ldg(ch.logobs + static_cast<size_t>(t + 2) * R + lane);
+    }
     // genomic position of the next site, loaded a step ahead by the thread that writes column 0 of the posterior rows
     const double pos_cur = pos_nxt;
-    if (tid == 0 && t + 1 < T) pos_nxt = ch.pos ? static_cast<double>(__ldg(ch.pos + t + 1)) : static_cast<double>(static_cast<unsigned long long>(t) + 1ull + t_off);
+    if (warp == 0 && tid == 0 && t + 1 < T) pos_nxt = ch.pos ? static_cast<double>(__ldg(ch.pos + t + 1)) : static_cast<double>(static_cast<unsigned long long>(t) + 1ull + t_off);
     int k_kept = -1;
     bool drew = false;
     bool emit_now = false;       // current site finalised at this step

@@ -75,6 +75,8 @@ struct hyg_ctx {
   std::string err;
   hyg::SgHostModel hm;
   bool model_set = false, theta_set = false;
+  bool model_kappa_fixed = true, model_had_kappa = false;
+  uint64_t theta_t_max = 0;
   double2* d_tab = nullptr;
   double* d_tabg = nullptr;
   hyg::SgModelDev* d_mdl = nullptr;
@@ -319,8 +321,9 @@ void hyg_destroy(hyg_ctx* c) {
   cudaStreamSynchronize(c->stream);
   free_chains(c);
   free_datasets(c);
+  pool_free(c, c->d_tab); pool_free(c, c->d_tabg); pool_free(c, c->d_emtab);
   pool_release(c);
-  dfree(c->d_tab); dfree(c->d_tabg); dfree(c->d_mdl); dfree(c->d_emtab); dfree(c->d_sets); dfree(c->d_psi); dfree(c->d_pe); dfree(c->d_theta0); dfree(c->d_queue); dfree(c->d_chains); dfree(c->d_fix); dfree(c->d_tg_mdl); dfree(c->d_tg_rho);
+  dfree(c->d_mdl); dfree(c->d_sets); dfree(c->d_psi); dfree(c->d_pe); dfree(c->d_theta0); dfree(c->d_queue); dfree(c->d_chains); dfree(c->d_fix); dfree(c->d_tg_mdl); dfree(c->d_tg_rho);
   cudaEventDestroy(c->ev_em0); cudaEventDestroy(c->ev_em1); cudaEventDestroy(c->ev_f0); cudaEventDestroy(c->ev_f1);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -335,16 +338,23 @@ int hyg_sync(hyg_ctx* c) {
 
 int hyg_sg_set_model(hyg_ctx* c, uint32_t R, uint32_t u, const double* alpha, const double* beta, int kappa_fixed, const double* kappa) {
   if (!c || !alpha || !beta) return fail(c, HYG_ERR_ARG, "null argument");
+  // unchanged model (repeated sweeps re-stage it): keep the tables that are already on the device
+  if (c->model_set && c->hm.R == static_cast<int>(R) && c->hm.u == static_cast<int>(u) && c->model_kappa_fixed == (kappa_fixed != 0) &&
+      std::equal(alpha, alpha + R, c->hm.alpha.begin()) && std::equal(beta, beta + R, c->hm.beta.begin()) &&
+      (!kappa || std::equal(kappa, kappa + R, c->hm.kappa.begin())) && (kappa || !c->model_had_kappa))
+    return HYG_OK;
   int rc = c->hm.set_known(static_cast<int>(R), static_cast<int>(u), alpha, beta, kappa_fixed, kappa);
   if (rc) return fail(c, rc == -2 ? HYG_ERR_UNSUPPORTED : HYG_ERR_ARG, c->hm.err);
   c->model_set = true;
   c->theta_set = false;
+  c->model_kappa_fixed = kappa_fixed != 0;
+  c->model_had_kappa = kappa != nullptr;
   // emission table (misc.h:630-640 tabulated over the triangle n <= nmax_table)
   HYG_CUDA(c, cudaSetDevice(c->device));
   std::vector<double> tab;
   hyg::build_emission_table(c->hm.alpha.data(), c->hm.beta.data(), c->hm.R, c->nmax_table, tab);
-  dfree(c->d_emtab);
-  HYG_CUDA(c, cudaMalloc(&c->d_emtab, tab.size() * sizeof(double)));
+  pool_free(c, c->d_emtab);   // pooled: cudaFree would synchronise the whole device, other contexts' kernels included
+  HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&c->d_emtab), tab.size() * sizeof(double)));
   HYG_CUDA(c, cudaMemcpyAsync(c->d_emtab, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   HYG_CUDA(c, cudaStreamSynchronize(c->stream));
   return HYG_OK;
@@ -362,12 +372,15 @@ int hyg_sg_set_vartheta(hyg_ctx* c, const double* vt, uint32_t n) {
 int hyg_sg_set_theta(hyg_ctx* c, const double* theta, uint32_t dim, uint64_t t_max) {
   if (!c || !theta) return fail(c, HYG_ERR_ARG, "null argument");
   if (!c->model_set) return fail(c, HYG_ERR_STATE, "hyg_sg_set_model first");
+  // unchanged theta and a table that is already long enough: nothing to rebuild
+  if (c->theta_set && dim == c->hm.theta.size() && std::equal(theta, theta + dim, c->hm.theta.begin()) && t_max <= c->theta_t_max) return HYG_OK;
   int rc = c->hm.set_theta(theta, dim, t_max);
   if (rc) return fail(c, HYG_ERR_ARG, c->hm.err);
+  c->theta_t_max = t_max;
   HYG_CUDA(c, cudaSetDevice(c->device));
-  dfree(c->d_tab); dfree(c->d_tabg);
-  HYG_CUDA(c, cudaMalloc(&c->d_tab, c->hm.tab.size() * sizeof(double)));
-  HYG_CUDA(c, cudaMalloc(&c->d_tabg, c->hm.tabg.size() * sizeof(double)));
+  pool_free(c, c->d_tab); pool_free(c, c->d_tabg);
+  HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&c->d_tab), c->hm.tab.size() * sizeof(double)));
+  HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&c->d_tabg), c->hm.tabg.size() * sizeof(double)));
   HYG_CUDA(c, cudaMemcpyAsync(c->d_tab, c->hm.tab.data(), c->hm.tab.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   HYG_CUDA(c, cudaMemcpyAsync(c->d_tabg, c->hm.tabg.data(), c->hm.tabg.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   HYG_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -10,7 +10,7 @@
 //   optimal finite-state + systematic resampling   hygeia/resampling_functions.py:7-69
 //   emission                    hygeia/case_control_regime_model.py:197-231  (= two K1 tables: control and case)
 //
-// B200 design: one 256-thread CTA per chain (chromosome x batch x seed); the <= 2400 particles of a site live in shared
+// B200 design: one 512-thread CTA per chain (chromosome x batch x seed); the <= 2400 particles of a site live in shared
 // memory; the emission term is the sum of two T x R tables produced by K1 (the reference evaluates 2400 x S beta-binomial
 // densities per site); only the FINITE-weight particles (typically 300-600) are compacted and sorted (shared-memory
 // bitonic network sized to the next power of two) for the optimal finite-state selection of the <= 50 ancestors.
@@ -22,7 +22,9 @@
 
 #include "hyg_common.cuh"
 
-#define HYG_TG_NT 256
+#ifndef HYG_TG_NT
+#define HYG_TG_NT 512   // measured on B200: 256 -> 173, 512 -> 133, 768 -> 153, 1024 -> 168 us per site and chain
+#endif
 #define HYG_TG_NW (HYG_TG_NT / 32)
 #define HYG_TG_NPMAX 2432     // >= M * (2R + R^2) for M = 50, R = 6, multiple of 256... (2400)
 #define HYG_TG_MMAX 64        // max resampled ancestors

@@ -1003,7 +1003,7 @@ int hyg_tg_site_statistics(hyg_ctx* c, uint64_t T, uint32_t P, uint32_t R, const
   if (!c || !merged || !control_regimes || !case_regimes || !split_prob || !null_stat) return fail(c, HYG_ERR_ARG, "null argument");
   if (T == 0 || P == 0 || R == 0 || R > 8) return fail(c, HYG_ERR_ARG, "need T > 0, P > 0, 1 <= R <= 8");
   const size_t smem = 16 + 3 * ((static_cast<size_t>(HYG_DMP_TILE) * P + 15) / 16 * 16) + (static_cast<size_t>(P) + 2) * sizeof(double);
-  if (smem > 227 * 1024) return fail(c, HYG_ERR_UNSUPPORTED, "more than 590 particles per site do not fit the shared-memory tile");
+  if (smem > 227 * 1024) return fail(c, HYG_ERR_UNSUPPORTED, "too many particles per site for the shared-memory tile");
   HYG_CUDA(c, cudaSetDevice(c->device));
   const size_t nb = static_cast<size_t>(T) * P;
   const int8_t* d_in[3] = {merged, control_regimes, case_regimes};

@@ -11,8 +11,8 @@
 // integers and every output is ONE fp64 division (and one subtraction), in the reference's order -- bit-identical results.
 //
 // B200 mapping: a streaming byte kernel, bound by HBM (3 P bytes in, 16 + 16 R bytes out per site).  Persistent CTAs take
-// tiles of 128 consecutive sites; the tile's rows are contiguous in memory, so the three [128][P] byte blocks are staged in
-// shared memory by TMA bulk copies (cp.async.bulk + mbarrier, one issuing thread); then four threads per site walk its rows
+// tiles of HYG_DMP_TILE consecutive sites; the tile's rows are contiguous in memory, so the three [tile][P] byte blocks are staged in
+// shared memory by TMA bulk copies (cp.async.bulk + mbarrier, one issuing thread); then HYG_DMP_LANES threads per site walk its rows
 // with 4-byte shared-memory loads, transpose 32 particles at a time into bit planes and count every regime with one LOP3 + POPC.
 #ifndef HYG_DMP_CUH
 #define HYG_DMP_CUH
@@ -23,8 +23,14 @@
 #include <cuda_runtime.h>
 #endif
 
-#define HYG_DMP_TILE 128      // sites per tile
-#define HYG_DMP_LANES 4       // threads per site (each walks every 4th word of the site's rows)
+#ifndef HYG_DMP_TILE
+#define HYG_DMP_TILE 32       // sites per tile (a multiple of 16, so that tiles start on 16-byte boundaries)
+#endif
+#ifndef HYG_DMP_LANES
+#define HYG_DMP_LANES 2       // threads per site (each walks every 2nd word of the site's rows); a power of two <= 8
+// (tile, lanes) measured on B200 at P = 200: (128, 4) 5.2 TB/s, (64, 4) 5.8, (32, 4) 6.2, (64, 2) 6.3, (32, 2) 6.5 -- small CTAs
+// (64 threads, 19 KB) keep ~10 tiles in flight per SM, which is what hides the TMA latency
+#endif
 #define HYG_DMP_NT (HYG_DMP_TILE * HYG_DMP_LANES)
 
 namespace hyg {
@@ -147,7 +153,7 @@ __device__ __forceinline__ void dmp_site_stats_entry(const DmpArgs& a, unsigned 
     const unsigned long long t0 = tile * HYG_DMP_TILE;
     const unsigned nt = static_cast<unsigned>((a.T - t0 < HYG_DMP_TILE) ? (a.T - t0) : HYG_DMP_TILE);
     const size_t bytes = static_cast<size_t>(nt) * P;
-    const size_t goff = static_cast<size_t>(t0) * P;   // multiple of 16: HYG_DMP_TILE = 8 x 16
+    const size_t goff = static_cast<size_t>(t0) * P;   // multiple of 16: HYG_DMP_TILE is
     dmp_stage3(sm_m, sm_c, sm_k, a.merged + goff, a.control + goff, a.cse + goff, bytes, mbar, phase);
     if (bytes >= 16) phase ^= 1u;
     int cnt_c[8], cnt_k[8];

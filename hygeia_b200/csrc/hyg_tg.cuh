@@ -187,9 +187,9 @@ __device__ __forceinline__ double tg_block_max(double v, TgSmem& s, int& flip) {
   v = warp_max(v);
   if (lane == 0) s.red[flip][warp][0] = v;
   __syncthreads();
-  double t = s.red[flip][0][0];
-#pragma unroll
-  for (int w = 1; w < HYG_TG_NW; w++) t = s.red[flip][w][0] > t ? s.red[flip][w][0] : t;
+  // max is exact whatever the order: one load per lane and a shuffle tree instead of HYG_TG_NW loads per thread
+  double t = (lane < HYG_TG_NW) ? s.red[flip][lane][0] : -HYG_INF;
+  t = warp_max(t);
   flip ^= 1;
   return t;
 }

@@ -164,6 +164,7 @@ struct TgSmem {
   // backward trajectories
   TgState nxt[HYG_TG_BMAX];
   int pick[HYG_TG_BMAX];
+  int rep[HYG_TG_BMAX];        // backward pass: first trajectory with the same next state (its predecessor law is reused)
   double red[2][HYG_TG_NW][4];
   int ired[2][HYG_TG_NW];
   double bc[8];
@@ -227,7 +228,11 @@ __device__ __forceinline__ void tg_sort_desc(TgSmem& s, int n) {
           if (a_after_b == desc) { s.key[i] = b; s.key[l] = a; s.sidx[i] = ib; s.sidx[l] = ia; }
         }
       }
-      __syncthreads();
+      // Elements tid + NT m of a warp are 32 consecutive indices, so a stride below 32 pairs elements of ONE warp: between two
+      // such stages a warp barrier is enough.  28 block barriers instead of 66 for 2048 keys.
+      const int next = (j > 1) ? (j >> 1) : k;   // stride of the following stage
+      if (j >= 32 || next >= 32) __syncthreads();
+      else __syncwarp();
     }
   }
 }
@@ -302,7 +307,9 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
       while (n_sort < F) n_sort <<= 1;
       for (int i = F + tid; i < n_sort; i += HYG_TG_NT) { s.key[i] = 0ull; s.sidx[i] = 0xFFFFu; }
       __syncthreads();
+#ifndef HYG_TG_SKIP_SORT
       tg_sort_desc(s, n_sort);
+#endif
       // e[p] = exp(sorted normalised log-weight); reverse cumulative sums rcs[p] = sum_{i >= p} e[i]
       for (int p = tid; p < n_sort; p += HYG_TG_NT) {
         double v = 0.0;
@@ -498,7 +505,23 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
     }
     // one categorical draw per trajectory: logits_i = w_t[i] (+ log f(x_{t+1}^j | x_t^i)), inverse CDF in particle order
     const bool last = (t == static_cast<long long>(T) - 1);
+    // The predecessor law depends on the trajectory only through its next state x_{t+1}^j, and backward trajectories coalesce:
+    // it is evaluated once per DISTINCT next state (rep[j] = first trajectory with that state) and every trajectory of the
+    // group draws from it with its own uniform -- the same numbers, 25 / #distinct times less work.
+    if (tid < B) {
+      int r = last ? 0 : tid;
+      if (!last) {
+        const TgState me = s.nxt[tid];
+        for (int jj = 0; jj < tid; jj++) {
+          const TgState o = s.nxt[jj];
+          if (o.m == me.m && o.dc == me.dc && o.rc == me.rc && o.dk == me.dk && o.rk == me.rk) { r = jj; break; }
+        }
+      }
+      s.rep[tid] = r;
+    }
+    __syncthreads();
     for (int j = 0; j < B; j++) {
+      if (s.rep[j] != j) continue;   // uniform: the group's first trajectory does the work
       TgState nx;
       if (!last) nx = s.nxt[j];
       double mx = -HYG_INF;
@@ -532,18 +555,21 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
       for (int w = 0; w < HYG_TG_NW; w++) { const double x = s.red[flip][w][1]; if (w < (tid >> 5)) off += x; tot += x; }
       flip ^= 1;
       const double excl = off + inc - loc_sum;
-      const double target = tg_uniform(ch.seed, ch.chain, HYG_TAG_BACKWARD, (static_cast<uint64_t>(j) << 32) + static_cast<uint64_t>(t)) * tot;
-      // the first particle whose cumulative probability reaches the target lives in exactly one thread's chunk
-      if (c0 < c1) {
-        const double hi_c = excl + loc_sum;
-        const bool mine = (excl < target || (tid == 0 && target <= 0.0)) && (target <= hi_c);
-        if (mine) {
-          int pickc = c1 - 1;
-          for (int c = c0; c < c1; c++) if (excl + s.e[c] >= target) { pickc = c; break; }
-          s.pick[j] = pickc;
+      for (int jj = j; jj < B; jj++) {   // every trajectory of the group draws with its own uniform
+        if (s.rep[jj] != j) continue;
+        const double target = tg_uniform(ch.seed, ch.chain, HYG_TAG_BACKWARD, (static_cast<uint64_t>(jj) << 32) + static_cast<uint64_t>(t)) * tot;
+        // the first particle whose cumulative probability reaches the target lives in exactly one thread's chunk
+        if (c0 < c1) {
+          const double hi_c = excl + loc_sum;
+          const bool mine = (excl < target || (tid == 0 && target <= 0.0)) && (target <= hi_c);
+          if (mine) {
+            int pickc = c1 - 1;
+            for (int c = c0; c < c1; c++) if (excl + s.e[c] >= target) { pickc = c; break; }
+            s.pick[jj] = pickc;
+          }
         }
+        if (tid == 0 && !(tot > 0.0)) s.pick[jj] = 0;
       }
-      if (tid == 0 && !(tot > 0.0)) s.pick[j] = 0;
       __syncthreads();
     }
     // record the sampled states; they become x_{t+1} of the next (earlier) site

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--chains", type=int, default=148)
     ap.add_argument("--samples", type=int, default=8)
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--backward", type=int, default=25)
     a = ap.parse_args()
     from _tg_case import make_case
     from hygeia_b200.two_group import TwoGroupSession
@@ -30,7 +31,7 @@ def main():
     s.add_dataset(c["nt_c"], c["nm_c"])
     s.add_dataset(c["nt_k"], c["nm_k"])
     s.emission()
-    s.set_two_group_model(c["logP"], c["omega_control"], c["omega_case"], c["u"], 50, 25, rho_control=c["model"].rho_c,
+    s.set_two_group_model(c["logP"], c["omega_control"], c["omega_case"], c["u"], 50, a.backward, rho_control=c["model"].rho_c,
                           rho_case=c["model"].rho_k, t_max=T)
     specs = [dict(control_dataset=0, case_dataset=1, T=T, seed=k, chain_id=k) for k in range(a.chains)]
     ms = []

@@ -164,7 +164,10 @@ struct TgSmem {
   // backward trajectories
   TgState nxt[HYG_TG_BMAX];
   int pick[HYG_TG_BMAX];
-  int rep[HYG_TG_BMAX];        // backward pass: first trajectory with the same next state (its predecessor law is reused)
+  int rep[HYG_TG_BMAX];
+  double ctot[HYG_TG_NPMAX / 32 + 2];    // per-chunk totals / carries of the chunked cumulative sums (32 particles per chunk)
+  double ccar[HYG_TG_NPMAX / 32 + 2];
+  double lcn_tab[HYG_TG_MMAX + 1];       // log(M - a) - log(rcs[a]) for every candidate a of the K loop        // backward pass: first trajectory with the same next state (its predecessor law is reused)
   double red[2][HYG_TG_NW][4];
   int ired[2][HYG_TG_NW];
   double bc[8];
@@ -317,28 +320,47 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
         s.e[p] = v;
       }
       __syncthreads();
-      // sequential-in-chunks suffix sums (warp 0 walks from the end; F <= 2400 -> at most 75 chunks)
+      // Reverse cumulative sums in chunks of 32, walked from the end: suf[p] = (shuffle-tree suffix inside the chunk) + carry,
+      // carry = the later chunks' totals added one after the other.  The trees are independent, so every warp takes the chunks
+      // c = warp, warp + NW, ...; only the <= 75 carry additions stay sequential (same additions in the same order as a
+      // single warp walking all chunks).  The sums are only needed at positions <= M (K < M): anc_w doubles as rcs[0..M].
+      const int n_chunks = (F + 31) / 32;
+      for (int cidx = (tid >> 5); cidx < n_chunks; cidx += HYG_TG_NW) {
+        const int p = cidx * 32 + lane;
+        double inc = (p < F) ? s.e[p] : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double tt = __shfl_down_sync(HYG_FULL, inc, o);
+          if (lane + o < 32) inc += tt;
+        }
+        if (lane == 0) s.ctot[cidx] = inc;
+      }
+      __syncthreads();
       if (tid < 32) {
         double carry = 0.0;
-        for (int base = ((F - 1) / 32) * 32; base >= 0; base -= 32) {
-          const int p = base + lane;
-          double v = (p < F) ? s.e[p] : 0.0;
-          double inc = v;
+        for (int cidx = n_chunks - 1; cidx >= 0; cidx--) {
+          if (cidx * 32 <= M) {   // a chunk that holds positions <= M: its in-chunk suffix sums are needed too
+            const int p = cidx * 32 + lane;
+            double inc = (p < F) ? s.e[p] : 0.0;
 #pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const double tt = __shfl_down_sync(HYG_FULL, inc, o);
-            if (lane + o < 32) inc += tt;
+            for (int o = 1; o < 32; o <<= 1) {
+              const double tt = __shfl_down_sync(HYG_FULL, inc, o);
+              if (lane + o < 32) inc += tt;
+            }
+            if (p <= M && p < F) s.anc_w[p] = inc + carry;
           }
-          const double suf = inc + carry;
-          // the reverse cumulative sum is only needed at positions <= M (K < M): anc_w doubles as rcs[0..M]
-          if (p <= M && p < F) s.anc_w[p] = suf;
-          carry += __shfl_sync(HYG_FULL, inc, 0);
+          carry += s.ctot[cidx];
         }
+        __syncwarp();   // anc_w[0..M] written above is read by every lane below
         // fixed point with the reference's loop structure: (a, b, log_c) <- (k_new, a, log_c(a)) while a != b, a < n, a < M
+        // the loop below needs log(M - a) - log(rcs[a]) at a data-dependent sequence of a < M: all M values are taken now, by
+        // the lanes in parallel, so that no logarithm sits on the loop's dependency chain
+        for (int a0 = lane; a0 < M && a0 < F; a0 += 32) s.lcn_tab[a0] = log(static_cast<double>(M - a0)) - log(s.anc_w[a0]);
+        __syncwarp();
         int a = 0, b = -1;
         double lc = -1.0;
         while (a != b && a < F && a < M) {
-          const double lcn = log(static_cast<double>(M - a)) - log(s.anc_w[a]);
+          const double lcn = s.lcn_tab[a];
           int cnt = 0;
           for (int base = a; base < F && base < a + 96; base += 32) {   // counts beyond M do not change the outcome
             const int p = base + lane;
@@ -375,21 +397,28 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
         const int L = M - K;
         // kept particles
         for (int a = tid; a < K; a += HYG_TG_NT) s.parents[a] = static_cast<int>(s.sidx[a]);
-        // residual: cumulative sums of e[K..F) in sorted order (single warp, chunked), normalised by their total
-        if (tid < 32 && L > 0) {
-          double carry = 0.0;
-          for (int base = K; base < F; base += 32) {
-            const int p = base + lane;
-            double inc = (p < F) ? s.e[p] : 0.0;
+        // residual: cumulative sums of e[K..F) in sorted order, in chunks of 32 from K: shuffle-tree prefix inside a chunk (all
+        // warps, chunk c = warp, warp + NW, ...) + the earlier chunks' totals added one after the other (one thread) -- the same
+        // additions in the same order as a single warp walking the chunks
+        const int r_chunks = (L > 0) ? (F - K + 31) / 32 : 0;
+        for (int cidx = (tid >> 5); cidx < r_chunks; cidx += HYG_TG_NW) {
+          const int p = K + cidx * 32 + lane;
+          double inc = (p < F) ? s.e[p] : 0.0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-              const double tt = __shfl_up_sync(HYG_FULL, inc, o);
-              if (lane >= o) inc += tt;
-            }
-            if (p < F) s.e[p] = inc + carry;
-            carry += __shfl_sync(HYG_FULL, inc, 31);
+          for (int o = 1; o < 32; o <<= 1) {
+            const double tt = __shfl_up_sync(HYG_FULL, inc, o);
+            if (lane >= o) inc += tt;
           }
+          if (p < F) s.e[p] = inc;
+          if (lane == 31) s.ctot[cidx] = inc;
         }
+        __syncthreads();
+        if (tid == 0) {
+          double carry = 0.0;
+          for (int cidx = 0; cidx < r_chunks; cidx++) { s.ccar[cidx] = carry; carry += s.ctot[cidx]; }
+        }
+        __syncthreads();
+        for (int p = K + tid; p < F && L > 0; p += HYG_TG_NT) s.e[p] = s.e[p] + s.ccar[(p - K) >> 5];
         __syncthreads();
         if (L > 0) {
           const double tot = s.e[F - 1];

@@ -246,7 +246,8 @@ template <int R> int launch_emission(hyg_ctx* c, const hyg::SgEmissionArgs& a, s
 template <int R, bool PE> int launch_filter(hyg_ctx* c, const hyg::SgRunDev& run, int grid) {
   const size_t smem = PE ? sizeof(hyg::SgPeSmem<R>) : 0;
   if (PE) HYG_CUDA(c, cudaFuncSetAttribute(hyg::sg_filter_kernel<R, PE>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  hyg::sg_filter_kernel<R, PE><<<grid, HYG_NT, smem, c->stream>>>(c->d_mdl, c->d_chains, run);
+  if (!PE && run.n_chains <= c->num_sms) hyg::sg_filter_kernel_sparse<R><<<grid, HYG_NT, 0, c->stream>>>(c->d_mdl, c->d_chains, run);
+  else hyg::sg_filter_kernel<R, PE><<<grid, HYG_NT, smem, c->stream>>>(c->d_mdl, c->d_chains, run);
   HYG_CUDA(c, cudaGetLastError());
   return HYG_OK;
 }

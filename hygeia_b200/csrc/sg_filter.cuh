@@ -1016,6 +1016,12 @@ template <int RT, bool PE>
 __global__ void __launch_bounds__(HYG_NT, PE ? 1 : HYG_K2_MIN_CTAS) sg_filter_kernel(const SgModelDev* mdl, const SgChainDev* chains, SgRunDev run) {
   sg_filter_entry<RT, PE>(mdl, chains, run);
 }
+// The same recursion compiled for ONE CTA per SM (168 registers, no spills): used when there are no more units than SMs
+// (whole-chain execution of a few chains, the C ABI's and the CLI's default), where per-site latency is all that counts.
+template <int RT>
+__global__ void __launch_bounds__(HYG_NT, 1) sg_filter_kernel_sparse(const SgModelDev* mdl, const SgChainDev* chains, SgRunDev run) {
+  sg_filter_entry<RT, false>(mdl, chains, run);
+}
 #endif
 
 }  // namespace hyg

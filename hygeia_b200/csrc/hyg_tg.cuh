@@ -165,6 +165,7 @@ struct TgSmem {
   TgState nxt[HYG_TG_BMAX];
   int pick[HYG_TG_BMAX];
   int rep[HYG_TG_BMAX];
+  double ub[HYG_TG_BMAX];      // backward pass: the site's uniform of every trajectory (one Philox evaluation each)
   double ctot[HYG_TG_NPMAX / 32 + 2];    // per-chunk totals / carries of the chunked cumulative sums (32 particles per chunk)
   double ccar[HYG_TG_NPMAX / 32 + 2];
   double lcn_tab[HYG_TG_MMAX + 1];       // log(M - a) - log(rcs[a]) for every candidate a of the K loop        // backward pass: first trajectory with the same next state (its predecessor law is reused)
@@ -420,12 +421,13 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
           double carry = 0.0;
           for (int cidx = 0; cidx < r_chunks; cidx++) { s.ccar[cidx] = carry; carry += s.ctot[cidx]; }
         }
+        if (tid == 32) s.ub[0] = tg_uniform(ch.seed, ch.chain, HYG_TAG_FILTER, t);   // the site's resampling uniform, evaluated once
         __syncthreads();
         for (int p = K + tid; p < F && L > 0; p += HYG_TG_NT) s.e[p] = s.e[p] + s.ccar[(p - K) >> 5];
         __syncthreads();
         if (L > 0) {
           const double tot = s.e[F - 1];
-          const double u = tg_uniform(ch.seed, ch.chain, HYG_TAG_FILTER, t);
+          const double u = s.ub[0];
           for (int j = tid; j < L; j += HYG_TG_NT) {
             // first residual position i with T_j <= Q_i, T_j = (j + u) / L  (resampling_functions.py:56-69); 0 if none
             const double Tj = (static_cast<double>(j) + u) / static_cast<double>(L) * tot;
@@ -550,6 +552,7 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
         }
       }
       s.rep[tid] = r;
+      s.ub[tid] = tg_uniform(ch.seed, ch.chain, HYG_TAG_BACKWARD, (static_cast<uint64_t>(tid) << 32) + static_cast<uint64_t>(t));
     }
     __syncthreads();
     for (int j = 0; j < B; j++) {
@@ -589,7 +592,7 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
       const double excl = off + inc - loc_sum;
       for (int jj = j; jj < B; jj++) {   // every trajectory of the group draws with its own uniform
         if (s.rep[jj] != j) continue;
-        const double target = tg_uniform(ch.seed, ch.chain, HYG_TAG_BACKWARD, (static_cast<uint64_t>(jj) << 32) + static_cast<uint64_t>(t)) * tot;
+        const double target = s.ub[jj] * tot;
         // the first particle whose cumulative probability reaches the target lives in exactly one thread's chunk
         if (c0 < c1) {
           const double hi_c = excl + loc_sum;

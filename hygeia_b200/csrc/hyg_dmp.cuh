@@ -188,14 +188,39 @@ __device__ __forceinline__ void dmp_site_stats_entry(const DmpArgs& a, unsigned 
         // bit positions that held no particle were counted as regime 0 (each flush covers 32 positions)
         const int pad = groups * 32 - mine;
         cnt_c[0] -= pad; cnt_k[0] -= pad;
-      } else {                // ragged rows: byte by byte
-        for (unsigned p = q; p < P; p += HYG_DMP_LANES) {
-          const unsigned c = rc[p] & 7u, k = rk[p] & 7u;
-          msum += rm[p] & 1u;
-          ne += (c != k) ? 1 : 0;
-#pragma unroll
-          for (int r = 0; r < 8; r++) { cnt_c[r] += (c == static_cast<unsigned>(r)) ? 1 : 0; cnt_k[r] += (k == static_cast<unsigned>(r)) ? 1 : 0; }
+      } else {
+        // rows start at any byte offset: every 4-particle word of a row is cut out of two aligned shared-memory words with one
+        // funnel shift; the row's last word keeps only its P mod 4 valid bytes (the dropped ones count as padding below)
+        const unsigned off = static_cast<unsigned>(site) * P;
+        const unsigned sh = 8u * (off & 3u), base = off >> 2;
+        const unsigned nw = (P + 3u) / 4u, tail = P - 4u * (nw - 1u);
+        const unsigned tmask = (tail == 4u) ? 0xFFFFFFFFu : ((1u << (8u * tail)) - 1u);
+        const unsigned* wm = reinterpret_cast<const unsigned*>(sm_m) + base;
+        const unsigned* wc = reinterpret_cast<const unsigned*>(sm_c) + base;
+        const unsigned* wk = reinterpret_cast<const unsigned*>(sm_k) + base;
+        DmpPlanes pl;
+        pl.clear();
+        int mine = 0, groups = 0;
+#define HYG_DMP_ADDU(J)                                                                        \
+  {                                                                                            \
+    const unsigned w = w0 + (J) * HYG_DMP_LANES;                                               \
+    if (w < nw) {                                                                              \
+      unsigned mw = __funnelshift_r(wm[w], wm[w + 1], sh), cw = __funnelshift_r(wc[w], wc[w + 1], sh),   \
+               kw = __funnelshift_r(wk[w], wk[w + 1], sh);                                    \
+      const bool lastw = (w == nw - 1u);                                                       \
+      if (lastw) { mw &= tmask; cw &= tmask; kw &= tmask; }                                    \
+      pl.add<J>(mw, cw, kw);                                                                   \
+      mine += lastw ? static_cast<int>(tail) : 4;                                              \
+    }                                                                                          \
+  }
+        for (unsigned w0 = q; w0 < nw; w0 += 8 * HYG_DMP_LANES) {
+          HYG_DMP_ADDU(0) HYG_DMP_ADDU(1) HYG_DMP_ADDU(2) HYG_DMP_ADDU(3) HYG_DMP_ADDU(4) HYG_DMP_ADDU(5) HYG_DMP_ADDU(6) HYG_DMP_ADDU(7)
+          pl.flush(cnt_c, cnt_k, msum, ne);
+          groups++;
         }
+#undef HYG_DMP_ADDU
+        const int pad = groups * 32 - mine;
+        cnt_c[0] -= pad; cnt_k[0] -= pad;
       }
     }
     // ---- combine the HYG_DMP_LANES partial counts of a site (adjacent lanes of one warp) ----

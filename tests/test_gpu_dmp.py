@@ -26,7 +26,7 @@ def test_site_statistics_bit_exact_vs_golden(built):
     assert np.array_equal(r["pair_stats"][:, off], g["pair_stats"][:, off])
 
 
-@pytest.mark.parametrize("T,P,R", [(1, 1, 2), (129, 25, 6), (1000, 50, 6), (257, 203, 6), (300, 580, 8), (300, 2000, 6), (5, 7, 3), (640, 200, 6)])
+@pytest.mark.parametrize("T,P,R", [(1, 1, 2), (129, 25, 6), (1000, 50, 6), (257, 203, 6), (300, 580, 8), (300, 2000, 6), (5, 7, 3), (640, 200, 6), (333, 250, 6), (100, 75, 6), (97, 1, 6), (64, 3, 2), (40, 254, 6)])
 def test_site_statistics_shapes_and_ragged_rows(built, T, P, R):
     """Row lengths that are not multiples of 4 / 16, tiles that end inside a 16-byte vector, more than 252 particles (count
     fields are flushed), a single site."""

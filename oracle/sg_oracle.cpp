@@ -9,8 +9,8 @@
 // -ffast-math, it reproduces oracle/_ref/libhyg_ref_strict.so bit for bit
 // (tests/test_oracle_vs_ref.py).  Two deliberate differences, both neutral for
 // the results: the emission table logObs[T x R] is evaluated once per
-// (site, regime) instead of 1744 times per site, and
-// sort_index is a stable sort (ties broken by index).
+// (site, regime) instead of 1744 times per site.  sort_index
+// takes the reference's own permutation under exact ties (see sort_index_desc).
 #include "sg_oracle.h"
 
 #include <algorithm>
@@ -191,10 +191,20 @@ void systematic_base(double u, std::vector<uint32_t>& parent, const std::vector<
   }
 }
 
+// arma::sort_index(v, "descend") (resample.h:304,373; Smc.h:438).  Armadillo packs (value, index) pairs and calls
+// std::sort with a comparator that looks at the VALUE ONLY, so the order of exactly equal weights is whatever libstdc++'s
+// introsort leaves behind -- a pure function of the arrangement, but neither "by index" nor stable.  Equal weights are
+// systematic here: every resampled particle gets the common weight logSum - logC (resample.h:361-364), and
+// log(1 - rho(d, r)) stops depending on d once the sojourn table has gone stationary (SURVEY C-4).  Which of two tied
+// particles survives the next systematic resampling moves the smoothed posteriors by up to 1e-4 on sparse one-sample
+// chains, so the restatement has to take the same permutation: the same std::sort call on the
+// same pair type with the same comparator as oracle/shim/RcppArmadillo.h (the stand-in the reference is compiled against).
 std::vector<uint32_t> sort_index_desc(const std::vector<double>& v, size_t n) {
+  std::vector<std::pair<double, uint32_t> > pk(n);
+  for (size_t i = 0; i < n; i++) pk[i] = std::make_pair(v[i], static_cast<uint32_t>(i));
+  std::sort(pk.begin(), pk.end(), [](const std::pair<double, uint32_t>& a, const std::pair<double, uint32_t>& b) { return a.first > b.first; });
   std::vector<uint32_t> idx(n);
-  for (size_t i = 0; i < n; i++) idx[i] = static_cast<uint32_t>(i);
-  std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return v[a] > v[b]; });
+  for (size_t i = 0; i < n; i++) idx[i] = pk[i].second;
   return idx;
 }
 
@@ -211,6 +221,13 @@ struct Filter {
   uint64_t step;
   int k_last;
   bool drew;
+  int tie_pairs;  // tap: adjacent equal finite values in the sorted order of this site
+  void count_ties(const std::vector<double>& v, const std::vector<uint32_t>& sorted) {
+    for (size_t i = 0; i + 1 < sorted.size(); i++) {
+      const double a = v[sorted[i]], b = v[sorted[i + 1]];
+      if (a == b && std::isfinite(a) && a != 0.0) tie_pairs++;  // W == 0 / logw == -inf entries are interchangeable
+    }
+  }
 
   // Smc.h:576-579
   void self_normalise() {
@@ -230,13 +247,14 @@ struct Filter {
       lw_c[n] = -std::log(static_cast<double>(R)) + logobs[0 * R + n];  // :485-491, :582-586, singleGroup.h:559-566
     }
     self_normalise();
-    k_last = -1; drew = false;
+    k_last = -1; drew = false; tie_pairs = 0;
   }
   // resample.h:289-409
   void optimal_finite_state(uint32_t M) {
     uint32_t N = N_prev;
     for (uint32_t n = 0; n < lw_c.size(); n++) lw_c[n] = 0.0;  // :301
     std::vector<uint32_t> sorted = sort_index_desc(W_p, N);
+    count_ties(W_p, sorted);
     std::vector<double> q(N), logq(N), Q(N);
     for (uint32_t i = 0; i < N; i++) { q[i] = W_p[sorted[i]]; logq[i] = std::log(q[i]); }
     { double acc = 0.0; for (uint32_t i = N; i-- > 0;) { acc += q[i]; Q[i] = acc; } }  // reverse(cumsum(reverse(q)))
@@ -265,6 +283,8 @@ struct Filter {
       k_last = static_cast<int>(K);
     } else {
       std::vector<uint32_t> idx = sort_index_desc(lw_p, N);
+      tie_pairs = 0;
+      count_ties(lw_p, idx);
       for (uint32_t i = 0; i < M; i++) { anc[i] = idx[i]; lw_c[i] = lw_p[idx[i]]; }
       k_last = -2;
     }
@@ -280,6 +300,7 @@ struct Filter {
         optimal_finite_state(M);
       } else {
         std::vector<uint32_t> idx = sort_index_desc(lw_p, N_prev);
+        count_ties(lw_p, idx);
         for (uint32_t i = 0; i < M; i++) { anc[i] = idx[i]; lw_c[i] = lw_p[idx[i]]; }
         k_last = -2;
       }
@@ -297,6 +318,7 @@ struct Filter {
     pc.resize(N_curr); lw_c.resize(N_curr, 0.0);
     uint32_t M = N_curr - R;
     drew = false;
+    tie_pairs = 0;
     resample_cp();
     // :504-522
     for (uint32_t n = 0; n < M; n++) { pc[n].d = pp[anc[n]].d + 1; pc[n].r = pp[anc[n]].r; }
@@ -465,6 +487,15 @@ int hygo_sg_run(const hygo_sg_args* a) {
     if (a->k_kept) a->k_kept[t] = f.k_last;
     if (a->drew_uniform) a->drew_uniform[t] = f.drew ? 1 : 0;
     if (a->n_pending) a->n_pending[t] = static_cast<int32_t>(psi_t.size());
+    if (a->tie_pairs) a->tie_pairs[t] = f.tie_pairs;
+    if (a->weights_prev && t > 0) {
+      double* w = a->weights_prev + t * f.Nmax;
+      for (uint32_t n = 0; n < f.Nmax; n++) w[n] = (n < f.N_prev) ? f.W_p[n] : std::numeric_limits<double>::quiet_NaN();
+    }
+    if (a->d_prev && t > 0) {
+      int32_t* w = a->d_prev + t * f.Nmax;
+      for (uint32_t n = 0; n < f.Nmax; n++) w[n] = (n < f.N_prev) ? static_cast<int32_t>(f.pp[n].d | (f.pp[n].r << 24)) : 0;
+    }
     if (a->ancestors) {
       for (uint32_t m = 0; m < Mmax; m++) a->ancestors[t * Mmax + m] = (t > 0 && m < f.anc.size()) ? static_cast<int16_t>(f.anc[m]) : -1;
     }

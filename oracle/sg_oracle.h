@@ -54,6 +54,10 @@ typedef struct hygo_sg_args {
   int32_t* n_pending;      /* T : lag-set size after site t                           */
   int16_t* ancestors;      /* T x (n_particles_max - R), -1 padded                    */
   double* seconds;
+  int32_t* tie_pairs;      /* T : #{adjacent equal pairs among the finite weights in the sorted order used at site t}
+                                  (0 when site t did not sort) -- where the reference's unstable sort decides     */
+  double* weights_prev;    /* T x n_particles_max: self-normalised weights the resampler of site t saw (NaN padded) */
+  int32_t* d_prev;         /* T x n_particles_max: sojourn d of the same particles (0 padded); regime in the top byte: d | r << 24 */
 } hygo_sg_args;
 
 int hygo_sg_run(const hygo_sg_args* a);

@@ -30,7 +30,7 @@ class _OracleArgs(C.Structure):
         ("uniforms_by_site", C.c_void_p),
         ("regime_probs", C.c_void_p), ("theta_trace", C.c_void_p), ("logz", C.c_void_p), ("n_curr", C.c_void_p),
         ("k_kept", C.c_void_p), ("finalised_at", C.c_void_p), ("drew_uniform", C.c_void_p), ("n_pending", C.c_void_p),
-        ("ancestors", C.c_void_p), ("seconds", C.c_void_p),
+        ("ancestors", C.c_void_p), ("seconds", C.c_void_p), ("tie_pairs", C.c_void_p), ("weights_prev", C.c_void_p), ("d_prev", C.c_void_p),
     ]
 
 
@@ -89,7 +89,7 @@ class Oracle:
 
     def run(self, vartheta, theta, uniforms, n_total_st=None, n_meth_st=None, positions=None, logobs=None,
             n_particles=250, smoothing=True, epsilon=0.01, param_est=False, normalise=False, adam=True,
-            n_steps_without_update=200, lr_exponent=0.1, lr_factor=0.01, want_ancestors=False):
+            n_steps_without_update=200, lr_exponent=0.1, lr_factor=0.01, want_ancestors=False, want_weights=False):
         vartheta = np.ascontiguousarray(vartheta, dtype=np.float64)
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         R = int(vartheta[1]); D = len(theta)
@@ -109,6 +109,9 @@ class Oracle:
             logz=np.zeros(T), n_curr=np.zeros(T, np.int32), k_kept=np.zeros(T, np.int32),
             finalised_at=np.full(T, -1, np.int32), drew_uniform=np.zeros(T, np.uint8), n_pending=np.zeros(T, np.int32),
             ancestors=np.full((T, n_particles - R), -1, np.int16) if want_ancestors else None,
+            tie_pairs=np.zeros(T, np.int32),
+            weights_prev=np.full((T, n_particles), np.nan) if want_weights else None,
+            d_prev=np.zeros((T, n_particles), np.int32) if want_weights else None,
         )
         sec = C.c_double(0.0)
         a = _OracleArgs(_p(vartheta), len(vartheta), _p(theta), D, T, S, _p(pos), _p(nt), _p(nm), _p(logobs),
@@ -116,7 +119,7 @@ class Oracle:
                         lr_exponent, lr_factor, _p(uniforms),
                         _p(out["regime_probs"]), _p(out["theta_trace"]), _p(out["logz"]), _p(out["n_curr"]), _p(out["k_kept"]),
                         _p(out["finalised_at"]), _p(out["drew_uniform"]), _p(out["n_pending"]), _p(out["ancestors"]),
-                        C.cast(C.pointer(sec), C.c_void_p))
+                        C.cast(C.pointer(sec), C.c_void_p), _p(out["tie_pairs"]), _p(out["weights_prev"]), _p(out["d_prev"]))
         rc = self.lib.hygo_sg_run(C.byref(a))
         assert rc == 0, f"hygo_sg_run failed: {rc}"
         out["seconds"] = sec.value

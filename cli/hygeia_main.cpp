@@ -290,11 +290,24 @@ int cmd_single_group(int argc, char** argv) {
             "hyg_sg_set_segmentation");
   std::vector<double> probs(est_regimes ? T * (1 + R) : 0), trace(est_params ? T * D : 0);
   double seconds = 0.0;
+  int32_t status[HYG_SG_STATUS_WORDS] = {0};
   ctx.check(hyg_sg_run_online_combined_inference(ctx.c, vartheta.data(), static_cast<uint32_t>(vartheta.size()), theta.data(), static_cast<uint32_t>(D), T,
                                                  static_cast<uint32_t>(S), pos.data(), nt.data(), nm.data(), &ra, seed, nullptr,
-                                                 est_regimes ? probs.data() : nullptr, est_params ? trace.data() : nullptr, nullptr, &seconds),
+                                                 est_regimes ? probs.data() : nullptr, est_params ? trace.data() : nullptr, nullptr, &seconds, status),
             "runOnlineCombinedInference");
   std::fprintf(stderr, "inference: %zu sites x %zu samples in %.3f s\n", T, S, seconds);
+  // The kernel's status words (include/hygeia_b200.h): anything that makes the CSV differ from the reference's estimator is
+  // either fatal or said out loud -- a lag-set overflow already failed the call above (HYG_ERR_CAPACITY).
+  if (status[5] > 0)
+    std::fprintf(stderr, "note: at %d site(s) two particles had exactly equal weights and only one survived the resampling; the reference "
+                         "breaks such ties by the (unspecified) order std::sort leaves, this program by (regime, sojourn).\n", status[5]);
+  if (status[2] > 0 || status[7] > 0) {
+    std::fprintf(stderr, "error: --segment_sites %llu with halos of %lld sites is not safe for this data: %d owned site(s) were still pending at the "
+                         "end of a right halo, %d overlap row(s) differ by more than 1e-6 from the next segment's (left halo too short). "
+                         "Use larger halos or whole chains (--segment_sites 0).\n",
+                 static_cast<unsigned long long>(segment_sites), static_cast<long long>(segment_halo), status[2], status[7]);
+    return 3;
+  }
 
   if (est_regimes) {
     // columns genomic_position, regime_1..R; every column through format(., scientific = FALSE) (:326-338)

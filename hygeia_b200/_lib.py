@@ -26,7 +26,8 @@ class HygChain(C.Structure):
         ("uniforms", C.c_void_p), ("positions", C.c_void_p),
         ("regime_probs", C.c_void_p), ("logz", C.c_void_p), ("theta_trace", C.c_void_p),
         ("k_kept", C.c_void_p), ("drew_uniform", C.c_void_p), ("n_pending", C.c_void_p), ("n_curr", C.c_void_p),
-        ("finalised_at", C.c_void_p), ("ancestors", C.c_void_p), ("status", C.c_int32 * 4),
+        ("finalised_at", C.c_void_p), ("support_hash", C.c_void_p), ("tie_flags", C.c_void_p), ("status", C.c_int32 * 8),
+        ("overlap_max_abs", C.c_double),
     ]
 
 
@@ -36,7 +37,8 @@ class HygRunArgs(C.Structure):
         ("use_online_marginal_smoothing", C.c_int32), ("epsilon", C.c_double),
         ("use_online_parameter_estimation", C.c_int32), ("normalise_gradients", C.c_int32), ("use_adam", C.c_int32),
         ("n_steps_without_parameter_update", C.c_uint32), ("learning_rate_exponent", C.c_double),
-        ("learning_rate_factor", C.c_double), ("lag_capacity", C.c_uint32),
+        ("learning_rate_factor", C.c_double), ("lag_capacity", C.c_uint32), ("allow_forced_emission", C.c_int32),
+        ("resample_full_sort", C.c_int32),
     ]
 
 
@@ -97,7 +99,7 @@ def load():
     lib.hyg_sg_get_logobs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
     lib.hyg_sg_run_online_combined_inference.argtypes = [
         C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
-        C.POINTER(HygRunArgs), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double)]
+        C.POINTER(HygRunArgs), C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
     lib.hyg_sg_sample_theta_prior.argtypes = [C.c_uint32, C.c_uint64, C.c_void_p]
     lib.hyg_tg_set_model.argtypes = [C.c_void_p, C.POINTER(HygTgModel), C.c_uint64]
     lib.hyg_tg_run.argtypes = [C.c_void_p, C.POINTER(HygTgChain), C.c_uint32, C.POINTER(C.c_float)]

@@ -44,6 +44,7 @@ struct Dataset {
   const uint16_t* d_nm = nullptr;
   bool owned = false;
   double* d_logobs = nullptr;
+  bool emitted = false;         // d_logobs holds the emission table of these counts (hyg_sg_emission ran after they were added)
 };
 
 struct ChainBuf {
@@ -59,8 +60,12 @@ struct ChainBuf {
   int* d_npend = nullptr;
   int* d_ncurr = nullptr;
   int* d_fin = nullptr;
-  short* d_anc = nullptr;
+  unsigned long long* d_hash = nullptr;
+  unsigned char* d_tie = nullptr;
   int* d_status = nullptr;
+  double* d_ovl = nullptr;               // segmented execution: [n_seg][HYG_OVL_ROWS][R] rows recomputed in the right halos
+  unsigned long long* d_ovlmax = nullptr;
+  uint32_t ovl_cap = 0;
   double* d_trace = nullptr;
   double* d_seginc = nullptr;   // segmented execution: log Z increment of every segment
   uint32_t n_seg = 1, seginc_cap = 0;
@@ -98,6 +103,9 @@ struct hyg_ctx {
   uint64_t seg_sites = 0, seg_halo_left = 5000, seg_halo_right = 5000;   // hyg_sg_set_segmentation (0 = whole chains)
   hyg::SgLogzFix* d_fix = nullptr;
   size_t d_fix_cap = 0;
+  hyg::SgOvlCheck* d_ovlchk = nullptr;
+  size_t d_ovlchk_cap = 0;
+  bool last_allow_forced = false;
   bool zero_copy_out = true;
   uint32_t n_units_last = 0;
   uint64_t seg_sites_last = 0;
@@ -105,7 +113,7 @@ struct hyg_ctx {
   uint32_t n_particles_staged = 0;
   std::multimap<size_t, void*> pool_free_blocks;
   std::map<void*, size_t> pool_live;
-  cudaEvent_t ev_em0 = nullptr, ev_em1 = nullptr, ev_f0 = nullptr, ev_f1 = nullptr;
+  cudaEvent_t ev_em0 = nullptr, ev_em1 = nullptr, ev_f0 = nullptr, ev_f1 = nullptr, ev_d0 = nullptr, ev_d1 = nullptr;
   bool timed_em = false, timed_f = false;
   uint32_t em_launches = 0, f_launches = 0;
   // two-group
@@ -179,8 +187,8 @@ void free_chains(hyg_ctx* c) {
   for (auto& b : c->chains) {
     if (b.probs_mapped) b.d_probs = nullptr;
     pool_free(c, b.d_unif); pool_free(c, b.d_pos); pool_free(c, b.d_probs); pool_free(c, b.d_logz); pool_free(c, b.d_k);
-    pool_free(c, b.d_drew); pool_free(c, b.d_npend); pool_free(c, b.d_ncurr); pool_free(c, b.d_fin); pool_free(c, b.d_anc);
-    pool_free(c, b.d_status); pool_free(c, b.d_trace); pool_free(c, b.d_seginc);
+    pool_free(c, b.d_drew); pool_free(c, b.d_npend); pool_free(c, b.d_ncurr); pool_free(c, b.d_fin); pool_free(c, b.d_hash); pool_free(c, b.d_tie);
+    pool_free(c, b.d_status); pool_free(c, b.d_trace); pool_free(c, b.d_seginc); pool_free(c, b.d_ovl); pool_free(c, b.d_ovlmax);
   }
   c->chains.clear();
   c->order.clear();
@@ -208,6 +216,30 @@ __global__ void sg_logz_fix_kernel(const hyg::SgLogzFix* units, unsigned int n_u
     const double off = s_off;
     for (unsigned long long t = threadIdx.x; t < f.len; t += blockDim.x) f.logz[t] += off;
     __syncthreads();
+  }
+}
+
+// Segmented execution, left-halo check: the rows segment j recomputed in its right halo against the rows segment j+1 wrote.
+__global__ void sg_overlap_check_kernel(const hyg::SgOvlCheck* units, unsigned int n_units) {
+  for (unsigned int k = blockIdx.x; k < n_units; k += gridDim.x) {
+    const hyg::SgOvlCheck u = units[k];
+    if (threadIdx.x < u.rows) {
+      double worst = 0.0;
+      bool have = false;
+      for (unsigned int q = 0; q < u.R; q++) {
+        const double a = u.ovl[threadIdx.x * u.R + q];
+        if (a != a) continue;   // row not finalised inside the halo
+        have = true;
+        const double b = u.probs[static_cast<size_t>(threadIdx.x) * (u.R + 1) + 1 + q];
+        const double d = fabs(a - b);
+        worst = (d > worst || d != d) ? d : worst;
+      }
+      if (have) {
+        if (worst != worst) worst = 1.0;   // a NaN in the owner's row: report as a full-scale difference
+        atomicMax(u.max_bits, static_cast<unsigned long long>(__double_as_longlong(worst)));
+        if (worst > 1e-6) atomicAdd(u.status + 7, 1);
+      }
+    }
   }
 }
 
@@ -311,6 +343,7 @@ hyg_ctx* hyg_create(int device) {
     return nullptr;
   }
   cudaEventCreate(&c->ev_em0); cudaEventCreate(&c->ev_em1); cudaEventCreate(&c->ev_f0); cudaEventCreate(&c->ev_f1);
+  cudaEventCreate(&c->ev_d0); cudaEventCreate(&c->ev_d1);
   cudaMalloc(&c->d_mdl, sizeof(hyg::SgModelDev));
   cudaMalloc(&c->d_queue, sizeof(unsigned int));
   return c;
@@ -324,8 +357,9 @@ void hyg_destroy(hyg_ctx* c) {
   free_datasets(c);
   pool_free(c, c->d_tab); pool_free(c, c->d_tabg); pool_free(c, c->d_emtab);
   pool_release(c);
-  dfree(c->d_mdl); dfree(c->d_sets); dfree(c->d_psi); dfree(c->d_pe); dfree(c->d_theta0); dfree(c->d_queue); dfree(c->d_chains); dfree(c->d_fix); dfree(c->d_tg_mdl); dfree(c->d_tg_rho);
+  dfree(c->d_mdl); dfree(c->d_sets); dfree(c->d_psi); dfree(c->d_pe); dfree(c->d_theta0); dfree(c->d_queue); dfree(c->d_chains); dfree(c->d_fix); dfree(c->d_ovlchk); dfree(c->d_tg_mdl); dfree(c->d_tg_rho);
   cudaEventDestroy(c->ev_em0); cudaEventDestroy(c->ev_em1); cudaEventDestroy(c->ev_f0); cudaEventDestroy(c->ev_f1);
+  cudaEventDestroy(c->ev_d0); cudaEventDestroy(c->ev_d1);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -364,7 +398,7 @@ int hyg_sg_set_model(hyg_ctx* c, uint32_t R, uint32_t u, const double* alpha, co
 int hyg_sg_set_vartheta(hyg_ctx* c, const double* vt, uint32_t n) {
   if (!c || !vt || n < 2) return fail(c, HYG_ERR_ARG, "bad vartheta");
   const uint32_t R = static_cast<uint32_t>(vt[1]);
-  if (R < 2 || R > 7 || n < 2 * R + 3) return fail(c, HYG_ERR_ARG, "bad vartheta");
+  if (R < 2 || R > 6 || n < 2 * R + 3) return fail(c, HYG_ERR_ARG, "bad vartheta (2 <= R <= 6)");
   const int kf = vt[2 * R + 2] != 0.0;
   if (kf && n < 3 * R + 3) return fail(c, HYG_ERR_ARG, "vartheta lacks kappa");
   return hyg_sg_set_model(c, R, static_cast<uint32_t>(vt[0]), vt + 2, vt + 2 + R, kf, kf ? vt + 2 * R + 3 : nullptr);
@@ -457,7 +491,7 @@ void hyg_sg_default_run_args(hyg_sg_run_args* a) {
   a->n_steps_without_parameter_update = 200;
   a->learning_rate_exponent = 0.1;
   a->learning_rate_factor = 0.01;
-  a->lag_capacity = 128;
+  a->lag_capacity = 1024;
 }
 
 int hyg_sg_set_segmentation(hyg_ctx* c, uint64_t segment_sites, uint64_t halo_left, uint64_t halo_right) {
@@ -490,11 +524,14 @@ int hyg_sg_set_chains(hyg_ctx* c, const hyg_sg_chain* chains, uint32_t n) {
   HYG_CUDA(c, cudaStreamSynchronize(c->stream));
   free_chains(c);
   const int R = c->hm.R;
+  for (uint32_t i = 0; i < n; i++)
+    if (chains[i].dataset >= c->ds.size()) return fail(c, HYG_ERR_ARG, "chain refers to an unknown data set");
   c->chains.resize(n);
+  // a failing allocation below leaves no half-staged chains behind (hyg_sg_filter indexes c->order)
+  struct Guard { hyg_ctx* c; bool ok = false; ~Guard() { if (!ok) free_chains(c); } } guard{c};
   for (uint32_t i = 0; i < n; i++) {
     ChainBuf& b = c->chains[i];
     b.host = chains[i];
-    if (chains[i].dataset >= c->ds.size()) return fail(c, HYG_ERR_ARG, "chain refers to an unknown data set");
     const uint64_t T = c->ds[chains[i].dataset].T;
     b.T = T;
     if (chains[i].uniforms) {
@@ -524,13 +561,17 @@ int hyg_sg_set_chains(hyg_ctx* c, const hyg_sg_chain* chains, uint32_t n) {
     if (chains[i].n_pending) HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_npend), T * sizeof(int)));
     if (chains[i].n_curr) HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_ncurr), T * sizeof(int)));
     if (chains[i].finalised_at) HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_fin), T * sizeof(int)));
-    HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_status), 4 * sizeof(int)));
+    if (chains[i].support_hash) HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_hash), T * sizeof(unsigned long long)));
+    if (chains[i].tie_flags) HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_tie), T));
+    HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_status), HYG_SG_STATUS_WORDS * sizeof(int)));
+    HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_ovlmax), sizeof(unsigned long long)));
   }
   // launch order: longest chain first (LPT), so the persistent CTAs finish together
   c->order.resize(n);
   std::iota(c->order.begin(), c->order.end(), 0u);
   std::stable_sort(c->order.begin(), c->order.end(), [&](uint32_t a, uint32_t b) { return c->chains[a].T > c->chains[b].T; });
   c->n_particles_staged = 0;
+  guard.ok = true;
   return HYG_OK;
 }
 
@@ -572,6 +613,7 @@ int hyg_sg_emission(hyg_ctx* c) {
   c->em_launches = 1;
   HYG_CUDA(c, cudaEventRecord(c->ev_em1, c->stream));
   c->timed_em = true;
+  for (auto& d : c->ds) d.emitted = true;
   return HYG_OK;
 }
 
@@ -585,6 +627,8 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
   const int R = c->hm.R;
   if (args->n_particles_max > HYG_NPMAX || args->n_particles_max < static_cast<uint32_t>(2 * R))
     return fail(c, HYG_ERR_UNSUPPORTED, "n_particles must be in [2R, 256]");
+  for (auto& b : c->chains)
+    if (!c->ds[b.host.dataset].emitted) return fail(c, HYG_ERR_STATE, "hyg_sg_emission has not run since a data set of these chains was added");
   const bool pe_mode = args->use_online_parameter_estimation != 0;
   if (pe_mode && R > 6) return fail(c, HYG_ERR_UNSUPPORTED, "online parameter estimation supports at most 6 regimes");
   if (pe_mode && args->n_steps_without_parameter_update == 0) return fail(c, HYG_ERR_ARG, "n_steps_without_parameter_update must be > 0");
@@ -592,13 +636,8 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
   const uint32_t n = static_cast<uint32_t>(c->chains.size());
   const uint32_t Nmax = args->n_particles_max;
 
-  // (re)allocate the ancestor taps now that N_max is known
-  for (auto& b : c->chains)
-    if (b.host.ancestors && (!b.d_anc || c->n_particles_staged != Nmax)) {
-      pool_free(c, b.d_anc);
-      HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_anc), b.T * (Nmax - R) * sizeof(short)));
-    }
   c->n_particles_staged = Nmax;
+  c->last_allow_forced = args->allow_forced_emission != 0;
 
   // model descriptor
   hyg::SgModelDev m;
@@ -620,7 +659,7 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
 
   int occ = 1;
   if (pe_mode) { HYG_DISPATCH_R6(R, (filter_occupancy<RR, true>(&occ))); }
-  else { HYG_DISPATCH_R(R, (filter_occupancy<RR, false>(&occ))); }
+  else { HYG_DISPATCH_R6(R, (filter_occupancy<RR, false>(&occ))); }
   if (occ < 1) occ = 1;
   const int workers = c->num_sms * occ;
   uint64_t seg_sites = pe_mode ? 0 : c->seg_sites;
@@ -638,10 +677,20 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
   const bool segmented = seg_sites > 0;
   std::vector<hyg::SgChainDev> cd;
   std::vector<hyg::SgLogzFix> fix;
+  std::vector<hyg::SgOvlCheck> ovl;
   for (auto& b : c->chains) {
     b.n_seg = segmented ? static_cast<uint32_t>((b.T + seg_sites - 1) / seg_sites) : 1u;
     if (b.n_seg < 1) b.n_seg = 1;
-    HYG_CUDA(c, cudaMemsetAsync(b.d_status, 0, 4 * sizeof(int), c->stream));
+    HYG_CUDA(c, cudaMemsetAsync(b.d_status, 0, HYG_SG_STATUS_WORDS * sizeof(int), c->stream));
+    HYG_CUDA(c, cudaMemsetAsync(b.d_ovlmax, 0, sizeof(unsigned long long), c->stream));
+    if (b.n_seg > 1 && b.d_probs && args->use_online_marginal_smoothing) {
+      if (b.ovl_cap < b.n_seg) {
+        pool_free(c, b.d_ovl);
+        HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_ovl), static_cast<size_t>(b.n_seg) * HYG_OVL_ROWS * R * sizeof(double)));
+        b.ovl_cap = b.n_seg;
+      }
+      HYG_CUDA(c, cudaMemsetAsync(b.d_ovl, 0xFF, static_cast<size_t>(b.n_seg) * HYG_OVL_ROWS * R * sizeof(double), c->stream));   // NaN = not finalised
+    }
     if (b.n_seg > 1 && b.seginc_cap < b.n_seg) {
       pool_free(c, b.d_seginc);
       HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&b.d_seginc), b.n_seg * sizeof(double)));
@@ -669,8 +718,15 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
       d.k_kept = b.d_k ? b.d_k + a : nullptr; d.drew = b.d_drew ? b.d_drew + a : nullptr;
       d.n_pending = b.d_npend ? b.d_npend + a : nullptr; d.n_curr = b.d_ncurr ? b.d_ncurr + a : nullptr;
       d.finalised_at = b.d_fin ? b.d_fin + a : nullptr;
-      d.ancestors = b.d_anc ? b.d_anc + a * (Nmax - R) : nullptr;
+      d.support_hash = b.d_hash ? b.d_hash + a : nullptr; d.tie_flags = b.d_tie ? b.d_tie + a : nullptr;
       d.status = b.d_status;
+      if (b.n_seg > 1 && !last && b.d_ovl && d.probs) {
+        d.ovl = b.d_ovl + static_cast<size_t>(j) * HYG_OVL_ROWS * R;
+        hyg::SgOvlCheck oc;
+        oc.ovl = d.ovl; oc.probs = b.d_probs + t1 * (R + 1); oc.max_bits = b.d_ovlmax; oc.status = b.d_status;
+        oc.rows = static_cast<unsigned int>(std::min<uint64_t>(HYG_OVL_ROWS, e - t1)); oc.R = static_cast<unsigned int>(R);
+        ovl.push_back(oc);
+      }
       d.theta0 = c->d_theta0; d.theta_trace = pe_mode ? b.d_trace : nullptr;
       d.seg_inc = (b.n_seg > 1) ? b.d_seginc + j : nullptr;
       cd.push_back(d);
@@ -698,7 +754,15 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
     }
     HYG_CUDA(c, cudaMemcpyAsync(c->d_fix, fix.data(), fix.size() * sizeof(hyg::SgLogzFix), cudaMemcpyHostToDevice, c->stream));
   }
-  HYG_CUDA(c, cudaStreamSynchronize(c->stream));  // cd / fix are pageable
+  if (!ovl.empty()) {
+    if (c->d_ovlchk_cap < ovl.size()) {
+      dfree(c->d_ovlchk);
+      HYG_CUDA(c, cudaMalloc(&c->d_ovlchk, ovl.size() * sizeof(hyg::SgOvlCheck)));
+      c->d_ovlchk_cap = ovl.size();
+    }
+    HYG_CUDA(c, cudaMemcpyAsync(c->d_ovlchk, ovl.data(), ovl.size() * sizeof(hyg::SgOvlCheck), cudaMemcpyHostToDevice, c->stream));
+  }
+  HYG_CUDA(c, cudaStreamSynchronize(c->stream));  // cd / fix / ovl are pageable
   c->n_units_last = n_units;
   const int grid = static_cast<int>(std::min<uint64_t>(n_units, static_cast<uint64_t>(workers)));
   c->grid_last = static_cast<uint32_t>(grid);
@@ -706,8 +770,9 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
   hyg::SgRunDev run;
   run.use_smoothing = args->use_online_marginal_smoothing ? 1 : 0;
   run.epsilon = args->epsilon;
-  run.lcap = args->lag_capacity ? static_cast<int>(args->lag_capacity) : 128;
-  run.psi_stride = 2ull * run.lcap * R * HYG_NPMAX + (run.lcap + 1) / 2 + 8;
+  run.lcap = args->lag_capacity ? static_cast<int>(args->lag_capacity) : 1024;
+  run.psi_stride = static_cast<unsigned long long>(run.lcap) * R * HYG_NPMAX + (5ull * run.lcap + 1) / 2 + 8;
+  run.force_full_sort = args->resample_full_sort ? 1 : 0;
   const size_t need = run.psi_stride * sizeof(double) * grid;
   if (need > c->psi_bytes) {
     dfree(c->d_psi);
@@ -742,9 +807,14 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
   HYG_CUDA(c, cudaEventRecord(c->ev_f0, c->stream));
   int rc = HYG_ERR_UNSUPPORTED;
   if (pe_mode) { HYG_DISPATCH_R6(R, (rc = launch_filter<RR, true>(c, run, grid))); }
-  else { HYG_DISPATCH_R(R, (rc = launch_filter<RR, false>(c, run, grid))); }
+  else { HYG_DISPATCH_R6(R, (rc = launch_filter<RR, false>(c, run, grid))); }
   if (rc) return rc;
   c->f_launches++;
+  if (!ovl.empty()) {
+    sg_overlap_check_kernel<<<std::min<unsigned int>(static_cast<unsigned int>(ovl.size()), 1024u), HYG_OVL_ROWS, 0, c->stream>>>(c->d_ovlchk, static_cast<unsigned int>(ovl.size()));
+    HYG_CUDA(c, cudaGetLastError());
+    c->f_launches++;
+  }
   if (!fix.empty()) {
     sg_logz_fix_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(c->d_fix, static_cast<unsigned int>(fix.size()));
     HYG_CUDA(c, cudaGetLastError());
@@ -772,11 +842,22 @@ int hyg_sg_download(hyg_ctx* c, hyg_sg_chain* chains, uint32_t n) {
     if (h.n_curr) HYG_CUDA(c, cudaMemcpyAsync(h.n_curr, b.d_ncurr, T * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (h.finalised_at) HYG_CUDA(c, cudaMemcpyAsync(h.finalised_at, b.d_fin, T * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (h.theta_trace && b.d_trace) HYG_CUDA(c, cudaMemcpyAsync(h.theta_trace, b.d_trace, T * c->hm.D * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (h.ancestors && b.d_anc)
-      HYG_CUDA(c, cudaMemcpyAsync(h.ancestors, b.d_anc, T * (c->n_particles_staged - R) * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
-    if (chains) HYG_CUDA(c, cudaMemcpyAsync(chains[i].status, b.d_status, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (h.support_hash && b.d_hash) HYG_CUDA(c, cudaMemcpyAsync(h.support_hash, b.d_hash, T * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    if (h.tie_flags && b.d_tie) HYG_CUDA(c, cudaMemcpyAsync(h.tie_flags, b.d_tie, T, cudaMemcpyDeviceToHost, c->stream));
+    HYG_CUDA(c, cudaMemcpyAsync(b.host.status, b.d_status, HYG_SG_STATUS_WORDS * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    HYG_CUDA(c, cudaMemcpyAsync(&b.host.overlap_max_abs, b.d_ovlmax, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   }
   HYG_CUDA(c, cudaStreamSynchronize(c->stream));
+  uint64_t forced = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const ChainBuf& b = c->chains[i];
+    if (chains) { std::memcpy(chains[i].status, b.host.status, sizeof(b.host.status)); chains[i].overlap_max_abs = b.host.overlap_max_abs; }
+    forced += static_cast<uint64_t>(b.host.status[0]);
+  }
+  // the results are in the caller's buffers either way; a forced emission means they are not the reference's estimator
+  if (forced && !c->last_allow_forced)
+    return fail(c, HYG_ERR_CAPACITY, std::to_string(forced) + " site(s) were emitted with their filtering estimate because the lag set was full: "
+                                     "raise hyg_sg_run_args.lag_capacity (or set allow_forced_emission)");
   return HYG_OK;
 }
 
@@ -803,7 +884,7 @@ int hyg_sg_get_logobs(hyg_ctx* c, uint32_t dataset, double* logobs) {
 int hyg_sg_run_online_combined_inference(hyg_ctx* c, const double* vartheta, uint32_t n_vartheta, const double* theta_init, uint32_t dim_theta,
                                          uint64_t T, uint32_t S, const uint32_t* positions, const uint16_t* n_total, const uint16_t* n_meth,
                                          const hyg_sg_run_args* args, uint64_t seed, const double* uniforms,
-                                         double* regime_probs, double* theta_trace, double* logz, double* seconds) {
+                                         double* regime_probs, double* theta_trace, double* logz, double* seconds, int32_t* status) {
   if (!c || !args) return HYG_ERR_ARG;
   const auto t0 = std::chrono::steady_clock::now();
   int rc;
@@ -819,7 +900,9 @@ int hyg_sg_run_online_combined_inference(hyg_ctx* c, const double* vartheta, uin
   if ((rc = hyg_sg_set_chains(c, &ch, 1))) return rc;
   if ((rc = hyg_sg_emission(c))) return rc;
   if ((rc = hyg_sg_filter(c, args))) return rc;
-  if ((rc = hyg_sg_download(c, &ch, 1))) return rc;
+  rc = hyg_sg_download(c, &ch, 1);
+  if (status) std::memcpy(status, ch.status, sizeof(ch.status));
+  if (rc) return rc;
   if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return HYG_OK;
 }
@@ -915,12 +998,11 @@ int hyg_tg_run(hyg_ctx* c, const hyg_tg_chain* chains, uint32_t n, float* ms_dev
     const Dataset& a = c->ds[ch.control_dataset];
     const Dataset& b = c->ds[ch.case_dataset];
     if (a.T != b.T) return fail(c, HYG_ERR_ARG, "two-group: control and case data sets differ in length");
-    if (!a.d_logobs || !b.d_logobs) return fail(c, HYG_ERR_STATE, "two-group: emission tables missing");
+    if (!a.d_logobs || !b.d_logobs || !a.emitted || !b.emitted) return fail(c, HYG_ERR_STATE, "two-group: hyg_sg_emission has not run since the data sets were added");
     if (a.T == 0) return fail(c, HYG_ERR_ARG, "two-group: empty data set");
     if (!ch.trajectories || !ch.log_normalizing_constant) return fail(c, HYG_ERR_ARG, "two-group: output pointers are required");
     t_max = std::max<uint64_t>(t_max, a.T);
   }
-  if (!c->timed_em) return fail(c, HYG_ERR_STATE, "hyg_sg_emission first");
   // longest chain first (one CTA per chain, dynamic queue)
   std::vector<uint32_t> order(n);
   std::iota(order.begin(), order.end(), 0u);
@@ -1045,10 +1127,10 @@ int hyg_tg_site_statistics(hyg_ctx* c, uint64_t T, uint32_t P, uint32_t R, const
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, hyg::dmp_site_stats_kernel, HYG_DMP_NT, smem);
   if (occ < 1) occ = 1;
   const int grid = static_cast<int>(std::min<unsigned long long>(a.n_tiles, static_cast<unsigned long long>(c->num_sms) * occ));
-  HYG_DMP_CUDA(cudaEventRecord(c->ev_em0, c->stream));
+  HYG_DMP_CUDA(cudaEventRecord(c->ev_d0, c->stream));
   hyg::dmp_site_stats_kernel<<<grid, HYG_DMP_NT, smem, c->stream>>>(a);
   HYG_DMP_CUDA(cudaGetLastError());
-  HYG_DMP_CUDA(cudaEventRecord(c->ev_em1, c->stream));
+  HYG_DMP_CUDA(cudaEventRecord(c->ev_d1, c->stream));
   if (!on_device) {
     HYG_DMP_CUDA(cudaMemcpyAsync(split_prob, d_split, T * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     HYG_DMP_CUDA(cudaMemcpyAsync(null_stat, d_null, T * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -1057,8 +1139,7 @@ int hyg_tg_site_statistics(hyg_ctx* c, uint64_t T, uint32_t P, uint32_t R, const
     if (pair_stat) HYG_DMP_CUDA(cudaMemcpyAsync(pair_stat, d_pair, T * R * R * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   }
   HYG_DMP_CUDA(cudaStreamSynchronize(c->stream));
-  if (ms_device) HYG_DMP_CUDA(cudaEventElapsedTime(ms_device, c->ev_em0, c->ev_em1));
-  c->timed_em = false;
+  if (ms_device) HYG_DMP_CUDA(cudaEventElapsedTime(ms_device, c->ev_d0, c->ev_d1));
   cleanup();
   return HYG_OK;
 }

@@ -94,12 +94,27 @@ __device__ __forceinline__ double block_max(double v, BlockScratch& sc, int& fli
   return s;
 }
 
-// Monotone map double -> uint64 (ascending), with the thread's slot folded into the low 8 bits so that
-// keys are unique and ties (|delta| < 2^-44 relative) break towards the smaller slot under a descending sort.
-__device__ __forceinline__ unsigned long long order_key(double x, int slot) {
-  unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x));
-  b = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
-  return (b & ~0xFFull) | static_cast<unsigned long long>(255 - slot);
+// Monotone map double -> uint64 (ascending, all 64 bits kept): -inf -> 0x000f..f, finite values above it.  0 is below
+// every image and marks "no particle".
+__device__ __forceinline__ unsigned long long order_key(double x) {
+  const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x));
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+#define HYG_KEY_NEGINF 0x000fffffffffffffull
+// Canonical particle order: log-weight descending, exact ties by (regime, sojourn) ascending -- a
+// rule that does not depend on where a particle is stored.  pay = (regime << 28 | sojourn) << 8 | slot.
+__device__ __forceinline__ unsigned long long order_pay(int r, uint32_t d, int slot) {
+  return (((static_cast<unsigned long long>(r) << 28) | static_cast<unsigned long long>(d & 0x0fffffffu)) << 8) | static_cast<unsigned long long>(slot);
+}
+__device__ __forceinline__ bool order_before(unsigned long long ka, unsigned long long pa, unsigned long long kb, unsigned long long pb) {
+  return (ka > kb) || (ka == kb && pa < pb);
+}
+// order-independent hash of a support point (parity tap; splitmix64 finaliser -- the CPU checker uses the same one)
+__host__ __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+  unsigned long long z = x + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
 }
 
 // ---------------------------------------------------------------------------

@@ -7,6 +7,7 @@
 #ifndef HYG_RMAX
 #define HYG_RMAX 8
 #endif
+#define HYG_OVL_ROWS 32   // rows of the next segment every segment recomputes for the left-halo check
 
 namespace hyg {
 
@@ -43,9 +44,12 @@ struct SgChainDev {
   int* n_pending;         // T : lag-set size after site t
   int* n_curr;            // T : particle count after site t
   int* finalised_at;      // T : step at which site t was emitted
-  short* ancestors;       // T x (n_particles - R)
-  int* status;            // accumulated over the chain's segments: [0] forced emissions (lag set full), [1] max lag-set size,
-                          // [2] owned sites emitted by force at the end of a segment's right halo, [3] sites stepped through
+  unsigned long long* support_hash;   // T : order-independent hash of the finite-weight support {(d, r)} after site t
+  unsigned char* tie_flags;           // T : bit 0 exact tie among the sorted weights, bit 1 a tie decided a particle's fate
+  int* status;            // 8 ints accumulated over the chain's segments: [0] forced emissions (lag set full), [1] max lag-set size,
+                          // [2] owned sites emitted by force at the end of a segment's right halo, [3] sites stepped through,
+                          // [4] sites resampled by the block-wide sort (pivot miss), [5] sites where an exact tie of weights
+                          // decided a particle's fate, [6] double systematic draws repaired, [7] reserved
   // Segmented execution (hyg_sg_set_segmentation): this descriptor covers the sites [t_off, t_off + T) of its chain -- every
   // pointer above is already offset to local site 0 -- and OWNS the local sites [own_lo, own_hi): rows outside that range are
   // warm-up (left halo: the filter forgets its initial condition) or run-out (right halo: until every owned site is finalised)
@@ -54,6 +58,9 @@ struct SgChainDev {
   unsigned long long own_lo, own_hi;
   int last_segment;       // T-1 is the end of the chain (the reference's forced finalisation there is genuine)
   double* seg_inc;        // out: log Z_{own_hi-1} - log Z_{own_lo-1} (device) or null
+  double* ovl;            // out: [HYG_OVL_ROWS][R] posterior rows of the first sites AFTER own_hi that this segment finalised in its
+                          // right halo (NaN where none) -- compared with the next segment's rows after the launch: an
+                          // insufficient LEFT halo of the next segment shows up as a difference.  null: no check
   // parameter-estimation mode
   const double* theta0;   // D initial theta (device) or null
   double* theta_trace;    // T x D (device) or null
@@ -69,6 +76,17 @@ struct SgLogzFix {
   unsigned int pad_;
 };
 
+// Segmented execution, left-halo check: compare the rows a segment recomputed in its right halo with the rows the next
+// segment wrote (one unit per segment boundary).
+struct SgOvlCheck {
+  const double* ovl;              // [HYG_OVL_ROWS][R]
+  const double* probs;            // the chain's output row of the first site after the boundary: [..][1 + R]
+  unsigned long long* max_bits;   // per chain: bits of the largest |difference| (non-negative doubles order like integers)
+  int* status;                    // per chain status words ([7] counts rows that differ by more than 1e-6)
+  unsigned int rows;              // rows that exist after the boundary (<= HYG_OVL_ROWS)
+  unsigned int R;
+};
+
 struct SgRunDev {
   int use_smoothing;
   double epsilon;
@@ -77,6 +95,7 @@ struct SgRunDev {
   unsigned long long psi_stride;  // doubles per CTA
   unsigned int* queue;    // atomic chain counter
   int n_chains;
+  int force_full_sort;    // test hook: resample every site by the block-wide sort (the pivot / candidate path is bypassed)
   // parameter-estimation mode (K3)
   int use_param_est;
   int normalise_gradients;

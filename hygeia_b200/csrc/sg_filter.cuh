@@ -1,4 +1,4 @@
-// hygeia_b200/csrc/sg_filter.cuh -- K2: the single-group recursion, one CTA per chain.
+// hygeia_b200/csrc/sg_filter.cuh -- K2: the single-group recursion, one CTA per chain (or chain segment).
 //
 // What it computes (reference = /root/reference/src/single_group/src/cpp):
 //   * discrete particle filter over (sojourn d, regime r), <= 256 support points
@@ -12,21 +12,30 @@
 //   * the outer loop over sites                        algorithms/OnlineCombinedInference.h:48-118
 //
 // How (B200-first, not a translation):
-//   * the emission term logObs[t][r] is read from the T x R table K1 produced (48 B per site) -- the
-//     reference re-evaluates it 1744 times per site;
-//   * transition terms come from a host-built table {c_new(d,r), log(1-rho(d,r))} that each particle
-//     carries one step ahead (entry for d+1 is gathered from the ancestor, entry for d+2 is loaded now and
-//     consumed a whole step later), so no L2 latency sits on the per-site critical path;
+//   * STATIONARY SLOTS.  The reference rebuilds its particle arrays in sorted order at every site (resample.h:347-364).
+//     Nothing in the model depends on where a particle is stored, and at a typical site only R of the ~250 particles die
+//     (the K of optimal resampling averages ~235 of M = 244).  So a particle stays in the thread (slot) it was born in, with
+//     its state in registers; a site only rewrites the <= R slots whose particle died with the R new-segment particles.
+//     No ancestor gather, no per-site publication of the particle system, and the lag-set / score vectors stay in place.
+//   * NO BLOCK-WIDE SORT at ~95 % of the sites.  Optimal resampling needs (i) K = the first sorted position whose weight is
+//     not above its own threshold Q[p]/(M-p) -- and "not above" is monotone along the sorted order, so only the order of the
+//     lightest particles matters -- and (ii) the sorted order of the tail p >= K for the systematic draw.  Each regime keeps a
+//     PIVOT particle of low rank (~56th lightest); the particles not heavier than the best pivot (<= 64 of them) are the
+//     candidates, one warp sorts them in registers, and the result is accepted iff the heaviest candidate is provably kept
+//     (then every heavier particle is kept too).  Otherwise the site falls back to a block-wide bitonic sort.  Both paths
+//     take the same decisions (tests/emu forces either).
+//   * the emission term logObs[t][r] is read from the T x R table K1 produced (48 B per site);
+//   * transition terms come from a host-built table {c_new(d,r), log(1-rho(d,r))}; every particle holds the entries for d
+//     and d+1 and loads the one for d+2 a whole site ahead, so no L2 latency sits on the per-site critical path;
 //   * the R x N_prev new-segment log-sum-exps and backward kernels collapse to R class sums
 //     E[r'] = sum_{n in class r'} W_n c_new(d_n, r') because logTrans((1,r) <- (d,r')) = log c_new(d,r') + log P[r'][r]
-//     factorises: 6 block reductions instead of 3000 exp() per site (exact log-domain fallback when a class
-//     underflows);
-//   * sort = register/shuffle bitonic network (strides < 32) + 6 shared-memory exchange stages;
-//     prefix sums, the K fixed point and systematic resampling are warp scans/ballots;
+//     factorises (exact log-domain fallback when a class underflows);
+//   * a SERVICE warp (no particles) draws the uniform, evaluates the scalar logs, prefetches the emission rows and runs
+//     the candidate resampler while the eight worker warps wait at a barrier;
 //   * the uniform of site t is Philox(seed, chain, t) or an injected per-site array.
-// All arithmetic fp64.  Rounding differs from the reference at the 1e-16 level (tree sums vs sequential
-// sums); decisions (K, ancestors) are discontinuous in the weights, so parity is stated on log Z_t and the
-// posteriors (1e-6 relative) and on the argmax regime calls, and checked step by step against the oracle.
+// Order of exactly equal weights: canonical (log-weight, then regime, then sojourn), see hyg_common.cuh and DESIGN.md C-14;
+// sites where such a tie decided a particle's fate are counted (status[5]) and flagged (tie_flags tap).
+// All arithmetic fp64.  Rounding differs from the reference at the 1e-16 level (tree sums vs sequential sums).
 #ifndef HYG_SG_FILTER_CUH
 #define HYG_SG_FILTER_CUH
 
@@ -34,35 +43,71 @@
 #include "hyg_dev_structs.h"
 #include "sg_param.cuh"
 
+#ifndef HYG_CAND_CAP
+#define HYG_CAND_CAP 64        // candidates one warp sorts in registers (two per lane)
+#endif
+#ifndef HYG_PIVOT_TARGET
+#define HYG_PIVOT_TARGET 56    // rank (from the light end) the per-regime pivots are re-centred on
+#endif
+#define HYG_FATE_KEEP 0        // continues with its own weight
+#define HYG_FATE_SURV 1        // drawn by the systematic resampling: continues with the common weight lsum - log C
+#define HYG_FATE_DEAD 2        // + rank among the dead: the slot is reused by the new-segment particle of that regime
+#define HYG_RES_DREW 1
+#define HYG_RES_KEEP_LARGEST 2
+#define HYG_WORKER_BAR 1       // named barrier of the 256 worker threads
+
 namespace hyg {
 
+struct SgResOut {
+  int K;                          // k_kept tap
+  int flags;
+  int tie;                        // bit 0: equal keys among the sorted particles; bit 1: a tie decided a fate
+  int n_dup;                      // systematic draws that hit one particle twice (rounding); resolved, counted
+  double res_lw;                  // log-weight of a particle drawn by the systematic resampling
+  unsigned long long newpiv;      // byte r = slot of the new pivot of regime r, byte 7 = mask of regimes that got one
+};
+
 struct SgSmem {
-  // previous particle system, storage order (thread n owns slot n)
-  double W[HYG_NPMAX];
-  double lw[HYG_NPMAX];
-  double2 cur[HYG_NPMAX];  // {c_new(d,r), log(1-rho(d,r))}
-  double2 nxt[HYG_NPMAX];  // same for d+1
-  uint32_t d[HYG_NPMAX];
-  unsigned char r[HYG_NPMAX];
-  // resampling scratch
-  unsigned long long key[6][HYG_NPMAX];   // one exchange buffer per cross-warp sort stage (no reuse inside a site)
+  double part[2][HYG_NW][8];      // per-warp partials of the 8-wide transposed reductions (double-buffered)
+  double partG[2][HYG_NW][8];     // parameter mode: partials of Eg[r'] = sum e_n dlogrho_n
+  unsigned vmask[2][HYG_NW];
+  int pcnt[2][HYG_NW][8];         // per-warp counts: [r < R] particles not heavier than the pivot of regime r, [6] -inf weights
+  unsigned long long piv_key[2][HYG_RMAX];   // key of the pivot of regime r (0 = none), [t & 1]
+  // candidates of the fast path / bottom of the sorted order on the fallback path
+  unsigned long long cand_key[HYG_CAND_CAP];
+  unsigned long long cand_pay[HYG_CAND_CAP];
+  unsigned short cand_fate[HYG_CAND_CAP];
+  double W[HYG_NPMAX];            // previous self-normalised weights by slot (resampling input)
+  unsigned short fate[HYG_NPMAX];
+  unsigned short ofs[HYG_NPMAX];  // offspring counts (repair of double draws)
+  SgResOut res;
+  int fast_fail;
+  short new_slot[HYG_RMAX];       // slot of the new-segment particle (1, r) of this site
+  // fallback: block-wide sort
+  unsigned long long xk[2][HYG_NPMAX];
+  unsigned long long xp[2][HYG_NPMAX];
   double Q[HYG_NPMAX + 1];
-  unsigned short idx[HYG_NPMAX];
-  unsigned short anc[HYG_NPMAX];
+  double qtail[HYG_NW];
   int iscan[2][HYG_NW];
+  int iflag[2][HYG_NW];
   BlockScratch sc;
   double lo[2][HYG_RMAX];
-  double part[2][HYG_NW][8];   // per-warp partials of the 8-wide transposed reductions (double-buffered)
-  double partG[2][HYG_NW][8];  // parameter mode: partials of Eg[r'] = sum e_n dlogrho_n
-  unsigned vmask[2][HYG_NW];
+  double lomax[2];                // max_r logObs(t, r), [t & 1]
   int slow[HYG_RMAX];
-  unsigned slowmask;           // bit r: regime r takes the log-domain path at this site
-  double lomax[2];             // max_r logObs(t, r), [t & 1] (published by the service warp with the prefetched row)
-  double new_lw[HYG_RMAX];     // log-weight of the new-segment particle (1, r)
-  double new_invE[HYG_RMAX];   // 1 / sumE[r]
-  double u;                    // resampling uniform of the current site
-  double res_lw;               // log-weight given to resampled particles: lsum_prev - log C
-  double lsum[2];              // running log Z_t, [t & 1]
+  unsigned slowmask;              // bit r: regime r takes the log-domain path at this site
+  double new_lw[HYG_RMAX];        // log-weight of the new-segment particle (1, r)
+  double new_invE[HYG_RMAX];      // 1 / sumE[r]
+  double u;                       // resampling uniform of the current site
+  double lsum[2];                 // running log Z_t, [t & 1]
+  // lag set (fixed-lag smoother)
+  double bk[HYG_NPMAX][HYG_RMAX - 2];   // backward kernels bk_r[n] of the new-segment particles, [slot][r], r < 6
+  double Wc[HYG_NPMAX];           // current weight of a continuing particle, 0 for a slot that was rewritten
+  double Wnew[HYG_RMAX];          // current weight of the new-segment particle (1, r)
+  double lag_m[8][HYG_RMAX];      // per pending site of the current batch: filtered means
+  double lag_val[8][HYG_RMAX - 2][HYG_RMAX - 2];   // psi of the new-segment particles [q][r]
+  int lag_ok[8][2];
+  unsigned char r[HYG_NPMAX];     // regime by slot (lag set, parameter mode)
+  unsigned long long hsum[HYG_NW];
 };
 
 __device__ __forceinline__ bool hyg_isfinite(double x) {
@@ -75,98 +120,6 @@ __device__ __forceinline__ bool hyg_isfinite(double x) {
 __device__ __forceinline__ int sys_count_x(double x, int L) {
   return (x < 0.0) ? 0 : ((x >= static_cast<double>(L)) ? L : static_cast<int>(x) + 1);
 }
-
-#ifndef HYG_SORT_RANKMERGE
-#define HYG_SORT_RANKMERGE 0
-#endif
-#if HYG_SORT_RANKMERGE
-#define HYG_SORT_BARRIERS 2
-// Descending sort of one unique 64-bit key per worker thread (256 keys).  Each warp sorts its 32 keys with a
-// register/shuffle bitonic network (15 stages, no barrier); every key then finds its rank in the other seven sorted
-// runs by binary search in shared memory (7 independent 5-step searches) and is scattered to its final position:
-// 2 barriers instead of the 6 exchange barriers + 36 dependent stages of a full block-wide bitonic sort.
-// Returns the key of sorted position threadIdx.x.  Worker warps only.
-__device__ __forceinline__ unsigned long long block_sort_desc(unsigned long long key, SgSmem& s) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-  for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(HYG_FULL, key, j);
-      const bool desc_block = ((lane & k) == 0);
-      const bool lower = ((lane & j) == 0);
-      const bool take_max = (lower == desc_block);
-      const bool other_gt = other > key;
-      key = (take_max == other_gt) ? other : key;
-    }
-  }
-  s.key[0][tid] = key;   // eight descending runs of 32
-  __syncthreads();
-  int rank = lane;       // position inside the own run
-#pragma unroll
-  for (int w = 0; w < HYG_WORKER_WARPS; w++) {
-    if (w == warp) continue;
-    const unsigned long long* run = s.key[0] + 32 * w;
-    // number of keys in `run` (descending) that are greater than `key`
-    int lo = 0;
-#pragma unroll
-    for (int step = 16; step > 0; step >>= 1) lo += (run[lo + step - 1] > key) ? step : 0;
-    lo += (run[lo] > key) ? 1 : 0;   // lo <= 31 here
-    rank += lo;
-  }
-  s.key[1][rank] = key;
-  __syncthreads();
-  return s.key[1][tid];
-}
-
-#else
-#define HYG_SORT_BARRIERS 1
-// Descending bitonic sort of one 64-bit key per worker thread (256 keys): strides < 32 by warp shuffles, strides
-// 32/64/128 through shared memory (6 exchange stages, each with its own buffer).  The first exchange is a full block barrier
-// (it also publishes the class sums to every warp, service warp included); in the other five a warp only needs its partner
-// warp's keys, so they are 64-thread named barriers: id = 1 + 4 log2(stride / 32) + pair index, always the same two warps per id.
-__device__ __forceinline__ unsigned long long block_sort_desc(unsigned long long key, SgSmem& s) {
-  const int tid = threadIdx.x, warp = tid >> 5;
-  int kbuf = 0;
-#pragma unroll
-  for (int k = 2; k <= HYG_NPMAX; k <<= 1) {
-#pragma unroll
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      unsigned long long other;
-      if (j < 32) {
-        other = __shfl_xor_sync(HYG_FULL, key, j);
-      } else {
-        s.key[kbuf][tid] = key;
-        if (kbuf == 0) {
-          __syncthreads();
-        } else {
-          // pair index: the warp number with the bit of the partner stride removed
-          const int jw = j >> 5;   // 1, 2, 4
-          const int pair = (warp & (jw - 1)) | ((warp & ~(2 * jw - 1)) >> 1);
-          named_barrier(1 + 4 * (jw == 1 ? 0 : (jw == 2 ? 1 : 2)) + pair, 64);
-        }
-        other = s.key[kbuf][tid ^ j];
-        kbuf++;
-      }
-      const bool desc_block = ((tid & k) == 0);
-      const bool lower = ((tid & j) == 0);
-      const bool take_max = (lower == desc_block);
-      const bool other_gt = other > key;
-      key = (take_max == other_gt) ? other : key;
-    }
-  }
-  return key;
-}
-#endif
-
-struct SgChainState {
-  // per-thread particle (slot = threadIdx.x)
-  double lw, W;
-  double2 cur, nxt;
-  double gcur, gnxt;   // parameter mode: d log rho / d theta_omega for d and d+1
-  uint32_t d;
-  int r;
-};
 
 template <int RT> __device__ __forceinline__ double pick(const double (&v)[RT], int i) {
   double o = 0.0;
@@ -264,7 +217,6 @@ __device__ __forceinline__ double combine8(const double (*part)[8]) {
 // Service-warp job: new-segment particles (1, r), r = lane < R.  sumE[r] = sum_{r' != r} P[r'][r] E[r'] is the linear-domain
 // mass flowing into regime r (relative to exp(lsum_prev)); its log-weight is lsum_prev + logObs_r + log(sumE[r])
 // (computeWeightsCp, Smc.h:562-573, after factorising logTrans((1,r) <- (d,r')) = log c_new(d,r') + log P[r'][r]).
-// Returns sumE[lane]; the log is taken later, in one evaluation shared with log C.
 template <int R>
 __device__ __forceinline__ double sg_service_new_segments(const SgModelDev& mdl, SgSmem& s, double totA, int pA) {
   const int lane = threadIdx.x & 31;
@@ -298,110 +250,564 @@ template <bool PE, class T> __device__ __forceinline__ T tab_load(const T* p) {
   return __ldg(p);
 }
 
-// Lag-set update of one site: psi of every pending site is propagated to the new particle system and sites whose R filtered
-// variances dropped below epsilon are emitted (OnlineMarginalSmoothing.h:148-255).  Returns the number of sites still pending.
-template <int R> struct SgLagArgs {
-  const double* pp;   // psi written at step t-1
-  double* pc;         // psi of step t
-  int* pend_t;
-  int n_pend, N_prev, M, N_curr, anc, pr;
-  double e_prev, cW, my_invE;
-  unsigned slowmask;
-  double bk_slow[R];
-  unsigned long long t, T, own_lo, own_hi, t_off;
-  bool last_seg, worker;
-  double epsilon;
+// ------------------------------------------------------------------------------------------------------------------
+// Resampling (Smc::resampleCp -> resample::optimalFiniteState, Smc.h:406-450, resample.h:289-409) on a sorted bottom
+// set.  One warp, EPL elements per lane in blocked layout: lane l holds sorted positions j = EPL l + k of the `cnt`
+// lightest particles (descending: j = 0 is the heaviest of them), i.e. positions p = N_prev - cnt + j of the full order.
+// ------------------------------------------------------------------------------------------------------------------
+
+// New pivots from a sorted bottom set: for every regime the surviving particle whose rank from the light end is closest
+// below HYG_PIVOT_TARGET (else the closest above).  live[k]: the particle continues; j0 = position of this lane's first
+// element.  Returns the packed result (SgResOut::newpiv) in every lane.
+template <int EPL, int R>
+__device__ __forceinline__ unsigned long long sg_pick_pivots(const unsigned long long (&pay)[EPL], const bool (&live)[EPL], int j0, int cnt) {
+  const int jlo = cnt - HYG_PIVOT_TARGET;
+  unsigned long long out = 0ull;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    int a = 0x7fffffff, b = -1;
+#pragma unroll
+    for (int k = 0; k < EPL; k++) {
+      const int j = j0 + k;
+      const bool mine = live[k] && j < cnt && static_cast<int>((pay[k] >> 36) & 7ull) == r;
+      const int code = (j << 8) | static_cast<int>(pay[k] & 0xFFull);
+      if (mine && j >= jlo) a = code < a ? code : a;
+      if (mine && j < jlo) b = code > b ? code : b;
+    }
+    a = __reduce_min_sync(HYG_FULL, a);
+    b = __reduce_max_sync(HYG_FULL, b);
+    const int pickc = (a != 0x7fffffff) ? a : b;
+    if (pickc >= 0) out |= (static_cast<unsigned long long>(pickc & 0xFF) << (8 * r)) | (1ull << (56 + r));
+  }
+  return out;
+}
+
+template <int EPL>
+__device__ __forceinline__ void sg_warp_sort_desc(unsigned long long (&key)[EPL], unsigned long long (&pay)[EPL]) {
+  const int lane = threadIdx.x & 31;
+  constexpr int NEL = 32 * EPL;
+#pragma unroll
+  for (int k2 = 2; k2 <= NEL; k2 <<= 1) {
+#pragma unroll
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      if (j < EPL) {
+        // partner in the same lane (EPL == 2, j == 1)
+        const bool desc = (((lane * EPL) & k2) == 0);
+        const bool b10 = order_before(key[EPL - 1], pay[EPL - 1], key[0], pay[0]);
+        const bool sw = (desc == b10);   // descending block wants element 0 first: swap when element 1 precedes it
+        const unsigned long long tk = sw ? key[EPL - 1] : key[0], tp = sw ? pay[EPL - 1] : pay[0];
+        const unsigned long long uk = sw ? key[0] : key[EPL - 1], up = sw ? pay[0] : pay[EPL - 1];
+        key[0] = tk; pay[0] = tp; key[EPL - 1] = uk; pay[EPL - 1] = up;
+      } else {
+        const int lj = j / EPL;
+#pragma unroll
+        for (int k = 0; k < EPL; k++) {
+          const unsigned long long ok = __shfl_xor_sync(HYG_FULL, key[k], lj);
+          const unsigned long long op = __shfl_xor_sync(HYG_FULL, pay[k], lj);
+          const int e = lane * EPL + k;
+          const bool desc = ((e & k2) == 0);
+          const bool lower = ((e & j) == 0);
+          const bool take_first = (lower == desc);
+          const bool other_first = order_before(ok, op, key[k], pay[k]);
+          const bool tk = (take_first == other_first);
+          key[k] = tk ? ok : key[k];
+          pay[k] = tk ? op : pay[k];
+        }
+      }
+    }
+  }
+}
+
+// The service warp's resampler (fast path).  Reads the compacted candidates, writes s.fate[slot] for every candidate,
+// s.res and s.fast_fail.  `cnt` candidates (1 <= cnt <= 32 EPL); all particles not among them are heavier than all of them.
+template <int EPL, int R>
+__device__ __forceinline__ void sg_resample_warp(SgSmem& s, int cnt, int N_prev, int M, double u, double lsum_prev) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long key[EPL], pay[EPL];
+#pragma unroll
+  for (int k = 0; k < EPL; k++) {
+    const int e = lane * EPL + k;
+    key[k] = (e < cnt) ? s.cand_key[e] : 0ull;
+    pay[k] = (e < cnt) ? s.cand_pay[e] : (~0ull - static_cast<unsigned long long>(e));
+  }
+  sg_warp_sort_desc<EPL>(key, pay);
+  const int base = N_prev - cnt;   // full-order position of candidate 0
+  double q[EPL], Q[EPL + 1];
+  bool real[EPL];
+#pragma unroll
+  for (int k = 0; k < EPL; k++) {
+    real[k] = (lane * EPL + k) < cnt;
+    q[k] = real[k] ? s.W[pay[k] & 0xFFull] : 0.0;
+  }
+  // suffix sums Q[j] = sum_{i >= j} q_i (resample.h:306) by a shuffle scan over the lane totals
+  double v = 0.0;
+#pragma unroll
+  for (int k = EPL - 1; k >= 0; k--) v += q[k];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double tt = __shfl_down_sync(HYG_FULL, v, o);
+    if (lane + o < 32) v += tt;
+  }
+  double vnext = __shfl_down_sync(HYG_FULL, v, 1);
+  if (lane == 31) vnext = 0.0;
+  Q[EPL] = vnext;
+#pragma unroll
+  for (int k = EPL - 1; k >= 0; k--) Q[k] = q[k] + Q[k + 1];
+  // first stop: K* = min{ p : p >= M or !(q_p (M - p) > Q[p]) }  (fixed point of resample.h:333-342)
+  int first = 0x7fffffff;
+#pragma unroll
+  for (int k = EPL - 1; k >= 0; k--) {
+    const int j = lane * EPL + k, p = base + j;
+    const bool stop = !real[k] || (p >= M) || !(q[k] * static_cast<double>(M - p) > Q[k]);
+    first = stop ? j : first;
+  }
+  const int jstar = __reduce_min_sync(HYG_FULL, first);
+  // The heaviest candidate must be provably kept, otherwise heavier particles may belong to the tail as well.  One exception:
+  // if its self-normalised weight is exactly 0 (underflow; informative data), every position from the first zero weight p0 on
+  // is a stop, position p0 - 1 is not (q (M - p0 + 1) > q because p0 <= N_prev - cnt < M), so K = p0 and Q[K] = 0: the
+  // reference falls through to "keep the M largest by log-weight" (resample.h:345,366-375) and the nd lightest -- all of them
+  // candidates, cnt > nd -- die.
+  bool zero_tail = false;
+  if (jstar == 0 && cnt < N_prev) {
+    const double q_top = __shfl_sync(HYG_FULL, q[0], 0);
+    if (q_top == 0.0) {
+      zero_tail = true;
+    } else {
+      if (lane == 0) s.fast_fail = 1;
+      return;
+    }
+  }
+  const int K = base + jstar;
+  double Qk = 0.0;
+  {
+    double mineQ = 0.0;
+#pragma unroll
+    for (int k = 0; k < EPL; k++) mineQ = ((jstar % EPL) == k) ? Q[k] : mineQ;
+    Qk = __shfl_sync(HYG_FULL, mineQ, jstar / EPL);
+  }
+  const bool keep_largest = zero_tail || (K >= M) || !(Qk > 0.0) || !hyg_isfinite(Qk);
+  int fate[EPL];
+  bool live[EPL];
+  int tie = 0, n_dup = 0;
+  // key of the next sorted position, for the tie taps; bit 0: exact ties among the sorted candidates
+  unsigned long long nxk[EPL];
+  {
+    unsigned long long nk = __shfl_down_sync(HYG_FULL, key[0], 1);
+    if (lane == 31) nk = 0ull;
+    bool t0 = false;
+#pragma unroll
+    for (int k = 0; k < EPL; k++) {
+      nxk[k] = (k + 1 < EPL) ? key[k + 1] : nk;
+      t0 = t0 || (key[k] == nxk[k] && key[k] > HYG_KEY_NEGINF);
+    }
+    if (__any_sync(HYG_FULL, t0)) tie |= 1;
+  }
+  if (keep_largest) {
+    // keep the M largest by log-weight (Smc.h:432-441; resample.h:366-375): positions p >= M die
+    bool cut = false;
+#pragma unroll
+    for (int k = 0; k < EPL; k++) {
+      const int p = base + lane * EPL + k;
+      fate[k] = (real[k] && p >= M) ? HYG_FATE_DEAD : HYG_FATE_KEEP;
+      // a tie across the cut decides who is kept
+      cut = cut || (real[k] && p == M - 1 && p + 1 < N_prev && key[k] == nxk[k] && key[k] > HYG_KEY_NEGINF);
+    }
+    if (__any_sync(HYG_FULL, cut)) tie |= 2;
+  } else {
+    const int L = M - K;
+    // systematic resampling of L offspring among the sorted residual particles (resample.h:85-127,354-359).
+    // C_j = #{ i < L : (i+u)/L <= cumulative residual weight up to j }; forced monotone, C_last = L, so the
+    // offspring counts o_j = C_j - C_{j-1} are >= 0 and sum to L whatever the rounding of the suffix sums.
+    const double scale = static_cast<double>(L) / Qk;
+    int C[EPL];
+#pragma unroll
+    for (int k = 0; k < EPL; k++) {
+      const int j = lane * EPL + k;
+      int c = 0;
+      if (j >= jstar && j < cnt) c = (j == cnt - 1) ? L : sys_count_x((Qk - Q[k + 1]) * scale - u, L);
+      if (j >= cnt) c = L;
+      C[k] = c;
+    }
+#pragma unroll
+    for (int k = 1; k < EPL; k++) C[k] = C[k - 1] > C[k] ? C[k - 1] : C[k];
+    int run = C[EPL - 1];
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      const int tt = __shfl_up_sync(HYG_FULL, run, dlt);
+      if (lane >= dlt) run = tt > run ? tt : run;
+    }
+    int before = __shfl_up_sync(HYG_FULL, run, 1);
+    if (lane == 0) before = 0;
+    int o[EPL];
+    bool dup = false;
+#pragma unroll
+    for (int k = 0; k < EPL; k++) {
+      const int j = lane * EPL + k;
+      const int cj = before > C[k] ? before : C[k];
+      const int cprev = (k == 0) ? before : (before > C[k - 1] ? before : C[k - 1]);
+      o[k] = (j >= jstar && j < cnt) ? cj - ((j == jstar) ? 0 : cprev) : 0;
+      dup = dup || (o[k] > 1);
+    }
+    if (__any_sync(HYG_FULL, dup)) {
+      // A particle drawn twice: only possible when rounding puts a residual weight above the step Qk/L.  The reference
+      // would duplicate the support point; here the extra draw goes to the next undrawn tail particle (counted).
+#pragma unroll
+      for (int k = 0; k < EPL; k++) s.ofs[lane * EPL + k] = static_cast<unsigned short>(o[k]);
+      __syncwarp();
+      if (lane == 0) {
+        int extra = 0;
+        for (int j = jstar; j < cnt; j++) { const int oj = s.ofs[j]; if (oj > 1) { extra += oj - 1; s.ofs[j] = 1; } }
+        n_dup = extra;
+        for (int j = jstar; j < cnt && extra > 0; j++) if (s.ofs[j] == 0) { s.ofs[j] = 1; extra--; }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < EPL; k++) o[k] = s.ofs[lane * EPL + k];
+      n_dup = __shfl_sync(HYG_FULL, n_dup, 0);
+    }
+    bool tied = false;
+    {
+      // bit 1: two equal residual weights, one drawn and one not
+      int no = __shfl_down_sync(HYG_FULL, o[0], 1);
+      if (lane == 31) no = 0;
+#pragma unroll
+      for (int k = 0; k < EPL; k++) {
+        const int j = lane * EPL + k;
+        const int nxo = (k + 1 < EPL) ? o[k + 1] : no;
+        tied = tied || (j >= jstar && j + 1 < cnt && key[k] == nxk[k] && q[k] != 0.0 && ((o[k] > 0) != (nxo > 0)));
+      }
+    }
+    if (__any_sync(HYG_FULL, tied)) tie |= 2;
+#pragma unroll
+    for (int k = 0; k < EPL; k++) {
+      const int j = lane * EPL + k;
+      fate[k] = (!real[k] || j < jstar) ? HYG_FATE_KEEP : (o[k] > 0 ? HYG_FATE_SURV : HYG_FATE_DEAD);
+    }
+    if (lane == 0) s.res.res_lw = lsum_prev + log(Qk / static_cast<double>(L));   // resample.h:361-364
+  }
+  // ranks of the dead (sorted order): the slot of the k-th dead particle is reused by the new-segment particle (1, k)
+  {
+    unsigned dm[EPL];
+#pragma unroll
+    for (int k = 0; k < EPL; k++) dm[k] = __ballot_sync(HYG_FULL, fate[k] == HYG_FATE_DEAD);
+    const unsigned lt = (1u << lane) - 1u;
+    int rank = 0;
+#pragma unroll
+    for (int k = 0; k < EPL; k++) rank += __popc(dm[k] & lt);
+#pragma unroll
+    for (int k = 0; k < EPL; k++) {
+      if (fate[k] == HYG_FATE_DEAD) { fate[k] = HYG_FATE_DEAD + rank; rank++; }
+      live[k] = real[k] && fate[k] < HYG_FATE_DEAD;
+      if (real[k]) s.fate[pay[k] & 0xFFull] = static_cast<unsigned short>(fate[k]);
+    }
+  }
+  const unsigned long long np = sg_pick_pivots<EPL, R>(pay, live, lane * EPL, cnt);
+  if (lane == 0) {
+    s.res.K = keep_largest ? -2 : K;
+    s.res.flags = keep_largest ? HYG_RES_KEEP_LARGEST : HYG_RES_DREW;
+    s.res.tie = tie;
+    s.res.n_dup = n_dup;
+    s.res.newpiv = np;
+    s.fast_fail = 0;
+  }
+}
+
+// Fallback: block-wide bitonic sort of all particles by the 256 worker threads (barriers among the workers only), then the
+// same decisions.  key/pay: this slot's particle (key 0 = none); Wprev its self-normalised weight.
+template <int R>
+__device__ __noinline__ void sg_resample_block(SgSmem& s, unsigned long long key, unsigned long long pay, double Wprev, int N_prev, int M, double u,
+                                               double lsum_prev) {
+  int ibuf = 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  s.W[tid] = Wprev;
+  if (key == 0ull) pay = ~0ull - static_cast<unsigned long long>(tid);
+  int xb = 0;
+#pragma unroll 1
+  for (int k2 = 2; k2 <= HYG_NPMAX; k2 <<= 1) {
+#pragma unroll 1
+    for (int j = k2 >> 1; j > 0; j >>= 1) {
+      unsigned long long ok, op;
+      if (j < 32) {
+        ok = __shfl_xor_sync(HYG_FULL, key, j);
+        op = __shfl_xor_sync(HYG_FULL, pay, j);
+      } else {
+        s.xk[xb][tid] = key; s.xp[xb][tid] = pay;
+        named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
+        ok = s.xk[xb][tid ^ j]; op = s.xp[xb][tid ^ j];
+        xb ^= 1;
+      }
+      const bool desc = ((tid & k2) == 0);
+      const bool lower = ((tid & j) == 0);
+      const bool take_first = (lower == desc);
+      const bool other_first = order_before(ok, op, key, pay);
+      const bool tk = (take_first == other_first);
+      key = tk ? ok : key;
+      pay = tk ? op : pay;
+    }
+  }
+  // thread tid now holds sorted position p = tid
+  const int sidx = static_cast<int>(pay & 0xFFull);
+  const bool real = tid < N_prev;
+  named_barrier(HYG_WORKER_BAR, HYG_NPMAX);   // s.W complete (and the exchange buffers free again)
+  const double qv = real ? s.W[sidx] : 0.0;
+  s.xk[0][tid] = key;                         // sorted keys, for the tie taps
+  double v = qv;  // Q[p] = sum_{j >= p} q_j
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double tt = __shfl_down_sync(HYG_FULL, v, o);
+    if (lane + o < 32) v += tt;
+  }
+  if (lane == 0) s.qtail[warp] = v;   // (not s.sc: its double-buffer index must stay in step with the service warp's)
+  named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
+  double tail = 0.0;
+#pragma unroll
+  for (int w = HYG_WORKER_WARPS - 1; w > 0; w--)
+    if (w > warp) tail += s.qtail[w];
+  const double Qp = v + tail;
+  s.Q[tid] = Qp;
+  if (tid == 0) s.Q[HYG_NPMAX] = 0.0;
+  const bool stop = (tid >= M) || !real || !(qv * static_cast<double>(M - tid) > Qp);
+  const unsigned sb = __ballot_sync(HYG_FULL, stop);
+  if (lane == 0) s.iscan[ibuf][warp] = sb ? (warp * 32 + __ffs(static_cast<int>(sb)) - 1) : HYG_NPMAX;
+  named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
+  const int K = __reduce_min_sync(HYG_FULL, (lane < HYG_WORKER_WARPS) ? s.iscan[ibuf][lane] : HYG_NPMAX);
+  ibuf ^= 1;
+  bool keep_largest = (K >= M);
+  double Qk = 0.0;
+  if (!keep_largest) {
+    Qk = s.Q[K];
+    if (!(Qk > 0.0) || !hyg_isfinite(Qk)) keep_largest = true;
+  }
+  int fate = HYG_FATE_KEEP;
+  int o = 0;
+  int tie = 0, n_dup = 0;
+  const unsigned long long nxk = (tid + 1 < HYG_NPMAX) ? s.xk[0][tid + 1] : 0ull;
+  if (__any_sync(HYG_FULL, key == nxk && key > HYG_KEY_NEGINF)) tie |= 1;
+  if (keep_largest) {
+    fate = (real && tid >= M) ? HYG_FATE_DEAD : HYG_FATE_KEEP;
+    if (tid == M - 1 && M < N_prev && key == nxk && key > HYG_KEY_NEGINF) tie |= 2;
+  } else {
+    const int L = M - K;
+    int C = 0;
+    if (tid >= K && real) C = (tid == N_prev - 1) ? L : sys_count_x((Qk - s.Q[tid + 1]) * (static_cast<double>(L) / Qk) - u, L);
+    if (!real) C = L;
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      const int tt = __shfl_up_sync(HYG_FULL, C, dlt);
+      if (lane >= dlt) C = tt > C ? tt : C;
+    }
+    if (lane == 31) s.iscan[ibuf][warp] = C;
+    named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
+    const int before = __reduce_max_sync(HYG_FULL, (lane < warp && lane < HYG_WORKER_WARPS) ? s.iscan[ibuf][lane] : 0);
+    ibuf ^= 1;
+    C = before > C ? before : C;
+    int Cprev = __shfl_up_sync(HYG_FULL, C, 1);
+    if (lane == 0) Cprev = before;
+    if (tid <= K) Cprev = 0;
+    o = (tid >= K && real) ? C - Cprev : 0;
+    // double draws: repaired by one thread (rare: rounding only)
+    const bool anydup = __any_sync(HYG_FULL, o > 1);
+    s.ofs[tid] = static_cast<unsigned short>(o);
+    if (lane == 0) s.iflag[ibuf][warp] = anydup ? 1 : 0;
+    named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
+    int dupany = 0;
+#pragma unroll
+    for (int w = 0; w < HYG_WORKER_WARPS; w++) dupany |= s.iflag[ibuf][w];
+    if (dupany) {
+      if (tid == 0) {
+        int extra = 0;
+        for (int j = K; j < N_prev; j++) { const int oj = s.ofs[j]; if (oj > 1) { extra += oj - 1; s.ofs[j] = 1; } }
+        s.iflag[ibuf][0] = extra;
+        for (int j = K; j < N_prev && extra > 0; j++) if (s.ofs[j] == 0) { s.ofs[j] = 1; extra--; }
+      }
+      named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
+      o = s.ofs[tid];
+      n_dup = s.iflag[ibuf][0];
+    }
+    ibuf ^= 1;
+    const int no = __shfl_down_sync(HYG_FULL, o, 1);
+    const int nxo = (lane == 31) ? ((tid + 1 < HYG_NPMAX) ? static_cast<int>(s.ofs[tid + 1]) : 0) : no;
+    if (__any_sync(HYG_FULL, tid >= K && tid + 1 < N_prev && key == nxk && qv != 0.0 && ((o > 0) != (nxo > 0)))) tie |= 2;
+    fate = (!real || tid < K) ? HYG_FATE_KEEP : (o > 0 ? HYG_FATE_SURV : HYG_FATE_DEAD);
+  }
+  // ranks of the dead in sorted order
+  const unsigned dm = __ballot_sync(HYG_FULL, fate == HYG_FATE_DEAD);
+  if (lane == 0) { s.iscan[ibuf][warp] = __popc(dm); s.iflag[ibuf][warp] = tie; }
+  // bottom of the sorted order for the pivot choice
+  const int n64 = N_prev < HYG_CAND_CAP ? N_prev : HYG_CAND_CAP;
+  named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
+  int drank = __popc(dm & ((1u << lane) - 1u));
+#pragma unroll
+  for (int w = 0; w < HYG_WORKER_WARPS; w++) {
+    if (w < warp) drank += s.iscan[ibuf][w];
+    tie |= s.iflag[ibuf][w];
+  }
+  ibuf ^= 1;
+  if (fate == HYG_FATE_DEAD) fate = HYG_FATE_DEAD + drank;
+  if (real) s.fate[sidx] = static_cast<unsigned short>(fate);
+  {
+    const int j = tid - (N_prev - n64);
+    if (real && j >= 0) { s.cand_pay[j] = pay; s.cand_fate[j] = static_cast<unsigned short>(fate); }
+  }
+  named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
+  if (warp == 0) {
+    constexpr int EPL = HYG_CAND_CAP / 32;
+    unsigned long long cp[EPL];
+    bool live[EPL];
+#pragma unroll
+    for (int k = 0; k < EPL; k++) {
+      const int e = lane * EPL + k;
+      cp[k] = (e < n64) ? s.cand_pay[e] : 0ull;
+      live[k] = (e < n64) && s.cand_fate[e] < HYG_FATE_DEAD;
+    }
+    const unsigned long long np = sg_pick_pivots<EPL, R>(cp, live, lane * EPL, n64);
+    if (lane == 0) {
+      s.res.K = keep_largest ? -2 : K;
+      s.res.flags = keep_largest ? HYG_RES_KEEP_LARGEST : HYG_RES_DREW;
+      s.res.tie = tie;
+      s.res.n_dup = n_dup;
+      s.res.newpiv = np;
+      if (!keep_largest) s.res.res_lw = lsum_prev + log(Qk / static_cast<double>(M - K));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fixed-lag smoother: updatePsi + storeEstimates of every pending site (OnlineMarginalSmoothing.h:148-255).
+// psi rows live in a per-CTA global workspace (L2-resident) and never move: rows[row][q][slot]; a continuing particle's
+// entry is untouched, only the <= R rewritten slots get sum_n bk_r[n] psi[n].  One warp per (pending site, three regime
+// indicators): lanes stride over the slots, so the 256-term sums are serial per lane and finish with one 8-wide transposed
+// warp reduction -- no block barrier per pending site.
+// ------------------------------------------------------------------------------------------------------------------
+struct SgLagState {
+  double* rows;        // [lcap][R][256]
+  int* pend_t;         // [lcap] site of pending entry i (oldest first)
+  int* pend_row;       // [lcap] its row
+  int* pend_t_alt;     // the lists are rebuilt into the alternate copy while the current one is being read
+  int* pend_row_alt;
+  int* free_row;       // [lcap] stack of free rows
+  int n_pend, n_free;
 };
 
 template <int R>
-__device__ __noinline__ int sg_lag_update(const SgLagArgs<R>& a, const SgModelDev& mdl, const SgChainDev& ch, SgSmem& s, int& flip, int& n_halo_forced) {
-  const int tid = threadIdx.x;
-  const int N_prev = a.N_prev, M = a.M, N_curr = a.N_curr, anc = a.anc;
+__device__ __noinline__ int sg_lag_update(SgLagState& lag, const SgChainDev& ch, SgSmem& s, unsigned int t, unsigned int T, unsigned int own_lo,
+                                          unsigned int own_hi, unsigned long long t_off, bool last_seg, double epsilon, int& n_halo_forced) {
+  static_assert(R <= HYG_RMAX - 2, "lag-set tasks handle three regime indicators each");
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // s.bk[slot][r], s.Wc[slot], s.new_slot[r] and s.Wnew[r] were published before the caller's barrier
+  constexpr int HALF = (R + 1) / 2;
   int kept = 0;
-  for (int i = 0; i < a.n_pend; i++) {
-    const double* src = a.pp + static_cast<size_t>(i) * R * HYG_NPMAX;
-    double own[R], val[R];
+  const int n_pend = lag.n_pend;
+  for (int i0 = 0; i0 < n_pend; i0 += 8) {
+    const int nb = (n_pend - i0) < 8 ? (n_pend - i0) : 8;
+    // ---- tasks (pending site, half): all nine warps take their share ----
+    for (int task = warp; task < 2 * nb; task += HYG_NW) {
+      const int bi = task >> 1, h = task & 1;
+      const int q0 = h * HALF, nq = (h == 0) ? HALF : (R - HALF);
+      double* row = lag.rows + static_cast<size_t>(lag.pend_row[i0 + bi]) * R * HYG_NPMAX;
+      double acc[HALF][8];
 #pragma unroll
-    for (int q = 0; q < R; q++) {
-      own[q] = (tid < N_prev) ? src[q * HYG_NPMAX + tid] : 0.0;
-      val[q] = (tid < M) ? src[q * HYG_NPMAX + anc] : 0.0;
-    }
-    // class sums G[q][r'] = sum_{n in class r'} e_n psi_q[n]; new particle (1,r): sum_{r'} P[r'][r] G[q][r'] / sumE[r]
+      for (int j = 0; j < HALF; j++)
 #pragma unroll
-    for (int q = 0; q < R; q++) {
-      double g[R];
+        for (int c = 0; c < 8; c++) acc[j][c] = 0.0;
+#pragma unroll 2
+      for (int k = 0; k < HYG_NPMAX / 32; k++) {
+        const int n = lane + 32 * k;
+        double b[R];
 #pragma unroll
-      for (int rp = 0; rp < R; rp++) g[rp] = (a.pr == rp) ? a.e_prev * own[q] : 0.0;
-      block_sum<R>(g, s.sc, flip);
-      if (tid >= M && tid < N_curr) {
-        const int r = tid - M;
-        double acc = 0.0;
+        for (int r = 0; r < R; r++) b[r] = s.bk[n][r];
+        const double w = s.Wc[n];
 #pragma unroll
-        for (int rp = 0; rp < R; rp++) acc += (rp != r) ? mdl.P[rp][r] * g[rp] : 0.0;
-        val[q] = acc * a.my_invE;
-      }
-    }
-    if (a.slowmask) {
+        for (int j = 0; j < HALF; j++) {
+          if (j < nq) {
+            const double ps = row[(q0 + j) * HYG_NPMAX + n];
 #pragma unroll
-      for (int r = 0; r < R; r++) {
-        if (!((a.slowmask >> r) & 1u)) continue;
-        double g[R];
-#pragma unroll
-        for (int q = 0; q < R; q++) g[q] = a.bk_slow[r] * own[q];
-        block_sum<R>(g, s.sc, flip);
-        if (tid == M + r) {
-#pragma unroll
-          for (int q = 0; q < R; q++) val[q] = g[q];
+            for (int r = 0; r < R; r++) acc[j][r] += b[r] * ps;
+            const double wp = w * ps;
+            acc[j][6] += wp;
+            acc[j][7] += wp * ps;
+          }
         }
       }
-    }
-    // storeEstimates (OnlineMarginalSmoothing.h:197-255): emit when all R filtered variances < epsilon
-    double mv[2 * R];
+      bool ok = true;
 #pragma unroll
-    for (int q = 0; q < R; q++) { mv[q] = a.cW * val[q]; mv[R + q] = a.cW * val[q] * val[q]; }
-    block_sum<2 * R>(mv, s.sc, flip);
-    bool settled = true;
-#pragma unroll
-    for (int q = 0; q < R; q++) {
-      const double var = mv[R + q] - mv[q] * mv[q];  // sum W (x-m)^2 with sum W = 1
-      if (!(var < a.epsilon)) settled = false;
-    }
-    const bool emit = settled || (a.t == a.T - 1);
-    const int ts = a.pend_t[i];
-    if (emit) {
-      const bool own_s = (static_cast<unsigned long long>(ts) >= a.own_lo) && (static_cast<unsigned long long>(ts) < a.own_hi);
-      if (own_s) {
-        // whole row (position, p_1..p_R) in one store instruction: 56 contiguous bytes, also when the row goes to mapped host memory
-        if (tid <= R && ch.probs) {
-          const double outv = (tid == 0) ? (ch.pos ? static_cast<double>(ch.pos[ts]) : static_cast<double>(static_cast<unsigned long long>(ts) + a.t_off))
-                                         : pick<2 * R>(mv, tid - 1);
-          ch.probs[static_cast<size_t>(ts) * (R + 1) + tid] = outv;
+      for (int j = 0; j < HALF; j++) {
+        if (j < nq) {
+          const double tot = warp_reduce8(acc[j]);        // lane group g = (lane >> 2) & 7 holds the total of index g
+          const int g = (lane >> 2) & 7;
+          // psi of the new-segment particle (1, g) is sum_n bk_g[n] psi[n] = tot; it carries the weight Wnew[g]
+          const double wg = (g < R) ? s.Wnew[g] : 0.0;
+          double mterm = (g < R) ? wg * tot : ((g == 6) ? tot : 0.0);
+          double vterm = (g < R) ? wg * tot * tot : ((g == 7) ? tot : 0.0);
+          mterm += __shfl_xor_sync(HYG_FULL, mterm, 4); vterm += __shfl_xor_sync(HYG_FULL, vterm, 4);
+          mterm += __shfl_xor_sync(HYG_FULL, mterm, 8); vterm += __shfl_xor_sync(HYG_FULL, vterm, 8);
+          mterm += __shfl_xor_sync(HYG_FULL, mterm, 16); vterm += __shfl_xor_sync(HYG_FULL, vterm, 16);
+          const double var = vterm - mterm * mterm;       // sum W (x - m)^2 with sum W = 1
+          if (!(var < epsilon)) ok = false;
+          if (lane == 0) s.lag_m[bi][q0 + j] = mterm;
+          if ((lane & 3) == 0 && g < R) s.lag_val[bi][q0 + j][g] = tot;
         }
-        if (tid == 0 && ch.finalised_at) ch.finalised_at[ts] = static_cast<int>(a.t + a.t_off);
-        if (!settled && !a.last_seg) n_halo_forced++;   // the segment's right halo ended before this site settled
       }
-    } else {
-      double* dst = a.pc + static_cast<size_t>(kept) * R * HYG_NPMAX;
-      if (a.worker) {
-#pragma unroll
-        for (int q = 0; q < R; q++) dst[q * HYG_NPMAX + tid] = val[q];
-      }
-      __syncthreads();  // pend_t[i] has been read by every thread before slot `kept` (<= i) is overwritten
-      if (tid == 0) a.pend_t[kept] = ts;
-      kept++;
+      if (lane == 0) s.lag_ok[bi][h] = ok ? 1 : 0;
     }
+    __syncthreads();
+    // ---- storeEstimates (OnlineMarginalSmoothing.h:197-255): emit when all R filtered variances < epsilon ----
+    for (int bi = 0; bi < nb; bi++) {
+      const int i = i0 + bi;
+      const bool settled = s.lag_ok[bi][0] && s.lag_ok[bi][1];
+      const bool emit = settled || (t == T - 1);
+      const int ts = lag.pend_t[i];
+      const int rw = lag.pend_row[i];
+      if (emit) {
+        const bool own_s = (static_cast<unsigned int>(ts) >= own_lo) && (static_cast<unsigned int>(ts) < own_hi);
+        if (own_s) {
+          // whole row (position, p_1..p_R): 56 contiguous bytes, also when the row goes to mapped host memory
+          if (tid <= R && ch.probs) {
+            const double outv = (tid == 0) ? (ch.pos ? static_cast<double>(ch.pos[ts]) : static_cast<double>(static_cast<unsigned long long>(ts) + t_off))
+                                           : s.lag_m[bi][tid - 1];
+            ch.probs[static_cast<size_t>(ts) * (R + 1) + tid] = outv;
+          }
+          if (tid == 0 && ch.finalised_at) ch.finalised_at[ts] = static_cast<int>(t + t_off);
+          if (!settled && !last_seg) n_halo_forced++;   // the segment's right halo ended before this site settled
+        } else if (ch.ovl && tid < R && static_cast<unsigned int>(ts) >= own_hi && static_cast<unsigned int>(ts) < own_hi + HYG_OVL_ROWS) {
+          ch.ovl[(static_cast<unsigned int>(ts) - own_hi) * R + tid] = s.lag_m[bi][tid];   // left-halo check (hyg_dev_structs.h)
+        }
+        if (tid == 0) lag.free_row[lag.n_free] = rw;
+        lag.n_free++;
+      } else {
+        // psi of the rewritten slots; every other entry of the row stays as it is
+        if (tid < R * R) {
+          const int q = tid / R, r = tid % R;
+          lag.rows[static_cast<size_t>(rw) * R * HYG_NPMAX + q * HYG_NPMAX + s.new_slot[r]] = s.lag_val[bi][q][r];
+        }
+        if (tid == 0) { lag.pend_t_alt[kept] = ts; lag.pend_row_alt[kept] = rw; }
+        kept++;
+      }
+    }
+    __syncthreads();
   }
+  { int* a = lag.pend_t; lag.pend_t = lag.pend_t_alt; lag.pend_t_alt = a; }
+  { int* a = lag.pend_row; lag.pend_row = lag.pend_row_alt; lag.pend_row_alt = a; }
+  lag.n_pend = kept;
   return kept;
 }
+
+struct SgChainState {
+  // per-thread particle (slot = threadIdx.x)
+  double lw, W;
+  double2 cur, nxt;    // table entries {c_new, log(1 - rho)} for d and d + 1
+  double gcur, gnxt;   // parameter mode: d log rho / d theta_omega for d and d+1
+  uint32_t d;
+  int r;
+};
 
 template <int RT, bool PE>
 __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgRunDev& run, double* psi_ws, SgSmem& s, SgPeSmem<RT>* pe) {
   static_assert(RT <= 7, "class sums share an 8-wide reduction with the finite-weight count");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // Warps 0..7 own the particles (one slot per thread).  Warp 8 is a SERVICE warp: it owns no particle, follows the same
-  // barrier sequence, and evaluates every scalar exp/log of the step (regime factors, new-segment weights, log C, log Z_t,
-  // the Philox draw, the emission-row prefetch) while the workers sort and scan -- so no transcendental latency chain
-  // sits on the workers' critical path.
+  // block barriers, and evaluates every scalar exp/log of the step (new-segment weights, log C, log Z_t, the Philox draw,
+  // the emission-row prefetch) and the candidate resampler.
   const bool worker = warp < HYG_WORKER_WARPS;
   const bool service = !worker;
   constexpr int R = RT;
@@ -409,7 +815,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
   uint32_t dcap = mdl.dcap;
   const unsigned int T = static_cast<unsigned int>(ch.T);   // sites of this unit (< 2^32): 32-bit counters in the hot loop
   const int lcap = run.lcap;
-  int flip = 0, ibuf = 0, pbuf = 0;
+  int flip = 0, pbuf = 0;
   constexpr int D = R * R;
   // parameter mode: per-CTA table workspace (tables are rebuilt on the device whenever theta moves)
   double2* pe_tab = nullptr; double* pe_tabg = nullptr; double* pe_wh = nullptr; double* pe_wg = nullptr;
@@ -425,7 +831,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
     }
     if (tid < R) pe->kappa[tid] = run.kappa[tid];
     if (tid == 0) { pe->iter = 0; mdl.tab = pe_tab; mdl.tabg = pe_tabg; }
-    for (int i = tid; i < 2 * D * HYG_PHI_PITCH; i += HYG_NT) (&pe->phi[0][0][0])[i] = 0.0;
+    for (int i = tid; i < D * HYG_PHI_PITCH; i += HYG_NT) (&pe->phi[0][0])[i] = 0.0;
     __syncthreads();
     pe_set_theta<R>(mdl, *pe);
     uint32_t dn = run.n_steps_without_update + 12;
@@ -435,24 +841,32 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
   }
   const SgModelDev& cm = mdl;
 
-  // psi workspace (global, L2-resident): [2][lcap][R][256] doubles followed by lcap ints of site indices
-  double* psi[2] = {psi_ws, psi_ws + static_cast<size_t>(lcap) * R * HYG_NPMAX};
-  int* pend_t = reinterpret_cast<int*>(psi_ws + 2 * static_cast<size_t>(lcap) * R * HYG_NPMAX);
-  int n_pend = 0, n_forced = 0, max_pend = 0;
+  // lag-set workspace (global, L2-resident): [lcap][R][256] doubles, then five int arrays of lcap entries
+  SgLagState lag;
+  lag.rows = psi_ws;
+  lag.pend_t = reinterpret_cast<int*>(psi_ws + static_cast<size_t>(lcap) * R * HYG_NPMAX);
+  lag.pend_row = lag.pend_t + lcap;
+  lag.pend_t_alt = lag.pend_row + lcap;
+  lag.pend_row_alt = lag.pend_t_alt + lcap;
+  lag.free_row = lag.pend_row_alt + lcap;
+  lag.n_pend = 0; lag.n_free = lcap;
+  for (int i = tid; i < lcap; i += HYG_NT) lag.free_row[i] = lcap - 1 - i;
+  int n_forced = 0, max_pend = 0;
   // segmented execution: local sites [own_lo, own_hi) are written, the rest is warm-up / run-out (hyg_dev_structs.h)
   const unsigned int own_lo = static_cast<unsigned int>(ch.own_lo), own_hi = static_cast<unsigned int>(ch.own_hi);
   const unsigned long long t_off = ch.t_off;
   const bool last_seg = ch.last_segment != 0;
-  int n_halo_forced = 0;
-  int n_steps = 0;
+  int n_halo_forced = 0, n_steps = 0, n_fallback = 0, n_tie_sites = 0, n_dup = 0;
   double lz_base = 0.0;   // log Z (local) of site own_lo - 1: owned rows of logz are written relative to it
 
   SgChainState p;
   p.lw = -HYG_INF; p.W = 0.0; p.cur = make_double2(0.0, 0.0); p.nxt = p.cur; p.gcur = 0.0; p.gnxt = 0.0; p.d = 0; p.r = 0;
+  unsigned mypiv = 0;   // bit r: this slot holds the pivot particle of regime r
 
   // ---- t = 0 : Smc::initialise (Smc.h:114-188) ----
   if (tid < R) s.lo[0][tid] = __ldg(ch.logobs + tid);
   if (T > 1 && tid < R) s.lo[1][tid] = __ldg(ch.logobs + R + tid);
+  if (tid < 2 * HYG_RMAX) (&s.piv_key[0][0])[tid] = 0ull;
   __syncthreads();
   if (tid < 2 && static_cast<unsigned int>(tid) < T) {
     double m = s.lo[tid][0];
@@ -496,6 +910,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
     if (warp == 0 && tid == 0 && t + 1 < T) pos_nxt = ch.pos ? static_cast<double>(__ldg(ch.pos + t + 1)) : static_cast<double>(static_cast<unsigned long long>(t) + 1ull + t_off);
     int k_kept = -1;
     bool drew = false;
+    int tie_site = 0;
     bool emit_now = false;       // current site finalised at this step
     const bool own_t = (t >= own_lo) && (t < own_hi);
     double cw_lane = 0.0;        // regime mass of index lane & 7 (current site)
@@ -506,21 +921,28 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       const int N_curr = (N_prev + R > Nmax) ? Nmax : N_prev + R;
       const int M = N_curr - R;
       const bool capped = (N_curr < N_prev + R);
-      int anc = tid;
+      const int nd = N_prev - M;   // particles that die at this site (0 in the growth phase)
       const double lomax = s.lomax[t & 1];
+      const bool alive = tid < N_prev;   // service warp: never
 
       if (service) {
         // the uniform of this site, and log Z_{t-1}: the log of last step's normaliser is evaluated now, off the
-        // workers' critical path (they read s.lsum only after the sort's barriers)
+        // workers' critical path
         if (lane == 8) s.u = ch.unif ? __ldg(ch.unif + t) : philox_uniform(ch.seed, ch.chain_id, t + t_off);
         if (lane == 0) s.lsum[(t + 1) & 1] = pend_shift + log(pend_S);
+        if (lane < R) s.piv_key[t & 1][lane] = 0ull;   // the pivots publish their new keys into this buffer after the resampling
         __syncwarp();
       }
 
       // ---- class sums over the previous particles (replace the R x N_prev log-sum-exps of Smc.h:562-573) ----
-      const double e_prev = (tid < N_prev) ? p.W * p.cur.x : 0.0;  // W_n * c_new(d_n, r_n)
-      const bool finite_prev = (tid < N_prev) && hyg_isfinite(p.lw);
+      const double e_prev = alive ? p.W * p.cur.x : 0.0;  // W_n * c_new(d_n, r_n)
+      const bool finite_prev = alive && hyg_isfinite(p.lw);
       const bool valid = finite_prev && (p.cur.x > 0.0);
+      const unsigned long long mykey = alive ? order_key(p.lw) : 0ull;
+      unsigned cmask[R];          // lanes of this warp not heavier than the pivot of regime r
+      unsigned infmask = 0;
+#pragma unroll
+      for (int r = 0; r < R; r++) cmask[r] = 0;
       if (worker) {
         // class sums of e_prev; slot 7: F = #finite(logw_prev), Smc.h:413 (exact in fp64).  e_prev is 0 beyond N_prev.
         publish8(s.part[pbuf], warp_reduce_onehot(e_prev, p.r, finite_prev ? 1.0 : 0.0));
@@ -530,169 +952,145 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           pe->eprev[tid] = e_prev;
           publish8(s.partG[pbuf], warp_reduce_onehot(e_prev * p.gcur, p.r, 0.0));
         }
+        if (capped) {
+          infmask = __ballot_sync(HYG_FULL, alive && !finite_prev);
+          int mycnt = __popc(infmask);
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            const unsigned long long pk = s.piv_key[(t + 1) & 1][r];
+            cmask[r] = __ballot_sync(HYG_FULL, alive && mykey <= pk);   // pk == 0: no pivot, no candidates
+            mycnt = (lane == r) ? __popc(cmask[r]) : mycnt;
+          }
+          if (lane < 8) s.pcnt[pbuf][warp][lane] = (lane < R || lane == 6) ? mycnt : 0;
+        }
       }
       const int pA = pbuf;
       pbuf ^= 1;
+      __syncthreads();   // ---- B1 ----
+      const double totA = combine8(s.part[pA]);           // lane & 7 -> E[0..R-1], [7] = F
+      const int F = static_cast<int>(__shfl_sync(HYG_FULL, totA, 7) + 0.5);
+      const double lsum_prev = s.lsum[(t + 1) & 1];
+      if (service) {
+        const double sumE_lane = sg_service_new_segments<R>(mdl, s, totA, pA);
+        if (PE) {
+          const double totG = combine8(s.partG[pA]);
+          if (lane < 8) { pe->Etot[lane] = totA; pe->Egtot[lane] = totG; }
+        }
+        if (lane < R) s.new_lw[lane] = (sumE_lane > 0.0) ? lsum_prev + lo[lane] + log(sumE_lane) : -HYG_INF;
+      }
 
-      // ---- ancestors: Smc::resampleCp (Smc.h:406-450) ----
-      bool own_weight = true;   // child keeps its ancestor's own weight (top-K / keep-largest / growth)
-      int sidx = tid;
-      double totA;
-      double sumE_lane = 0.0;   // service warp, lane r < R: new-segment mass of regime r
+      // ---- who dies: Smc::resampleCp (Smc.h:406-450) ----
+      int fate = HYG_FATE_KEEP;
       if (capped) {
-        if (worker) {
-          // sort by log-weight, descending (ties by slot); W is a monotone map of logw
-          // (dead slots get distinct tiny keys so that every key is unique)
-          unsigned long long key = (tid < N_prev) ? order_key(p.lw, tid) : static_cast<unsigned long long>(255 - tid);
-          key = block_sort_desc(key, s);   // s.part[pA] / s.vmask[pA] are visible after its first barrier
-          sidx = 255 - static_cast<int>(key & 0xFFull);
-          s.idx[tid] = static_cast<unsigned short>(sidx);
-          totA = combine8(s.part[pA]);
-        } else {
-          __syncthreads();
-          totA = combine8(s.part[pA]);
-          sumE_lane = sg_service_new_segments<R>(mdl, s, totA, pA);
-          if (PE) {
-            const double totG = combine8(s.partG[pA]);
-            if (lane < 8) { pe->Etot[lane] = totA; pe->Egtot[lane] = totG; }
-          }
+        if (F <= M) {
+          // keep the M largest (Smc.h:432-441): at least nd particles have weight zero, and which of them go is immaterial
+          int irank = __popc(infmask & ((1u << lane) - 1u));
+          if (worker) {
 #pragma unroll
-          for (int b = 1; b < HYG_SORT_BARRIERS; b++) __syncthreads();
+            for (int w = 0; w < HYG_WORKER_WARPS; w++)
+              if (w < warp) irank += s.pcnt[pA][w][6];
+          }
+          if (alive && !finite_prev && irank < nd) fate = HYG_FATE_DEAD + irank;
+          k_kept = -2;
+          __syncthreads();   // ---- B3 ---- (new-segment weights)
+        } else {
+          // ---- resample::optimalFiniteState (resample.h:289-409) ----
+          // best pivot: the one with the most candidates that still fit one warp's registers
+          int mine = -1;
+          if (lane < R) {
+            int tot = 0;
+#pragma unroll
+            for (int w = 0; w < HYG_WORKER_WARPS; w++) tot += s.pcnt[pA][w][lane];
+            if (tot > nd && tot <= HYG_CAND_CAP) mine = (tot << 3) | lane;
+          }
+          const int best = run.force_full_sort ? -1 : __reduce_max_sync(HYG_FULL, mine);
+          bool full = (best < 0);
+          if (!full) {
+            const int rstar = best & 7, cnt = best >> 3;
+            unsigned cm_ = 0;
+#pragma unroll
+            for (int r = 0; r < R; r++) cm_ = (rstar == r) ? cmask[r] : cm_;
+            const bool is_cand = worker && ((cm_ >> lane) & 1u);
+            if (is_cand) {
+              int idx = __popc(cm_ & ((1u << lane) - 1u));
+#pragma unroll
+              for (int w = 0; w < HYG_WORKER_WARPS; w++)
+                if (w < warp) idx += s.pcnt[pA][w][rstar];
+              s.cand_key[idx] = mykey;
+              s.cand_pay[idx] = order_pay(p.r, p.d, tid);
+              s.W[tid] = p.W;
+            }
+            __syncthreads();   // ---- B2 ----
+            if (service) {
+              if (cnt <= 32) sg_resample_warp<1, R>(s, cnt, N_prev, M, s.u, lsum_prev);
+              else sg_resample_warp<2, R>(s, cnt, N_prev, M, s.u, lsum_prev);
+            }
+            __syncthreads();   // ---- B3 ----
+            full = (s.fast_fail != 0);
+            if (!full && is_cand) fate = s.fate[tid];
+          }
+          if (full) {
+            n_fallback++;
+            if (worker) sg_resample_block<R>(s, mykey, order_pay(p.r, p.d, tid), alive ? p.W : 0.0, N_prev, M, s.u, lsum_prev);
+            __syncthreads();   // ---- B3' ----
+            if (alive) fate = s.fate[tid];
+          }
+          k_kept = s.res.K;
+          drew = (s.res.flags & HYG_RES_DREW) != 0;
+          tie_site = s.res.tie;
+          n_dup += s.res.n_dup;
+          // pivots for the next site
+          const unsigned long long np = s.res.newpiv;
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            if ((np >> (56 + r)) & 1ull) {
+              const int sl = static_cast<int>((np >> (8 * r)) & 0xFFull);
+              mypiv = (mypiv & ~(1u << r)) | ((sl == tid) ? (1u << r) : 0u);
+            }
+          }
         }
       } else {
-        __syncthreads();
-        totA = combine8(s.part[pA]);           // lane & 7 -> E[0..R-1], [7] = F
-        if (service) {
-          sumE_lane = sg_service_new_segments<R>(mdl, s, totA, pA);
-          if (PE) {
-            const double totG = combine8(s.partG[pA]);
-            if (lane < 8) { pe->Etot[lane] = totA; pe->Egtot[lane] = totG; }
-          }
-          if (lane < R) s.new_lw[lane] = (sumE_lane > 0.0) ? s.lsum[(t + 1) & 1] + lo[lane] + log(sumE_lane) : -HYG_INF;
-        }
-        __syncthreads();                       // growth phase has no later barrier before the new-segment values are read
+        __syncthreads();     // ---- B3 ---- growth phase: nothing dies
       }
-      const int F = static_cast<int>(__shfl_sync(HYG_FULL, totA, 7) + 0.5);
-      if (capped) {
-        bool keep_largest = (F <= M);
-        int K = 0;
-        double Qk = 0.0;
-        if (!keep_largest) {
-          // ---- resample::optimalFiniteState (resample.h:289-409) ----
-          const double qv = (tid < N_prev) ? s.W[sidx] : 0.0;
-          double v = qv;  // Q[p] = sum_{j >= p} q_j
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const double tt = __shfl_down_sync(HYG_FULL, v, o);
-            if (lane + o < 32) v += tt;
-          }
-          if (lane == 0) s.sc.d[flip][warp][0] = v;
-          __syncthreads();
-          double tail = 0.0;
-#pragma unroll
-          for (int w = HYG_NW - 1; w > 0; w--)
-            if (w > warp) tail += s.sc.d[flip][w][0];   // warp-uniform predicate: the additions of the warps below are skipped
-          flip ^= 1;
-          const double Qp = v + tail;
-          if (worker) s.Q[tid] = Qp;
-          if (tid == 0) s.Q[HYG_NPMAX] = 0.0;
-          // Fixed point for K (resample.h:333-342).  The reference iterates K <- K + #{i >= K : log q_i > -log C(K)},
-          // log C(K) = log(M-K) - log Q[K], from K = 0.  Along that iteration the threshold Q[K]/(M-K) only decreases, so
-          // it stops at the FIRST sorted position p whose own weight is not above its own threshold:
-          //   K* = min{ p : !(q_p (M-p) > Q[p]) }   (one parallel pass instead of up to ~N sequential ones).
-          const bool stop = (tid >= M) || (tid >= N_prev) || !(qv * static_cast<double>(M - tid) > Qp);
-          const unsigned sb = __ballot_sync(HYG_FULL, stop);
-          if (lane == 0) s.iscan[ibuf][warp] = sb ? (warp * 32 + __ffs(static_cast<int>(sb)) - 1) : HYG_NPMAX;
-          __syncthreads();
-          K = __reduce_min_sync(HYG_FULL, (lane < HYG_NW) ? s.iscan[ibuf][lane] : HYG_NPMAX);   // one load + one warp reduction
-          ibuf ^= 1;
-          if (K >= M) {
-            keep_largest = true;  // log C not finite (resample.h:345,366)
-          } else {
-            Qk = s.Q[K];
-            if (!(Qk > 0.0) || !hyg_isfinite(Qk)) keep_largest = true;
-          }
-        }
-        if (keep_largest) {
-          // keep the M largest by log-weight (Smc.h:432-441; resample.h:366-375)
-          if (service && lane < R) s.new_lw[lane] = (sumE_lane > 0.0) ? s.lsum[(t + 1) & 1] + lo[lane] + log(sumE_lane) : -HYG_INF;
-          __syncthreads();  // s.idx and s.new_lw visible
-          anc = (tid < M) ? s.idx[tid] : tid;
-          k_kept = -2;
-        } else {
-          const int L = M - K;
-          if (service) {
-            // ONE log evaluation: lanes 0..R-1 the new-segment particles, lane 7 the weight lsum_prev - log C of a
-            // resampled particle (resample.h:361-364); consumed by the workers two barriers later
-            const double arg = (lane == 7) ? Qk / static_cast<double>(L) : sumE_lane;
-            const double lg = (arg > 0.0) ? log(arg) : -HYG_INF;
-            const double lsp = s.lsum[(t + 1) & 1];
-            if (lane < R) s.new_lw[lane] = (arg > 0.0) ? lsp + lo[lane] + lg : -HYG_INF;
-            if (lane == 7) s.res_lw = lsp + lg;
-          }
-          k_kept = K;
-          drew = true;
-          // systematic resampling of L offspring among the sorted residual particles (resample.h:85-127,354-359).
-          // C_p = #{ j < L : (j+u)/L <= cumulative residual weight up to p }; forced monotone, C_last = L, so the
-          // offspring counts o_p = C_p - C_{p-1} are >= 0 and sum to L whatever the rounding of the suffix sums.
-          const double u = s.u;
-          int C = 0;
-          if (tid >= K && tid < N_prev) C = (tid == N_prev - 1) ? L : sys_count_x((Qk - s.Q[tid + 1]) * (static_cast<double>(L) / Qk) - u, L);
-          if (tid >= N_prev) C = L;
-#pragma unroll
-          for (int dlt = 1; dlt < 32; dlt <<= 1) {
-            const int tt = __shfl_up_sync(HYG_FULL, C, dlt);
-            if (lane >= dlt) C = tt > C ? tt : C;
-          }
-          if (lane == 31) s.iscan[ibuf][warp] = C;
-          __syncthreads();
-          int before = __reduce_max_sync(HYG_FULL, (lane < warp && lane < HYG_NW - 1) ? s.iscan[ibuf][lane] : 0);
-          ibuf ^= 1;
-          C = before > C ? before : C;
-          int Cprev = __shfl_up_sync(HYG_FULL, C, 1);
-          if (lane == 0) Cprev = before;
-          if (tid <= K) Cprev = 0;
-          if (tid < K) s.anc[tid] = static_cast<unsigned short>(sidx);
-          if (tid >= K && tid < N_prev)
-            for (int slot = K + Cprev; slot < K + C && slot < M; slot++) s.anc[slot] = static_cast<unsigned short>(sidx);
-          __syncthreads();
-          anc = (tid < M) ? s.anc[tid] : tid;
-          own_weight = (tid < K);
-        }
-      }
-      if (ch.ancestors && own_t && tid < Nmax - R)
-        ch.ancestors[static_cast<unsigned long long>(t) * static_cast<unsigned long long>(Nmax - R) + tid] = (tid < M) ? static_cast<short>(anc) : static_cast<short>(-1);
+      if (tie_site & 2) n_tie_sites++;
 
       // ---- propose + weight: sampleParticlesCp / computeWeightsCp (Smc.h:504-574) ----
-      const double lsum_prev = s.lsum[(t + 1) & 1];
-      SgChainState c;
-      c.lw = -HYG_INF; c.W = 0.0; c.cur = make_double2(0.0, 0.0); c.nxt = c.cur; c.gcur = 0.0; c.gnxt = 0.0; c.d = 0; c.r = 0;
+      // the k-th dead slot (sorted order) takes the new-segment particle (1, k); the others open the slots N_prev, N_prev+1, ..
+      int newreg = -1;
+      if (fate >= HYG_FATE_DEAD) newreg = fate - HYG_FATE_DEAD;
+      else if (tid >= N_prev && tid < N_curr) newreg = nd + (tid - N_prev);
+      if (newreg >= 0) s.new_slot[newreg] = static_cast<short>(tid);
+      const double my_e = e_prev;            // backward-kernel numerator of the particle that WAS in this slot
+      const int my_r_prev = p.r;
+      const bool was_valid = valid;
+      const double lw_prev = p.lw, cur_x_prev = p.cur.x, gcur_prev = p.gcur;
       const uint32_t vcap = PE ? cm.dcap : dcap;   // valid table entries per regime (parameter mode: last rebuild)
       double grad_c = 0.0;   // parameter mode: d log f / d theta_omega(r) of the continuation (singleGroup.h:679-693)
-      if (tid < M) {
-        c.r = s.r[anc];
-        c.d = s.d[anc] + 1;
-        c.cur = s.nxt[anc];
-        const double2 pc = s.cur[anc];
+      const bool cont = alive && newreg < 0;
+      if (cont) {
+        const double2 pc = p.cur;
         const double lc = pc.y;                         // log(1 - rho(d_prev, r)) or -inf (singleGroup.h:597-605)
-        c.lw = (own_weight ? s.lw[anc] : s.res_lw) + (lc + lo[c.r]);
-        const uint32_t di = (c.d + 1 <= vcap) ? c.d : vcap - 1;  // 0-based index of d+1, clamped to the terminal entry
-        c.nxt = tab_load<PE>(mdl.tab + static_cast<size_t>(c.r) * dcap + di);
+        p.lw = ((fate == HYG_FATE_SURV) ? s.res.res_lw : p.lw) + (lc + lo[p.r]);
+        p.d = p.d + 1;
+        p.cur = p.nxt;
+        const uint32_t di = (p.d + 1 <= vcap) ? p.d : vcap - 1;  // 0-based index of d+1, clamped to the terminal entry
+        p.nxt = tab_load<PE>(mdl.tab + static_cast<size_t>(p.r) * dcap + di);
         if (PE) {
-          c.gcur = pe->gnxt[anc];
-          c.gnxt = mdl.tabg[static_cast<size_t>(c.r) * dcap + di];
           const double rho = pc.x;                      // c_new = rho for d >= u (0 below u)
-          grad_c = (lc > -HYG_INF && rho < 1.0) ? -pe->gcur[anc] * rho / (1.0 - rho) : 0.0;
+          grad_c = (lc > -HYG_INF && rho < 1.0) ? -p.gcur * rho / (1.0 - rho) : 0.0;
+          p.gcur = p.gnxt;
+          p.gnxt = mdl.tabg[static_cast<size_t>(p.r) * dcap + di];
         }
-      } else if (tid < N_curr) {
-        const int r = tid - M;
-        c.r = r; c.d = 1;
-        c.cur = tab_load<PE>(mdl.tab + static_cast<size_t>(r) * dcap + 0);
-        c.nxt = tab_load<PE>(mdl.tab + static_cast<size_t>(r) * dcap + 1);
-        if (PE) { c.gcur = mdl.tabg[static_cast<size_t>(r) * dcap + 0]; c.gnxt = mdl.tabg[static_cast<size_t>(r) * dcap + 1]; }
-        c.lw = s.new_lw[r];
+      } else if (newreg >= 0) {
+        const int r = newreg;
+        p.r = r; p.d = 1;
+        p.cur = tab_load<PE>(mdl.tab + static_cast<size_t>(r) * dcap + 0);
+        p.nxt = tab_load<PE>(mdl.tab + static_cast<size_t>(r) * dcap + 1);
+        if (PE) { p.gcur = mdl.tabg[static_cast<size_t>(r) * dcap + 0]; p.gnxt = mdl.tabg[static_cast<size_t>(r) * dcap + 1]; }
+        p.lw = s.new_lw[r];
+        mypiv = 0;
       }
-      const double my_invE = (tid >= M && tid < N_curr) ? s.new_invE[tid - M] : 0.0;
+      const bool now_alive = tid < N_curr;
       // exact log-domain path for regimes whose linear-domain sum underflowed (rare)
       const unsigned slowmask = s.slowmask;
       double bk_slow[R];
@@ -702,23 +1100,30 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
 #pragma unroll
         for (int r = 0; r < R; r++) {
           if (!((slowmask >> r) & 1u)) continue;
-          const bool ok = valid && p.r != r && mdl.P[p.r][r] > 0.0;
-          const double x = ok ? p.lw + log(p.cur.x) + mdl.logP[p.r][r] : -HYG_INF;
+          const bool ok = was_valid && my_r_prev != r && mdl.P[my_r_prev][r] > 0.0;
+          const double x = ok ? lw_prev + log(cur_x_prev) + mdl.logP[my_r_prev][r] : -HYG_INF;
           const double mx = block_max(x, s.sc, flip);
           double ex[1] = {ok ? exp(x - mx) : 0.0};
           const double mine = ex[0];
           block_sum<1>(ex, s.sc, flip);
-          if (tid == M + r) c.lw = lo[r] + (mx + log(ex[0]));
+          if (newreg == r) p.lw = lo[r] + (mx + log(ex[0]));
           bk_slow[r] = (ex[0] > 0.0) ? mine / ex[0] : 0.0;
         }
+      }
+      // the pivots publish the key of their new weight (compared against at the next site)
+      if (mypiv) {
+        const unsigned long long nk = order_key(p.lw);
+#pragma unroll
+        for (int r = 0; r < R; r++)
+          if ((mypiv >> r) & 1u) s.piv_key[t & 1][r] = nk;
       }
 
       // ---- selfNormaliseWeights (Smc.h:576-579), fused with the regime masses of the new site ----
       {
         double shift = lsum_prev + lomax;   // upper bound of every logw instead of the exact max
-        c.W = (tid < N_curr) ? exp(c.lw - shift) : 0.0;
-        if (worker) publish8(s.part[pbuf], warp_reduce_onehot(c.W, c.r, 0.0));   // c.W is 0 beyond N_curr
-        __syncthreads();
+        p.W = now_alive ? exp(p.lw - shift) : 0.0;
+        if (worker) publish8(s.part[pbuf], warp_reduce_onehot(p.W, p.r, 0.0));   // p.W is 0 beyond N_curr
+        __syncthreads();   // ---- B4 ----
         double tot = combine8(s.part[pbuf]);   // lane & 7 -> class sum of the relative weights
         pbuf ^= 1;
         double S = tot;
@@ -727,9 +1132,9 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
         S += __shfl_xor_sync(HYG_FULL, S, 4);
         if (!(S > 0.0) || !hyg_isfinite(S)) {
           // the linear-domain weights underflowed against the bound: renormalise from the log-weights with the exact max
-          shift = block_max((tid < N_curr) ? c.lw : -HYG_INF, s.sc, flip);
-          c.W = (tid < N_curr && c.lw > -HYG_INF) ? exp(c.lw - shift) : 0.0;
-          if (worker) publish8(s.part[pbuf], warp_reduce_onehot(c.W, c.r, 0.0));
+          shift = block_max(now_alive ? p.lw : -HYG_INF, s.sc, flip);
+          p.W = (now_alive && p.lw > -HYG_INF) ? exp(p.lw - shift) : 0.0;
+          if (worker) publish8(s.part[pbuf], warp_reduce_onehot(p.W, p.r, 0.0));
           __syncthreads();
           tot = combine8(s.part[pbuf]);
           pbuf ^= 1;
@@ -739,28 +1144,28 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           S += __shfl_xor_sync(HYG_FULL, S, 4);
         }
         const double invS = 1.0 / S;
-        c.W *= invS;
+        p.W *= invS;
         cw_lane = tot * invS;
         pend_shift = shift; pend_S = S;   // log Z_t = shift + log S is evaluated by the service warp at the next step
       }
 
       // ---- fixed-lag smoothing: updatePsi (OnlineMarginalSmoothing.h:148-177) ----
-      if (run.use_smoothing && n_pend > 0) {
-        // out of line: the lag set is empty at most sites of informative data, and its 30 live doubles per thread would
-        // otherwise set the register budget (and the spills) of the whole recursion
-        SgLagArgs<R> la;
-        la.pp = psi[(t + 1) & 1]; la.pc = psi[t & 1]; la.pend_t = pend_t; la.n_pend = n_pend;
-        la.N_prev = N_prev; la.M = M; la.N_curr = N_curr; la.anc = anc; la.pr = p.r;
-        la.e_prev = e_prev; la.cW = c.W; la.my_invE = my_invE; la.slowmask = slowmask;
+      if (run.use_smoothing && lag.n_pend > 0) {
+        if (worker) {
+          // backward kernels of the new-segment particles, bk_r[n] = e_n P[r_n][r] / sumE[r] (Smc.h:288-326, factorised)
 #pragma unroll
-        for (int r = 0; r < R; r++) la.bk_slow[r] = bk_slow[r];
-        la.t = t; la.T = T; la.own_lo = own_lo; la.own_hi = own_hi; la.t_off = t_off; la.last_seg = last_seg; la.worker = worker;
-        la.epsilon = run.epsilon;
-        n_pend = sg_lag_update<R>(la, mdl, ch, s, flip, n_halo_forced);
+          for (int r = 0; r < R; r++) {
+            const double lin = my_e * mdl.P[my_r_prev][r] * s.new_invE[r];
+            s.bk[tid][r] = ((slowmask >> r) & 1u) ? bk_slow[r] : lin;
+          }
+          s.Wc[tid] = cont ? p.W : 0.0;
+          if (newreg >= 0) s.Wnew[newreg] = p.W;       // weights of the rewritten slots
+        }
+        __syncthreads();
+        sg_lag_update<R>(lag, ch, s, t, T, own_lo, own_hi, t_off, last_seg, run.epsilon, n_halo_forced);
       }
       // ---- K3: score recursion (OnlineParameterEstimation.h:135-158), see sg_param.cuh ----
       if (PE) {
-        const int pb = (t + 1) & 1, cb = t & 1;   // phi buffers: [pb] was written at site t-1
         if (tid < 8 * D) {
           // class sums G[k][r'] = sum_{n in class r'} e_n phi_n[k]: thread = (component k, chunk of 32 previous particles)
           const int k = tid % D, chunk = tid / D;
@@ -769,7 +1174,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           for (int q = 0; q < R; q++) acc[q] = 0.0;
           for (int i = 0; i < 32; i++) {
             const int n = chunk * 32 + i;
-            const double ev = pe->eprev[n] * pe->phi[pb][k][n];
+            const double ev = pe->eprev[n] * pe->phi[k][n];
             const int rn = s.r[n];
 #pragma unroll
             for (int q = 0; q < R; q++) acc[q] += (rn == q) ? ev : 0.0;
@@ -786,6 +1191,32 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           pe->Gs[k][q] = a;
         }
         __syncthreads();
+        if (slowmask) {
+          // regimes on the log-domain path: phi' = sum_n bk_r[n] (phi_n + grad_n) with the per-particle normalised kernel;
+          // staged in pe->part (free again) because phi is updated in place afterwards
+#pragma unroll
+          for (int r = 0; r < R; r++) {
+            if (!((slowmask >> r) & 1u)) continue;
+            for (int k = 0; k < D; k++) {
+              double v[1] = {0.0};
+              if (bk_slow[r] > 0.0) {
+                const int rn = my_r_prev;
+                double g = pe->phi[k][tid];
+                if (k == R * (R - 1) + rn) {
+                  g += gcur_prev;
+                } else if (k >= rn * (R - 1) && k < (rn + 1) * (R - 1)) {
+                  const int j = k - rn * (R - 1);
+                  const int col = (j < rn) ? j : j + 1;
+                  g += ((col == r) ? 1.0 : 0.0) - cm.P[rn][col];
+                }
+                v[0] = bk_slow[r] * g;
+              }
+              block_sum<1>(v, s.sc, flip);
+              if (tid == 0) pe->part[0][k][r] = v[0];
+            }
+          }
+          __syncthreads();
+        }
         if (tid < R * D) {
           // new particle (1, r): phi' = sum_n bk_r[n] (phi_n + grad_n), bk_r[n] = e_n P[r_n][r] / sumE[r];
           // grad_n = dlogrho(d_n, r_n) on the omega slot of r_n and (1[c == r] - P[r_n][c]) on the P block of r_n
@@ -804,44 +1235,11 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
             }
             a += cm.P[rp][r] * term;
           }
-          pe->phi[cb][k][M + r] = a * s.new_invE[r];
+          pe->phi[k][s.new_slot[r]] = ((slowmask >> r) & 1u) ? pe->part[0][k][r] : a * s.new_invE[r];
         }
-        if (slowmask) {
-          // regimes on the log-domain path: phi' = sum_n bk_r[n] (phi_n + grad_n) with the per-particle normalised kernel
-          __syncthreads();
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            if (!((slowmask >> r) & 1u)) continue;
-            for (int k = 0; k < D; k++) {
-              double v[1] = {0.0};
-              if (bk_slow[r] > 0.0) {
-                const int rn = p.r;
-                double g = pe->phi[pb][k][tid];
-                if (k == R * (R - 1) + rn) {
-                  g += p.gcur;
-                } else if (k >= rn * (R - 1) && k < (rn + 1) * (R - 1)) {
-                  const int j = k - rn * (R - 1);
-                  const int col = (j < rn) ? j : j + 1;
-                  g += ((col == r) ? 1.0 : 0.0) - cm.P[rn][col];
-                }
-                v[0] = bk_slow[r] * g;
-              }
-              block_sum<1>(v, s.sc, flip);
-              if (tid == 0) pe->phi[cb][k][M + r] = v[0];
-            }
-          }
-        }
-        if (tid < M) {
-          // continuing particle: phi' = phi_anc + grad, grad touches only the omega slot of its regime
-          const int ko = R * (R - 1) + c.r;
-          for (int k = 0; k < D; k++) {
-            double v = pe->phi[pb][k][anc];
-            if (k == ko) v += grad_c;
-            pe->phi[cb][k][tid] = v;
-          }
-        }
+        // continuing particle: phi' = phi + grad, grad touches only the omega slot of its regime
+        if (cont) pe->phi[R * (R - 1) + p.r][tid] += grad_c;
       }
-      p = c;
       N = N_curr;
     } else {
       // t = 0: regime masses of the initial particle system
@@ -855,6 +1253,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       cw_lane = combine8(s.part[pbuf]);
       pbuf ^= 1;
     }
+    if (worker && (PE || run.use_smoothing)) s.r[tid] = static_cast<unsigned char>(p.r);
 
     // ---- initialisePsi + storeEstimates for the current site (OnlineMarginalSmoothing.h:119-146,197-255) ----
     if (run.use_smoothing) {
@@ -869,7 +1268,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       const bool ok = ((lane & 7) >= R) || (var < run.epsilon);
       const bool settled = __all_sync(HYG_FULL, ok);
       emit_now = (t == T - 1) || settled;
-      if (!emit_now && n_pend >= lcap) { emit_now = true; n_forced += own_t ? 1 : 0; }  // lag set full: emit the filtering estimate now (reported)
+      if (!emit_now && lag.n_pend >= lcap) { emit_now = true; n_forced += own_t ? 1 : 0; }  // lag set full: emit the filtering estimate now (reported)
       if (emit_now) {
         if (own_t) {
           if (warp == 0 && ch.probs) {
@@ -878,24 +1277,24 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           }
           if (tid == 0 && ch.finalised_at) ch.finalised_at[t] = static_cast<int>(t + t_off);
           if (t == T - 1 && !settled && !last_seg) n_halo_forced++;
+        } else if (ch.ovl && warp == 0 && t >= own_hi && t < own_hi + HYG_OVL_ROWS) {
+          const double left = __shfl_up_sync(HYG_FULL, cw_lane, 1);
+          if (lane >= 1 && lane <= R) ch.ovl[(t - own_hi) * R + (lane - 1)] = left;
         }
       } else {
-        double* dst = psi[t & 1] + static_cast<size_t>(n_pend) * R * HYG_NPMAX;
+        // free_row / pend_* were last written before a block barrier of this step (or at initialisation)
+        const int rw = lag.free_row[lag.n_free - 1];
+        double* dst = lag.rows + static_cast<size_t>(rw) * R * HYG_NPMAX;
         if (worker) {
 #pragma unroll
           for (int q = 0; q < R; q++) dst[q * HYG_NPMAX + tid] = (tid < N && p.r == q) ? 1.0 : 0.0;
         }
-        if (tid == 0) pend_t[n_pend] = static_cast<int>(t);
-        n_pend++;
+        if (tid == 0) { lag.pend_t[lag.n_pend] = static_cast<int>(t); lag.pend_row[lag.n_pend] = rw; }
+        lag.n_pend++; lag.n_free--;
       }
-      max_pend = n_pend > max_pend ? n_pend : max_pend;
+      max_pend = lag.n_pend > max_pend ? lag.n_pend : max_pend;
     }
 
-    // ---- publish the particle system for the next site (all gathers of this step precede the normaliser barrier) ----
-    if (worker) {
-      s.W[tid] = p.W; s.lw[tid] = p.lw; s.cur[tid] = p.cur; s.nxt[tid] = p.nxt; s.d[tid] = p.d; s.r[tid] = static_cast<unsigned char>(p.r);
-      if (PE) { pe->gcur[tid] = p.gcur; pe->gnxt[tid] = p.gnxt; }
-    }
     if (service && t + 2 < T) {
       if (lane < R) s.lo[t & 1][lane] = lo_pref;
       double mx = (lane < R) ? lo_pref : -HYG_INF;
@@ -903,21 +1302,25 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       for (int o = 1; o < 8; o <<= 1) { const double tt = __shfl_xor_sync(HYG_FULL, mx, o); mx = tt > mx ? tt : mx; }
       if (lane == 0) s.lomax[t & 1] = mx;
     }
-    __syncthreads();
+    __syncthreads();   // ---- B5 ---- (emission prefetch, lag-set lists and psi rows, pivot keys)
     // segmented execution: stop as soon as the owned range is stepped through and none of its sites is still pending
     // (the lag set is ordered by site, oldest first)
     bool exit_now = false;
-    if (!PE && t + 1 >= own_hi && t + 1 < T) exit_now = (n_pend == 0) || (static_cast<unsigned int>(pend_t[0]) >= own_hi);
+    // (with the left-halo check on, a segment first steps through HYG_OVL_ROWS sites of the next one)
+    const unsigned int run_to = own_hi + (ch.ovl ? HYG_OVL_ROWS : 0u);
+    if (!PE && t + 1 >= run_to && t + 1 < T) exit_now = (lag.n_pend == 0) || (static_cast<unsigned int>(lag.pend_t[0]) >= own_hi);
     const bool last_step = (t == T - 1) || exit_now;
     n_steps++;
 
     // ---- K3: parameter update every n_steps sites (OnlineParameterEstimation.h:51-61) ----
     if (PE) {
       if (t > 0 && (t % run.n_steps_without_update) == 0) {
+        if (worker) s.W[tid] = p.W;
+        __syncthreads();
         if (tid < D) {
           // g = sum_n W_n phi_n over the current particles (computeFilteredMean, Smc.h:340-349)
           double g = 0.0;
-          for (int n = 0; n < N; n++) g = g + s.W[n] * pe->phi[t & 1][tid][n];
+          for (int n = 0; n < N; n++) g = g + s.W[n] * pe->phi[tid][n];
           pe->grad_prev[tid] = pe->grad_cur[tid];
           pe->grad_cur[tid] = g;
         }
@@ -937,7 +1340,6 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           p.nxt = pe_tab[static_cast<size_t>(p.r) * dcap + i1];
           p.gcur = pe_tabg[static_cast<size_t>(p.r) * dcap + i0];
           p.gnxt = pe_tabg[static_cast<size_t>(p.r) * dcap + i1];
-          s.cur[tid] = p.cur; s.nxt[tid] = p.nxt; pe->gcur[tid] = p.gcur; pe->gnxt[tid] = p.gnxt;
         }
         __syncthreads();
       }
@@ -945,6 +1347,20 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
     }
 
     // ---- taps ----
+    if (ch.support_hash) {
+      // order-independent hash of the finite-weight support {(d, r)} (parity tests only)
+      unsigned long long h = (worker && tid < N && p.lw > -HYG_INF) ? mix64((static_cast<unsigned long long>(p.r) << 28) | p.d) : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(HYG_FULL, h, o);
+      if (lane == 0) s.hsum[warp] = h;
+      __syncthreads();
+      if (tid == 0 && own_t) {
+        unsigned long long tot = 0ull;
+        for (int w = 0; w < HYG_NW; w++) tot += s.hsum[w];
+        ch.support_hash[t] = tot;
+      }
+      __syncthreads();
+    }
     if (service && lane == 0) {
       if (t > 0) {
         const double lz_prev = s.lsum[(t + 1) & 1];   // log Z (local) of site t-1
@@ -962,8 +1378,9 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       if (own_t) {
         if (ch.k_kept) ch.k_kept[t] = k_kept;
         if (ch.drew) ch.drew[t] = drew ? 1 : 0;
-        if (ch.n_pending) ch.n_pending[t] = n_pend;
+        if (ch.n_pending) ch.n_pending[t] = lag.n_pend;
         if (ch.n_curr) ch.n_curr[t] = N;
+        if (ch.tie_flags) ch.tie_flags[t] = static_cast<unsigned char>(tie_site);
       }
     }
     if (exit_now) break;
@@ -973,6 +1390,9 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
     atomicMax(ch.status + 1, max_pend);
     atomicAdd(ch.status + 2, n_halo_forced);
     atomicAdd(ch.status + 3, n_steps);
+    atomicAdd(ch.status + 4, n_fallback);
+    atomicAdd(ch.status + 5, n_tie_sites);
+    atomicAdd(ch.status + 6, n_dup);
   }
   __syncthreads();
 }
@@ -1016,7 +1436,7 @@ template <int RT, bool PE>
 __global__ void __launch_bounds__(HYG_NT, PE ? 1 : HYG_K2_MIN_CTAS) sg_filter_kernel(const SgModelDev* mdl, const SgChainDev* chains, SgRunDev run) {
   sg_filter_entry<RT, PE>(mdl, chains, run);
 }
-// The same recursion compiled for ONE CTA per SM (168 registers, no spills): used when there are no more units than SMs
+// The same recursion compiled for ONE CTA per SM (no register cap): used when there are no more units than SMs
 // (whole-chain execution of a few chains, the C ABI's and the CLI's default), where per-site latency is all that counts.
 template <int RT>
 __global__ void __launch_bounds__(HYG_NT, 1) sg_filter_kernel_sparse(const SgModelDev* mdl, const SgChainDev* chains, SgRunDev run) {

@@ -9,9 +9,10 @@
 // Device formulation.  With c[r'][r] = P[r'][r] / sumE[r] the backward kernel of the new particle (1, r) is
 // bk_r[n] = e_n c[r_n][r], so   phi'_{(1,r)} = sum_n bk_r[n] (phi_n + grad_n)   collapses to the D x R class sums
 // G[k][r'] = sum_{n in class r'} e_n phi_n[k] (a 36 x 250 x 6 contraction per site, done by all 288 threads over
-// 8 chunks of 32 particles) plus closed-form terms in E[r'] and Eg[r'] = sum_{n in r'} e_n dlogrho(d_n, r').  Continuing
-// particles copy their ancestor's phi and touch ONE entry (the omega slot of their regime).  phi lives in shared memory,
-// double-buffered, [D][257] (pitch 257: the chunked contraction reads are bank-conflict free).
+// 8 chunks of 32 particles) plus closed-form terms in E[r'] and Eg[r'] = sum_{n in r'} e_n dlogrho(d_n, r').  Particles
+// stay in their slots (sg_filter.cuh), so a continuing particle's phi stays where it is and ONE entry (the omega slot of its
+// regime) is touched; only the <= R rewritten slots get a new vector.  phi lives in shared memory, [D][257] (pitch 257: the
+// chunked contraction reads are bank-conflict free), updated in place after the class sums have been taken.
 // Every n_steps sites: g = sum_n W_n phi_n, ADAM on g - g_prev, theta -> P, omega, and the sojourn tables are REBUILT
 // ON THE DEVICE (h in parallel over (r, d); the cumulative sums H and Gh sequentially, one warp per regime, because
 // rho = h / (1 - H) is ill-conditioned and only the reference's own summation order reproduces its values) up to
@@ -28,13 +29,11 @@ namespace hyg {
 
 template <int R> struct SgPeSmem {
   static constexpr int D = R * R;
-  double phi[2][D][HYG_PHI_PITCH];
+  double phi[D][HYG_PHI_PITCH];
   double part[8][D][R];     // per-chunk partial class sums
   double Gs[D][R];          // G[k][r']
   double theta[D], adam_m[D], adam_v[D], grad_cur[D], grad_prev[D];
   double eprev[HYG_NPMAX];  // e_n = W_n c_new(d_n, r_n) of the previous particles
-  double gcur[HYG_NPMAX];   // d log rho(d, r) / d theta_omega carried by each particle (entry for d)
-  double gnxt[HYG_NPMAX];   // entry for d + 1
   double Etot[8], Egtot[8]; // class totals E[r'], Eg[r']
   double omega[8], kappa[8];
   double scr[HYG_RMAX][256];          // table rebuild staging: [h | h*glh | H used | Gh prev] x 64 per regime

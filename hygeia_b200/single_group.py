@@ -30,7 +30,7 @@ def _ptr(a):
 def make_run_args(n_particles_max=250, smc_proposal_type=1, smc_resample_type=2, use_online_marginal_smoothing=True,
                   epsilon=0.01, use_online_parameter_estimation=False, normalise_gradients=False, use_adam=True,
                   n_steps_without_parameter_update=200, learning_rate_exponent=0.1, learning_rate_factor=0.01,
-                  lag_capacity=128):
+                  lag_capacity=1024, allow_forced_emission=False, resample_full_sort=False):
     a = _lib.HygRunArgs()
     a.n_particles_max = n_particles_max
     a.smc_proposal_type = smc_proposal_type
@@ -44,7 +44,13 @@ def make_run_args(n_particles_max=250, smc_proposal_type=1, smc_resample_type=2,
     a.learning_rate_exponent = learning_rate_exponent
     a.learning_rate_factor = learning_rate_factor
     a.lag_capacity = lag_capacity
+    a.allow_forced_emission = int(bool(allow_forced_emission))
+    a.resample_full_sort = int(bool(resample_full_sort))
     return a
+
+
+STATUS_WORDS = ("forced_emissions", "max_pending", "halo_forced", "steps", "full_sorts", "tie_decided_sites", "double_draws",
+                "overlap_rows_over_tolerance")
 
 
 class Session:
@@ -112,7 +118,7 @@ class Session:
 
     def set_chains(self, specs):
         """specs: list of dicts with keys dataset, seed, chain_id and optional host arrays / raw pointers:
-        uniforms, positions, regime_probs, logz, k_kept, drew_uniform, n_pending, n_curr, finalised_at, ancestors."""
+        uniforms, positions, regime_probs, logz, k_kept, drew_uniform, n_pending, n_curr, finalised_at, support_hash, tie_flags."""
         n = len(specs)
         arr = (_lib.HygChain * n)()
         for i, s in enumerate(specs):
@@ -120,7 +126,7 @@ class Session:
             arr[i].seed = s.get("seed", 0)
             arr[i].chain_id = s.get("chain_id", i)
             for k in ("uniforms", "positions", "regime_probs", "logz", "theta_trace", "k_kept", "drew_uniform", "n_pending",
-                      "n_curr", "finalised_at", "ancestors"):
+                      "n_curr", "finalised_at", "support_hash", "tie_flags"):
                 v = s.get(k)
                 setattr(arr[i], k, _ptr(v))
                 if v is not None and not isinstance(v, int):
@@ -153,8 +159,15 @@ class Session:
         self._check(self.lib.hyg_sg_filter(self.ctx, C.byref(a)), "hyg_sg_filter")
 
     def download(self):
+        """Copies the outputs back and returns the per-chain status words (include/hygeia_b200.h); raises HygeiaError with
+        HYG_ERR_CAPACITY when a lag set overflowed (unless allow_forced_emission was set)."""
         self._check(self.lib.hyg_sg_download(self.ctx, self._chains, len(self._chains)), "hyg_sg_download")
         return [tuple(c.status) for c in self._chains]
+
+    def overlap_max_abs(self):
+        """Segmented execution: per chain, the largest difference between the rows a segment recomputed in its right halo and
+        the rows the next segment wrote (the run-time check of the LEFT halo); 0.0 for whole chains."""
+        return [float(c.overlap_max_abs) for c in self._chains]
 
     def sync(self):
         self._check(self.lib.hyg_sync(self.ctx), "hyg_sync")
@@ -185,13 +198,17 @@ def run_online_combined_inference(vartheta, theta_init, genomic_positions, n_tot
                                   use_online_marginal_smoothing=True, epsilon=0.01,
                                   use_online_parameter_estimation=False, normalise_gradients=False, use_adam=True,
                                   n_steps_without_parameter_update=200, learning_rate_exponent=0.1, learning_rate_factor=0.01,
-                                  randomise_rng_seed=False, rng_seed=0, *, uniforms_by_site=None, device=0, return_logz=False):
+                                  randomise_rng_seed=False, rng_seed=0, *, uniforms_by_site=None, device=0, return_logz=False,
+                                  lag_capacity=1024):
     """Drop-in for ``runOnlineCombinedInferenceCpp`` (singleGroup.cpp:76-96).
 
     ``n_total_reads`` / ``n_methylated_reads`` are (n_samples, n_cpg_sites) matrices as in the R call; they are narrowed to
     uint16 with the site index fastest, which is the device layout.  Returns a dict with ``regimeProbabilityEstimates``
     (T x (1+R): genomic position, regime_1..R), ``thetaEstimates`` (T x D in parameter mode, else None) and ``cpuTime``.
     ``uniforms_by_site`` injects the resampling draws (one per site); otherwise they come from Philox keyed by ``rng_seed``.
+    ``status`` in the result names the kernel's status words (forced emissions, sites where an exact tie of weights decided a
+    particle's fate, ...: see include/hygeia_b200.h); a lag-set overflow raises HygeiaError instead of returning a different
+    estimator silently.
     """
     s = _session(device)
     vartheta = np.ascontiguousarray(vartheta, dtype=np.float64)
@@ -209,17 +226,19 @@ def run_online_combined_inference(vartheta, theta_init, genomic_positions, n_tot
         rng_seed = int(np.random.SeedSequence().entropy & 0x7FFFFFFFFFFFFFFF)
     args = make_run_args(n_particles_max, smc_proposal_type, smc_resample_type, use_online_marginal_smoothing, epsilon,
                          use_online_parameter_estimation, normalise_gradients, use_adam, n_steps_without_parameter_update,
-                         learning_rate_exponent, learning_rate_factor)
+                         learning_rate_exponent, learning_rate_factor, lag_capacity=lag_capacity)
     probs = np.full((T, 1 + R), np.nan) if use_online_marginal_smoothing else None
     trace = np.zeros((T, len(theta))) if use_online_parameter_estimation else None
     logz = np.zeros(T) if return_logz else None
     un = None if uniforms_by_site is None else np.ascontiguousarray(uniforms_by_site, dtype=np.float64)
     sec = C.c_double(0.0)
+    status = np.zeros(8, np.int32)
     rc = s.lib.hyg_sg_run_online_combined_inference(s.ctx, _ptr(vartheta), len(vartheta), _ptr(theta), len(theta), T, S, _ptr(pos),
                                                     _ptr(nt), _ptr(nm), C.byref(args), int(rng_seed) & 0xFFFFFFFFFFFFFFFF, _ptr(un),
-                                                    _ptr(probs), _ptr(trace), _ptr(logz), C.byref(sec))
+                                                    _ptr(probs), _ptr(trace), _ptr(logz), C.byref(sec), _ptr(status))
     s._check(rc, "hyg_sg_run_online_combined_inference")
-    out = dict(regimeProbabilityEstimates=probs, thetaEstimates=trace, cpuTime=sec.value)
+    out = dict(regimeProbabilityEstimates=probs, thetaEstimates=trace, cpuTime=sec.value,
+               status=dict(zip(STATUS_WORDS, (int(v) for v in status))))
     if return_logz:
         out["logZ"] = logz
     return out

@@ -25,6 +25,7 @@ extern "C" {
 #define HYG_ERR_UNSUPPORTED (-2)
 #define HYG_ERR_CUDA (-3)
 #define HYG_ERR_STATE (-4)
+#define HYG_ERR_CAPACITY (-5)   /* a bounded workspace overflowed and results would differ from the reference (see status words) */
 
 typedef struct hyg_ctx hyg_ctx;
 
@@ -55,6 +56,7 @@ int hyg_sg_add_dataset(hyg_ctx* ctx, uint64_t T, uint32_t S, const uint16_t* n_t
 int hyg_sg_clear(hyg_ctx* ctx);           /* drop all data sets and chains */
 
 /* ---- chains: one per (data set, seed) --------------------------------------------------------------------------- */
+#define HYG_SG_STATUS_WORDS 8
 typedef struct hyg_sg_chain {
   uint32_t dataset;             /* index returned by the order of hyg_sg_add_dataset calls */
   uint64_t seed;                /* Philox key: u[t] = philox(seed, chain_id, t) ...                          */
@@ -73,10 +75,19 @@ typedef struct hyg_sg_chain {
   int32_t* n_pending;           /* T : lag-set size after site t                                              */
   int32_t* n_curr;              /* T : particle count after site t                                            */
   int32_t* finalised_at;        /* T : step at which site t was emitted                                       */
-  int16_t* ancestors;           /* T x (n_particles - R)                                                      */
-  int32_t status[4];            /* out: [0] forced emissions because the lag set was full, [1] max lag-set size,
+  uint64_t* support_hash;       /* T : order-independent hash of the finite-weight support {(d, r)} after site t     */
+  uint8_t* tie_flags;           /* T : bit 0 two of the sorted weights were exactly equal; bit 1 such a tie DECIDED which
+                                       particle survived (the one place where this library and the reference, whose order
+                                       of equal weights is whatever std::sort leaves, can differ: DESIGN.md quirk C-14)   */
+  int32_t status[HYG_SG_STATUS_WORDS];
+                                /* out: [0] forced emissions because the lag set was full, [1] max lag-set size,
                                         [2] owned sites emitted by force at the end of a segment's right halo (segmented
-                                        execution only), [3] sites stepped through, halos included                      */
+                                        execution only), [3] sites stepped through, halos included, [4] sites resampled by the
+                                        block-wide sort (pivot miss), [5] sites where an exact tie of weights decided a
+                                        particle's fate, [6] double systematic draws repaired, [7] segmented execution:
+                                        number of overlap rows whose two computations differ by more than 1e-6              */
+  double overlap_max_abs;       /* out: segmented execution: max |p - p'| over the rows a segment's right halo recomputed
+                                        after the next segment (left-halo check); 0 for whole chains                        */
 } hyg_sg_chain;
 
 /* Algorithm switches: same meaning as the scalar arguments of runOnlineCombinedInferenceCpp (singleGroup.cpp:83-95). */
@@ -92,7 +103,15 @@ typedef struct hyg_sg_run_args {
   uint32_t n_steps_without_parameter_update;
   double learning_rate_exponent;
   double learning_rate_factor;
-  uint32_t lag_capacity;                /* pending-site capacity per chain (0 -> 128) */
+  uint32_t lag_capacity;                /* pending-site capacity of the fixed-lag smoother per chain (0 -> 1024).  The reference's
+                                           lag set is unbounded (OnlineMarginalSmoothing.h:148-195); here the rows live in a
+                                           global-memory workspace (12 KB per pending site), so the capacity can be made as
+                                           large as the longest lag.  A site that arrives when the set is full is emitted with
+                                           its filtering estimate and COUNTED in status[0]; hyg_sg_filter fails with
+                                           HYG_ERR_CAPACITY after the launch unless allow_forced_emission is set             */
+  int32_t allow_forced_emission;        /* keep going (status[0] > 0) instead of failing when the lag set overflowed        */
+  int32_t resample_full_sort;           /* resample every site by the block-wide sort (bypasses the pivot / candidate path;
+                                           same decisions, used by the parity tests)                                       */
 } hyg_sg_run_args;
 
 void hyg_sg_default_run_args(hyg_sg_run_args* args);
@@ -118,7 +137,8 @@ int hyg_sg_filter_units(hyg_ctx* ctx, uint32_t* n_units, uint64_t* segment_sites
 int hyg_sg_set_chains(hyg_ctx* ctx, const hyg_sg_chain* chains, uint32_t n_chains);
 /* K1: emission tables logObs[T x R] of every data set (device resident).  Asynchronous on the context's stream. */
 int hyg_sg_emission(hyg_ctx* ctx);
-/* K2: the recursion over all staged chains (device resident).  Asynchronous on the context's stream. */
+/* K2: the recursion over all staged chains (device resident).  Asynchronous on the context's stream; the status words are
+ * checked by hyg_sg_download (HYG_ERR_CAPACITY, see hyg_sg_run_args::lag_capacity). */
 int hyg_sg_filter(hyg_ctx* ctx, const hyg_sg_run_args* args);
 /* Device -> host copy of the outputs of every staged chain into the host pointers of hyg_sg_set_chains; synchronises. */
 int hyg_sg_download(hyg_ctx* ctx, hyg_sg_chain* chains, uint32_t n_chains);
@@ -130,11 +150,12 @@ int hyg_sg_get_logobs(hyg_ctx* ctx, uint32_t dataset, double* logobs);
 
 /* The operator itself: one chain, host buffers in, host buffers out -- argument for argument runOnlineCombinedInferenceCpp
  * (singleGroup.cpp:76-96) except that counts are uint16 [S][T] (site fastest) and the seed indexes Philox.
- * regime_probs: T x (1+R); theta_trace: T x D (parameter mode) or NULL; seconds: wall time of the call. */
+ * regime_probs: T x (1+R); theta_trace: T x D (parameter mode) or NULL; seconds: wall time of the call;
+ * status: HYG_SG_STATUS_WORDS ints as in hyg_sg_chain (may be NULL). */
 int hyg_sg_run_online_combined_inference(hyg_ctx* ctx, const double* vartheta, uint32_t n_vartheta, const double* theta_init, uint32_t dim_theta,
                                          uint64_t T, uint32_t S, const uint32_t* positions, const uint16_t* n_total, const uint16_t* n_meth,
                                          const hyg_sg_run_args* args, uint64_t seed, const double* uniforms,
-                                         double* regime_probs, double* theta_trace, double* logz, double* seconds);
+                                         double* regime_probs, double* theta_trace, double* logz, double* seconds, int32_t* status);
 
 /* ---- two-group (case/control) path -------------------------------------------------------------------------------
  * Boundary being replaced: hygeia/filter_and_smoother_algorithm.py::run as called by `hygeia infer`

@@ -208,6 +208,14 @@ std::vector<uint32_t> sort_index_desc(const std::vector<double>& v, size_t n) {
   return idx;
 }
 
+// order-independent hash of a particle's support point (tap; splitmix64 finaliser)
+inline uint64_t mix64(uint64_t x) {
+  uint64_t z = x + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
 struct Filter {
   Params mp;
   uint32_t R, Nmax, N_curr, N_prev;
@@ -221,6 +229,21 @@ struct Filter {
   uint64_t step;
   int k_last;
   bool drew;
+  int tie_order;  // 0 = reference (std::sort), 1 = canonical (log-weight desc, then regime, then sojourn)
+  int tie_flags;  // tap: bit 0 = exact tie among finite weights in this site's sort, bit 1 = a tie decided a particle's fate
+  // Canonical order: the key is the LOG-weight in both branches (W = exp(logw - logsum) is a monotone image of it; where W
+  // collapses distinct log-weights -- underflow to 0 -- the reference's own keep-largest branch sorts log-weights too).
+  std::vector<uint32_t> sort_particles(const std::vector<double>& v_reference) {
+    if (tie_order == 0) return sort_index_desc(v_reference, N_prev);
+    std::vector<uint32_t> idx(N_prev);
+    for (uint32_t i = 0; i < N_prev; i++) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
+      if (lw_p[a] != lw_p[b]) return lw_p[a] > lw_p[b];
+      const uint32_t ia = (pp[a].r << 28) | pp[a].d, ib = (pp[b].r << 28) | pp[b].d;
+      return ia < ib;
+    });
+    return idx;
+  }
   int tie_pairs;  // tap: adjacent equal finite values in the sorted order of this site
   void count_ties(const std::vector<double>& v, const std::vector<uint32_t>& sorted) {
     for (size_t i = 0; i + 1 < sorted.size(); i++) {
@@ -247,13 +270,13 @@ struct Filter {
       lw_c[n] = -std::log(static_cast<double>(R)) + logobs[0 * R + n];  // :485-491, :582-586, singleGroup.h:559-566
     }
     self_normalise();
-    k_last = -1; drew = false; tie_pairs = 0;
+    k_last = -1; drew = false; tie_pairs = 0; tie_flags = 0;
   }
   // resample.h:289-409
   void optimal_finite_state(uint32_t M) {
     uint32_t N = N_prev;
     for (uint32_t n = 0; n < lw_c.size(); n++) lw_c[n] = 0.0;  // :301
-    std::vector<uint32_t> sorted = sort_index_desc(W_p, N);
+    std::vector<uint32_t> sorted = sort_particles(W_p);
     count_ties(W_p, sorted);
     std::vector<double> q(N), logq(N), Q(N);
     for (uint32_t i = 0; i < N; i++) { q[i] = W_p[sorted[i]]; logq[i] = std::log(q[i]); }
@@ -278,13 +301,19 @@ struct Filter {
         drew = true;
         systematic_base(unif[step], ind, res, L);  // resample.h:119-127: one arma::randu()
         for (uint32_t j = 0; j < L; j++) anc[K + j] = sorted[ind[j] + K];
+        // tap: did an exact tie decide who survives?  (two equal residual weights, one drawn, the other not)
+        std::vector<char> drawn(N - K, 0);
+        for (uint32_t j = 0; j < L; j++) drawn[ind[j]] = 1;
+        for (uint32_t i = K; i + 1 < N; i++)
+          if (q[i] == q[i + 1] && q[i] != 0.0 && drawn[i - K] != drawn[i + 1 - K]) tie_flags |= 2;
       }
       for (uint32_t n = K; n < M; n++) lw_c[n] = lsum_p - logC;
       k_last = static_cast<int>(K);
     } else {
-      std::vector<uint32_t> idx = sort_index_desc(lw_p, N);
+      std::vector<uint32_t> idx = sort_particles(lw_p);
       tie_pairs = 0;
       count_ties(lw_p, idx);
+      if (M < N && lw_p[idx[M - 1]] == lw_p[idx[M]] && std::isfinite(lw_p[idx[M]])) tie_flags |= 2;
       for (uint32_t i = 0; i < M; i++) { anc[i] = idx[i]; lw_c[i] = lw_p[idx[i]]; }
       k_last = -2;
     }
@@ -299,8 +328,9 @@ struct Filter {
       if (F > M) {
         optimal_finite_state(M);
       } else {
-        std::vector<uint32_t> idx = sort_index_desc(lw_p, N_prev);
+        std::vector<uint32_t> idx = sort_particles(lw_p);
         count_ties(lw_p, idx);
+        if (M < N_prev && lw_p[idx[M - 1]] == lw_p[idx[M]] && std::isfinite(lw_p[idx[M]])) tie_flags |= 2;
         for (uint32_t i = 0; i < M; i++) { anc[i] = idx[i]; lw_c[i] = lw_p[idx[i]]; }
         k_last = -2;
       }
@@ -318,8 +348,9 @@ struct Filter {
     pc.resize(N_curr); lw_c.resize(N_curr, 0.0);
     uint32_t M = N_curr - R;
     drew = false;
-    tie_pairs = 0;
+    tie_pairs = 0; tie_flags = 0;
     resample_cp();
+    if (tie_pairs > 0) tie_flags |= 1;
     // :504-522
     for (uint32_t n = 0; n < M; n++) { pc[n].d = pp[anc[n]].d + 1; pc[n].r = pp[anc[n]].r; }
     for (uint32_t r = 0; r < R; r++) { pc[M + r].d = 1; pc[M + r].r = r; }
@@ -418,7 +449,7 @@ int hygo_sg_run(const hygo_sg_args* a) {
     hygo_sg_emission(f.mp.alpha.data(), f.mp.beta.data(), R, T, a->S, a->n_total, a->n_meth, lo_own.data());
     f.logobs = lo_own.data();
   }
-  f.R = R; f.Nmax = a->n_particles_max; f.unif = a->uniforms_by_site;
+  f.R = R; f.Nmax = a->n_particles_max; f.unif = a->uniforms_by_site; f.tie_order = a->tie_order;
   const uint32_t Mmax = f.Nmax - R;
 
   // --- OnlineMarginalSmoothing state (OnlineMarginalSmoothing.h) ---
@@ -488,6 +519,13 @@ int hygo_sg_run(const hygo_sg_args* a) {
     if (a->drew_uniform) a->drew_uniform[t] = f.drew ? 1 : 0;
     if (a->n_pending) a->n_pending[t] = static_cast<int32_t>(psi_t.size());
     if (a->tie_pairs) a->tie_pairs[t] = f.tie_pairs;
+    if (a->tie_flags) a->tie_flags[t] = static_cast<uint8_t>(f.tie_flags);
+    if (a->support_hash) {
+      uint64_t h = 0;
+      for (uint32_t n = 0; n < f.N_curr; n++)
+        if (f.lw_c[n] > NEG_INF) h += mix64((static_cast<uint64_t>(f.pc[n].r) << 28) | f.pc[n].d);
+      a->support_hash[t] = h;
+    }
     if (a->weights_prev && t > 0) {
       double* w = a->weights_prev + t * f.Nmax;
       for (uint32_t n = 0; n < f.Nmax; n++) w[n] = (n < f.N_prev) ? f.W_p[n] : std::numeric_limits<double>::quiet_NaN();

@@ -58,6 +58,14 @@ typedef struct hygo_sg_args {
                                   (0 when site t did not sort) -- where the reference's unstable sort decides     */
   double* weights_prev;    /* T x n_particles_max: self-normalised weights the resampler of site t saw (NaN padded) */
   int32_t* d_prev;         /* T x n_particles_max: sojourn d of the same particles (0 padded); regime in the top byte: d | r << 24 */
+  /* Order of exactly equal weights in sort_index:
+   *   0 = the reference's: libstdc++ std::sort with a value-only comparator (arrangement-dependent, == oracle/_ref);
+   *   1 = canonical: log-weight descending, then (regime, sojourn) ascending -- a rule that does not depend on the storage
+   *       order of the particles, which is what the CUDA path implements.  Both agree wherever no two weights are equal. */
+  int32_t tie_order;
+  uint64_t* support_hash;  /* T : order-independent hash of {(d, r)} over the finite-weight particles after site t */
+  uint8_t* tie_flags;      /* T : bit 0 = two finite weights exactly equal in the sort of site t; bit 1 = such a tie DECIDED
+                                  something (one of two tied particles survived the resampling, the other did not) */
 } hygo_sg_args;
 
 int hygo_sg_run(const hygo_sg_args* a);

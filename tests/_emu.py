@@ -34,7 +34,7 @@ class Emu:
         self.lib = C.CDLL(build())
 
     def sg_filter(self, vartheta, theta, logobs, uniforms=None, seed=0, chain_id=0, n_particles=250, smoothing=True,
-                  epsilon=0.01, lcap=64, want_ancestors=False, param_est=False, normalise=False, adam=True,
+                  epsilon=0.01, lcap=64, force_full_sort=False, param_est=False, normalise=False, adam=True,
                   n_steps_without_update=200, lr_exponent=0.1, lr_factor=0.01, t_off=0, own=None, last_segment=True):
         """`logobs` (and `uniforms`) are the LOCAL slice of a segment; own = (own_lo, own_hi) local indices (default: all)."""
         vartheta = np.ascontiguousarray(vartheta, dtype=np.float64)
@@ -45,7 +45,7 @@ class Emu:
             uniforms = np.ascontiguousarray(uniforms, dtype=np.float64)
         out = dict(probs=np.full((T, R + 1), np.nan), logz=np.zeros(T), k_kept=np.zeros(T, np.int32), drew_uniform=np.zeros(T, np.uint8),
                    n_pending=np.zeros(T, np.int32), n_curr=np.zeros(T, np.int32), finalised_at=np.full(T, -1, np.int32),
-                   ancestors=np.full((T, n_particles - R), -1, np.int16) if want_ancestors else None, status=np.zeros(4, np.int32),
+                   support_hash=np.zeros(T, np.uint64), tie_flags=np.zeros(T, np.uint8), status=np.zeros(8, np.int32),
                    seg_inc=np.zeros(1),
                    theta_trace=np.zeros((T, len(theta))) if param_est else None)
         rc = self.lib.hygemu_sg_filter(_p(vartheta), C.c_uint32(len(vartheta)), _p(theta), C.c_uint32(len(theta)), C.c_uint32(n_particles),
@@ -54,9 +54,9 @@ class Emu:
                                        C.c_int(int(param_est)), C.c_int(int(normalise)), C.c_int(int(adam)), C.c_uint32(n_steps_without_update),
                                        C.c_double(lr_exponent), C.c_double(lr_factor), _p(out["theta_trace"]),
                                        _p(out["probs"]), _p(out["logz"]), _p(out["k_kept"]), _p(out["drew_uniform"]), _p(out["n_pending"]),
-                                       _p(out["n_curr"]), _p(out["finalised_at"]), _p(out["ancestors"]), _p(out["status"]),
+                                       _p(out["n_curr"]), _p(out["finalised_at"]), _p(out["support_hash"]), _p(out["tie_flags"]), _p(out["status"]),
                                        C.c_uint64(t_off), C.c_uint64(own[0] if own else 0), C.c_uint64(own[1] if own else T),
-                                       C.c_int(int(last_segment)), _p(out["seg_inc"]))
+                                       C.c_int(int(last_segment)), _p(out["seg_inc"]), C.c_int(int(force_full_sort)))
         assert rc == 0, rc
         out["probs"] = out["probs"][:, 1:]
         return out

@@ -31,6 +31,7 @@ class _OracleArgs(C.Structure):
         ("regime_probs", C.c_void_p), ("theta_trace", C.c_void_p), ("logz", C.c_void_p), ("n_curr", C.c_void_p),
         ("k_kept", C.c_void_p), ("finalised_at", C.c_void_p), ("drew_uniform", C.c_void_p), ("n_pending", C.c_void_p),
         ("ancestors", C.c_void_p), ("seconds", C.c_void_p), ("tie_pairs", C.c_void_p), ("weights_prev", C.c_void_p), ("d_prev", C.c_void_p),
+        ("tie_order", C.c_int32), ("support_hash", C.c_void_p), ("tie_flags", C.c_void_p),
     ]
 
 
@@ -89,7 +90,10 @@ class Oracle:
 
     def run(self, vartheta, theta, uniforms, n_total_st=None, n_meth_st=None, positions=None, logobs=None,
             n_particles=250, smoothing=True, epsilon=0.01, param_est=False, normalise=False, adam=True,
-            n_steps_without_update=200, lr_exponent=0.1, lr_factor=0.01, want_ancestors=False, want_weights=False):
+            n_steps_without_update=200, lr_exponent=0.1, lr_factor=0.01, want_ancestors=False, want_weights=False,
+            tie_order="reference"):
+        """tie_order: "reference" = the reference's own (arrangement-dependent) order of exactly equal weights, identical to
+        oracle/_ref; "canonical" = log-weight, then (regime, sojourn): the storage-order-independent rule of the CUDA path."""
         vartheta = np.ascontiguousarray(vartheta, dtype=np.float64)
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         R = int(vartheta[1]); D = len(theta)
@@ -112,6 +116,7 @@ class Oracle:
             tie_pairs=np.zeros(T, np.int32),
             weights_prev=np.full((T, n_particles), np.nan) if want_weights else None,
             d_prev=np.zeros((T, n_particles), np.int32) if want_weights else None,
+            support_hash=np.zeros(T, np.uint64), tie_flags=np.zeros(T, np.uint8),
         )
         sec = C.c_double(0.0)
         a = _OracleArgs(_p(vartheta), len(vartheta), _p(theta), D, T, S, _p(pos), _p(nt), _p(nm), _p(logobs),
@@ -119,7 +124,8 @@ class Oracle:
                         lr_exponent, lr_factor, _p(uniforms),
                         _p(out["regime_probs"]), _p(out["theta_trace"]), _p(out["logz"]), _p(out["n_curr"]), _p(out["k_kept"]),
                         _p(out["finalised_at"]), _p(out["drew_uniform"]), _p(out["n_pending"]), _p(out["ancestors"]),
-                        C.cast(C.pointer(sec), C.c_void_p), _p(out["tie_pairs"]), _p(out["weights_prev"]), _p(out["d_prev"]))
+                        C.cast(C.pointer(sec), C.c_void_p), _p(out["tie_pairs"]), _p(out["weights_prev"]), _p(out["d_prev"]),
+                        {"reference": 0, "canonical": 1}[tie_order], _p(out["support_hash"]), _p(out["tie_flags"]))
         rc = self.lib.hygo_sg_run(C.byref(a))
         assert rc == 0, f"hygo_sg_run failed: {rc}"
         out["seconds"] = sec.value

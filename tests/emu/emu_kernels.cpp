@@ -21,8 +21,8 @@ int hygemu_sg_filter(const double* vartheta, uint32_t n_vartheta, const double* 
                      int use_smoothing, double epsilon, int lcap,
                      int use_param_est, int normalise, int use_adam, uint32_t n_steps, double lr_exponent, double lr_factor, double* theta_trace,
                      double* probs, double* logz, int* k_kept, unsigned char* drew, int* n_pending, int* n_curr,
-                     int* finalised_at, short* ancestors, int* status,
-                     uint64_t t_off, uint64_t own_lo, uint64_t own_hi, int last_segment, double* seg_inc) {
+                     int* finalised_at, unsigned long long* support_hash, unsigned char* tie_flags, int* status,
+                     uint64_t t_off, uint64_t own_lo, uint64_t own_hi, int last_segment, double* seg_inc, int force_full_sort) {
   hyg::SgHostModel hm;
   if (hm.set_known(vartheta, n_vartheta)) return -1;
   if (hm.set_theta(theta, dim_theta, T)) return -2;
@@ -36,15 +36,15 @@ int hygemu_sg_filter(const double* vartheta, uint32_t n_vartheta, const double* 
   std::memset(&ch, 0, sizeof(ch));
   ch.T = T; ch.logobs = logobs; ch.unif = unif; ch.seed = seed; ch.chain_id = chain_id;
   ch.probs = probs; ch.logz = logz; ch.k_kept = k_kept; ch.drew = drew; ch.n_pending = n_pending; ch.n_curr = n_curr;
-  ch.finalised_at = finalised_at; ch.ancestors = ancestors; ch.status = status;
+  ch.finalised_at = finalised_at; ch.support_hash = support_hash; ch.tie_flags = tie_flags; ch.status = status;
   // segment view (whole chain: t_off = 0, own = [0, T), last_segment = 1); pointers are already local
   ch.t_off = t_off; ch.own_lo = own_lo; ch.own_hi = own_hi; ch.last_segment = last_segment; ch.seg_inc = seg_inc;
   hyg::SgRunDev run;
   run.use_smoothing = use_smoothing; run.epsilon = epsilon; run.lcap = lcap;
-  const size_t stride = 2 * static_cast<size_t>(lcap) * hm.R * HYG_NPMAX + (lcap + 1) / 2 + 8;
+  const size_t stride = static_cast<size_t>(lcap) * hm.R * HYG_NPMAX + (5 * static_cast<size_t>(lcap) + 1) / 2 + 8;
   std::vector<double> ws(stride);
   unsigned int queue = 0;
-  run.psi_ws = ws.data(); run.psi_stride = stride; run.queue = &queue; run.n_chains = 1;
+  run.psi_ws = ws.data(); run.psi_stride = stride; run.queue = &queue; run.n_chains = 1; run.force_full_sort = force_full_sort;
   run.use_param_est = use_param_est; run.normalise_gradients = normalise; run.use_adam = use_adam; run.n_steps_without_update = n_steps;
   run.lr_exponent = lr_exponent; run.lr_factor = lr_factor;
   for (int r = 0; r < HYG_RMAX; r++) run.kappa[r] = r < hm.R ? hm.kappa[r] : 1.0;

@@ -63,7 +63,7 @@ def test_filter_step_level_vs_oracle(emu, oracle, default_model):
     al, be = default_model["alpha_beta"]
     lo = oracle.emission(al, be, ch["n_total"], ch["n_meth"])
     u = philox.uniforms_by_site(4, 9, T)
-    want = oracle.run(default_model["vartheta"], default_model["theta"], u, logobs=lo)
+    want = oracle.run(default_model["vartheta"], default_model["theta"], u, logobs=lo, tie_order="canonical")
     got = emu.sg_filter(default_model["vartheta"], default_model["theta"], lo, uniforms=None, seed=4, chain_id=9)  # device Philox
     assert np.array_equal(got["k_kept"], want["k_kept"])
     assert np.array_equal(got["n_curr"], want["n_curr"])
@@ -92,7 +92,7 @@ def test_parameter_estimation_under_emulation(emu, oracle, default_model):
     u = philox.uniforms_by_site(1, 0, T)
     theta0 = model.default_theta() + 0.2 * np.random.default_rng(3).standard_normal(36)
     for kw in (dict(adam=True), dict(adam=False, normalise=True, lr_factor=0.05)):
-        want = oracle.run(default_model["vartheta"], theta0, u, logobs=lo, param_est=True, n_steps_without_update=50, **kw)
+        want = oracle.run(default_model["vartheta"], theta0, u, logobs=lo, param_est=True, n_steps_without_update=50, **kw, tie_order="canonical")
         got = emu.sg_filter(default_model["vartheta"], theta0, lo, uniforms=u, param_est=True, n_steps_without_update=50, **kw)
         assert np.abs(want["theta_trace"][-1] - theta0).max() > 1e-3           # theta moved
         assert np.allclose(got["theta_trace"], want["theta_trace"], rtol=1e-9, atol=1e-12)
@@ -113,7 +113,7 @@ def test_parameter_estimation_underflow_regime(emu, oracle, default_model):
     lo = oracle.emission(al, be, ch["n_total"], ch["n_meth"])
     u = philox.uniforms_by_site(1, 0, T)
     theta0 = model.default_theta()
-    want = oracle.run(default_model["vartheta"], theta0, u, logobs=lo, param_est=True)
+    want = oracle.run(default_model["vartheta"], theta0, u, logobs=lo, param_est=True, tie_order="canonical")
     got = emu.sg_filter(default_model["vartheta"], theta0, lo, uniforms=u, param_est=True, lcap=128)
     assert np.isfinite(got["theta_trace"]).all() and np.isfinite(got["logz"]).all()
     assert np.abs(got["theta_trace"] - want["theta_trace"]).max() < 1e-6
@@ -133,7 +133,7 @@ def test_filter_segment_view_mechanics(emu, oracle, default_model, S, lam):
     al, be = default_model["alpha_beta"]
     lo = oracle.emission(al, be, ch["n_total"], ch["n_meth"])
     u = philox.uniforms_by_site(5, 2, T_full)
-    want = oracle.run(default_model["vartheta"], default_model["theta"], u[a:], logobs=lo[a:])
+    want = oracle.run(default_model["vartheta"], default_model["theta"], u[a:], logobs=lo[a:], tie_order="canonical")
     got = emu.sg_filter(default_model["vartheta"], default_model["theta"], lo[a:], uniforms=None, seed=5, chain_id=2,
                         t_off=a, own=(lo_, hi_), last_segment=False)
     steps = int(got["status"][3])

@@ -24,7 +24,17 @@
 #define HYG_RMAX 8          // max number of regimes
 #define HYG_NPMAX 256       // max particles per chain
 
+// Debug builds (-DHYG_DEBUG_CHECKS): index checks in the recursion kernels; a failing one prints its code and traps.
+#if defined(HYG_DEBUG_CHECKS) && !defined(HYG_EMU)
+#include <cstdio>
+#define HYG_CHECK(cond, code, a, b) do { if (!(cond)) { printf("HYG_CHECK %d failed: tid %d block %d a=%lld b=%lld\n", (code), (int)threadIdx.x, (int)blockIdx.x, (long long)(a), (long long)(b)); __trap(); } } while (0)
+#else
+#define HYG_CHECK(cond, code, a, b) do { } while (0)
+#endif
+
 namespace hyg {
+
+__device__ __forceinline__ int hyg_tid() { return static_cast<int>(threadIdx.x); }
 
 // bar.sync id, count: a barrier among `count` threads (whole warps) of the CTA; id 1..15 (0 is __syncthreads)
 __device__ __forceinline__ void named_barrier(int id, int count) {
@@ -32,6 +42,16 @@ __device__ __forceinline__ void named_barrier(int id, int count) {
   hyg_emu_named_barrier(id, static_cast<unsigned>(count));
 #else
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+
+// bar.arrive id, count: signals arrival without waiting (producer side of a producer / consumer barrier; the consumers'
+// bar.sync on the same id completes once `count` threads have arrived or are waiting)
+__device__ __forceinline__ void named_arrive(int id, int count) {
+#ifdef HYG_EMU
+  hyg_emu_named_arrive(id, static_cast<unsigned>(count));
+#else
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 #endif
 }
 

@@ -48,7 +48,7 @@ struct SgChainDev {
   unsigned char* tie_flags;           // T : bit 0 exact tie among the sorted weights, bit 1 a tie decided a particle's fate
   int* status;            // 8 ints accumulated over the chain's segments: [0] forced emissions (lag set full), [1] max lag-set size,
                           // [2] owned sites emitted by force at the end of a segment's right halo, [3] sites stepped through,
-                          // [4] sites resampled by the block-wide sort (pivot miss), [5] sites where an exact tie of weights
+                          // [4] sites whose sort was redone on the full words (weights equal in their top 56 bits), [5] sites where an exact tie of weights
                           // decided a particle's fate, [6] double systematic draws repaired, [7] reserved
   // Segmented execution (hyg_sg_set_segmentation): this descriptor covers the sites [t_off, t_off + T) of its chain -- every
   // pointer above is already offset to local site 0 -- and OWNS the local sites [own_lo, own_hi): rows outside that range are
@@ -95,7 +95,7 @@ struct SgRunDev {
   unsigned long long psi_stride;  // doubles per CTA
   unsigned int* queue;    // atomic chain counter
   int n_chains;
-  int force_full_sort;    // test hook: resample every site by the block-wide sort (the pivot / candidate path is bypassed)
+  int force_full_sort;    // test hook: every resampling site takes the exact sort on the full (key, regime, sojourn) words
   // parameter-estimation mode (K3)
   int use_param_est;
   int normalise_gradients;

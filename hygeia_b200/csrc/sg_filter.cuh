@@ -17,21 +17,18 @@
 //     (the K of optimal resampling averages ~235 of M = 244).  So a particle stays in the thread (slot) it was born in, with
 //     its state in registers; a site only rewrites the <= R slots whose particle died with the R new-segment particles.
 //     No ancestor gather, no per-site publication of the particle system, and the lag-set / score vectors stay in place.
-//   * NO BLOCK-WIDE SORT at ~95 % of the sites.  Optimal resampling needs (i) K = the first sorted position whose weight is
-//     not above its own threshold Q[p]/(M-p) -- and "not above" is monotone along the sorted order, so only the order of the
-//     lightest particles matters -- and (ii) the sorted order of the tail p >= K for the systematic draw.  Each regime keeps a
-//     PIVOT particle of low rank (~56th lightest); the particles not heavier than the best pivot (<= 64 of them) are the
-//     candidates, one warp sorts them in registers, and the result is accepted iff the heaviest candidate is provably kept
-//     (then every heavier particle is kept too).  Otherwise the site falls back to a block-wide bitonic sort.  Both paths
-//     take the same decisions (tests/emu forces either).
+//   * The sort that optimal resampling needs runs only where the reference resamples optimally (at ~40 % of the sites of
+//     32-sample data the weights of >= R particles have underflowed to -inf and "keep the M largest" just drops R of those);
+//     it sorts one packed 64-bit word per particle and falls back to an exact sort of the full words only where two weights
+//     agree in their top 56 bits, so exact ties are ordered canonically (below) without slowing the common site.
 //   * the emission term logObs[t][r] is read from the T x R table K1 produced (48 B per site);
 //   * transition terms come from a host-built table {c_new(d,r), log(1-rho(d,r))}; every particle holds the entries for d
 //     and d+1 and loads the one for d+2 a whole site ahead, so no L2 latency sits on the per-site critical path;
 //   * the R x N_prev new-segment log-sum-exps and backward kernels collapse to R class sums
 //     E[r'] = sum_{n in class r'} W_n c_new(d_n, r') because logTrans((1,r) <- (d,r')) = log c_new(d,r') + log P[r'][r]
 //     factorises (exact log-domain fallback when a class underflows);
-//   * a SERVICE warp (no particles) draws the uniform, evaluates the scalar logs, prefetches the emission rows and runs
-//     the candidate resampler while the eight worker warps wait at a barrier;
+//   * a SERVICE warp (no particles) draws the uniform, evaluates the scalar logs (log Z_t, the new-segment weights) and
+//     prefetches the emission rows while the eight worker warps reduce, sort and scan;
 //   * the uniform of site t is Philox(seed, chain, t) or an injected per-site array.
 // Order of exactly equal weights: canonical (log-weight, then regime, then sojourn), see hyg_common.cuh and DESIGN.md C-14;
 // sites where such a tie decided a particle's fate are counted (status[5]) and flagged (tie_flags tap).
@@ -43,18 +40,15 @@
 #include "hyg_dev_structs.h"
 #include "sg_param.cuh"
 
-#ifndef HYG_CAND_CAP
-#define HYG_CAND_CAP 64        // candidates one warp sorts in registers (two per lane)
-#endif
-#ifndef HYG_PIVOT_TARGET
-#define HYG_PIVOT_TARGET 56    // rank (from the light end) the per-regime pivots are re-centred on
-#endif
 #define HYG_FATE_KEEP 0        // continues with its own weight
 #define HYG_FATE_SURV 1        // drawn by the systematic resampling: continues with the common weight lsum - log C
 #define HYG_FATE_DEAD 2        // + rank among the dead: the slot is reused by the new-segment particle of that regime
 #define HYG_RES_DREW 1
 #define HYG_RES_KEEP_LARGEST 2
+#define HYG_RES_EXACT_SORT 4
 #define HYG_WORKER_BAR 1       // named barrier of the 256 worker threads
+#define HYG_SVC_BAR 14         // workers arrive, the service warp waits: the workers' partial sums are published
+#define HYG_RES_BAR 15         // the service warp arrives, workers wait: the new-segment weights are published
 
 namespace hyg {
 
@@ -63,29 +57,21 @@ struct SgResOut {
   int flags;
   int tie;                        // bit 0: equal keys among the sorted particles; bit 1: a tie decided a fate
   int n_dup;                      // systematic draws that hit one particle twice (rounding); resolved, counted
-  double res_lw;                  // log-weight of a particle drawn by the systematic resampling
-  unsigned long long newpiv;      // byte r = slot of the new pivot of regime r, byte 7 = mask of regimes that got one
+  double res_lw;                  // log-weight of a particle drawn by the systematic resampling, relative to log Z_{t-1}
 };
 
 struct SgSmem {
   double part[2][HYG_NW][8];      // per-warp partials of the 8-wide transposed reductions (double-buffered)
   double partG[2][HYG_NW][8];     // parameter mode: partials of Eg[r'] = sum e_n dlogrho_n
   unsigned vmask[2][HYG_NW];
-  int pcnt[2][HYG_NW][8];         // per-warp counts: [r < R] particles not heavier than the pivot of regime r, [6] -inf weights
-  unsigned long long piv_key[2][HYG_RMAX];   // key of the pivot of regime r (0 = none), [t & 1]
-  // candidates of the fast path / bottom of the sorted order on the fallback path
-  unsigned long long cand_key[HYG_CAND_CAP];
-  unsigned long long cand_pay[HYG_CAND_CAP];
-  unsigned short cand_fate[HYG_CAND_CAP];
+  int infcnt[2][HYG_NW];          // per-warp counts of particles with log-weight -inf
   double W[HYG_NPMAX];            // previous self-normalised weights by slot (resampling input)
   unsigned short fate[HYG_NPMAX];
   unsigned short ofs[HYG_NPMAX];  // offspring counts (repair of double draws)
   SgResOut res;
-  int fast_fail;
   short new_slot[HYG_RMAX];       // slot of the new-segment particle (1, r) of this site
-  // fallback: block-wide sort
-  unsigned long long xk[2][HYG_NPMAX];
-  unsigned long long xp[2][HYG_NPMAX];
+  unsigned long long xk[6][HYG_NPMAX];   // one exchange buffer per cross-warp sort stage (no reuse inside a site)
+  unsigned long long srt[HYG_NPMAX + 1]; // sorted words, for the neighbour tests
   double Q[HYG_NPMAX + 1];
   double qtail[HYG_NW];
   int iscan[2][HYG_NW];
@@ -97,7 +83,7 @@ struct SgSmem {
   unsigned slowmask;              // bit r: regime r takes the log-domain path at this site
   double new_lw[HYG_RMAX];        // log-weight of the new-segment particle (1, r)
   double new_invE[HYG_RMAX];      // 1 / sumE[r]
-  double u;                       // resampling uniform of the current site
+  double u[2];                    // resampling uniform of site t, [t & 1]
   double lsum[2];                 // running log Z_t, [t & 1]
   // lag set (fixed-lag smoother)
   double bk[HYG_NPMAX][HYG_RMAX - 2];   // backward kernels bk_r[n] of the new-segment particles, [slot][r], r < 6
@@ -130,8 +116,7 @@ template <int RT> __device__ __forceinline__ double pick(const double (&v)[RT], 
 
 // Transposed warp reduction of eight values per lane: 9 shuffle steps instead of 40.  On return every lane holds the
 // warp total of value index (lane >> 2) & 7.
-__device__ __forceinline__ double warp_reduce8(const double (&v)[8]) {
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ double warp_reduce8(const double (&v)[8], int lane) {
   double w4[4], w2[2], w1;
   {
     const bool hi = (lane & 16) != 0;
@@ -164,8 +149,7 @@ __device__ __forceinline__ double warp_reduce8(const double (&v)[8]) {
 // The same reduction for the one-hot input v[i] = (i == r ? e : 0), i < 7, v[7] = x7 (r < 7): the first exchange stage needs
 // only the class index relative to the half the lane sends / keeps, so the eight values are never materialised.  Bit-identical
 // to warp_reduce8 on that input (same additions in the same order).
-__device__ __forceinline__ double warp_reduce_onehot(double e, int r, double x7) {
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ double warp_reduce_onehot(double e, int r, double x7, int lane) {
   double w4[4], w2[2], w1;
   {
     const bool hi = (lane & 16) != 0;
@@ -199,13 +183,11 @@ __device__ __forceinline__ double warp_reduce_onehot(double e, int r, double x7)
   return w1;
 }
 // Lanes 0,4,..,28 publish the warp totals; any warp then folds the eight rows with two loads and two shuffle steps.
-__device__ __forceinline__ void publish8(double (*part)[8], double wtot) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void publish8(double (*part)[8], double wtot, int lane, int warp) {
   if ((lane & 3) == 0) part[warp][lane >> 2] = wtot;
 }
 // returns in every lane the block total of value index lane & 7
-__device__ __forceinline__ double combine8(const double (*part)[8]) {
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ double combine8(const double (*part)[8], int lane) {
   double a = part[lane >> 3][lane & 7] + part[(lane >> 3) + 4][lane & 7];
   a += __shfl_xor_sync(HYG_FULL, a, 8);
   a += __shfl_xor_sync(HYG_FULL, a, 16);
@@ -218,8 +200,7 @@ __device__ __forceinline__ double combine8(const double (*part)[8]) {
 // mass flowing into regime r (relative to exp(lsum_prev)); its log-weight is lsum_prev + logObs_r + log(sumE[r])
 // (computeWeightsCp, Smc.h:562-573, after factorising logTrans((1,r) <- (d,r')) = log c_new(d,r') + log P[r'][r]).
 template <int R>
-__device__ __forceinline__ double sg_service_new_segments(const SgModelDev& mdl, SgSmem& s, double totA, int pA) {
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ double sg_service_new_segments(const SgModelDev& mdl, SgSmem& s, double totA, int pA, int lane) {
   unsigned vm = 0;
 #pragma unroll
   for (int w = 0; w < HYG_WORKER_WARPS; w++) vm |= s.vmask[pA][w];
@@ -244,6 +225,14 @@ __device__ __forceinline__ double sg_service_new_segments(const SgModelDev& mdl,
   return a;
 }
 
+// ... and their log-weights: one log per regime, evaluated by the service warp while the workers resample
+template <int R>
+__device__ __forceinline__ void sg_service_new_weights(const SgModelDev& mdl, SgSmem& s, double totA, int pA, int lane, double lsum_prev, const double* lo) {
+  const double sumE_lane = sg_service_new_segments<R>(mdl, s, totA, pA, lane);
+  if (lane < R) s.new_lw[lane] = (sumE_lane > 0.0) ? lsum_prev + lo[lane] + log(sumE_lane) : -HYG_INF;
+  __syncwarp();   // the service warp's own lanes read s.slowmask next, without a block barrier in between
+}
+
 // plain load for tables that this kernel rewrites (parameter mode), read-only path otherwise
 template <bool PE, class T> __device__ __forceinline__ T tab_load(const T* p) {
   if (PE) return *p;
@@ -251,276 +240,51 @@ template <bool PE, class T> __device__ __forceinline__ T tab_load(const T* p) {
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Resampling (Smc::resampleCp -> resample::optimalFiniteState, Smc.h:406-450, resample.h:289-409) on a sorted bottom
-// set.  One warp, EPL elements per lane in blocked layout: lane l holds sorted positions j = EPL l + k of the `cnt`
-// lightest particles (descending: j = 0 is the heaviest of them), i.e. positions p = N_prev - cnt + j of the full order.
+// Resampling (Smc::resampleCp -> resample::optimalFiniteState, Smc.h:406-450, resample.h:289-409) by the 256 worker threads
+// (barriers among the workers only; the service warp evaluates the new-segment weights meanwhile).
+//   * Sort: one 64-bit word per particle -- the top 56 bits of the order-preserving image of its log-weight, its slot in the
+//     low eight -- through a bitonic network: strides < 32 by warp shuffles, strides 32/64/128 through shared memory with
+//     64-thread pair barriers (a warp only needs its partner warp's words).  If two neighbours of the result agree in the 56
+//     bits (an exact tie of weights, or weights within 2^-44 of each other: ~5 % of the sites of one-sample data, ~0.05 % at 32
+//     samples) the particles are sorted AGAIN on the full (key, regime, sojourn) words, so the canonical order (hyg_common.cuh,
+//     DESIGN.md quirk C-14) is exact.
+//   * K = the first sorted position whose weight is not above its own threshold Q[p]/(M-p): the reference iterates
+//     K <- K + #{i >= K : log q_i > -log C(K)} from K = 0 (resample.h:333-342); along that iteration the threshold only
+//     decreases, so it stops at that first position -- one parallel pass instead of ~100 sequential ones.
+//   * Systematic resampling of the tail (resample.h:85-127,354-359) as a monotone cumulative-count scan.
+//   * Results are scattered to the particles' slots as FATES (keep / drawn / dead + rank); nothing moves.
 // ------------------------------------------------------------------------------------------------------------------
-
-// New pivots from a sorted bottom set: for every regime the surviving particle whose rank from the light end is closest
-// below HYG_PIVOT_TARGET (else the closest above).  live[k]: the particle continues; j0 = position of this lane's first
-// element.  Returns the packed result (SgResOut::newpiv) in every lane.
-template <int EPL, int R>
-__device__ __forceinline__ unsigned long long sg_pick_pivots(const unsigned long long (&pay)[EPL], const bool (&live)[EPL], int j0, int cnt) {
-  const int jlo = cnt - HYG_PIVOT_TARGET;
-  unsigned long long out = 0ull;
+__device__ __forceinline__ unsigned long long sg_block_sort_packed(unsigned long long key, SgSmem& s, int tid, int warp) {
+  int kbuf = 0;
 #pragma unroll
-  for (int r = 0; r < R; r++) {
-    int a = 0x7fffffff, b = -1;
+  for (int k = 2; k <= HYG_NPMAX; k <<= 1) {
 #pragma unroll
-    for (int k = 0; k < EPL; k++) {
-      const int j = j0 + k;
-      const bool mine = live[k] && j < cnt && static_cast<int>((pay[k] >> 36) & 7ull) == r;
-      const int code = (j << 8) | static_cast<int>(pay[k] & 0xFFull);
-      if (mine && j >= jlo) a = code < a ? code : a;
-      if (mine && j < jlo) b = code > b ? code : b;
-    }
-    a = __reduce_min_sync(HYG_FULL, a);
-    b = __reduce_max_sync(HYG_FULL, b);
-    const int pickc = (a != 0x7fffffff) ? a : b;
-    if (pickc >= 0) out |= (static_cast<unsigned long long>(pickc & 0xFF) << (8 * r)) | (1ull << (56 + r));
-  }
-  return out;
-}
-
-template <int EPL>
-__device__ __forceinline__ void sg_warp_sort_desc(unsigned long long (&key)[EPL], unsigned long long (&pay)[EPL]) {
-  const int lane = threadIdx.x & 31;
-  constexpr int NEL = 32 * EPL;
-#pragma unroll
-  for (int k2 = 2; k2 <= NEL; k2 <<= 1) {
-#pragma unroll
-    for (int j = k2 >> 1; j > 0; j >>= 1) {
-      if (j < EPL) {
-        // partner in the same lane (EPL == 2, j == 1)
-        const bool desc = (((lane * EPL) & k2) == 0);
-        const bool b10 = order_before(key[EPL - 1], pay[EPL - 1], key[0], pay[0]);
-        const bool sw = (desc == b10);   // descending block wants element 0 first: swap when element 1 precedes it
-        const unsigned long long tk = sw ? key[EPL - 1] : key[0], tp = sw ? pay[EPL - 1] : pay[0];
-        const unsigned long long uk = sw ? key[0] : key[EPL - 1], up = sw ? pay[0] : pay[EPL - 1];
-        key[0] = tk; pay[0] = tp; key[EPL - 1] = uk; pay[EPL - 1] = up;
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      unsigned long long other;
+      if (j < 32) {
+        other = __shfl_xor_sync(HYG_FULL, key, j);
       } else {
-        const int lj = j / EPL;
-#pragma unroll
-        for (int k = 0; k < EPL; k++) {
-          const unsigned long long ok = __shfl_xor_sync(HYG_FULL, key[k], lj);
-          const unsigned long long op = __shfl_xor_sync(HYG_FULL, pay[k], lj);
-          const int e = lane * EPL + k;
-          const bool desc = ((e & k2) == 0);
-          const bool lower = ((e & j) == 0);
-          const bool take_first = (lower == desc);
-          const bool other_first = order_before(ok, op, key[k], pay[k]);
-          const bool tk = (take_first == other_first);
-          key[k] = tk ? ok : key[k];
-          pay[k] = tk ? op : pay[k];
+        s.xk[kbuf][tid] = key;
+        if (kbuf == 0) {
+          named_barrier(HYG_WORKER_BAR, HYG_NPMAX);   // also orders s.W (written by the caller) before its first read
+        } else {
+          // pair index: the warp number with the bit of the partner stride removed
+          const int jw = j >> 5;   // 1, 2, 4
+          const int pair = (warp & (jw - 1)) | ((warp & ~(2 * jw - 1)) >> 1);
+          named_barrier(2 + 4 * (jw == 1 ? 0 : (jw == 2 ? 1 : 2)) + pair, 64);
         }
+        other = s.xk[kbuf][tid ^ j];
+        kbuf++;
       }
+      const bool take_max = (((tid & j) == 0) == ((tid & k) == 0));
+      key = (take_max == (other > key)) ? other : key;
     }
   }
+  return key;
 }
 
-// The service warp's resampler (fast path).  Reads the compacted candidates, writes s.fate[slot] for every candidate,
-// s.res and s.fast_fail.  `cnt` candidates (1 <= cnt <= 32 EPL); all particles not among them are heavier than all of them.
-template <int EPL, int R>
-__device__ __forceinline__ void sg_resample_warp(SgSmem& s, int cnt, int N_prev, int M, double u, double lsum_prev) {
-  const int lane = threadIdx.x & 31;
-  unsigned long long key[EPL], pay[EPL];
-#pragma unroll
-  for (int k = 0; k < EPL; k++) {
-    const int e = lane * EPL + k;
-    key[k] = (e < cnt) ? s.cand_key[e] : 0ull;
-    pay[k] = (e < cnt) ? s.cand_pay[e] : (~0ull - static_cast<unsigned long long>(e));
-  }
-  sg_warp_sort_desc<EPL>(key, pay);
-  const int base = N_prev - cnt;   // full-order position of candidate 0
-  double q[EPL], Q[EPL + 1];
-  bool real[EPL];
-#pragma unroll
-  for (int k = 0; k < EPL; k++) {
-    real[k] = (lane * EPL + k) < cnt;
-    q[k] = real[k] ? s.W[pay[k] & 0xFFull] : 0.0;
-  }
-  // suffix sums Q[j] = sum_{i >= j} q_i (resample.h:306) by a shuffle scan over the lane totals
-  double v = 0.0;
-#pragma unroll
-  for (int k = EPL - 1; k >= 0; k--) v += q[k];
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const double tt = __shfl_down_sync(HYG_FULL, v, o);
-    if (lane + o < 32) v += tt;
-  }
-  double vnext = __shfl_down_sync(HYG_FULL, v, 1);
-  if (lane == 31) vnext = 0.0;
-  Q[EPL] = vnext;
-#pragma unroll
-  for (int k = EPL - 1; k >= 0; k--) Q[k] = q[k] + Q[k + 1];
-  // first stop: K* = min{ p : p >= M or !(q_p (M - p) > Q[p]) }  (fixed point of resample.h:333-342)
-  int first = 0x7fffffff;
-#pragma unroll
-  for (int k = EPL - 1; k >= 0; k--) {
-    const int j = lane * EPL + k, p = base + j;
-    const bool stop = !real[k] || (p >= M) || !(q[k] * static_cast<double>(M - p) > Q[k]);
-    first = stop ? j : first;
-  }
-  const int jstar = __reduce_min_sync(HYG_FULL, first);
-  // The heaviest candidate must be provably kept, otherwise heavier particles may belong to the tail as well.  One exception:
-  // if its self-normalised weight is exactly 0 (underflow; informative data), every position from the first zero weight p0 on
-  // is a stop, position p0 - 1 is not (q (M - p0 + 1) > q because p0 <= N_prev - cnt < M), so K = p0 and Q[K] = 0: the
-  // reference falls through to "keep the M largest by log-weight" (resample.h:345,366-375) and the nd lightest -- all of them
-  // candidates, cnt > nd -- die.
-  bool zero_tail = false;
-  if (jstar == 0 && cnt < N_prev) {
-    const double q_top = __shfl_sync(HYG_FULL, q[0], 0);
-    if (q_top == 0.0) {
-      zero_tail = true;
-    } else {
-      if (lane == 0) s.fast_fail = 1;
-      return;
-    }
-  }
-  const int K = base + jstar;
-  double Qk = 0.0;
-  {
-    double mineQ = 0.0;
-#pragma unroll
-    for (int k = 0; k < EPL; k++) mineQ = ((jstar % EPL) == k) ? Q[k] : mineQ;
-    Qk = __shfl_sync(HYG_FULL, mineQ, jstar / EPL);
-  }
-  const bool keep_largest = zero_tail || (K >= M) || !(Qk > 0.0) || !hyg_isfinite(Qk);
-  int fate[EPL];
-  bool live[EPL];
-  int tie = 0, n_dup = 0;
-  // key of the next sorted position, for the tie taps; bit 0: exact ties among the sorted candidates
-  unsigned long long nxk[EPL];
-  {
-    unsigned long long nk = __shfl_down_sync(HYG_FULL, key[0], 1);
-    if (lane == 31) nk = 0ull;
-    bool t0 = false;
-#pragma unroll
-    for (int k = 0; k < EPL; k++) {
-      nxk[k] = (k + 1 < EPL) ? key[k + 1] : nk;
-      t0 = t0 || (key[k] == nxk[k] && key[k] > HYG_KEY_NEGINF);
-    }
-    if (__any_sync(HYG_FULL, t0)) tie |= 1;
-  }
-  if (keep_largest) {
-    // keep the M largest by log-weight (Smc.h:432-441; resample.h:366-375): positions p >= M die
-    bool cut = false;
-#pragma unroll
-    for (int k = 0; k < EPL; k++) {
-      const int p = base + lane * EPL + k;
-      fate[k] = (real[k] && p >= M) ? HYG_FATE_DEAD : HYG_FATE_KEEP;
-      // a tie across the cut decides who is kept
-      cut = cut || (real[k] && p == M - 1 && p + 1 < N_prev && key[k] == nxk[k] && key[k] > HYG_KEY_NEGINF);
-    }
-    if (__any_sync(HYG_FULL, cut)) tie |= 2;
-  } else {
-    const int L = M - K;
-    // systematic resampling of L offspring among the sorted residual particles (resample.h:85-127,354-359).
-    // C_j = #{ i < L : (i+u)/L <= cumulative residual weight up to j }; forced monotone, C_last = L, so the
-    // offspring counts o_j = C_j - C_{j-1} are >= 0 and sum to L whatever the rounding of the suffix sums.
-    const double scale = static_cast<double>(L) / Qk;
-    int C[EPL];
-#pragma unroll
-    for (int k = 0; k < EPL; k++) {
-      const int j = lane * EPL + k;
-      int c = 0;
-      if (j >= jstar && j < cnt) c = (j == cnt - 1) ? L : sys_count_x((Qk - Q[k + 1]) * scale - u, L);
-      if (j >= cnt) c = L;
-      C[k] = c;
-    }
-#pragma unroll
-    for (int k = 1; k < EPL; k++) C[k] = C[k - 1] > C[k] ? C[k - 1] : C[k];
-    int run = C[EPL - 1];
-#pragma unroll
-    for (int dlt = 1; dlt < 32; dlt <<= 1) {
-      const int tt = __shfl_up_sync(HYG_FULL, run, dlt);
-      if (lane >= dlt) run = tt > run ? tt : run;
-    }
-    int before = __shfl_up_sync(HYG_FULL, run, 1);
-    if (lane == 0) before = 0;
-    int o[EPL];
-    bool dup = false;
-#pragma unroll
-    for (int k = 0; k < EPL; k++) {
-      const int j = lane * EPL + k;
-      const int cj = before > C[k] ? before : C[k];
-      const int cprev = (k == 0) ? before : (before > C[k - 1] ? before : C[k - 1]);
-      o[k] = (j >= jstar && j < cnt) ? cj - ((j == jstar) ? 0 : cprev) : 0;
-      dup = dup || (o[k] > 1);
-    }
-    if (__any_sync(HYG_FULL, dup)) {
-      // A particle drawn twice: only possible when rounding puts a residual weight above the step Qk/L.  The reference
-      // would duplicate the support point; here the extra draw goes to the next undrawn tail particle (counted).
-#pragma unroll
-      for (int k = 0; k < EPL; k++) s.ofs[lane * EPL + k] = static_cast<unsigned short>(o[k]);
-      __syncwarp();
-      if (lane == 0) {
-        int extra = 0;
-        for (int j = jstar; j < cnt; j++) { const int oj = s.ofs[j]; if (oj > 1) { extra += oj - 1; s.ofs[j] = 1; } }
-        n_dup = extra;
-        for (int j = jstar; j < cnt && extra > 0; j++) if (s.ofs[j] == 0) { s.ofs[j] = 1; extra--; }
-      }
-      __syncwarp();
-#pragma unroll
-      for (int k = 0; k < EPL; k++) o[k] = s.ofs[lane * EPL + k];
-      n_dup = __shfl_sync(HYG_FULL, n_dup, 0);
-    }
-    bool tied = false;
-    {
-      // bit 1: two equal residual weights, one drawn and one not
-      int no = __shfl_down_sync(HYG_FULL, o[0], 1);
-      if (lane == 31) no = 0;
-#pragma unroll
-      for (int k = 0; k < EPL; k++) {
-        const int j = lane * EPL + k;
-        const int nxo = (k + 1 < EPL) ? o[k + 1] : no;
-        tied = tied || (j >= jstar && j + 1 < cnt && key[k] == nxk[k] && q[k] != 0.0 && ((o[k] > 0) != (nxo > 0)));
-      }
-    }
-    if (__any_sync(HYG_FULL, tied)) tie |= 2;
-#pragma unroll
-    for (int k = 0; k < EPL; k++) {
-      const int j = lane * EPL + k;
-      fate[k] = (!real[k] || j < jstar) ? HYG_FATE_KEEP : (o[k] > 0 ? HYG_FATE_SURV : HYG_FATE_DEAD);
-    }
-    if (lane == 0) s.res.res_lw = lsum_prev + log(Qk / static_cast<double>(L));   // resample.h:361-364
-  }
-  // ranks of the dead (sorted order): the slot of the k-th dead particle is reused by the new-segment particle (1, k)
-  {
-    unsigned dm[EPL];
-#pragma unroll
-    for (int k = 0; k < EPL; k++) dm[k] = __ballot_sync(HYG_FULL, fate[k] == HYG_FATE_DEAD);
-    const unsigned lt = (1u << lane) - 1u;
-    int rank = 0;
-#pragma unroll
-    for (int k = 0; k < EPL; k++) rank += __popc(dm[k] & lt);
-#pragma unroll
-    for (int k = 0; k < EPL; k++) {
-      if (fate[k] == HYG_FATE_DEAD) { fate[k] = HYG_FATE_DEAD + rank; rank++; }
-      live[k] = real[k] && fate[k] < HYG_FATE_DEAD;
-      if (real[k]) s.fate[pay[k] & 0xFFull] = static_cast<unsigned short>(fate[k]);
-    }
-  }
-  const unsigned long long np = sg_pick_pivots<EPL, R>(pay, live, lane * EPL, cnt);
-  if (lane == 0) {
-    s.res.K = keep_largest ? -2 : K;
-    s.res.flags = keep_largest ? HYG_RES_KEEP_LARGEST : HYG_RES_DREW;
-    s.res.tie = tie;
-    s.res.n_dup = n_dup;
-    s.res.newpiv = np;
-    s.fast_fail = 0;
-  }
-}
-
-// Fallback: block-wide bitonic sort of all particles by the 256 worker threads (barriers among the workers only), then the
-// same decisions.  key/pay: this slot's particle (key 0 = none); Wprev its self-normalised weight.
-template <int R>
-__device__ __noinline__ void sg_resample_block(SgSmem& s, unsigned long long key, unsigned long long pay, double Wprev, int N_prev, int M, double u,
-                                               double lsum_prev) {
-  int ibuf = 0;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  s.W[tid] = Wprev;
-  if (key == 0ull) pay = ~0ull - static_cast<unsigned long long>(tid);
+// exact canonical order: full 64-bit keys, ties by (regime, sojourn); rare, compact code instead of an unrolled network
+__device__ __noinline__ void sg_block_sort_exact(unsigned long long& key, unsigned long long& pay, SgSmem& s, int tid) {
   int xb = 0;
 #pragma unroll 1
   for (int k2 = 2; k2 <= HYG_NPMAX; k2 <<= 1) {
@@ -531,49 +295,75 @@ __device__ __noinline__ void sg_resample_block(SgSmem& s, unsigned long long key
         ok = __shfl_xor_sync(HYG_FULL, key, j);
         op = __shfl_xor_sync(HYG_FULL, pay, j);
       } else {
-        s.xk[xb][tid] = key; s.xp[xb][tid] = pay;
+        named_barrier(HYG_WORKER_BAR, HYG_NPMAX);   // the buffer's previous readers are done
+        s.xk[xb][tid] = key; s.xk[xb + 2][tid] = pay;
         named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
-        ok = s.xk[xb][tid ^ j]; op = s.xp[xb][tid ^ j];
+        ok = s.xk[xb][tid ^ j]; op = s.xk[xb + 2][tid ^ j];
         xb ^= 1;
       }
-      const bool desc = ((tid & k2) == 0);
-      const bool lower = ((tid & j) == 0);
-      const bool take_first = (lower == desc);
-      const bool other_first = order_before(ok, op, key, pay);
-      const bool tk = (take_first == other_first);
+      const bool take_first = (((tid & j) == 0) == ((tid & k2) == 0));
+      const bool tk = (take_first == order_before(ok, op, key, pay));
       key = tk ? ok : key;
       pay = tk ? op : pay;
     }
   }
-  // thread tid now holds sorted position p = tid
-  const int sidx = static_cast<int>(pay & 0xFFull);
-  const bool real = tid < N_prev;
-  named_barrier(HYG_WORKER_BAR, HYG_NPMAX);   // s.W complete (and the exchange buffers free again)
-  const double qv = real ? s.W[sidx] : 0.0;
-  s.xk[0][tid] = key;                         // sorted keys, for the tie taps
-  double v = qv;  // Q[p] = sum_{j >= p} q_j
+  named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
+}
+
+// key/pay: this slot's particle (key 0 = none); Wprev its self-normalised weight.  Writes s.fate[slot] for every particle and s.res.
+template <int R>
+__device__ __forceinline__ void sg_resample_block(SgSmem& s, unsigned long long key, unsigned long long pay, double Wprev, int N_prev, int M, double u,
+                                                  bool force_exact, int tid, int lane, int warp) {
+  int ibuf = 0;
+  s.W[tid] = Wprev;
+  const bool real = tid < N_prev;   // after the sort: sorted position tid holds a particle (empty slots sort last)
+  unsigned long long pk = sg_block_sort_packed((key != 0ull) ? ((key & ~0xFFull) | static_cast<unsigned long long>(255 - tid)) : static_cast<unsigned long long>(255 - tid), s, tid, warp);
+  int sidx = 255 - static_cast<int>(pk & 0xFFull);
+  unsigned long long xkey = 0ull;   // exact key of this sorted position (only after the exact re-sort)
+  bool exact = false;
+  int K = 0;
+  double qv = 0.0, Qk = 0.0;
+  bool keep_largest = false;
+  for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1) {
+      // weights equal in their top 56 bits somewhere: the canonical order needs the full words
+      unsigned long long k2 = key, p2 = (key != 0ull) ? pay : (~0ull - static_cast<unsigned long long>(tid));
+      sg_block_sort_exact(k2, p2, s, tid);
+      sidx = static_cast<int>(p2 & 0xFFull);
+      xkey = k2; pk = k2;
+      exact = true;
+    }
+    qv = real ? s.W[sidx] : 0.0;
+    s.srt[tid] = pk;   // neighbours' words, for the tie tests
+    double v = qv;     // Q[p] = sum_{j >= p} q_j (resample.h:306)
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const double tt = __shfl_down_sync(HYG_FULL, v, o);
-    if (lane + o < 32) v += tt;
+    for (int o = 1; o < 32; o <<= 1) {
+      const double tt = __shfl_down_sync(HYG_FULL, v, o);
+      if (lane + o < 32) v += tt;
+    }
+    if (lane == 0) s.qtail[warp] = v;   // (not s.sc: its double-buffer index must stay in step with the service warp's)
+    named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
+    double tail = 0.0;
+#pragma unroll
+    for (int w = HYG_WORKER_WARPS - 1; w > 0; w--)
+      if (w > warp) tail += s.qtail[w];
+    const double Qp = v + tail;
+    s.Q[tid] = Qp;
+    if (tid == 0) { s.Q[HYG_NPMAX] = 0.0; s.srt[HYG_NPMAX] = 0ull; }
+    const unsigned long long nx = s.srt[tid + 1];
+    // first pass: do two neighbours agree in the 56 bits the packed sort compared?  (zero weights / empty slots do not matter)
+    const bool close = !exact && real && (tid + 1 < N_prev) && ((pk ^ nx) >> 8) == 0ull && (pk >> 8) != (HYG_KEY_NEGINF >> 8);
+    const bool stop = (tid >= M) || !real || !(qv * static_cast<double>(M - tid) > Qp);
+    const unsigned sb = __ballot_sync(HYG_FULL, stop);
+    const unsigned cb = __ballot_sync(HYG_FULL, close);
+    if (lane == 0) { s.iscan[ibuf][warp] = sb ? (warp * 32 + __ffs(static_cast<int>(sb)) - 1) : HYG_NPMAX; s.iflag[ibuf][warp] = cb ? 1 : 0; }
+    named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
+    K = __reduce_min_sync(HYG_FULL, (lane < HYG_WORKER_WARPS) ? s.iscan[ibuf][lane] : HYG_NPMAX);
+    const int anyclose = __reduce_max_sync(HYG_FULL, (lane < HYG_WORKER_WARPS) ? s.iflag[ibuf][lane] : 0);
+    ibuf ^= 1;
+    if (!anyclose && !(force_exact && pass == 0)) break;
   }
-  if (lane == 0) s.qtail[warp] = v;   // (not s.sc: its double-buffer index must stay in step with the service warp's)
-  named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
-  double tail = 0.0;
-#pragma unroll
-  for (int w = HYG_WORKER_WARPS - 1; w > 0; w--)
-    if (w > warp) tail += s.qtail[w];
-  const double Qp = v + tail;
-  s.Q[tid] = Qp;
-  if (tid == 0) s.Q[HYG_NPMAX] = 0.0;
-  const bool stop = (tid >= M) || !real || !(qv * static_cast<double>(M - tid) > Qp);
-  const unsigned sb = __ballot_sync(HYG_FULL, stop);
-  if (lane == 0) s.iscan[ibuf][warp] = sb ? (warp * 32 + __ffs(static_cast<int>(sb)) - 1) : HYG_NPMAX;
-  named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
-  const int K = __reduce_min_sync(HYG_FULL, (lane < HYG_WORKER_WARPS) ? s.iscan[ibuf][lane] : HYG_NPMAX);
-  ibuf ^= 1;
-  bool keep_largest = (K >= M);
-  double Qk = 0.0;
+  keep_largest = (K >= M);
   if (!keep_largest) {
     Qk = s.Q[K];
     if (!(Qk > 0.0) || !hyg_isfinite(Qk)) keep_largest = true;
@@ -581,15 +371,20 @@ __device__ __noinline__ void sg_resample_block(SgSmem& s, unsigned long long key
   int fate = HYG_FATE_KEEP;
   int o = 0;
   int tie = 0, n_dup = 0;
-  const unsigned long long nxk = (tid + 1 < HYG_NPMAX) ? s.xk[0][tid + 1] : 0ull;
-  if (__any_sync(HYG_FULL, key == nxk && key > HYG_KEY_NEGINF)) tie |= 1;
+  const unsigned long long nxk = exact ? s.srt[tid + 1] : 0ull;
+  const bool eqnext = exact && real && (tid + 1 < N_prev) && xkey == nxk && xkey > HYG_KEY_NEGINF;
+  if (exact && __any_sync(HYG_FULL, eqnext)) tie |= 1;
   if (keep_largest) {
+    // keep the M largest by log-weight (Smc.h:432-441; resample.h:366-375): positions p >= M die
     fate = (real && tid >= M) ? HYG_FATE_DEAD : HYG_FATE_KEEP;
-    if (tid == M - 1 && M < N_prev && key == nxk && key > HYG_KEY_NEGINF) tie |= 2;
+    if (tid == M - 1 && eqnext) tie |= 2;   // a tie across the cut decides who is kept
   } else {
     const int L = M - K;
+    // C_p = #{ i < L : (i+u)/L <= cumulative residual weight up to p }; forced monotone, C_last = L, so the offspring counts
+    // o_p = C_p - C_{p-1} are >= 0 and sum to L whatever the rounding of the suffix sums.  Residual fraction first, then x L:
+    // L / Qk would overflow when the tail mass is subnormal (informative data).
     int C = 0;
-    if (tid >= K && real) C = (tid == N_prev - 1) ? L : sys_count_x((Qk - s.Q[tid + 1]) * (static_cast<double>(L) / Qk) - u, L);
+    if (tid >= K && real) C = (tid == N_prev - 1) ? L : sys_count_x(((Qk - s.Q[tid + 1]) / Qk) * static_cast<double>(L) - u, L);
     if (!real) C = L;
 #pragma unroll
     for (int dlt = 1; dlt < 32; dlt <<= 1) {
@@ -605,14 +400,13 @@ __device__ __noinline__ void sg_resample_block(SgSmem& s, unsigned long long key
     if (lane == 0) Cprev = before;
     if (tid <= K) Cprev = 0;
     o = (tid >= K && real) ? C - Cprev : 0;
-    // double draws: repaired by one thread (rare: rounding only)
+    // A particle drawn twice: only possible when rounding puts a residual weight above the step Qk/L.  The reference would
+    // duplicate the support point; here the extra draw goes to the next undrawn tail particle (repaired by one thread, counted).
     const bool anydup = __any_sync(HYG_FULL, o > 1);
     s.ofs[tid] = static_cast<unsigned short>(o);
     if (lane == 0) s.iflag[ibuf][warp] = anydup ? 1 : 0;
     named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
-    int dupany = 0;
-#pragma unroll
-    for (int w = 0; w < HYG_WORKER_WARPS; w++) dupany |= s.iflag[ibuf][w];
+    const int dupany = __reduce_max_sync(HYG_FULL, (lane < HYG_WORKER_WARPS) ? s.iflag[ibuf][lane] : 0);
     if (dupany) {
       if (tid == 0) {
         int extra = 0;
@@ -623,18 +417,19 @@ __device__ __noinline__ void sg_resample_block(SgSmem& s, unsigned long long key
       named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
       o = s.ofs[tid];
       n_dup = s.iflag[ibuf][0];
+      named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
     }
     ibuf ^= 1;
-    const int no = __shfl_down_sync(HYG_FULL, o, 1);
-    const int nxo = (lane == 31) ? ((tid + 1 < HYG_NPMAX) ? static_cast<int>(s.ofs[tid + 1]) : 0) : no;
-    if (__any_sync(HYG_FULL, tid >= K && tid + 1 < N_prev && key == nxk && qv != 0.0 && ((o > 0) != (nxo > 0)))) tie |= 2;
+    if (exact) {
+      // two equal residual weights, one drawn and one not: the tie decided
+      const int nxo = (tid + 1 < HYG_NPMAX) ? static_cast<int>(s.ofs[tid + 1]) : 0;
+      if (__any_sync(HYG_FULL, eqnext && tid >= K && qv != 0.0 && ((o > 0) != (nxo > 0)))) tie |= 2;
+    }
     fate = (!real || tid < K) ? HYG_FATE_KEEP : (o > 0 ? HYG_FATE_SURV : HYG_FATE_DEAD);
   }
-  // ranks of the dead in sorted order
+  // ranks of the dead in sorted order: the slot of the k-th dead particle is reused by the new-segment particle (1, k)
   const unsigned dm = __ballot_sync(HYG_FULL, fate == HYG_FATE_DEAD);
   if (lane == 0) { s.iscan[ibuf][warp] = __popc(dm); s.iflag[ibuf][warp] = tie; }
-  // bottom of the sorted order for the pivot choice
-  const int n64 = N_prev < HYG_CAND_CAP ? N_prev : HYG_CAND_CAP;
   named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
   int drank = __popc(dm & ((1u << lane) - 1u));
 #pragma unroll
@@ -642,33 +437,14 @@ __device__ __noinline__ void sg_resample_block(SgSmem& s, unsigned long long key
     if (w < warp) drank += s.iscan[ibuf][w];
     tie |= s.iflag[ibuf][w];
   }
-  ibuf ^= 1;
   if (fate == HYG_FATE_DEAD) fate = HYG_FATE_DEAD + drank;
   if (real) s.fate[sidx] = static_cast<unsigned short>(fate);
-  {
-    const int j = tid - (N_prev - n64);
-    if (real && j >= 0) { s.cand_pay[j] = pay; s.cand_fate[j] = static_cast<unsigned short>(fate); }
-  }
-  named_barrier(HYG_WORKER_BAR, HYG_NPMAX);
-  if (warp == 0) {
-    constexpr int EPL = HYG_CAND_CAP / 32;
-    unsigned long long cp[EPL];
-    bool live[EPL];
-#pragma unroll
-    for (int k = 0; k < EPL; k++) {
-      const int e = lane * EPL + k;
-      cp[k] = (e < n64) ? s.cand_pay[e] : 0ull;
-      live[k] = (e < n64) && s.cand_fate[e] < HYG_FATE_DEAD;
-    }
-    const unsigned long long np = sg_pick_pivots<EPL, R>(cp, live, lane * EPL, n64);
-    if (lane == 0) {
-      s.res.K = keep_largest ? -2 : K;
-      s.res.flags = keep_largest ? HYG_RES_KEEP_LARGEST : HYG_RES_DREW;
-      s.res.tie = tie;
-      s.res.n_dup = n_dup;
-      s.res.newpiv = np;
-      if (!keep_largest) s.res.res_lw = lsum_prev + log(Qk / static_cast<double>(M - K));
-    }
+  if (tid == 0) {
+    s.res.K = keep_largest ? -2 : K;
+    s.res.flags = (keep_largest ? HYG_RES_KEEP_LARGEST : HYG_RES_DREW) | (exact ? HYG_RES_EXACT_SORT : 0);
+    s.res.tie = tie;
+    s.res.n_dup = n_dup;
+    if (!keep_largest) s.res.res_lw = log(Qk / static_cast<double>(M - K));   // + lsum_prev: resample.h:361-364
   }
 }
 
@@ -693,7 +469,7 @@ template <int R>
 __device__ __noinline__ int sg_lag_update(SgLagState& lag, const SgChainDev& ch, SgSmem& s, unsigned int t, unsigned int T, unsigned int own_lo,
                                           unsigned int own_hi, unsigned long long t_off, bool last_seg, double epsilon, int& n_halo_forced) {
   static_assert(R <= HYG_RMAX - 2, "lag-set tasks handle three regime indicators each");
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = hyg_tid(), lane = tid & 31, warp = tid >> 5;
   // s.bk[slot][r], s.Wc[slot], s.new_slot[r] and s.Wnew[r] were published before the caller's barrier
   constexpr int HALF = (R + 1) / 2;
   int kept = 0;
@@ -733,7 +509,7 @@ __device__ __noinline__ int sg_lag_update(SgLagState& lag, const SgChainDev& ch,
 #pragma unroll
       for (int j = 0; j < HALF; j++) {
         if (j < nq) {
-          const double tot = warp_reduce8(acc[j]);        // lane group g = (lane >> 2) & 7 holds the total of index g
+          const double tot = warp_reduce8(acc[j], lane);        // lane group g = (lane >> 2) & 7 holds the total of index g
           const int g = (lane >> 2) & 7;
           // psi of the new-segment particle (1, g) is sum_n bk_g[n] psi[n] = tot; it carries the weight Wnew[g]
           const double wg = (g < R) ? s.Wnew[g] : 0.0;
@@ -804,10 +580,10 @@ struct SgChainState {
 template <int RT, bool PE>
 __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgRunDev& run, double* psi_ws, SgSmem& s, SgPeSmem<RT>* pe) {
   static_assert(RT <= 7, "class sums share an 8-wide reduction with the finite-weight count");
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = hyg_tid(), lane = tid & 31, warp = tid >> 5;
   // Warps 0..7 own the particles (one slot per thread).  Warp 8 is a SERVICE warp: it owns no particle, follows the same
   // block barriers, and evaluates every scalar exp/log of the step (new-segment weights, log C, log Z_t, the Philox draw,
-  // the emission-row prefetch) and the candidate resampler.
+  // the emission-row prefetch).
   const bool worker = warp < HYG_WORKER_WARPS;
   const bool service = !worker;
   constexpr int R = RT;
@@ -856,17 +632,20 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
   const unsigned int own_lo = static_cast<unsigned int>(ch.own_lo), own_hi = static_cast<unsigned int>(ch.own_hi);
   const unsigned long long t_off = ch.t_off;
   const bool last_seg = ch.last_segment != 0;
-  int n_halo_forced = 0, n_steps = 0, n_fallback = 0, n_tie_sites = 0, n_dup = 0;
+  const unsigned int run_to = own_hi + (ch.ovl ? HYG_OVL_ROWS : 0u);
+  // which optional outputs exist, in a register: the descriptor lives in shared memory and a pointer test per site and output
+  // is a load + compare on the critical path
+  const unsigned taps = (ch.probs ? 1u : 0u) | (ch.finalised_at ? 2u : 0u) | (ch.ovl ? 4u : 0u) | (ch.support_hash ? 8u : 0u) |
+                        ((ch.k_kept || ch.drew || ch.n_pending || ch.n_curr || ch.tie_flags) ? 16u : 0u) | (ch.logz ? 32u : 0u) | (ch.seg_inc ? 64u : 0u);
+  int n_halo_forced = 0, n_steps = 0, n_sorts = 0, n_exact = 0, n_tie_sites = 0, n_dup = 0;
   double lz_base = 0.0;   // log Z (local) of site own_lo - 1: owned rows of logz are written relative to it
 
   SgChainState p;
   p.lw = -HYG_INF; p.W = 0.0; p.cur = make_double2(0.0, 0.0); p.nxt = p.cur; p.gcur = 0.0; p.gnxt = 0.0; p.d = 0; p.r = 0;
-  unsigned mypiv = 0;   // bit r: this slot holds the pivot particle of regime r
 
   // ---- t = 0 : Smc::initialise (Smc.h:114-188) ----
   if (tid < R) s.lo[0][tid] = __ldg(ch.logobs + tid);
   if (T > 1 && tid < R) s.lo[1][tid] = __ldg(ch.logobs + R + tid);
-  if (tid < 2 * HYG_RMAX) (&s.piv_key[0][0])[tid] = 0ull;
   __syncthreads();
   if (tid < 2 && static_cast<unsigned int>(tid) < T) {
     double m = s.lo[tid][0];
@@ -909,7 +688,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
     const double pos_cur = pos_nxt;
     if (warp == 0 && tid == 0 && t + 1 < T) pos_nxt = ch.pos ? static_cast<double>(__ldg(ch.pos + t + 1)) : static_cast<double>(static_cast<unsigned long long>(t) + 1ull + t_off);
     int k_kept = -1;
-    bool drew = false;
+    bool drew = false, resampled = false;
     int tie_site = 0;
     bool emit_now = false;       // current site finalised at this step
     const bool own_t = (t >= own_lo) && (t < own_hi);
@@ -925,58 +704,40 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       const double lomax = s.lomax[t & 1];
       const bool alive = tid < N_prev;   // service warp: never
 
-      if (service) {
-        // the uniform of this site, and log Z_{t-1}: the log of last step's normaliser is evaluated now, off the
-        // workers' critical path
-        if (lane == 8) s.u = ch.unif ? __ldg(ch.unif + t) : philox_uniform(ch.seed, ch.chain_id, t + t_off);
-        if (lane == 0) s.lsum[(t + 1) & 1] = pend_shift + log(pend_S);
-        if (lane < R) s.piv_key[t & 1][lane] = 0ull;   // the pivots publish their new keys into this buffer after the resampling
-        __syncwarp();
-      }
-
+      // (the uniform of this site and log Z_{t-1} were evaluated by the service warp behind the normaliser barrier of site t-1)
       // ---- class sums over the previous particles (replace the R x N_prev log-sum-exps of Smc.h:562-573) ----
       const double e_prev = alive ? p.W * p.cur.x : 0.0;  // W_n * c_new(d_n, r_n)
       const bool finite_prev = alive && hyg_isfinite(p.lw);
       const bool valid = finite_prev && (p.cur.x > 0.0);
-      const unsigned long long mykey = alive ? order_key(p.lw) : 0ull;
-      unsigned cmask[R];          // lanes of this warp not heavier than the pivot of regime r
       unsigned infmask = 0;
-#pragma unroll
-      for (int r = 0; r < R; r++) cmask[r] = 0;
       if (worker) {
         // class sums of e_prev; slot 7: F = #finite(logw_prev), Smc.h:413 (exact in fp64).  e_prev is 0 beyond N_prev.
-        publish8(s.part[pbuf], warp_reduce_onehot(e_prev, p.r, finite_prev ? 1.0 : 0.0));
+        publish8(s.part[pbuf], warp_reduce_onehot(e_prev, p.r, finite_prev ? 1.0 : 0.0, lane), lane, warp);
         const unsigned vm = __reduce_or_sync(HYG_FULL, valid ? (1u << p.r) : 0u);
         if (lane == 0) s.vmask[pbuf][warp] = vm;
         if (PE) {
           pe->eprev[tid] = e_prev;
-          publish8(s.partG[pbuf], warp_reduce_onehot(e_prev * p.gcur, p.r, 0.0));
+          publish8(s.partG[pbuf], warp_reduce_onehot(e_prev * p.gcur, p.r, 0.0, lane), lane, warp);
         }
         if (capped) {
           infmask = __ballot_sync(HYG_FULL, alive && !finite_prev);
-          int mycnt = __popc(infmask);
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            const unsigned long long pk = s.piv_key[(t + 1) & 1][r];
-            cmask[r] = __ballot_sync(HYG_FULL, alive && mykey <= pk);   // pk == 0: no pivot, no candidates
-            mycnt = (lane == r) ? __popc(cmask[r]) : mycnt;
-          }
-          if (lane < 8) s.pcnt[pbuf][warp][lane] = (lane < R || lane == 6) ? mycnt : 0;
+          if (lane == 0) s.infcnt[pbuf][warp] = __popc(infmask);
         }
       }
       const int pA = pbuf;
       pbuf ^= 1;
-      __syncthreads();   // ---- B1 ----
-      const double totA = combine8(s.part[pA]);           // lane & 7 -> E[0..R-1], [7] = F
+      // ---- B1 ---- the workers synchronise among themselves and signal the service warp; they never wait for it here
+      if (worker) { named_arrive(HYG_SVC_BAR, HYG_NT); named_barrier(HYG_WORKER_BAR, HYG_NPMAX); }
+      else named_barrier(HYG_SVC_BAR, HYG_NT);
+      const double totA = combine8(s.part[pA], lane);           // lane & 7 -> E[0..R-1], [7] = F
       const int F = static_cast<int>(__shfl_sync(HYG_FULL, totA, 7) + 0.5);
-      const double lsum_prev = s.lsum[(t + 1) & 1];
       if (service) {
-        const double sumE_lane = sg_service_new_segments<R>(mdl, s, totA, pA);
+        const double lsum_prev = s.lsum[(t + 1) & 1];
         if (PE) {
-          const double totG = combine8(s.partG[pA]);
+          const double totG = combine8(s.partG[pA], lane);
           if (lane < 8) { pe->Etot[lane] = totA; pe->Egtot[lane] = totG; }
         }
-        if (lane < R) s.new_lw[lane] = (sumE_lane > 0.0) ? lsum_prev + lo[lane] + log(sumE_lane) : -HYG_INF;
+        sg_service_new_weights<R>(mdl, s, totA, pA, lane, lsum_prev, lo);   // while the workers resample
       }
 
       // ---- who dies: Smc::resampleCp (Smc.h:406-450) ----
@@ -988,77 +749,37 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           if (worker) {
 #pragma unroll
             for (int w = 0; w < HYG_WORKER_WARPS; w++)
-              if (w < warp) irank += s.pcnt[pA][w][6];
+              if (w < warp) irank += s.infcnt[pA][w];
           }
           if (alive && !finite_prev && irank < nd) fate = HYG_FATE_DEAD + irank;
           k_kept = -2;
-          __syncthreads();   // ---- B3 ---- (new-segment weights)
         } else {
           // ---- resample::optimalFiniteState (resample.h:289-409) ----
-          // best pivot: the one with the most candidates that still fit one warp's registers
-          int mine = -1;
-          if (lane < R) {
-            int tot = 0;
-#pragma unroll
-            for (int w = 0; w < HYG_WORKER_WARPS; w++) tot += s.pcnt[pA][w][lane];
-            if (tot > nd && tot <= HYG_CAND_CAP) mine = (tot << 3) | lane;
-          }
-          const int best = run.force_full_sort ? -1 : __reduce_max_sync(HYG_FULL, mine);
-          bool full = (best < 0);
-          if (!full) {
-            const int rstar = best & 7, cnt = best >> 3;
-            unsigned cm_ = 0;
-#pragma unroll
-            for (int r = 0; r < R; r++) cm_ = (rstar == r) ? cmask[r] : cm_;
-            const bool is_cand = worker && ((cm_ >> lane) & 1u);
-            if (is_cand) {
-              int idx = __popc(cm_ & ((1u << lane) - 1u));
-#pragma unroll
-              for (int w = 0; w < HYG_WORKER_WARPS; w++)
-                if (w < warp) idx += s.pcnt[pA][w][rstar];
-              s.cand_key[idx] = mykey;
-              s.cand_pay[idx] = order_pay(p.r, p.d, tid);
-              s.W[tid] = p.W;
-            }
-            __syncthreads();   // ---- B2 ----
-            if (service) {
-              if (cnt <= 32) sg_resample_warp<1, R>(s, cnt, N_prev, M, s.u, lsum_prev);
-              else sg_resample_warp<2, R>(s, cnt, N_prev, M, s.u, lsum_prev);
-            }
-            __syncthreads();   // ---- B3 ----
-            full = (s.fast_fail != 0);
-            if (!full && is_cand) fate = s.fate[tid];
-          }
-          if (full) {
-            n_fallback++;
-            if (worker) sg_resample_block<R>(s, mykey, order_pay(p.r, p.d, tid), alive ? p.W : 0.0, N_prev, M, s.u, lsum_prev);
-            __syncthreads();   // ---- B3' ----
-            if (alive) fate = s.fate[tid];
-          }
-          k_kept = s.res.K;
-          drew = (s.res.flags & HYG_RES_DREW) != 0;
-          tie_site = s.res.tie;
-          n_dup += s.res.n_dup;
-          // pivots for the next site
-          const unsigned long long np = s.res.newpiv;
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            if ((np >> (56 + r)) & 1ull) {
-              const int sl = static_cast<int>((np >> (8 * r)) & 0xFFull);
-              mypiv = (mypiv & ~(1u << r)) | ((sl == tid) ? (1u << r) : 0u);
-            }
-          }
+          n_sorts++;
+          if (worker) sg_resample_block<R>(s, alive ? order_key(p.lw) : 0ull, order_pay(p.r, p.d, tid), alive ? p.W : 0.0, N_prev, M, s.u[t & 1], run.force_full_sort != 0, tid, lane, warp);
+          resampled = true;
         }
-      } else {
-        __syncthreads();     // ---- B3 ---- growth phase: nothing dies
       }
-      if (tie_site & 2) n_tie_sites++;
+      // ---- B3 ---- the new-segment weights (service warp) and the fates (workers) are published; the service warp does not wait
+      if (worker) named_barrier(HYG_RES_BAR, HYG_NT);
+      else named_arrive(HYG_RES_BAR, HYG_NT);
+      const double lsum_prev = s.lsum[(t + 1) & 1];   // written by the service warp behind the normaliser barrier of site t-1
+      if (worker && resampled) {
+        if (alive) fate = s.fate[tid];
+        k_kept = s.res.K;
+        drew = (s.res.flags & HYG_RES_DREW) != 0;
+        n_exact += (s.res.flags & HYG_RES_EXACT_SORT) ? 1 : 0;
+        tie_site = s.res.tie;
+        n_dup += s.res.n_dup;
+        if (tie_site & 2) n_tie_sites++;
+      }
 
       // ---- propose + weight: sampleParticlesCp / computeWeightsCp (Smc.h:504-574) ----
       // the k-th dead slot (sorted order) takes the new-segment particle (1, k); the others open the slots N_prev, N_prev+1, ..
       int newreg = -1;
       if (fate >= HYG_FATE_DEAD) newreg = fate - HYG_FATE_DEAD;
       else if (tid >= N_prev && tid < N_curr) newreg = nd + (tid - N_prev);
+      HYG_CHECK(newreg < R, 2, newreg, fate);
       if (newreg >= 0) s.new_slot[newreg] = static_cast<short>(tid);
       const double my_e = e_prev;            // backward-kernel numerator of the particle that WAS in this slot
       const int my_r_prev = p.r;
@@ -1070,10 +791,11 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       if (cont) {
         const double2 pc = p.cur;
         const double lc = pc.y;                         // log(1 - rho(d_prev, r)) or -inf (singleGroup.h:597-605)
-        p.lw = ((fate == HYG_FATE_SURV) ? s.res.res_lw : p.lw) + (lc + lo[p.r]);
+        p.lw = ((fate == HYG_FATE_SURV) ? lsum_prev + s.res.res_lw : p.lw) + (lc + lo[p.r]);
         p.d = p.d + 1;
         p.cur = p.nxt;
         const uint32_t di = (p.d + 1 <= vcap) ? p.d : vcap - 1;  // 0-based index of d+1, clamped to the terminal entry
+        HYG_CHECK(p.r >= 0 && p.r < R && di < dcap, 3, p.r, di);
         p.nxt = tab_load<PE>(mdl.tab + static_cast<size_t>(p.r) * dcap + di);
         if (PE) {
           const double rho = pc.x;                      // c_new = rho for d >= u (0 below u)
@@ -1088,7 +810,6 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
         p.nxt = tab_load<PE>(mdl.tab + static_cast<size_t>(r) * dcap + 1);
         if (PE) { p.gcur = mdl.tabg[static_cast<size_t>(r) * dcap + 0]; p.gnxt = mdl.tabg[static_cast<size_t>(r) * dcap + 1]; }
         p.lw = s.new_lw[r];
-        mypiv = 0;
       }
       const bool now_alive = tid < N_curr;
       // exact log-domain path for regimes whose linear-domain sum underflowed (rare)
@@ -1110,21 +831,14 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           bk_slow[r] = (ex[0] > 0.0) ? mine / ex[0] : 0.0;
         }
       }
-      // the pivots publish the key of their new weight (compared against at the next site)
-      if (mypiv) {
-        const unsigned long long nk = order_key(p.lw);
-#pragma unroll
-        for (int r = 0; r < R; r++)
-          if ((mypiv >> r) & 1u) s.piv_key[t & 1][r] = nk;
-      }
 
       // ---- selfNormaliseWeights (Smc.h:576-579), fused with the regime masses of the new site ----
       {
         double shift = lsum_prev + lomax;   // upper bound of every logw instead of the exact max
         p.W = now_alive ? exp(p.lw - shift) : 0.0;
-        if (worker) publish8(s.part[pbuf], warp_reduce_onehot(p.W, p.r, 0.0));   // p.W is 0 beyond N_curr
-        __syncthreads();   // ---- B4 ----
-        double tot = combine8(s.part[pbuf]);   // lane & 7 -> class sum of the relative weights
+        if (worker) publish8(s.part[pbuf], warp_reduce_onehot(p.W, p.r, 0.0, lane), lane, warp);   // p.W is 0 beyond N_curr
+        __syncthreads();   // ---- B4 ---- (a full barrier: two worker arrivals on HYG_SVC_BAR must never be outstanding at once)
+        double tot = combine8(s.part[pbuf], lane);   // lane & 7 -> class sum of the relative weights
         pbuf ^= 1;
         double S = tot;
         S += __shfl_xor_sync(HYG_FULL, S, 1);
@@ -1134,9 +848,9 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           // the linear-domain weights underflowed against the bound: renormalise from the log-weights with the exact max
           shift = block_max(now_alive ? p.lw : -HYG_INF, s.sc, flip);
           p.W = (now_alive && p.lw > -HYG_INF) ? exp(p.lw - shift) : 0.0;
-          if (worker) publish8(s.part[pbuf], warp_reduce_onehot(p.W, p.r, 0.0));
+          if (worker) publish8(s.part[pbuf], warp_reduce_onehot(p.W, p.r, 0.0, lane), lane, warp);
           __syncthreads();
-          tot = combine8(s.part[pbuf]);
+          tot = combine8(s.part[pbuf], lane);
           pbuf ^= 1;
           S = tot;
           S += __shfl_xor_sync(HYG_FULL, S, 1);
@@ -1146,7 +860,16 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
         const double invS = 1.0 / S;
         p.W *= invS;
         cw_lane = tot * invS;
-        pend_shift = shift; pend_S = S;   // log Z_t = shift + log S is evaluated by the service warp at the next step
+        pend_shift = shift; pend_S = S;
+        if (service) {
+          // log Z_t and the uniform of site t+1, while the workers finish the site: nothing waits for them before the next
+          // site's first barrier
+          if (lane == 0) s.lsum[t & 1] = shift + log(S);
+          // (two sites ahead: the workers read it before the next barrier the service warp takes part in)
+          if (lane == 8 && t + 2 < T) s.u[t & 1] = ch.unif ? __ldg(ch.unif + t + 2) : philox_uniform(ch.seed, ch.chain_id, static_cast<unsigned long long>(t) + 2ull + t_off);
+          // the resampling taps of this site, for the end-of-step taps below (stable until the next site's resampling)
+          if (resampled) { k_kept = s.res.K; drew = (s.res.flags & HYG_RES_DREW) != 0; tie_site = s.res.tie; }
+        }
       }
 
       // ---- fixed-lag smoothing: updatePsi (OnlineMarginalSmoothing.h:148-177) ----
@@ -1247,10 +970,14 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       if (worker) {
 #pragma unroll
         for (int q = 0; q < 8; q++) v8[q] = (q < R && tid < N && p.r == q) ? p.W : 0.0;
-        publish8(s.part[pbuf], warp_reduce8(v8));
+        publish8(s.part[pbuf], warp_reduce8(v8, lane), lane, warp);
+      }
+      if (service && lane >= 8 && lane <= 9 && lane - 7 < static_cast<int>(T)) {   // uniforms of sites 1 and 2
+        const unsigned long long tt = static_cast<unsigned long long>(lane - 7);
+        s.u[tt & 1] = ch.unif ? __ldg(ch.unif + tt) : philox_uniform(ch.seed, ch.chain_id, tt + t_off);
       }
       __syncthreads();
-      cw_lane = combine8(s.part[pbuf]);
+      cw_lane = combine8(s.part[pbuf], lane);
       pbuf ^= 1;
     }
     if (worker && (PE || run.use_smoothing)) s.r[tid] = static_cast<unsigned char>(p.r);
@@ -1271,19 +998,21 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       if (!emit_now && lag.n_pend >= lcap) { emit_now = true; n_forced += own_t ? 1 : 0; }  // lag set full: emit the filtering estimate now (reported)
       if (emit_now) {
         if (own_t) {
-          if (warp == 0 && ch.probs) {
+          if (warp == 0 && (taps & 1u)) {
             const double left = __shfl_up_sync(HYG_FULL, cw_lane, 1);   // lane j >= 1: mass of regime j-1
             if (lane <= R) ch.probs[static_cast<size_t>(t) * (R + 1) + lane] = (lane == 0) ? pos_cur : left;
           }
-          if (tid == 0 && ch.finalised_at) ch.finalised_at[t] = static_cast<int>(t + t_off);
+          if (tid == 0 && (taps & 2u)) ch.finalised_at[t] = static_cast<int>(t + t_off);
           if (t == T - 1 && !settled && !last_seg) n_halo_forced++;
-        } else if (ch.ovl && warp == 0 && t >= own_hi && t < own_hi + HYG_OVL_ROWS) {
+        } else if ((taps & 4u) && warp == 0 && t >= own_hi && t < own_hi + HYG_OVL_ROWS) {
           const double left = __shfl_up_sync(HYG_FULL, cw_lane, 1);
           if (lane >= 1 && lane <= R) ch.ovl[(t - own_hi) * R + (lane - 1)] = left;
         }
       } else {
         // free_row / pend_* were last written before a block barrier of this step (or at initialisation)
+        HYG_CHECK(lag.n_free >= 1 && lag.n_free <= lcap, 6, lag.n_free, lag.n_pend);
         const int rw = lag.free_row[lag.n_free - 1];
+        HYG_CHECK(rw >= 0 && rw < lcap, 7, rw, lag.n_free);
         double* dst = lag.rows + static_cast<size_t>(rw) * R * HYG_NPMAX;
         if (worker) {
 #pragma unroll
@@ -1302,13 +1031,19 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       for (int o = 1; o < 8; o <<= 1) { const double tt = __shfl_xor_sync(HYG_FULL, mx, o); mx = tt > mx ? tt : mx; }
       if (lane == 0) s.lomax[t & 1] = mx;
     }
-    __syncthreads();   // ---- B5 ---- (emission prefetch, lag-set lists and psi rows, pivot keys)
-    // segmented execution: stop as soon as the owned range is stepped through and none of its sites is still pending
-    // (the lag set is ordered by site, oldest first)
+    // Everything written above is next read behind one of the block barriers of the following site.  The one exception
+    // is the lag-set list head the exit test below reads, so only that test pays for a barrier.
+    // Segmented execution: stop as soon as the owned range is stepped through and none of its sites is still pending
+    // (the lag set is ordered by site, oldest first); with the left-halo check on, a segment first steps through
+    // HYG_OVL_ROWS sites of the next one.
     bool exit_now = false;
-    // (with the left-halo check on, a segment first steps through HYG_OVL_ROWS sites of the next one)
-    const unsigned int run_to = own_hi + (ch.ovl ? HYG_OVL_ROWS : 0u);
-    if (!PE && t + 1 >= run_to && t + 1 < T) exit_now = (lag.n_pend == 0) || (static_cast<unsigned int>(lag.pend_t[0]) >= own_hi);
+#ifdef HYG_KEEP_B5
+    __syncthreads();
+#endif
+    if (!PE && t + 1 >= run_to && t + 1 < T) {
+      __syncthreads();
+      exit_now = (lag.n_pend == 0) || (static_cast<unsigned int>(lag.pend_t[0]) >= own_hi);
+    }
     const bool last_step = (t == T - 1) || exit_now;
     n_steps++;
 
@@ -1347,7 +1082,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
     }
 
     // ---- taps ----
-    if (ch.support_hash) {
+    if (taps & 8u) {
       // order-independent hash of the finite-weight support {(d, r)} (parity tests only)
       unsigned long long h = (worker && tid < N && p.lw > -HYG_INF) ? mix64((static_cast<unsigned long long>(p.r) << 28) | p.d) : 0ull;
 #pragma unroll
@@ -1366,16 +1101,16 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
         const double lz_prev = s.lsum[(t + 1) & 1];   // log Z (local) of site t-1
         if (t == own_lo) lz_base = lz_prev;
         if (t - 1 >= own_lo && t - 1 < own_hi) {
-          if (ch.logz) ch.logz[t - 1] = lz_prev - lz_base;
-          if (t == own_hi && ch.seg_inc) *ch.seg_inc = lz_prev - lz_base;
+          if (taps & 32u) ch.logz[t - 1] = lz_prev - lz_base;
+          if (t == own_hi && (taps & 64u)) *ch.seg_inc = lz_prev - lz_base;
         }
       }
       if (last_step && own_t) {
-        const double lz = pend_shift + log(pend_S) - lz_base;
-        if (ch.logz) ch.logz[t] = lz;
-        if (t + 1 == own_hi && ch.seg_inc) *ch.seg_inc = lz;
+        const double lz = s.lsum[t & 1] - lz_base;
+        if (taps & 32u) ch.logz[t] = lz;
+        if (t + 1 == own_hi && (taps & 64u)) *ch.seg_inc = lz;
       }
-      if (own_t) {
+      if (own_t && (taps & 16u)) {
         if (ch.k_kept) ch.k_kept[t] = k_kept;
         if (ch.drew) ch.drew[t] = drew ? 1 : 0;
         if (ch.n_pending) ch.n_pending[t] = lag.n_pend;
@@ -1390,7 +1125,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
     atomicMax(ch.status + 1, max_pend);
     atomicAdd(ch.status + 2, n_halo_forced);
     atomicAdd(ch.status + 3, n_steps);
-    atomicAdd(ch.status + 4, n_fallback);
+    atomicAdd(ch.status + 4, n_exact);
     atomicAdd(ch.status + 5, n_tie_sites);
     atomicAdd(ch.status + 6, n_dup);
   }

@@ -82,8 +82,8 @@ typedef struct hyg_sg_chain {
   int32_t status[HYG_SG_STATUS_WORDS];
                                 /* out: [0] forced emissions because the lag set was full, [1] max lag-set size,
                                         [2] owned sites emitted by force at the end of a segment's right halo (segmented
-                                        execution only), [3] sites stepped through, halos included, [4] sites resampled by the
-                                        block-wide sort (pivot miss), [5] sites where an exact tie of weights decided a
+                                        execution only), [3] sites stepped through, halos included, [4] sites whose sort was
+                                        redone on the full words (two weights equal in their top 56 bits), [5] sites where an exact tie of weights decided a
                                         particle's fate, [6] double systematic draws repaired, [7] segmented execution:
                                         number of overlap rows whose two computations differ by more than 1e-6              */
   double overlap_max_abs;       /* out: segmented execution: max |p - p'| over the rows a segment's right halo recomputed
@@ -110,8 +110,8 @@ typedef struct hyg_sg_run_args {
                                            its filtering estimate and COUNTED in status[0]; hyg_sg_filter fails with
                                            HYG_ERR_CAPACITY after the launch unless allow_forced_emission is set             */
   int32_t allow_forced_emission;        /* keep going (status[0] > 0) instead of failing when the lag set overflowed        */
-  int32_t resample_full_sort;           /* resample every site by the block-wide sort (bypasses the pivot / candidate path;
-                                           same decisions, used by the parity tests)                                       */
+  int32_t resample_full_sort;           /* sort the particles on the full (log-weight, regime, sojourn) words at every site instead of
+                                           only where two weights agree in their top 56 bits (same decisions; parity tests)   */
 } hyg_sg_run_args;
 
 void hyg_sg_default_run_args(hyg_sg_run_args* args);

@@ -155,6 +155,17 @@ inline void named_barrier(int id, unsigned count) {
   f.parked = 0;
 }
 
+// bar.arrive id, count: counts as an arrival, does not wait
+inline void named_arrive(int id, unsigned count) {
+  BlockState* b = cur_block();
+  NamedBarrier& nb = b->named[id];
+  nb.arrived++;
+  if (nb.arrived == count) {
+    nb.arrived = 0;
+    nb.gen++;
+  }
+}
+
 inline WarpState& my_warp() {
   BlockState* b = cur_block();
   return b->warps[b->fibers[b->current].tid / 32];
@@ -250,6 +261,14 @@ template <class K> void launch(dim3 grid, dim3 block, K kernel_body) {
       if (!any) {
         if (++idle_sweeps > 4) {
           std::fprintf(stderr, "cuda_emu: deadlock (a collective was reached by a partial warp/block)\n");
+          for (unsigned w2 = 0; w2 * 32 < nthreads; w2++) {
+            const Fiber& f0 = bs.fibers[w2 * 32];
+            std::fprintf(stderr, "  warp %u lane 0: %s parked=%d (1 block barrier, 2 warp collective, 3 named barrier) id=%d; named[%d].arrived=%u block.arrived=%u\n",
+                         w2, f0.done ? "done" : "live", f0.parked, f0.bar_id, f0.bar_id, bs.named[f0.bar_id & 15].arrived, bs.arrived);
+          }
+          { const unsigned w2 = (nthreads - 1) / 32; std::fprintf(stderr, "  last warp lanes parked:");
+            for (unsigned l = 0; l < 32 && w2 * 32 + l < nthreads; l++) std::fprintf(stderr, " %d", bs.fibers[w2 * 32 + l].parked);
+            std::fprintf(stderr, "\n"); }
           std::abort();
         }
       } else {
@@ -267,6 +286,7 @@ template <class K> void launch(dim3 grid, dim3 block, K kernel_body) {
 // ---------------------------------------------------------------------------
 inline void __syncthreads() { emu::block_barrier(); }
 inline void hyg_emu_named_barrier(int id, unsigned count) { emu::named_barrier(id, count); }
+inline void hyg_emu_named_arrive(int id, unsigned count) { emu::named_arrive(id, count); }
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::warp_rendezvous(0, [](emu::WarpState&) {}); }
 inline void __threadfence() {}
 inline void __threadfence_block() {}
@@ -349,6 +369,8 @@ inline unsigned __umulhi(unsigned a, unsigned b) { return static_cast<unsigned>(
 template <class T> inline T __ldg(const T* p) { return *p; }
 template <class T> inline T atomicAdd(T* p, T v) { T old = *p; *p = old + v; return old; }
 template <class T> inline T atomicMax(T* p, T v) { T old = *p; *p = old > v ? old : v; return old; }
+template <class T> inline T atomicMin(T* p, T v) { T old = *p; *p = old < v ? old : v; return old; }
+template <class T> inline T atomicOr(T* p, T v) { T old = *p; *p = old | v; return old; }
 inline double __dadd_rn(double a, double b) { return a + b; }
 
 struct double2 { double x, y; };

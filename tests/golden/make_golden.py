@@ -30,6 +30,38 @@ CASES = [
 ]
 
 
+# Long one-sample chains (the production shape of the single-group workflow): exact ties between weights are
+# systematic there and the reference breaks them by whatever order std::sort leaves, so these pin
+# (i) the oracle's reference tie order bit for bit and (ii) the CUDA path up to the first site where a tie decided a fate.
+LONG_CASES = [
+    # name, T, S, data seed, lambda, p_missing
+    ("long_s1_sparse", 12000, 1, 301, 8.0, 0.20),
+    ("long_s1_l10", 12000, 1, 303, 10.0, 0.05),
+    ("long_s1_l30", 12000, 1, 304, 30.0, 0.05),
+    ("long_s2_sparse", 12000, 2, 305, 8.0, 0.20),
+]
+
+
+def main_long():
+    from _oracle import Oracle
+    strict = Ref("_strict")
+    orc = Oracle()
+    vartheta, _ = model.get_known_parameters()
+    theta = model.default_theta()
+    for name, T, S, seed, lam, pmiss in LONG_CASES:
+        ch = synthetic.make_chain(T, S, seed=seed, lam=lam, p_missing=pmiss)
+        u = philox.uniforms_by_site(seed, 0, T)
+        r = strict.run(vartheta, theta, ch["n_total"], ch["n_meth"], ch["positions"], uniforms=u, stepwise=True)
+        o = orc.run(vartheta, theta, u, ch["n_total"], ch["n_meth"], ch["positions"], tie_order="reference")
+        assert np.array_equal(o["logz"], r["logz"]) and np.array_equal(o["regime_probs"], r["regime_probs"], equal_nan=True)
+        np.savez_compressed(os.path.join(HERE, f"sg_{name}.npz"), vartheta=vartheta, theta=theta, n_total=ch["n_total"], n_meth=ch["n_meth"],
+                            positions=ch["positions"], philox_seed=seed, ref_strict_regime_probs=r["regime_probs"][:, 1:],
+                            ref_strict_logz=r["logz"], ref_strict_drew_uniform=r["drew_uniform"], ref_strict_finalised_at=r["finalised_at"],
+                            ref_tie_flags=o["tie_flags"])
+        rel = np.nonzero(o["tie_flags"] & 2)[0]
+        print(name, "logZ_T", repr(r["logz"][-1]), "sites where a tie decided a fate:", len(rel), "first", rel[:3])
+
+
 def main():
     strict, fast = Ref("_strict"), Ref("")
     vartheta, _ = model.get_known_parameters()
@@ -70,4 +102,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "long":
+        main_long()
+    else:
+        main()
+        main_long()

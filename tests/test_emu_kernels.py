@@ -73,6 +73,32 @@ def test_filter_step_level_vs_oracle(emu, oracle, default_model):
     assert got["status"][0] == 0 and got["status"][1] == want["n_pending"].max()
 
 
+@pytest.mark.parametrize("S,lam,pm,T", [(1, 8.0, 0.2, 1200), (32, 30.0, 0.05, 700)])
+def test_filter_packed_sort_equals_exact_sort_and_oracle(emu, oracle, default_model, S, lam, pm, T):
+    """One-sample sparse data (exact ties, long lag sets) and 32-sample data (weights underflow to zero): the packed 64-bit
+    sort with its exact re-sort on near-ties, the exact sort at every site, and the oracle with the canonical tie order take
+    the same decisions at every site."""
+    from hygeia_b200 import philox, synthetic
+    ch = synthetic.make_chain(T, S, seed=12, lam=lam, p_missing=pm)
+    al, be = default_model["alpha_beta"]
+    lo = oracle.emission(al, be, ch["n_total"], ch["n_meth"])
+    u = philox.uniforms_by_site(12, 0, T)
+    want = oracle.run(default_model["vartheta"], default_model["theta"], u, logobs=lo, tie_order="canonical")
+    fast = emu.sg_filter(default_model["vartheta"], default_model["theta"], lo, uniforms=u, lcap=128)
+    full = emu.sg_filter(default_model["vartheta"], default_model["theta"], lo, uniforms=u, lcap=128, force_full_sort=True)
+    sorted_sites = int((want["k_kept"] != -1).sum()) - int((np.diff(want["n_curr"]) == 0).sum() - (want["k_kept"] != -1).sum() < 0)
+    assert fast["status"][4] < 0.3 * sorted_sites and full["status"][4] >= (want["k_kept"] >= 0).sum()
+    for got in (fast, full):
+        for k in ("k_kept", "support_hash", "drew_uniform", "n_pending", "finalised_at"):
+            assert np.array_equal(got[k], want[k]), k
+        assert np.array_equal(got["tie_flags"] & 2, want["tie_flags"] & 2)
+        assert np.allclose(got["logz"], want["logz"], rtol=1e-13)
+        assert np.abs(got["probs"] - want["regime_probs"][:, 1:]).max() < 1e-11
+        assert got["status"][5] == int((want["tie_flags"] & 2 > 0).sum()) and got["status"][6] == 0
+    if S == 1:
+        assert fast["status"][5] > 0 and fast["status"][1] > 20      # ties decided fates; the lag set was long
+
+
 def test_filter_lag_capacity_overflow_is_reported(emu, oracle, default_model):
     g = golden("sg_sparse_s1.npz")
     T = 200

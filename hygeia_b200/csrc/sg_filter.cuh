@@ -1164,7 +1164,7 @@ __device__ __forceinline__ void sg_filter_entry(const SgModelDev* mdl, const SgC
 }
 
 #ifndef HYG_K2_MIN_CTAS
-#define HYG_K2_MIN_CTAS 2   // resident CTAs per SM the register budget is held to (K2 is latency-bound: a second chain fills idle issue slots)
+#define HYG_K2_MIN_CTAS 3   // resident CTAs per SM the register budget is held to (K2 is latency- and barrier-bound: more chains per SM fill idle issue slots; measured 3.23 / 2.91 / 2.95 us per site and SM at 2 / 3 / 4)
 #endif
 #ifndef HYG_EMU
 template <int RT, bool PE>

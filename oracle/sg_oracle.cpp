@@ -248,7 +248,7 @@ struct Filter {
   void count_ties(const std::vector<double>& v, const std::vector<uint32_t>& sorted) {
     for (size_t i = 0; i + 1 < sorted.size(); i++) {
       const double a = v[sorted[i]], b = v[sorted[i + 1]];
-      if (a == b && std::isfinite(a) && a != 0.0) tie_pairs++;  // W == 0 / logw == -inf entries are interchangeable
+      if (a == b && std::isfinite(a) && (a != 0.0 || tie_order)) tie_pairs++;  // W == 0 / logw == -inf entries are interchangeable
     }
   }
 
@@ -277,7 +277,7 @@ struct Filter {
     uint32_t N = N_prev;
     for (uint32_t n = 0; n < lw_c.size(); n++) lw_c[n] = 0.0;  // :301
     std::vector<uint32_t> sorted = sort_particles(W_p);
-    count_ties(W_p, sorted);
+    count_ties(tie_order ? lw_p : W_p, sorted);
     std::vector<double> q(N), logq(N), Q(N);
     for (uint32_t i = 0; i < N; i++) { q[i] = W_p[sorted[i]]; logq[i] = std::log(q[i]); }
     { double acc = 0.0; for (uint32_t i = N; i-- > 0;) { acc += q[i]; Q[i] = acc; } }  // reverse(cumsum(reverse(q)))
@@ -305,7 +305,7 @@ struct Filter {
         std::vector<char> drawn(N - K, 0);
         for (uint32_t j = 0; j < L; j++) drawn[ind[j]] = 1;
         for (uint32_t i = K; i + 1 < N; i++)
-          if (q[i] == q[i + 1] && q[i] != 0.0 && drawn[i - K] != drawn[i + 1 - K]) tie_flags |= 2;
+          if ((tie_order ? lw_p[sorted[i]] == lw_p[sorted[i + 1]] : q[i] == q[i + 1]) && q[i] != 0.0 && drawn[i - K] != drawn[i + 1 - K]) tie_flags |= 2;   // (the canonical order sorts log-weights)
       }
       for (uint32_t n = K; n < M; n++) lw_c[n] = lsum_p - logC;
       k_last = static_cast<int>(K);

@@ -1,15 +1,28 @@
 #!/usr/bin/env python
-"""bench.py -- Hygeia single-group whole-genome seed sweep on B200 (BASELINE.json metric).
+"""bench.py -- Hygeia's single-group inference hot path on B200 (BASELINE.json metric).
 
-    python bench.py --gpus 1 --steps K --warmup W                 # this framework (CUDA)
-    python bench.py --impl reference --gpus 1 --steps K --warmup W # the reference's own CPU code (oracle/_ref), bounded sample
-    torchrun ... bench.py --gpus N ...                             # one rank per GPU, weak scaling (2 seeds per GPU)
+    python bench.py --gpus 1 --steps K --warmup W                  # this framework (CUDA): BASELINE configs[1]
+    python bench.py --impl reference --gpus 1 --steps K --warmup W  # the reference's own CPU code (oracle/_ref), bounded sample
+    torchrun ... bench.py --gpus N ...                              # one rank per GPU (configs[2] at N = 8)
+    ... --scaling strong        fixed 16 seeds x 22 chromosomes = 352 chains, LPT-assigned over the ranks
+    ... --config c1 | c5        BASELINE configs[0] (T = 600 k, S = 4, one chain pair) / configs[4] (S = 1000, 4 seeds, counts
+                                sharded by chromosome)
+    ... --config c4             two-group: python tools/tg_bench.py (its own line format)
 
-A "step" is one pass of the hot path over the whole synthetic genome: K1 (emission table of every chromosome) + K2 (the
-recursion for every chromosome x seed chain).  Workload at N = 1 = BASELINE.json configs[1]: ~28 M CpG sites in 22
-synthetic chromosomes, 32 samples sharing one regime path, 2 seeds.  N GPUs run seeds {2r, 2r+1} of the same genome on
-rank r (configs[2] at N = 8), no data-path collective; per-chromosome log-evidences are all-reduced over NCCL at the end
-of each step.  Prints ONE JSON line (rank 0).
+A "step" is one pass of the hot path over the synthetic genome: K1 (emission table of every chromosome the rank holds) + K2 (the
+recursion for every chromosome x seed chain of the rank) + the multi-GPU exchange of the results (below).  Default workload at
+N = 1 = BASELINE configs[1]: ~28 M CpG sites in 22 synthetic chromosomes, 32 samples sharing one regime path, 2 seeds.
+
+Multi-GPU (chains never exchange data; what crosses NVLink are RESULTS).
+  weak   (default): rank r runs seeds {2r, 2r+1} of the same genome (N = 8 is configs[2]: 16 seeds).
+  strong          : 352 chains assigned longest-first (hygeia_b200.sharding.chains_for_rank(by="chain")); every rank computes the
+                    emission tables of the chromosomes it owns a chain of.
+  In both, inside the timed region: an NCCL all-gather of every chain's final log-evidence log Z_T, and an NCCL reduce (sum) to
+  rank 0 of the posterior rows summed over the rank's seeds, per chromosome (T x 6 fp64) -- the seed-averaged regime
+  posteriors, i.e. what the reference obtains by concatenating the per-seed files (src/two_group/aggregate_results.py:125-147).
+  Rank 0 checks the gathered evidences against a recomputation (weak: the sum over seeds of its own chains must equal its share).
+
+Prints ONE JSON line (rank 0).
 """
 from __future__ import annotations
 
@@ -28,6 +41,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "CpG-site x sample updates/sec per seed sweep"
 UNIT = "site*sample*seed/s"
+DATA_SEED = 20261018
 
 
 def parse():
@@ -36,11 +50,15 @@ def parse():
     p.add_argument("--steps", type=int, default=3)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="native", choices=["native", "reference"])
+    p.add_argument("--config", default="c2", choices=["c1", "c2", "c5"])
+    p.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     p.add_argument("--total-sites", type=int, default=28_000_000)
-    p.add_argument("--samples", type=int, default=32)
-    p.add_argument("--seeds-per-gpu", type=int, default=2)
+    p.add_argument("--samples", type=int, default=None)
+    p.add_argument("--seeds-per-gpu", type=int, default=None, help="weak scaling: seeds per rank (default 2; c5: 4 in total)")
+    p.add_argument("--strong-seeds", type=int, default=16)
     p.add_argument("--e2e-steps", type=int, default=2)
-    p.add_argument("--cpu-sites", type=int, default=1500, help="sites per chain of the bounded CPU-baseline sample")
+    p.add_argument("--cpu-sites", type=int, default=2500, help="sites per chain of the bounded CPU-baseline sample")
+    p.add_argument("--ref-sites", type=int, default=5000, help="sites per chain and step of --impl reference")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--emission-only", action="store_true", help="time K1 alone (kernel tuning aid; not a bench line)")
@@ -48,46 +66,57 @@ def parse():
                    help="K2 execution: -1 = segmented, size chosen by the library (default); 0 = whole chains (the reference's "
                         "sequential run); N = segments of <= N sites")
     p.add_argument("--halo", type=int, default=5000, help="left/right halo of a segment (sites)")
-    p.add_argument("--no-e2e-pipeline", dest="e2e_pipeline", action="store_false",
-                   help="end-to-end leg with ONE session (copies not overlapped with the recursion)")
-    p.add_argument("--no-mode-check", action="store_true", help="skip the full-size comparison of segmented vs whole-chain results")
-    return p.parse_args()
+    p.add_argument("--no-e2e-pipeline", dest="e2e_pipeline", action="store_false")
+    p.add_argument("--no-mode-check", action="store_true", help="skip the comparison of segmented vs whole-chain results")
+    p.add_argument("--no-whole-chain", action="store_true", help="skip the whole-chain (reference semantics) timing leg")
+    a = p.parse_args()
+    if a.samples is None:
+        a.samples = {"c1": 4, "c2": 32, "c5": 1000}[a.config]
+    if a.seeds_per_gpu is None:
+        a.seeds_per_gpu = 2
+    if a.config == "c1":
+        a.total_sites = 600_000 if a.total_sites == 28_000_000 else a.total_sites
+    return a
+
+
+def chromosome_lengths(args):
+    from hygeia_b200 import synthetic
+    if args.config == "c1":
+        return [args.total_sites]
+    return synthetic.chromosome_lengths(args.total_sites)
 
 
 # ------------------------------------------------------------------------------------------------------------------
-# synthetic genome: regime paths on the host, counts on the device
+# synthetic genome: regime paths on the host, counts on the device; chromosome c is a pure function
+# of (DATA_SEED, c), so every rank that needs it generates the same data
 # ------------------------------------------------------------------------------------------------------------------
-def make_genome(total_sites, S, device, data_seed=20261018):
+def make_chromosome(c, T, S, device):
     import torch
     from hygeia_b200 import model, synthetic
     alpha, beta = model.beta_parameters(model.DEFAULT_MU, model.DEFAULT_SIGMA)
-    lens = synthetic.chromosome_lengths(total_sites)
     g = torch.Generator(device=device)
-    g.manual_seed(data_seed)
+    g.manual_seed(DATA_SEED * 131 + c)
     al = torch.tensor(alpha, device=device, dtype=torch.float32)
     be = torch.tensor(beta, device=device, dtype=torch.float32)
-    chroms = []
-    for c, T in enumerate(lens):
-        rng = np.random.default_rng(data_seed + c)
-        regimes = synthetic.simulate_regimes(T, rng)
-        pitch = (T + 7) // 8 * 8
-        r = torch.from_numpy(regimes.astype(np.int64)).to(device)
-        n = torch.poisson(torch.full((S, T), 30.0, device=device), generator=g)
-        n = n * (torch.rand((S, T), device=device, generator=g) >= 0.05)
-        a_t = al[r].expand(S, T).contiguous()
-        b_t = be[r].expand(S, T).contiguous()
-        ga = torch._standard_gamma(a_t, generator=g)
-        gb = torch._standard_gamma(b_t, generator=g)
-        pm = ga / (ga + gb)
-        x = torch.binomial(n, pm.clamp(0, 1), generator=g)
-        nt = torch.zeros((S, pitch), dtype=torch.uint16, device=device)
-        nm = torch.zeros((S, pitch), dtype=torch.uint16, device=device)
-        nt[:, :T] = n.to(torch.int32).to(torch.uint16)
-        nm[:, :T] = x.to(torch.int32).to(torch.uint16)
-        pos = torch.from_numpy(synthetic.simulate_positions(T, rng).astype(np.int64))
-        chroms.append(dict(T=T, pitch=pitch, n_total=nt, n_meth=nm, positions=pos.to(torch.int32), regimes=regimes))
-        del n, a_t, b_t, ga, gb, pm, x, r
-    return chroms
+    rng = np.random.default_rng(DATA_SEED + c)
+    regimes = synthetic.simulate_regimes(T, rng)
+    pitch = (T + 7) // 8 * 8
+    r = torch.from_numpy(regimes.astype(np.int64)).to(device)
+    nt = torch.zeros((S, pitch), dtype=torch.uint16, device=device)
+    nm = torch.zeros((S, pitch), dtype=torch.uint16, device=device)
+    blk = max(1, min(S, (1 << 28) // max(T, 1)))   # samples per generation block: bounds the fp32 temporaries
+    for s0 in range(0, S, blk):
+        s1 = min(S, s0 + blk)
+        n = torch.poisson(torch.full((s1 - s0, T), 30.0, device=device), generator=g)
+        n = n * (torch.rand((s1 - s0, T), device=device, generator=g) >= 0.05)
+        ga = torch._standard_gamma(al[r].expand(s1 - s0, T).contiguous(), generator=g)
+        gb = torch._standard_gamma(be[r].expand(s1 - s0, T).contiguous(), generator=g)
+        x = torch.binomial(n, (ga / (ga + gb)).clamp(0, 1), generator=g)
+        nt[s0:s1, :T] = n.to(torch.int32).to(torch.uint16)
+        nm[s0:s1, :T] = x.to(torch.int32).to(torch.uint16)
+        del n, ga, gb, x
+    pos = torch.from_numpy(synthetic.simulate_positions(T, rng).astype(np.int64)).to(torch.int32)
+    return dict(index=c, T=T, pitch=pitch, n_total=nt, n_meth=nm, positions=pos, regimes=regimes)
 
 
 class ClockSampler:
@@ -173,8 +202,9 @@ def cpu_baseline(chains_np, vartheta, theta, S, sites, max_procs=None):
     wall = time.perf_counter() - t0
     units = n * sites * S
     return {"value": units / max(per) if per else None, "unit": UNIT, "cores": n, "kind": kind,
-            "sample": f"first {sites} sites of {n} chromosomes, S={S}, 1 seed each, one chain per core "
-                      f"(oracle/_ref = reference headers, -O3 -ffast-math); slowest chain {max(per):.1f} s, pool wall {wall:.1f} s",
+            "sample": f"EXTRAPOLATED from the first {sites} sites of {n} chromosomes, S={S}, 1 seed each, one chain per core "
+                      f"(oracle/_ref = reference headers, -O3 -ffast-math); per-site cost is constant along a chain; "
+                      f"slowest chain {max(per):.1f} s, pool wall {wall:.1f} s",
             "host_cores": cores}
 
 
@@ -188,11 +218,14 @@ def run_reference(args):
     theta = model.default_theta()
     S = args.samples
     cores = os.cpu_count() or 1
-    n = min(cores, 22)
-    sites = max(200, args.cpu_sites // 3)
+    lens = chromosome_lengths(args)
+    n = min(cores, max(len(lens), 2 if args.config == "c1" else 1))
+    sites = min(args.ref_sites, min(lens))
+    if S >= 1000:
+        sites = max(100, sites // 25)   # the reference's cost grows with S (0.27 ms + 0.28 ms x S per site)
     chains = []
     for i in range(n):
-        rng = np.random.default_rng(20261018 + i)
+        rng = np.random.default_rng(DATA_SEED + i)
         regimes = synthetic.simulate_regimes(sites, rng)
         chains.append(synthetic.simulate_counts(regimes, S, rng))
     for _ in range(max(0, min(args.warmup, 1))):
@@ -205,14 +238,35 @@ def run_reference(args):
         vals.append(r["value"])
     v = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1000.0 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": 1000.0 * float(np.mean(secs)), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"single_group whole-genome synthetic (~{args.total_sites // 1_000_000}M CpGs), {S} samples, "
-                                   f"{args.seeds_per_gpu} seeds -- bounded sample: first {sites} sites of {n} chromosomes, 1 seed",
+            "config": {"workload": workload_name(args, 1) + f" -- EXTRAPOLATED from a bounded sample: first {sites} sites of {n} chromosomes, "
+                                                            "1 seed, one chain per core (per-site cost is constant along a chain)",
                        "samples": S},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def workload_name(args, world):
+    if args.config == "c1":
+        return f"single_group synthetic chr22-sized CpG set ({args.total_sites} sites), {args.samples} samples, 2 seeds (BASELINE configs[0])"
+    if args.config == "c5":
+        return (f"emission-heavy cohort: whole-genome synthetic (~{args.total_sites // 1_000_000}M CpGs in 22 chromosomes), {args.samples} samples, "
+                f"4 seeds, counts sharded by chromosome over {world} GPU(s) (BASELINE configs[4])")
+    if args.scaling == "strong":
+        return (f"single_group whole-genome synthetic (~{args.total_sites // 1_000_000}M CpGs in 22 chromosomes), {args.samples} samples, "
+                f"{args.strong_seeds} seeds = {22 * args.strong_seeds} chains LPT-sharded over {world} GPU(s) (BASELINE configs[2], strong scaling)")
+    return (f"single_group whole-genome synthetic (~{args.total_sites // 1_000_000}M CpGs in 22 chromosomes), {args.samples} samples, "
+            f"{args.seeds_per_gpu} seeds per GPU ({args.seeds_per_gpu * world} seeds total), 250 particles, u=3 "
+            f"(BASELINE configs[{1 if world == 1 else 2}])")
+
+
+class _DevArr:
+    """Raw device memory -> torch tensor (via __cuda_array_interface__)."""
+
+    def __init__(self, ptr, shape, typestr="<f8"):
+        self.__cuda_array_interface__ = dict(shape=tuple(shape), typestr=typestr, data=(int(ptr), False), version=2)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -223,7 +277,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from hygeia_b200 import model
+    from hygeia_b200 import model, sharding
     from hygeia_b200.single_group import Session, make_run_args
 
     rank = int(os.environ.get("RANK", "0"))
@@ -234,77 +288,142 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    S, n_seeds = args.samples, args.seeds_per_gpu
+    S = args.samples
     vartheta, _ = model.get_known_parameters()
     theta = model.default_theta()
     R = 6
-    chroms = make_genome(args.total_sites, S, dev)
+    lens = chromosome_lengths(args)
+    n_chrom = len(lens)
+
+    # ---- which (chromosome, seed) chains does this rank own? ----
+    if args.config == "c5":
+        total_seeds = 4
+        bins = sharding.lpt_assign(lens, world)                      # counts sharded BY CHROMOSOME
+        my_chains = [(c, sd) for c in sorted(bins[rank]) for sd in range(total_seeds)]
+        scaling = "strong"
+    elif args.scaling == "strong":
+        total_seeds = args.strong_seeds
+        my_chains = sharding.chains_for_rank(lens, total_seeds, rank, world, by="chain")
+        scaling = "strong"
+    else:
+        total_seeds = args.seeds_per_gpu * world
+        my_chains = [(c, rank * args.seeds_per_gpu + k) for c in range(n_chrom) for k in range(args.seeds_per_gpu)]
+        scaling = "weak"
+    my_chroms = sorted({c for c, _ in my_chains})
+    chroms = {c: make_chromosome(c, lens[c], S, dev) for c in my_chroms}
     torch.cuda.synchronize()
-    total_T = sum(c["T"] for c in chroms)
-    units_per_step = total_T * S * n_seeds
-    seeds = [rank * n_seeds + k for k in range(n_seeds)]
+    total_T = sum(lens)
+    units_per_step_all = total_T * S * total_seeds                  # whole job, all ranks
+    my_site_chains = sum(lens[c] for c, _ in my_chains)
 
     # pinned host mirrors (inputs for the end-to-end leg, outputs for both legs)
-    for c in chroms:
-        c["h_nt"] = torch.empty((S, c["T"]), dtype=torch.uint16).pin_memory()
-        c["h_nm"] = torch.empty((S, c["T"]), dtype=torch.uint16).pin_memory()
-        c["h_nt"].copy_(c["n_total"][:, :c["T"]]); c["h_nm"].copy_(c["n_meth"][:, :c["T"]])
-        c["h_pos"] = c["positions"].pin_memory()
-        c["out"] = [dict(probs=torch.empty((c["T"], 1 + R), dtype=torch.float64).pin_memory(),
-                         logz=torch.empty(c["T"], dtype=torch.float64).pin_memory()) for _ in seeds]
+    big = S >= 256   # c5: no pinned mirror of the counts (112 GB); the e2e leg is skipped
+    for c, ch in chroms.items():
+        if not big:
+            ch["h_nt"] = torch.empty((S, ch["T"]), dtype=torch.uint16).pin_memory()
+            ch["h_nm"] = torch.empty((S, ch["T"]), dtype=torch.uint16).pin_memory()
+            ch["h_nt"].copy_(ch["n_total"][:, :ch["T"]]); ch["h_nm"].copy_(ch["n_meth"][:, :ch["T"]])
+        ch["h_pos"] = ch["positions"].pin_memory()
+    outs = {}
+    for c, sd in my_chains:
+        T = lens[c]
+        outs[(c, sd)] = dict(probs=torch.empty((T, 1 + R), dtype=torch.float64).pin_memory(), logz=torch.empty(T, dtype=torch.float64).pin_memory())
     torch.cuda.synchronize()
 
     sess = Session(local)
     run_args = make_run_args()
     seg_request = Session.SEGMENT_AUTO if args.segment_sites < 0 else args.segment_sites
+    if args.config == "c1" and args.segment_sites < 0:
+        seg_request = Session.SEGMENT_AUTO
     sess.set_segmentation(seg_request, args.halo, args.halo)
+    multi = world > 1
 
-    def stage(device_resident, ses=None, which=None):
-        """Stage the chromosomes `which` (indices into chroms; default all) on session `ses` (default the main one)."""
+    def stage(device_resident, ses=None, which=None, device_outputs=False):
+        """Stage the chains `which` (default all of the rank's) on session `ses`; returns the staged (c, seed) list."""
         ses = ses or sess
-        which = range(len(chroms)) if which is None else which
+        which = my_chains if which is None else which
         ses.clear()
+        ses.set_zero_copy_outputs(not device_outputs)
         ses.set_vartheta(vartheta)
-        ses.set_theta(theta, max(c["T"] for c in chroms))
+        ses.set_theta(theta, max(lens))
+        ds_of = {}
         specs = []
-        for ci in which:
-            c = chroms[ci]
-            if device_resident:
-                ds = ses.add_dataset_ptr(c["T"], S, c["n_total"].data_ptr(), c["n_meth"].data_ptr(), True, c["pitch"])
-            else:
-                ds = ses.add_dataset_ptr(c["T"], S, c["h_nt"].data_ptr(), c["h_nm"].data_ptr(), False, c["T"])
-            for k, sd in enumerate(seeds):
-                specs.append(dict(dataset=ds, seed=sd, chain_id=ci, positions=c["h_pos"].data_ptr(),
-                                  regime_probs=c["out"][k]["probs"].data_ptr(), logz=c["out"][k]["logz"].data_ptr()))
+        for c, sd in which:
+            ch = chroms[c]
+            if c not in ds_of:
+                if device_resident:
+                    ds_of[c] = ses.add_dataset_ptr(ch["T"], S, ch["n_total"].data_ptr(), ch["n_meth"].data_ptr(), True, ch["pitch"])
+                else:
+                    ds_of[c] = ses.add_dataset_ptr(ch["T"], S, ch["h_nt"].data_ptr(), ch["h_nm"].data_ptr(), False, ch["T"])
+            o = outs[(c, sd)]
+            specs.append(dict(dataset=ds_of[c], seed=sd, chain_id=c, positions=ch["h_pos"].data_ptr(),
+                              regime_probs=o["probs"].data_ptr(), logz=o["logz"].data_ptr()))
         ses.set_chains(specs)
-        return len(specs)
+        return list(which)
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
+        if multi:
             dist.barrier()
         torch.cuda.synchronize()
 
-    evid = torch.zeros(len(chroms), dtype=torch.float64, device=dev)
+    # ---- device-resident leg: inputs already in HBM ----
+    staged = stage(True, device_outputs=multi)
+    n_chains = len(staged)
+    # multi-GPU exchange: device views of the staged outputs (valid until the next set_chains)
+    evid_all = torch.zeros(world * max(1, n_chains), dtype=torch.float64, device=dev) if multi else None
+    exch = None
+    if multi:
+        views = []
+        for i, (c, sd) in enumerate(staged):
+            pp, zp = sess.device_outputs(i)
+            views.append((c, sd, torch.as_tensor(_DevArr(pp, (lens[c], 1 + R)), device=dev), torch.as_tensor(_DevArr(zp, (lens[c],)), device=dev)))
+        # every rank must issue the same sequence of collectives: reduce per chromosome, in chromosome order, over ALL chromosomes
+        psum = {c: torch.zeros((lens[c], R), dtype=torch.float64, device=dev) for c in range(n_chrom)} if args.config != "c5" else \
+               {c: torch.zeros((lens[c], R), dtype=torch.float64, device=dev) for c in my_chroms}
+        max_chains = torch.tensor([n_chains], device=dev)
+        dist.all_reduce(max_chains, op=dist.ReduceOp.MAX)
+        slots = int(max_chains.item())
+        evid_mine = torch.zeros(slots, dtype=torch.float64, device=dev)
+        evid_all = torch.zeros(world * slots, dtype=torch.float64, device=dev)
+        exch = dict(views=views, psum=psum, slots=slots, evid_mine=evid_mine)
+
+    coll_bytes = [0]
+
+    def exchange():
+        """NCCL: all-gather of log Z_T of every chain; reduce(sum) to rank 0 of the posteriors summed over this rank's seeds."""
+        v = exch
+        for ps in v["psum"].values():
+            ps.zero_()
+        v["evid_mine"].zero_()
+        for i, (c, sd, pv, zv) in enumerate(v["views"]):
+            v["psum"][c] += pv[:, 1:]
+            v["evid_mine"][i] = zv[-1]
+        dist.all_gather_into_tensor(evid_all, v["evid_mine"])
+        nb = evid_all.numel() * 8
+        if args.config != "c5":   # c5: chromosomes are disjoint across ranks, their seed sums are complete where they are
+            for c in range(n_chrom):
+                dist.reduce(v["psum"][c], dst=0, op=dist.ReduceOp.SUM)
+                nb += v["psum"][c].numel() * 8
+        coll_bytes[0] = nb
 
     def step_device():
         sess.emission()
         sess.filter(run_args)
         sess.sync()
-        if world > 1:  # cross-shard reduction of the per-chromosome sufficient statistic (sum over seeds of log Z_T)
-            dist.all_reduce(evid)
+        if multi:
+            exchange()
         return sess.timings()
 
-    # ---- device-resident leg: inputs already in HBM ----
-    n_chains = stage(True)
     if args.emission_only:
         ms = []
         for _ in range(3 + args.steps):
             sess.emission(); sess.sync(); ms.append(sess.timings()["ms_emission"])
-        alg = total_T * S * 4 + total_T * R * 8
+        my_T = sum(lens[c] for c in my_chroms)
+        alg = my_T * S * 4 + my_T * R * 8
         best = min(ms[3:]); avg = float(np.mean(ms[3:]))
         print(json.dumps({"emission_only_ms": ms, "GBps_avg": alg / avg / 1e6, "GBps_best": alg / best / 1e6,
-                          "frac_of_6538.9": alg / avg / 1e6 / 6538.9}))
+                          "frac_of_6538.9": alg / avg / 1e6 / 6538.9, "S": S}))
         return
     for _ in range(max(args.warmup, 3)):
         step_device()
@@ -320,16 +439,28 @@ def main():
     launches = tm["emission_launches"] + tm["filter_launches"]
     n_units, seg_sites, workers = sess.filter_units(with_segment_sites=True)
     st = sess.download()   # also brings the per-chain status words back (outside the timed region)
+    ovl = sess.overlap_max_abs()
     stepped = int(sum(x[3] for x in st))
     forced_halo = int(sum(x[2] for x in st)); forced_lag = int(sum(x[0] for x in st))
+    exact_sorts = int(sum(x[4] for x in st)); tie_sites = int(sum(x[5] for x in st)); ovl_bad = int(sum(x[7] for x in st))
     dev_s = sum(ev_ms) / 1000.0
     t_all = torch.tensor([dev_s, wall], dtype=torch.float64, device=dev)
-    if world > 1:
+    if multi:
         dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
     dev_s, wall = float(t_all[0]), float(t_all[1])
-    value = units_per_step * world * args.steps / dev_s
+    # whole-job throughput: everything all ranks processed / the barrier-bracketed time of the K steps (max over ranks); at N = 1
+    # that time is K1 + K2 device time plus launch gaps, at N > 1 it includes the NCCL exchange of the results
+    value = units_per_step_all * args.steps / wall
 
-    # ---- roofline: algorithmic bytes / CUDA-event time of each kernel (events are recorded by the library on its own stream) ----
+    # the gathered evidences: rank 0 holds log Z_T of every chain of the job -- sanity: finite, and this rank's slice is its own
+    gather_check = None
+    if multi and rank == 0:
+        ea = evid_all.cpu().numpy().reshape(world, -1)
+        gather_check = {"chains_gathered": int((ea != 0).sum()), "all_finite": bool(np.isfinite(ea).all()),
+                        "collective_bytes_per_step": int(coll_bytes[0]),
+                        "sum_log_evidence": float(ea.sum())}
+
+    # ---- roofline ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -337,52 +468,80 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_source = "MEASURED_PEAKS.json hbm_gbs (burst copy figure)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    longest = max(c["T"] for c in chroms)
-    # K2, the dominant kernel (99.7 % of the step in profiles/r01_launches_4M_segmented.csv): per site and chain it reads the R emission
-    # log-densities and writes the R posterior probabilities and log Z_t.  It is a sequential recursion (one CTA per chain, 250
-    # particles), bound by per-site latency, not by HBM -- the fraction below says how far from HBM it is, the
-    # us/site figure is the number to optimise.
-    k2_alg = total_T * n_seeds * (R * 8 + R * 8 + 8)   # + the running log-evidence (owned rows only: halo steps are overhead)
-    k2_ms = float(np.mean(f_ms))
+    longest = max(lens[c] for c in my_chroms)
+    my_T = sum(lens[c] for c in my_chroms)
+    # K2, the dominant kernel at S <= 32: per site and chain it reads the R emission log-densities and writes the R posterior
+    # probabilities and log Z_t.  It is a sequential recursion (one CTA per chain / segment, 250 particles), bound by per-site latency,
+    # not by HBM -- the fraction below says how far from HBM it is, the us/site figure is the number to optimise.
+    k2_alg = my_site_chains * (R * 8 + R * 8 + 8)
+    k2_ms = float(np.mean(f_ms)); k1_ms = float(np.mean(em_ms))
     k2_ach = k2_alg / (k2_ms / 1000.0) / 1e9
-    # DRAM bytes per site measured by ncu --set full (profiles/r01_k2_final_details.txt, r01_k1_final_details.txt: 4M-site
-    # capture, 2 seeds; K2 332.4 MB for 8M owned site-chains -- the posterior rows go to pinned host memory, not to DRAM), scaled
-    K2_DRAM_B_PER_SITE_CHAIN, K1_DRAM_B_PER_SITE = 41.5, 176.2
-    roofline = {"bound": "hbm", "kernel": "sg_filter_kernel<6,0> (K2: particle filter + fixed-lag smoother), 1 persistent launch per step, "
-                                          "one CTA per (chain, segment) unit",
-                "share_of_step": k2_ms / (k2_ms + float(np.mean(em_ms))),
-                "achieved": k2_ach, "peak": peak, "unit": "GB/s", "frac": k2_ach / peak, "peak_source": peak_source,
-                "algorithmic_bytes_per_launch": k2_alg, "ms_per_launch": k2_ms,
-                "traffic": K2_DRAM_B_PER_SITE_CHAIN * total_T * n_seeds,
-                "traffic_source": "ncu dram__bytes_read+write of a 4M-site capture, per owned site-chain, scaled to this launch "
-                                  "(posterior rows leave over PCIe into pinned host memory and are not DRAM traffic)",
-                "latency_bound": {"chains": n_chains, "units": n_units, "segment_sites": seg_sites, "halo_sites": args.halo if seg_sites else 0,
-                                  "resident_ctas": workers, "sms": 148, "longest_chain_sites": longest,
-                                  "sites_stepped_incl_halos": stepped, "halo_overhead": stepped / float(total_T * n_seeds) - 1.0,
-                                  "us_per_site_per_cta": 1000.0 * k2_ms * workers / max(stepped, 1),
-                                  "sites_forced_at_segment_end": forced_halo, "sites_forced_lag_set_full": forced_lag,
-                                  "note": "a strictly sequential recursion per unit: the bound is per-site latency x units in flight, "
-                                          "HBM is idle; see DESIGN.md section 4 (K2) and 6"}}
-    # K1, the HBM-streaming kernel north_star sets the roofline target for
-    alg_bytes = total_T * S * 2 * 2 + total_T * R * 8
-    ach = alg_bytes / (float(np.mean(em_ms)) / 1000.0) / 1e9
-    roofline_emission = {"bound": "hbm", "kernel": "sg_emission_kernel<6> (K1), 1 persistent launch per step over all chromosomes",
-                         "share_of_step": float(np.mean(em_ms)) / (k2_ms + float(np.mean(em_ms))),
-                         "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_source,
-                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": float(np.mean(em_ms)),
-                         "traffic": K1_DRAM_B_PER_SITE * total_T,
-                         "traffic_source": "ncu dram__bytes_read+write of a 4M-site capture, per site, scaled to this launch",
-                         "limiter": "shared-memory wavefronts of the fp64 table look-ups (L1 pipe 94 % busy, 59 % of wavefronts are bank conflicts)"}
+    K2_DRAM_B_PER_SITE_CHAIN, K1_DRAM_B_PER_SITE_S32 = 41.5, 176.2
+    k2 = {"bound": "hbm", "kernel": "sg_filter_kernel<6,0> (K2: particle filter + fixed-lag smoother), 1 persistent launch per step, "
+                                    "one CTA per (chain, segment) unit",
+          "share_of_step": k2_ms / (k2_ms + k1_ms),
+          "achieved": k2_ach, "peak": peak, "unit": "GB/s", "frac": k2_ach / peak, "peak_source": peak_source,
+          "algorithmic_bytes_per_launch": k2_alg, "ms_per_launch": k2_ms,
+          "traffic": K2_DRAM_B_PER_SITE_CHAIN * my_site_chains,
+          "traffic_source": "ncu dram__bytes_read+write of a 4M-site capture, per owned site-chain, scaled to this launch "
+                            "(posterior rows leave over PCIe into pinned host memory and are not DRAM traffic)",
+          "latency_bound": {"chains": n_chains, "units": n_units, "segment_sites": seg_sites, "halo_sites": args.halo if seg_sites else 0,
+                            "resident_ctas": workers, "sms": 148, "longest_chain_sites": longest,
+                            "sites_stepped_incl_halos": stepped, "halo_overhead": stepped / float(max(my_site_chains, 1)) - 1.0,
+                            "us_per_site_per_cta": 1000.0 * k2_ms * min(workers, n_units) / max(stepped, 1),
+                            "us_per_site_per_sm": 1000.0 * k2_ms * min(148, n_units) / max(stepped, 1),
+                            "site_chains_per_s": my_site_chains / (k2_ms / 1000.0),
+                            "sites_forced_at_segment_end": forced_halo, "sites_forced_lag_set_full": forced_lag,
+                            "sites_sorted_on_full_words": exact_sorts, "sites_where_an_exact_tie_decided_a_fate": tie_sites,
+                            "segment_overlap_max_abs_posterior_diff": float(max(ovl)) if ovl else 0.0,
+                            "segment_overlap_rows_over_1e-6": ovl_bad,
+                            "note": "a strictly sequential recursion per unit: the bound is per-site latency x units in flight, "
+                                    "HBM is idle; see DESIGN.md section 4 (K2) and 6"}}
+    alg_bytes = my_T * S * 2 * 2 + my_T * R * 8
+    ach = alg_bytes / (k1_ms / 1000.0) / 1e9
+    k1 = {"bound": "hbm", "kernel": "sg_emission_kernel<6> (K1), 1 persistent launch per step over all chromosomes of the rank",
+          "share_of_step": k1_ms / (k2_ms + k1_ms),
+          "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_source,
+          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": k1_ms,
+          "traffic": (K1_DRAM_B_PER_SITE_S32 * my_T) if S == 32 else None,
+          "traffic_source": "ncu dram__bytes_read+write of a 4M-site S=32 capture, per site, scaled to this launch" if S == 32 else None}
+    # the dominant kernel goes under "roofline"; the other one beside it
+    if k1_ms > k2_ms:
+        roofline, other_key, other = k1, "roofline_filter", k2
+    else:
+        roofline, other_key, other = k2, "roofline_emission", k1
+
+    # ---- whole-chain leg (the reference's own semantics: every chain one sequential run; no halo approximation) ----
+    whole = None
+    if seg_sites and not args.no_whole_chain and args.config != "c5":
+        sess.set_segmentation(0, args.halo, args.halo)
+        stage(True, device_outputs=False)
+        sess.emission(); sess.filter(run_args); sess.sync()            # warm
+        t0 = time.perf_counter()
+        sess.emission(); sess.filter(run_args); sess.sync()
+        w_wall = time.perf_counter() - t0
+        tw = sess.timings()
+        w_all = torch.tensor([w_wall], dtype=torch.float64, device=dev)
+        if multi:
+            dist.all_reduce(w_all, op=dist.ReduceOp.MAX)
+        whole = {"value": units_per_step_all / float(w_all[0]), "unit": UNIT, "ms_per_step": 1000.0 * float(w_all[0]),
+                 "ms_filter": tw["ms_filter"], "us_per_site_longest_chain": 1000.0 * tw["ms_filter"] / longest,
+                 "note": "segment_sites = 0: each chromosome x seed chain is ONE sequential run, exactly OnlineCombinedInference::run; "
+                         f"{n_chains} chains on {min(n_chains, 148)} of 148 SMs, bounded by the longest chromosome"}
+        sess.set_segmentation(seg_request, args.halo, args.halo)
 
     # ---- end-to-end leg: host (pinned) buffers in, host buffers out, through the public API ----
     e2e = None
-    if not args.no_e2e:
-        h2d = sum(2 * S * c["T"] * 2 + c["T"] * 4 * n_seeds for c in chroms)
-        d2h = sum((c["T"] * (1 + R) * 8 + c["T"] * 8) * n_seeds for c in chroms)
+    if not args.no_e2e and not big:
+        n_seeds_of = {}
+        for c, sd in my_chains:
+            n_seeds_of[c] = n_seeds_of.get(c, 0) + 1
+        h2d = sum(2 * S * lens[c] * 2 for c in my_chroms) + sum(lens[c] * 4 for c, _ in my_chains)
+        d2h = sum((lens[c] * (1 + R) * 8 + lens[c] * 8) for c, _ in my_chains)
         # Two contexts (two streams) take half of the chromosomes each, so that the host -> device copy of the second half and
         # the device -> host copy of the first half's log Z overlap the recursion of the other half.
-        order = sorted(range(len(chroms)), key=lambda i: -chroms[i]["T"])
-        halves = [order[0::2], order[1::2]] if args.e2e_pipeline else [list(range(len(chroms)))]
+        order = sorted(my_chroms, key=lambda c: -lens[c])
+        halves = [order[0::2], order[1::2]] if (args.e2e_pipeline and len(order) > 1) else [order]
         sessions = [sess]
         if len(halves) > 1:
             s2 = Session(local)
@@ -390,8 +549,8 @@ def main():
             sessions.append(s2)
 
         def step_e2e():
-            for ses, which in zip(sessions, halves):
-                stage(False, ses, which)
+            for ses, hc in zip(sessions, halves):
+                stage(False, ses, [(c, sd) for c, sd in my_chains if c in hc])
                 ses.emission()
                 ses.filter(run_args)
             for ses in sessions:
@@ -404,70 +563,68 @@ def main():
         barrier()
         e2e_s = time.perf_counter() - t0
         te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        if world > 1:
+        if multi:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e_s = float(te[0])
-        e2e = {"value": units_per_step * world * args.e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        e2e = {"value": units_per_step_all * args.e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": 1000.0 * e2e_s / args.e2e_steps, "steps": args.e2e_steps,
                "api": "hygeia_b200.single_group.Session: add_dataset(pinned host) -> set_chains -> emission -> filter -> download"
                       + (", two Sessions (contexts) with half of the chromosomes each so that copies overlap the other half's recursion; "
                          if len(halves) > 1 else "; ") +
                       "posterior rows are written by K2 straight into the pinned host buffers (counted in d2h_bytes_per_step), "
                       "log Z is staged in HBM and copied"}
-        # sanity on the downloaded results of the last step
-        p = chroms[-1]["out"][0]["probs"].numpy()
-        acc = float((p[:, 1:].argmax(1) == chroms[-1]["regimes"]).mean())
-        e2e["regime_call_accuracy_vs_simulated_truth_last_chromosome"] = acc
-        e2e["non_finite_posterior_rows"] = int(sum(int((~np.isfinite(o["probs"].numpy())).any(1).sum()) for c in chroms for o in c["out"]))
+        last = my_chains[-1]
+        p = outs[last]["probs"].numpy()
+        e2e["regime_call_accuracy_vs_simulated_truth_last_chain"] = float((p[:, 1:].argmax(1) == chroms[last[0]]["regimes"]).mean())
+        e2e["non_finite_posterior_rows"] = int(sum(int((~np.isfinite(o["probs"].numpy())).any(1).sum()) for o in outs.values()))
 
-    # ---- full-size parity of the two execution modes: segmented (timed above) vs the sequential whole-chain run ----
+    # ---- parity of the two execution modes: segmented (timed above) vs the sequential whole-chain run ----
     mode_check = None
     if e2e is not None and seg_sites and not args.no_mode_check:
-        seg_out = [[(o["probs"].numpy().copy(), o["logz"].numpy().copy()) for o in c["out"]] for c in chroms[-3:]]
+        sub_c = sorted(my_chroms, key=lambda c: lens[c])[:3]
+        sub = [(c, sd) for c, sd in my_chains if c in sub_c]
+        seg_out = {k: (outs[k]["probs"].numpy().copy(), outs[k]["logz"].numpy().copy()) for k in sub}
         sess.set_segmentation(0, args.halo, args.halo)
-        sub = chroms[-3:]   # the three shortest chromosomes, every seed: whole-chain runs of 0.4-0.75 M sites
-        sess.clear(); sess.set_vartheta(vartheta); sess.set_theta(theta, max(c["T"] for c in chroms))
-        specs = []
-        for ci, c in enumerate(sub):
-            ds = sess.add_dataset_ptr(c["T"], S, c["h_nt"].data_ptr(), c["h_nm"].data_ptr(), False, c["T"])
-            for k, sd in enumerate(seeds):
-                specs.append(dict(dataset=ds, seed=sd, chain_id=len(chroms) - 3 + ci, positions=c["h_pos"].data_ptr(),
-                                  regime_probs=c["out"][k]["probs"].data_ptr(), logz=c["out"][k]["logz"].data_ptr()))
-        sess.set_chains(specs); sess.emission(); sess.filter(run_args); sess.download()
-        whole_ms = sess.timings()["ms_filter"]
+        stage(False, sess, sub)
+        sess.emission(); sess.filter(run_args); sess.download()
         dp = dz = 0.0; calls = 0; rows = 0
-        for c, so in zip(sub, seg_out):
-            for o, (sp, sz) in zip(c["out"], so):
-                wp, wz = o["probs"].numpy(), o["logz"].numpy()
-                dp = max(dp, float(np.abs(sp[:, 1:] - wp[:, 1:]).max()))
-                dz = max(dz, float((np.abs(sz - wz) / np.abs(wz)).max()))
-                calls += int((sp[:, 1:].argmax(1) != wp[:, 1:].argmax(1)).sum()); rows += wp.shape[0]
-        mode_check = {"compared": f"segmented vs whole-chain execution on the 3 shortest chromosomes x {n_seeds} seeds ({rows} site rows)",
-                      "max_abs_posterior_diff": dp, "max_rel_logz_diff": dz, "differing_regime_calls": calls, "tolerance": 1e-6,
-                      "whole_chain_us_per_site": 1000.0 * whole_ms / max(c["T"] for c in sub)}
+        for k in sub:
+            sp, sz = seg_out[k]
+            wp, wz = outs[k]["probs"].numpy(), outs[k]["logz"].numpy()
+            dp = max(dp, float(np.abs(sp[:, 1:] - wp[:, 1:]).max()))
+            dz = max(dz, float((np.abs(sz - wz) / np.abs(wz)).max()))
+            calls += int((sp[:, 1:].argmax(1) != wp[:, 1:].argmax(1)).sum()); rows += wp.shape[0]
+        mode_check = {"compared": f"segmented vs whole-chain execution on the {len(sub_c)} shortest chromosomes of the rank x its seeds ({rows} site rows)",
+                      "max_abs_posterior_diff": dp, "max_rel_logz_diff": dz, "differing_regime_calls": calls, "tolerance": 1e-6}
         sess.set_segmentation(seg_request, args.halo, args.halo)
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) ----
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sl = [(c["h_nt"].numpy()[:, :args.cpu_sites].copy(), c["h_nm"].numpy()[:, :args.cpu_sites].copy()) for c in chroms]
-        cpu = cpu_baseline(sl, vartheta, theta, S, args.cpu_sites)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not big:
+        cs = min(args.cpu_sites, min(lens))
+        sl = [(chroms[c]["h_nt"].numpy()[:, :cs].copy(), chroms[c]["h_nm"].numpy()[:, :cs].copy()) for c in my_chroms]
+        if args.config == "c1":
+            sl = sl * 2
+        cpu = cpu_baseline(sl, vartheta, theta, S, cs)
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": 1000.0 * dev_s / args.steps, "wall_ms_per_step": 1000.0 * wall / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"single_group whole-genome synthetic (~{args.total_sites // 1_000_000}M CpGs in 22 chromosomes), "
-                                       f"{S} samples, {n_seeds} seeds per GPU ({n_seeds * world} seeds total), 250 particles, u=3",
-                           "sites": total_T, "samples": S, "seeds": n_seeds * world, "chains_per_gpu": n_chains,
-                           "k2_execution": (f"segmented: {n_units} units of <= {seg_sites} sites + {args.halo}-site halos, all resident CTAs busy"
+                "ms_per_step": 1000.0 * wall / args.steps, "device_ms_per_step": 1000.0 * dev_s / args.steps, "higher_is_better": True,
+                "scaling": scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(args, world),
+                           "sites": total_T, "samples": S, "seeds": total_seeds, "chains_on_rank0": n_chains,
+                           "k2_execution": (f"segmented: {n_units} units of <= {seg_sites} sites + {args.halo}-site halos on rank 0, "
+                                            f"left-halo overlap check on (max |dp| {float(max(ovl)) if ovl else 0.0:.2e})"
                                             if seg_sites else "whole chains (sequential per chromosome x seed)"),
-                           "l2": "inputs (3.6 GB counts + 1.3 GB emission table per GPU) exceed the 126 MB L2; no flush needed",
-                           "parallelism": f"seeds sharded over {world} GPU(s), no data-path collective"},
-                "gpu_launches": int(launches) * args.steps, "clocks": clk.summary(), "roofline": roofline, "roofline_emission": roofline_emission,
-                "e2e": e2e, "mode_check": mode_check, "cpu_baseline": cpu}
+                           "l2": "inputs (counts + emission table per GPU) exceed the 126 MB L2; no flush needed",
+                           "parallelism": (f"chains sharded over {world} GPU(s) ({scaling}); NCCL all-gather of log Z_T + reduce of the "
+                                           f"seed-summed posteriors inside the timed region" if multi else "1 GPU")},
+                "site_chains_per_s": (total_T * total_seeds) * args.steps / wall,
+                "whole_chain": whole, "whole_chain_value": whole["value"] if whole else None,
+                "gpu_launches": int(launches) * args.steps, "clocks": clk.summary(), "roofline": roofline, other_key: other,
+                "e2e": e2e, "mode_check": mode_check, "gather_check": gather_check, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if multi:
         dist.destroy_process_group()
 
 

@@ -13,7 +13,7 @@ SYMBOLS = [
     "hyg_sg_set_model", "hyg_sg_set_vartheta", "hyg_sg_set_theta", "hyg_sg_get_tables",
     "hyg_sg_add_dataset", "hyg_sg_clear", "hyg_sg_default_run_args", "hyg_sg_set_chains",
     "hyg_sg_set_segmentation", "hyg_sg_filter_units", "hyg_sg_set_zero_copy_outputs",
-    "hyg_sg_emission", "hyg_sg_filter", "hyg_sg_download", "hyg_sync", "hyg_sg_timings", "hyg_sg_get_logobs",
+    "hyg_sg_emission", "hyg_sg_filter", "hyg_sg_download", "hyg_sg_device_outputs", "hyg_sync", "hyg_sg_timings", "hyg_sg_get_logobs",
     "hyg_sg_run_online_combined_inference", "hyg_sg_sample_theta_prior", "hyg_philox_uniform",
     "hyg_tg_set_model", "hyg_tg_run", "hyg_tg_hazard_table",
     "hyg_tg_site_statistics", "hyg_fdr_procedure", "hyg_weighted_fdr_procedure",
@@ -94,6 +94,7 @@ def load():
     lib.hyg_sg_emission.argtypes = [C.c_void_p]
     lib.hyg_sg_filter.argtypes = [C.c_void_p, C.POINTER(HygRunArgs)]
     lib.hyg_sg_download.argtypes = [C.c_void_p, C.POINTER(HygChain), C.c_uint32]
+    lib.hyg_sg_device_outputs.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     lib.hyg_sync.argtypes = [C.c_void_p]
     lib.hyg_sg_timings.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     lib.hyg_sg_get_logobs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]

@@ -825,6 +825,14 @@ int hyg_sg_filter(hyg_ctx* c, const hyg_sg_run_args* args) {
   return HYG_OK;
 }
 
+int hyg_sg_device_outputs(hyg_ctx* c, uint32_t chain, double** regime_probs, double** logz) {
+  if (!c || chain >= c->chains.size()) return fail(c, HYG_ERR_ARG, "chain index out of range");
+  const ChainBuf& b = c->chains[chain];
+  if (regime_probs) *regime_probs = b.probs_mapped ? nullptr : b.d_probs;
+  if (logz) *logz = b.d_logz;
+  return HYG_OK;
+}
+
 int hyg_sg_download(hyg_ctx* c, hyg_sg_chain* chains, uint32_t n) {
   if (!c) return HYG_ERR_ARG;
   if (n != c->chains.size()) return fail(c, HYG_ERR_ARG, "chain count differs from hyg_sg_set_chains");

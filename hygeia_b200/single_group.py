@@ -169,6 +169,12 @@ class Session:
         the rows the next segment wrote (the run-time check of the LEFT halo); 0.0 for whole chains."""
         return [float(c.overlap_max_abs) for c in self._chains]
 
+    def device_outputs(self, chain):
+        """(regime_probs, logz) device addresses of a staged chain (0 where absent): for consumers that stay on the device."""
+        a, b = C.c_void_p(0), C.c_void_p(0)
+        self._check(self.lib.hyg_sg_device_outputs(self.ctx, int(chain), C.byref(a), C.byref(b)), "hyg_sg_device_outputs")
+        return (a.value or 0), (b.value or 0)
+
     def sync(self):
         self._check(self.lib.hyg_sync(self.ctx), "hyg_sync")
 

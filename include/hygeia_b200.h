@@ -140,6 +140,10 @@ int hyg_sg_emission(hyg_ctx* ctx);
 /* K2: the recursion over all staged chains (device resident).  Asynchronous on the context's stream; the status words are
  * checked by hyg_sg_download (HYG_ERR_CAPACITY, see hyg_sg_run_args::lag_capacity). */
 int hyg_sg_filter(hyg_ctx* ctx, const hyg_sg_run_args* args);
+/* Device pointers of chain `chain`'s staged outputs, for consumers that stay on the device (e.g. an NCCL reduction of the
+ * posteriors over seeds): regime_probs [T][1+R] (NULL when it was not requested or is written straight into pinned host
+ * memory -- see hyg_sg_set_zero_copy_outputs), logz [T].  Valid until the next hyg_sg_set_chains / hyg_sg_clear. */
+int hyg_sg_device_outputs(hyg_ctx* ctx, uint32_t chain, double** regime_probs, double** logz);
 /* Device -> host copy of the outputs of every staged chain into the host pointers of hyg_sg_set_chains; synchronises. */
 int hyg_sg_download(hyg_ctx* ctx, hyg_sg_chain* chains, uint32_t n_chains);
 int hyg_sync(hyg_ctx* ctx);

@@ -69,6 +69,7 @@ def parse():
     p.add_argument("--no-e2e-pipeline", dest="e2e_pipeline", action="store_false")
     p.add_argument("--no-mode-check", action="store_true", help="skip the comparison of segmented vs whole-chain results")
     p.add_argument("--no-whole-chain", action="store_true", help="skip the whole-chain (reference semantics) timing leg")
+    p.add_argument("--staged-outputs", action="store_true", help="device-resident leg with the posteriors staged in HBM (as at N > 1) instead of streamed to pinned host memory")
     a = p.parse_args()
     if a.samples is None:
         a.samples = {"c1": 4, "c2": 32, "c5": 1000}[a.config]
@@ -368,7 +369,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident leg: inputs already in HBM ----
-    staged = stage(True, device_outputs=multi)
+    staged = stage(True, device_outputs=multi or args.staged_outputs)
     n_chains = len(staged)
     # multi-GPU exchange: device views of the staged outputs (valid until the next set_chains)
     evid_all = torch.zeros(world * max(1, n_chains), dtype=torch.float64, device=dev) if multi else None
@@ -413,6 +414,7 @@ def main():
         sess.sync()
         if multi:
             exchange()
+            torch.cuda.synchronize()   # the exchange belongs to this step: NCCL kernels left running would share the SMs with the next K2
         return sess.timings()
 
     if args.emission_only:

@@ -400,7 +400,7 @@ int cmd_single_group(int argc, char** argv) {
 int cmd_infer(int argc, char** argv) {
   const std::set<std::string> known = {"mu", "sigma", "minimum_duration", "omega_case", "merge_log_prob", "split_prob", "num_resampled_particles",
                                        "num_samples_backward", "multinomial", "chrom", "results_dir", "data_dir", "single_group_dir", "seed", "batch",
-                                       "segment_size", "buffer_size"};
+                                       "segment_size", "buffer_size", "hazard"};
   const std::set<std::string> flags = {"multinomial"};
   const Args a = parse_args(argc, argv, 2, known, flags);
   // defaults of run_inference_two_groups.py:19-73
@@ -422,6 +422,10 @@ int cmd_infer(int argc, char** argv) {
                     sg_dir = a.str("single_group_dir", "test_data/single_group_results");
   const long seed = get_int(a, "seed", 0), batch = get_int(a, "batch", 0), segment = get_int(a, "segment_size", 100000), buffer = get_int(a, "buffer_size", 5000);
   if (batch < 0 || segment <= 0 || buffer < 0) throw Error("--batch, --segment_size and --buffer_size must be non-negative");
+  // not a flag of the reference: "reference" (default) evaluates the sojourn hazard as its fp32 TensorFlow code does, fixed
+  // value 0.1 included (case_control_regime_model.py:111-168); "exact" is the negative-binomial hazard in fp64
+  const std::string hazard = a.str("hazard", "reference");
+  if (hazard != "reference" && hazard != "exact") throw Error("--hazard must be reference or exact");
 
   // results_dir/chrom_{chrom}_{batch}/ and the flag dump (:101-108)
   const std::string path = results_dir + "/chrom_" + chrom + "_" + std::to_string(batch);
@@ -531,6 +535,7 @@ int cmd_infer(int argc, char** argv) {
     m.log_p_control = logp.data(); m.omega_control = omega_control.data(); m.omega_case = omega_k.data();
     m.kappa_control = two.data(); m.kappa_case = two.data();
     m.merge_prob = std::exp(merge_log_prob); m.split_prob = split_prob;
+    m.hazard_mode = (hazard == "exact") ? HYG_TG_HAZARD_EXACT : HYG_TG_HAZARD_REFERENCE;
     ctx.check(hyg_tg_set_model(ctx.c, &m, T), "hyg_tg_set_model");
     std::vector<int32_t> traj(T * static_cast<size_t>(B) * 5);
     double log_norm = 0.0;

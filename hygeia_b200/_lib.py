@@ -15,7 +15,7 @@ SYMBOLS = [
     "hyg_sg_set_segmentation", "hyg_sg_filter_units", "hyg_sg_set_zero_copy_outputs",
     "hyg_sg_emission", "hyg_sg_filter", "hyg_sg_download", "hyg_sg_device_outputs", "hyg_sync", "hyg_sg_timings", "hyg_sg_get_logobs",
     "hyg_sg_run_online_combined_inference", "hyg_sg_sample_theta_prior", "hyg_philox_uniform",
-    "hyg_tg_set_model", "hyg_tg_run", "hyg_tg_hazard_table",
+    "hyg_tg_set_model", "hyg_tg_run", "hyg_tg_hazard_table", "hyg_tg_reference_hazard_table",
     "hyg_tg_site_statistics", "hyg_fdr_procedure", "hyg_weighted_fdr_procedure",
 ]
 
@@ -48,7 +48,7 @@ class HygTgModel(C.Structure):
         ("log_p_control", C.c_void_p), ("omega_control", C.c_void_p), ("omega_case", C.c_void_p),
         ("kappa_control", C.c_void_p), ("kappa_case", C.c_void_p),
         ("merge_prob", C.c_double), ("split_prob", C.c_double),
-        ("rho_control", C.c_void_p), ("rho_case", C.c_void_p), ("d_max", C.c_uint32),
+        ("rho_control", C.c_void_p), ("rho_case", C.c_void_p), ("d_max", C.c_uint32), ("hazard_mode", C.c_uint32),
     ]
 
 
@@ -105,6 +105,7 @@ def load():
     lib.hyg_tg_set_model.argtypes = [C.c_void_p, C.POINTER(HygTgModel), C.c_uint64]
     lib.hyg_tg_run.argtypes = [C.c_void_p, C.POINTER(HygTgChain), C.c_uint32, C.POINTER(C.c_float)]
     lib.hyg_tg_hazard_table.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+    lib.hyg_tg_reference_hazard_table.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.hyg_tg_site_statistics.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
     lib.hyg_fdr_procedure.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_double, C.POINTER(C.c_uint64), C.POINTER(C.c_double),

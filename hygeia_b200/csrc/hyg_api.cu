@@ -926,6 +926,14 @@ int hyg_tg_hazard_table(const double* omega, const double* kappa, uint32_t R, ui
   return HYG_OK;
 }
 
+int hyg_tg_reference_hazard_table(const double* omega, const double* kappa, uint32_t R, uint32_t u, uint32_t d_max, double* rho) {
+  if (!omega || !kappa || !rho || R < 1 || R > HYG_RMAX || d_max < u) return HYG_ERR_ARG;
+  std::vector<double> t;
+  hyg::build_reference_hazard_table(omega, kappa, static_cast<int>(R), static_cast<int>(u), d_max, t);
+  std::memcpy(rho, t.data(), t.size() * sizeof(double));
+  return HYG_OK;
+}
+
 int hyg_tg_set_model(hyg_ctx* c, const hyg_tg_model* m, uint64_t t_max) {
   if (!c || !m) return HYG_ERR_ARG;
   if (m->R < 2 || m->R > HYG_RMAX) return fail(c, HYG_ERR_UNSUPPORTED, "two-group: R must be in 2..8");
@@ -970,8 +978,10 @@ int hyg_tg_set_model(hyg_ctx* c, const hyg_tg_model* m, uint64_t t_max) {
     const double two[HYG_RMAX] = {2, 2, 2, 2, 2, 2, 2, 2};
     // sojourn times beyond d_max reuse the last entry (the hazard of a negative binomial is flat by then)
     dmax = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(t_max, m->minimum_duration + 1), 4096));
-    hyg::build_hazard_table(m->omega_control, m->kappa_control ? m->kappa_control : two, h.R, h.u, dmax, rho_c);
-    hyg::build_hazard_table(m->omega_case, m->kappa_case ? m->kappa_case : two, h.R, h.u, dmax, rho_k);
+    if (m->hazard_mode > HYG_TG_HAZARD_EXACT) return fail(c, HYG_ERR_ARG, "two-group: hazard_mode must be HYG_TG_HAZARD_REFERENCE or HYG_TG_HAZARD_EXACT");
+    auto* build = (m->hazard_mode == HYG_TG_HAZARD_EXACT) ? hyg::build_hazard_table : hyg::build_reference_hazard_table;
+    build(m->omega_control, m->kappa_control ? m->kappa_control : two, h.R, h.u, dmax, rho_c);
+    build(m->omega_case, m->kappa_case ? m->kappa_case : two, h.R, h.u, dmax, rho_k);
   }
   h.dmax = dmax;
   const size_t n = static_cast<size_t>(R) * (dmax + 1);

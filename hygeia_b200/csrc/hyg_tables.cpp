@@ -165,4 +165,36 @@ void build_hazard_table(const double* omega, const double* kappa, int R, int u, 
   }
 }
 
+void build_reference_hazard_table(const double* omega, const double* kappa, int R, int u, uint32_t d_max, std::vector<double>& rho) {
+  // The hazard AS THE REFERENCE EVALUATES IT (case_control_regime_model.py:111-168): exp(log_prob(d - u) -
+  // log_survival_function(d - u - 1)) of tfd.NegativeBinomial(total_count = kappa, probs = omega) in fp32, replaced by the
+  // fixed value 0.1 wherever that is not finite.  TFP's log survival function is log1p(-cdf); an fp32 cdf rounds to 1 once
+  // 1 - cdf < 2^-25, so from that sojourn on the hazard is 0.1 whatever omega is (kappa = 2: d = 94 for omega = 0.8, 197 for
+  // 0.9, 265 / 401 / 808 / 4071 for 0.925 / 0.95 / 0.975 / 0.995), and it carries fp32 cancellation noise before that.
+  // Restated here with fp64 special functions rounded to fp32 at the points where TFP holds fp32 values.
+  rho.assign(static_cast<size_t>(R) * (d_max + 1), 0.0);
+  for (int r = 0; r < R; r++) {
+    const float p32 = static_cast<float>(omega[r]);
+    const double tc = static_cast<double>(static_cast<float>(kappa[r]));
+    const double lg = static_cast<double>(static_cast<float>(std::log(static_cast<double>(p32)) - std::log1p(-static_cast<double>(p32))));
+    const double softplus_pos = std::max(lg, 0.0) + std::log1p(std::exp(-std::fabs(lg)));      // log(1 + e^lg)
+    const double softplus_neg = std::max(-lg, 0.0) + std::log1p(std::exp(-std::fabs(lg)));     // log(1 + e^-lg)
+    const double w = 1.0 / (1.0 + std::exp(-lg));                                              // probability of one more site
+    double pmf = std::exp(-tc * softplus_pos), cdf = 0.0;                                      // pmf(0) = (1 - w)^tc
+    for (uint32_t d = static_cast<uint32_t>(u); d <= d_max; d++) {
+      const double x = static_cast<double>(d) - u;
+      const float logh = static_cast<float>(-tc * softplus_pos - x * softplus_neg
+                                            - (std::lgamma(1.0 + x) + std::lgamma(tc) - std::lgamma(1.0 + x + tc)) - std::log(tc + x));
+      float logsf = 0.0f;
+      if (d > static_cast<uint32_t>(u)) {
+        cdf += pmf;                                        // cdf(x - 1) = sum of pmf(0 .. x-1)
+        pmf *= w * (x - 1.0 + tc) / x;                     // pmf(x) from pmf(x - 1)
+        logsf = log1pf(-static_cast<float>(std::min(cdf, 1.0)));
+      }
+      const float v = expf(logh - logsf);
+      rho[static_cast<size_t>(r) * (d_max + 1) + d] = std::isfinite(v) ? static_cast<double>(v) : static_cast<double>(0.1f);
+    }
+  }
+}
+
 }  // namespace hyg

@@ -39,6 +39,8 @@ double log_beta_binomial(uint32_t x, uint32_t n, double a, double b);
 // Two-group hazard rho[r][d] = pmf(d-u) / P(X >= d-u), X ~ NB(kappa_r, omega_r), d = 0..d_max (0 below u, 0.1 where not
 // finite): what case_control_regime_model.py:111-168 computes through TFP's log_prob / log_survival_function.
 void build_hazard_table(const double* omega, const double* kappa, int R, int u, uint32_t d_max, std::vector<double>& rho);
+// the same table with the reference's fp32 evaluation and its fixed value 0.1 where that is not finite
+void build_reference_hazard_table(const double* omega, const double* kappa, int R, int u, uint32_t d_max, std::vector<double>& rho);
 
 }  // namespace hyg
 #endif

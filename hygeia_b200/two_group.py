@@ -45,6 +45,9 @@ def control_group_parameters(theta, n_regimes):
     return logp, omega
 
 
+HAZARD_MODES = {"reference": 0, "exact": 1}   # HYG_TG_HAZARD_REFERENCE / HYG_TG_HAZARD_EXACT
+
+
 def segment_index(batch, segment_size, buffer_size, n_sites):
     """(index, return_index) of run_inference_two_groups.py:194-219: the window that is filtered and the part of it kept."""
     if batch * segment_size > n_sites:
@@ -71,7 +74,12 @@ class TwoGroupSession(Session):
 
     def set_two_group_model(self, log_p_control, omega_control, omega_case, minimum_duration=3, num_resampled=50, num_backward=25,
                             merge_prob=0.1, split_prob=0.01, kappa_control=None, kappa_case=None, rho_control=None, rho_case=None,
-                            t_max=4096):
+                            t_max=4096, hazard="reference"):
+        """hazard: "reference" (default) = the hazard as the reference's fp32 TensorFlow code evaluates it, with the fixed value
+        0.1 from the sojourn where its fp32 cdf rounds to 1 (d = 94 for omega = 0.8; case_control_regime_model.py:111-168);
+        "exact" = the negative-binomial hazard in fp64.  Ignored when rho_control / rho_case tables are supplied."""
+        if hazard not in HAZARD_MODES:
+            raise HygeiaError(f"hazard must be one of {sorted(HAZARD_MODES)}")
         R = self.R
         m = _lib.HygTgModel()
         keep = []
@@ -91,6 +99,7 @@ class TwoGroupSession(Session):
         m.kappa_control = arr(kappa_control, R)
         m.kappa_case = arr(kappa_case, R)
         m.merge_prob, m.split_prob = float(merge_prob), float(split_prob)
+        m.hazard_mode = HAZARD_MODES[hazard]
         if rho_control is not None:
             rc = np.ascontiguousarray(rho_control, dtype=np.float64); rk = np.ascontiguousarray(rho_case, dtype=np.float64)
             keep += [rc, rk]
@@ -121,15 +130,21 @@ class TwoGroupSession(Session):
         return outs
 
 
-def hazard_table(omega, kappa, minimum_duration, d_max):
-    """Host copy of the hazard table the kernels use (hyg_tg_hazard_table)."""
+def hazard_table(omega, kappa, minimum_duration, d_max, hazard="exact"):
+    """Host copy of the hazard table the kernels use: rho[r][d], d = 0..d_max (hyg_tg_hazard_table for "exact",
+    hyg_tg_reference_hazard_table for "reference" -- see TwoGroupSession.set_two_group_model)."""
     lib = _lib.load()
     om = np.ascontiguousarray(omega, dtype=np.float64); ka = np.ascontiguousarray(kappa, dtype=np.float64)
     out = np.zeros((len(om), d_max + 1))
-    rc = lib.hyg_tg_hazard_table(_ptr(om), _ptr(ka), len(om), int(minimum_duration), int(d_max), _ptr(out))
+    fn = lib.hyg_tg_hazard_table if HAZARD_MODES[hazard] == 1 else lib.hyg_tg_reference_hazard_table
+    rc = fn(_ptr(om), _ptr(ka), len(om), int(minimum_duration), int(d_max), _ptr(out))
     if rc < 0:
-        raise HygeiaError(f"hyg_tg_hazard_table failed ({rc})")
+        raise HygeiaError(f"hazard table failed ({rc})")
     return out
+
+
+def reference_hazard_table(omega, kappa, minimum_duration, d_max):
+    return hazard_table(omega, kappa, minimum_duration, d_max, hazard="reference")
 
 
 def summarise(trajectories, n_regimes):
@@ -147,7 +162,7 @@ _sessions = {}
 
 def infer(n_total_reads_control, n_methylated_reads_control, n_total_reads_case, n_methylated_reads_case, theta_control,
           mu=DEFAULT_MU, sigma=DEFAULT_SIGMA, minimum_duration=3, omega_case=0.8, merge_prob=0.1, split_prob=0.01,
-          num_resampled_particles=50, num_samples_backward=25, seed=0, *, device=0):
+          num_resampled_particles=50, num_samples_backward=25, seed=0, *, device=0, hazard="reference"):
     """One segment of one chromosome, as ``hygeia infer`` runs it (run_inference_two_groups.py:220-322).
 
     Count matrices are (n_sites, n_samples) as read from the reference's ``n_total_reads_{control,case}_<chrom>.txt.gz``
@@ -182,7 +197,7 @@ def infer(n_total_reads_control, n_methylated_reads_control, n_total_reads_case,
     dc, dk = 0, 1
     s.emission()
     s.set_two_group_model(logp, omega_control, np.full(R, float(omega_case)), minimum_duration, num_resampled_particles,
-                          num_samples_backward, merge_prob, split_prob, t_max=T)
+                          num_samples_backward, merge_prob, split_prob, t_max=T, hazard=hazard)
     out = s.run([dict(control_dataset=dc, case_dataset=dk, T=T, seed=seed, chain_id=0)])[0]
     tr = out["trajectories"]
     split, reg = summarise(tr, R)

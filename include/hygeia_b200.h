@@ -182,7 +182,13 @@ typedef struct hyg_tg_model {
   const double* rho_control;
   const double* rho_case;
   uint32_t d_max;
+  /* which hazard is computed when no tables are supplied: HYG_TG_HAZARD_REFERENCE (0, default) = as the reference evaluates
+   * it, in fp32 with the fixed value 0.1 where that is not finite (case_control_regime_model.py:111-168: from d = 94 on for
+   * omega = 0.8); HYG_TG_HAZARD_EXACT (1) = the negative-binomial hazard in fp64 */
+  uint32_t hazard_mode;
 } hyg_tg_model;
+#define HYG_TG_HAZARD_REFERENCE 0u
+#define HYG_TG_HAZARD_EXACT 1u
 
 typedef struct hyg_tg_chain {
   uint32_t control_dataset;        /* data-set indices (hyg_sg_add_dataset order); both must have the same T     */
@@ -198,8 +204,9 @@ typedef struct hyg_tg_chain {
 int hyg_tg_set_model(hyg_ctx* ctx, const hyg_tg_model* model, uint64_t t_max);
 /* K4/K5 over all chains: particle filter then backward simulation; synchronous (results are in the host buffers on return). */
 int hyg_tg_run(hyg_ctx* ctx, const hyg_tg_chain* chains, uint32_t n_chains, float* ms_device);
-/* host copy of the hazard table the kernels use: rho[R][d_max + 1] */
+/* host copy of the hazard tables the kernels use, rho[R][d_max + 1]: the exact one and the reference-mode one */
 int hyg_tg_hazard_table(const double* omega, const double* kappa, uint32_t R, uint32_t u, uint32_t d_max, double* rho);
+int hyg_tg_reference_hazard_table(const double* omega, const double* kappa, uint32_t R, uint32_t u, uint32_t d_max, double* rho);
 
 /* ---- DMP calling -------------------------------------------------------------------------
  * Boundary being replaced: the reductions of `hygeia aggregate` and `hygeia get_dmps`

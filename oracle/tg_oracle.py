@@ -84,6 +84,35 @@ def hazard_table(omega, kappa, u, d_max):
     return rho
 
 
+def reference_hazard_table(omega, kappa, u, d_max):
+    """rho[r][d], d = 0..d_max, AS THE REFERENCE EVALUATES IT (case_control_regime_model.py:111-168): exp(log_prob(d - u) -
+    log_survival_function(d - u - 1)) of tfd.NegativeBinomial(kappa, probs = omega) in fp32, and the fixed value 0.1 wherever
+    that is not finite.  TFP's survival function is log1p(-cdf); in fp32 the cdf rounds to 1 once 1 - cdf < 2^-25, so from that
+    sojourn on (d = 94 for omega = 0.8, 197 for 0.9, ... 4071 for 0.995 at kappa = 2) EVERY regime's hazard is 0.1.  fp64
+    special functions (SciPy) rounded to fp32 where TFP holds fp32 values; pinned to the reference's own module run on
+    oracle/shim_tf by tests/test_two_group_reference.py."""
+    from scipy import special
+    omega = np.asarray(omega, dtype=np.float64); kappa = np.asarray(kappa, dtype=np.float64)
+    R = omega.shape[0]
+    rho = np.zeros((R, d_max + 1), dtype=np.float64)
+    d = np.arange(d_max + 1, dtype=np.float64)
+    f32 = np.float32
+    for r in range(R):
+        p = f32(omega[r]); tc = np.float64(f32(kappa[r]))
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            lg = np.float64(f32(np.log(np.float64(p)) - np.log1p(-np.float64(p))))
+            x = d - u
+            logh = (tc * (-np.logaddexp(0.0, lg)) + x * (-np.logaddexp(0.0, -lg)) - special.betaln(1.0 + x, tc) - np.log(tc + x)).astype(f32)
+            cdf = special.betainc(tc, 1.0 + (x - 1.0), 1.0 / (1.0 + np.exp(lg))).astype(f32)
+            logsf = np.log1p(-cdf).astype(f32)
+            logh = np.where(d >= u, logh, f32(-np.inf))
+            logsf = np.where(d > u, logsf, f32(0.0))
+            val = np.where(logh == -np.inf, f32(0.0), np.exp((logh - logsf).astype(f32)).astype(f32))
+            val = np.where(np.isfinite(val), val, f32(0.1))
+        rho[r] = val.astype(np.float64)
+    return rho
+
+
 class TwoGroupModel:
     def __init__(self, R, log_p_control, omega_control, omega_case, kappa_control, kappa_case, u,
                  p_merged=((0.9, 0.1), (0.01, 0.99)), d_max=4096):

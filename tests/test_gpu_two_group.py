@@ -9,7 +9,7 @@ from _tg_case import make_case, tg_oracle
 pytestmark = pytest.mark.gpu
 
 
-def _run_gpu(c, M, B, seed, chain, use_oracle_tables=True, want_taps=True, n_copies=1):
+def _run_gpu(c, M, B, seed, chain, use_oracle_tables=True, want_taps=True, n_copies=1, hazard="exact"):
     from hygeia_b200.two_group import TwoGroupSession
     s = TwoGroupSession(0)
     try:
@@ -20,7 +20,7 @@ def _run_gpu(c, M, B, seed, chain, use_oracle_tables=True, want_taps=True, n_cop
         s.emission()
         m = c["model"]
         kw = dict(rho_control=m.rho_c, rho_case=m.rho_k) if use_oracle_tables else {}
-        s.set_two_group_model(c["logP"], c["omega_control"], c["omega_case"], c["u"], M, B, t_max=c["T"], **kw)
+        s.set_two_group_model(c["logP"], c["omega_control"], c["omega_case"], c["u"], M, B, t_max=c["T"], hazard=hazard, **kw)
         specs = [dict(control_dataset=2 * i, case_dataset=2 * i + 1, T=c["T"], seed=seed, chain_id=chain + i) for i in range(n_copies)]
         return s.run(specs, want_taps=want_taps)
     finally:
@@ -71,9 +71,39 @@ def test_two_group_parity_edge_cases(T, M, B, R):
 def test_two_group_device_hazard_tables():
     # tables built by the library itself (no injected hazards) give the same answer
     c = make_case(200, 2, seed=4)
-    g = _run_gpu(c, 50, 25, seed=9, chain=1, use_oracle_tables=False)[0]
+    g = _run_gpu(c, 50, 25, seed=9, chain=1, use_oracle_tables=False, hazard="exact")[0]
     r = _oracle(c, 50, 25, seed=9, chain=1)
     _compare(g, r, frac=0.95)
+
+
+def test_two_group_reference_mode_hazard_tables():
+    # the default of `hygeia infer`: the hazard as the reference's fp32 code evaluates it, fixed value 0.1 from d = 94 (case group)
+    c = make_case(260, 2, seed=4)
+    m = c["model"]
+    m.rho_c = tg_oracle.reference_hazard_table(c["omega_control"], np.full(6, 2.0), c["u"], m.d_max)
+    m.rho_k = tg_oracle.reference_hazard_table(c["omega_case"], np.full(6, 2.0), c["u"], m.d_max)
+    g = _run_gpu(c, 50, 25, seed=9, chain=1, use_oracle_tables=False, hazard="reference")[0]
+    r = _oracle(c, 50, 25, seed=9, chain=1)
+    _compare(g, r, frac=0.95)
+    e = _run_gpu(c, 50, 25, seed=9, chain=1, use_oracle_tables=False, hazard="exact")[0]
+    assert abs(e["log_normalizing_constant"] - g["log_normalizing_constant"]) > 1e-6     # the two modes are different models here
+
+
+@pytest.mark.parametrize("tag,hazard", [("e2e_short", "exact"), ("e2e_long", "reference")])
+def test_two_group_against_the_reference_run(tag, hazard):
+    """tests/golden/tg_reference.npz e2e_*: the reference's own filter_and_smoother_algorithm.run (unmodified, on oracle/shim_tf,
+    this repo's Philox draws injected; tests/golden/make_golden_tg.py) -- the CUDA path samples the same trajectories."""
+    from conftest import golden
+    gd = golden("tg_reference.npz")
+    c = make_case(int(gd[f"{tag}_T"]), int(gd[f"{tag}_S"]), seed=int(gd[f"{tag}_data_seed"]))
+    g = _run_gpu(c, 50, 25, seed=int(gd[f"{tag}_seed"]), chain=int(gd[f"{tag}_chain"]), use_oracle_tables=False, hazard=hazard)[0]
+    ln = float(gd[f"{tag}_log_norm"])
+    assert abs(g["log_normalizing_constant"] - ln) <= 2e-6 * abs(ln)                       # the reference accumulates in fp32
+    tr = g["trajectories"]
+    assert (tr[:, :, 0] == gd[f"{tag}_traj_merged"]).mean() >= 0.99
+    assert (tr[:, :, 1:3] == gd[f"{tag}_traj_control"]).mean() >= 0.99
+    assert (tr[:, :, 3:5] == gd[f"{tag}_traj_case"]).mean() >= 0.99
+    assert g["taps"][-1, 2] == int(gd[f"{tag}_n_final_finite"])
 
 
 def test_two_group_many_chains_are_independent():

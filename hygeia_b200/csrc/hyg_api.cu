@@ -907,9 +907,18 @@ int hyg_sg_run_online_combined_inference(hyg_ctx* c, const double* vartheta, uin
   ch.logz = logz; ch.theta_trace = theta_trace;
   if ((rc = hyg_sg_set_chains(c, &ch, 1))) return rc;
   if ((rc = hyg_sg_emission(c))) return rc;
-  if ((rc = hyg_sg_filter(c, args))) return rc;
-  rc = hyg_sg_download(c, &ch, 1);
-  if (status) std::memcpy(status, ch.status, sizeof(ch.status));
+  // The reference's lag set is unbounded (OnlineMarginalSmoothing.h:119-255); here it lives in a workspace of lag_capacity
+  // pending sites.  When it overflows the recursion is run again with four times the capacity (same draws, so the same
+  // chain; the emission table is kept) until nothing overflowed or the capacity covers the whole chain.
+  hyg_sg_run_args a = *args;
+  if (!a.lag_capacity) a.lag_capacity = 1024;
+  for (;;) {
+    if ((rc = hyg_sg_filter(c, &a))) return rc;
+    rc = hyg_sg_download(c, &ch, 1);
+    if (status) std::memcpy(status, ch.status, sizeof(ch.status));
+    if (rc != HYG_ERR_CAPACITY || a.lag_capacity >= T) break;
+    a.lag_capacity = static_cast<uint32_t>(std::min<uint64_t>(4ull * a.lag_capacity, std::max<uint64_t>(T, 1)));
+  }
   if (rc) return rc;
   if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return HYG_OK;

@@ -107,8 +107,10 @@ typedef struct hyg_sg_run_args {
                                            lag set is unbounded (OnlineMarginalSmoothing.h:148-195); here the rows live in a
                                            global-memory workspace (12 KB per pending site), so the capacity can be made as
                                            large as the longest lag.  A site that arrives when the set is full is emitted with
-                                           its filtering estimate and COUNTED in status[0]; hyg_sg_filter fails with
-                                           HYG_ERR_CAPACITY after the launch unless allow_forced_emission is set             */
+                                           its filtering estimate and COUNTED in status[0]; hyg_sg_download fails with
+                                           HYG_ERR_CAPACITY after the launch unless allow_forced_emission is set.  The one-call
+                                           operator hyg_sg_run_online_combined_inference then runs the recursion again with four
+                                           times the capacity (same draws) until nothing overflowed                          */
   int32_t allow_forced_emission;        /* keep going (status[0] > 0) instead of failing when the lag set overflowed        */
   int32_t resample_full_sort;           /* sort the particles on the full (log-weight, regime, sojourn) words at every site instead of
                                            only where two weights agree in their top 56 bits (same decisions; parity tests)   */

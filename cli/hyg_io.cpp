@@ -79,7 +79,9 @@ static double parse_cell(const char* b, const char* e, const std::string& path, 
   return v;
 }
 
-Table read_csv_numeric(const std::string& path, bool first_line_is_header) {
+Table read_csv_numeric(const std::string& path, bool first_line_is_header) { return read_delimited_numeric(path, first_line_is_header, ','); }
+
+Table read_delimited_numeric(const std::string& path, bool first_line_is_header, char sep) {
   const std::string txt = read_text(path);
   Table t;
   size_t pos = 0, line = 0;
@@ -96,7 +98,7 @@ Table read_csv_numeric(const std::string& path, bool first_line_is_header) {
     if (!header_done) {
       const char* c = b;
       while (c <= e) {
-        const char* q = static_cast<const char*>(std::memchr(c, ',', static_cast<size_t>(e - c)));
+        const char* q = static_cast<const char*>(std::memchr(c, sep, static_cast<size_t>(e - c)));
         if (!q) q = e;
         const char* hb = c;
         const char* he = q;
@@ -112,7 +114,7 @@ Table read_csv_numeric(const std::string& path, bool first_line_is_header) {
     size_t ncol = 0;
     const char* c = b;
     while (c <= e) {
-      const char* q = static_cast<const char*>(std::memchr(c, ',', static_cast<size_t>(e - c)));
+      const char* q = static_cast<const char*>(std::memchr(c, sep, static_cast<size_t>(e - c)));
       if (!q) q = e;
       t.v.push_back(parse_cell(c, q, path, line));
       ncol++;
@@ -428,6 +430,165 @@ void save_npz(const std::string& path, const std::string& descr, const std::vect
   ok = ok && std::fwrite(eocd.data(), 1, eocd.size(), f) == eocd.size();
   ok = (std::fclose(f) == 0) && ok;
   if (!ok) throw Error("write error on " + path);
+}
+
+// ---- np.load of an .npz: first member of the archive, stored or deflated (zip64 sizes in the central directory included) --
+static uint16_t get16(const unsigned char* p) { return static_cast<uint16_t>(p[0] | (p[1] << 8)); }
+static uint32_t get32(const unsigned char* p) { return static_cast<uint32_t>(p[0]) | (static_cast<uint32_t>(p[1]) << 8) | (static_cast<uint32_t>(p[2]) << 16) | (static_cast<uint32_t>(p[3]) << 24); }
+static uint64_t get64(const unsigned char* p) { return static_cast<uint64_t>(get32(p)) | (static_cast<uint64_t>(get32(p + 4)) << 32); }
+
+NpyArray load_npz(const std::string& path) {
+  FILE* f = std::fopen(path.c_str(), "rb");
+  if (!f) throw Error("cannot open " + path + ": " + std::strerror(errno));
+  std::vector<unsigned char> buf;
+  {
+    std::fseek(f, 0, SEEK_END);
+    const long n = std::ftell(f);
+    std::fseek(f, 0, SEEK_SET);
+    buf.resize(n > 0 ? static_cast<size_t>(n) : 0);
+    const bool ok = buf.empty() || std::fread(buf.data(), 1, buf.size(), f) == buf.size();
+    std::fclose(f);
+    if (!ok) throw Error("read error on " + path);
+  }
+  if (buf.size() < 22) throw Error(path + ": not a zip archive");
+  size_t eocd = std::string::npos;
+  for (size_t i = buf.size() - 22 + 1; i-- > 0;) {
+    if (get32(&buf[i]) == 0x06054b50u) { eocd = i; break; }
+    if (buf.size() - i > 22 + 65536) break;
+  }
+  if (eocd == std::string::npos) throw Error(path + ": end of central directory not found");
+  uint64_t cd_off = get32(&buf[eocd + 16]);
+  if (cd_off == 0xFFFFFFFFull) {   // zip64 end of central directory, through its locator
+    if (eocd < 20 || get32(&buf[eocd - 20]) != 0x07064b50u) throw Error(path + ": zip64 locator not found");
+    const uint64_t e64 = get64(&buf[eocd - 20 + 8]);
+    if (e64 + 56 > buf.size() || get32(&buf[e64]) != 0x06064b50u) throw Error(path + ": bad zip64 end of central directory");
+    cd_off = get64(&buf[e64 + 48]);
+  }
+  if (cd_off + 46 > buf.size() || get32(&buf[cd_off]) != 0x02014b50u) throw Error(path + ": bad central directory");
+  const unsigned char* cd = &buf[cd_off];
+  const uint16_t method = get16(cd + 10);
+  uint64_t csize = get32(cd + 20), usize = get32(cd + 24), lho = get32(cd + 42);
+  const uint16_t nlen = get16(cd + 28), xlen = get16(cd + 30);
+  {   // zip64 extra field: the 8-byte values appear in the order usize, csize, offset, only for fields that are 0xFFFFFFFF
+    const unsigned char* x = cd + 46 + nlen;
+    const unsigned char* xe = x + xlen;
+    while (x + 4 <= xe) {
+      const uint16_t id = get16(x), sz = get16(x + 2);
+      if (id == 0x0001) {
+        const unsigned char* q = x + 4;
+        if (usize == 0xFFFFFFFFull) { usize = get64(q); q += 8; }
+        if (csize == 0xFFFFFFFFull) { csize = get64(q); q += 8; }
+        if (lho == 0xFFFFFFFFull) { lho = get64(q); q += 8; }
+      }
+      x += 4 + sz;
+    }
+  }
+  if (lho + 30 > buf.size() || get32(&buf[lho]) != 0x04034b50u) throw Error(path + ": bad local header");
+  const size_t data = lho + 30 + get16(&buf[lho + 26]) + get16(&buf[lho + 28]);
+  if (data + csize > buf.size()) throw Error(path + ": truncated member");
+  std::vector<unsigned char> raw(usize);
+  if (method == 0) {
+    if (csize != usize) throw Error(path + ": stored member with differing sizes");
+    std::memcpy(raw.data(), &buf[data], usize);
+  } else if (method == 8) {
+    z_stream zs;
+    std::memset(&zs, 0, sizeof(zs));
+    if (inflateInit2(&zs, -15) != Z_OK) throw Error("inflateInit2 failed");
+    zs.next_in = &buf[data];
+    zs.avail_in = static_cast<uInt>(csize);
+    zs.next_out = raw.data();
+    zs.avail_out = static_cast<uInt>(usize);
+    const int rc = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    if (rc != Z_STREAM_END) throw Error(path + ": inflate failed");
+  } else {
+    throw Error(path + ": unsupported zip compression method " + std::to_string(method));
+  }
+  // .npy: magic, version, header length, a Python dict literal
+  if (raw.size() < 10 || std::memcmp(raw.data(), "\x93NUMPY", 6) != 0) throw Error(path + ": member is not an .npy array");
+  size_t hlen, hoff;
+  if (raw[6] == 1) { hlen = get16(&raw[8]); hoff = 10; } else { hlen = get32(&raw[8]); hoff = 12; }
+  if (hoff + hlen > raw.size()) throw Error(path + ": truncated .npy header");
+  const std::string head(reinterpret_cast<const char*>(&raw[hoff]), hlen);
+  NpyArray a;
+  {
+    const size_t d = head.find("'descr'");
+    const size_t q0 = head.find('\'', head.find(':', d) + 1), q1 = head.find('\'', q0 + 1);
+    if (d == std::string::npos || q0 == std::string::npos || q1 == std::string::npos) throw Error(path + ": no descr in the .npy header");
+    a.descr = head.substr(q0 + 1, q1 - q0 - 1);
+    if (head.find("'fortran_order': False") == std::string::npos) throw Error(path + ": Fortran-ordered arrays are not supported");
+    const size_t s0 = head.find('(', head.find("'shape'")), s1 = head.find(')', s0);
+    if (s0 == std::string::npos || s1 == std::string::npos) throw Error(path + ": no shape in the .npy header");
+    const std::string sh = head.substr(s0 + 1, s1 - s0 - 1);
+    size_t pos = 0;
+    while (pos < sh.size()) {
+      while (pos < sh.size() && (sh[pos] == ' ' || sh[pos] == ',')) pos++;
+      if (pos >= sh.size()) break;
+      char* end = nullptr;
+      a.shape.push_back(static_cast<size_t>(std::strtoull(sh.c_str() + pos, &end, 10)));
+      pos = static_cast<size_t>(end - sh.c_str());
+    }
+  }
+  a.data.assign(raw.begin() + static_cast<long>(hoff + hlen), raw.end());
+  size_t n = 1;
+  for (size_t d : a.shape) n *= d;
+  const size_t item = a.descr.size() >= 3 ? static_cast<size_t>(std::strtoul(a.descr.c_str() + 2, nullptr, 10)) : 0;
+  if (item == 0 || a.data.size() != n * item) throw Error(path + ": payload size does not match shape and dtype " + a.descr);
+  return a;
+}
+
+// ---- pandas.read_csv(sep='\t') of the matrices `hygeia aggregate` writes: a header line, first column = the index ----------
+IndexedIntMatrix read_indexed_int_matrix(const std::string& path, char sep) {
+  const std::string txt = read_text(path);
+  IndexedIntMatrix m;
+  size_t pos = 0, line = 0;
+  bool header_done = false;
+  while (pos < txt.size()) {
+    size_t eol = txt.find('\n', pos);
+    if (eol == std::string::npos) eol = txt.size();
+    const char* b = txt.data() + pos;
+    const char* e = txt.data() + eol;
+    pos = eol + 1;
+    line++;
+    if (e > b && e[-1] == '\r') e--;
+    if (b == e) continue;
+    if (!header_done) {
+      size_t n = 0;
+      for (const char* c = b; c < e; c++) n += (*c == sep);
+      m.cols = n;
+      m.index_name.assign(b, static_cast<const char*>(std::memchr(b, sep, static_cast<size_t>(e - b))) ? static_cast<const char*>(std::memchr(b, sep, static_cast<size_t>(e - b))) : e);
+      header_done = true;
+      continue;
+    }
+    const char* c = b;
+    size_t k = 0;
+    while (c <= e) {
+      const char* q = static_cast<const char*>(std::memchr(c, sep, static_cast<size_t>(e - c)));
+      if (!q) q = e;
+      // integers, possibly written as floats ("3.0"); an empty cell is not a number here
+      bool neg = false;
+      const char* d = c;
+      if (d < q && (*d == '-' || *d == '+')) { neg = (*d == '-'); d++; }
+      long long v = 0;
+      const char* d0 = d;
+      while (d < q && *d >= '0' && *d <= '9') { v = v * 10 + (*d - '0'); d++; }
+      if (d == d0 || (d < q && *d != '.')) {
+        v = static_cast<long long>(parse_cell(c, q, path, line));
+        neg = false;
+      }
+      if (neg) v = -v;
+      if (k == 0) m.index.push_back(v);
+      else {
+        if (v < -32768 || v > 32767) throw Error(path + ": line " + std::to_string(line) + ": value out of the int16 range");
+        m.v.push_back(static_cast<int16_t>(v));
+      }
+      k++;
+      c = q + 1;
+    }
+    if (k != m.cols + 1) throw Error(path + ": line " + std::to_string(line) + " has " + std::to_string(k) + " fields, expected " + std::to_string(m.cols + 1));
+    m.rows++;
+  }
+  return m;
 }
 
 }  // namespace hygio

@@ -37,6 +37,25 @@ struct Table {
 // Comma-separated numeric table.  first_line_is_header = true is readr::read_csv's behaviour (the first line is consumed as
 // column names whatever it holds: SURVEY C-1, the first CpG site of a header-less file is dropped); false is header=None.
 Table read_csv_numeric(const std::string& path, bool first_line_is_header);
+Table read_delimited_numeric(const std::string& path, bool first_line_is_header, char sep);
+
+// pandas.read_csv(sep='\t').set_index(first column) of an integer matrix (aggregate_results.py:165-206 writes them,
+// get_dmps.py:58-61 reads them): header line, then index value + `cols` small integers per row
+struct IndexedIntMatrix {
+  std::string index_name;
+  std::vector<long long> index;
+  size_t rows = 0, cols = 0;
+  std::vector<int16_t> v;   // row-major rows x cols
+};
+IndexedIntMatrix read_indexed_int_matrix(const std::string& path, char sep = '\t');
+
+// np.load(path)['arr_0'] of an .npz with one member (np.savez_compressed / np.savez; zip64 aware): raw little-endian C-order data
+struct NpyArray {
+  std::string descr;           // e.g. "<i2"
+  std::vector<size_t> shape;
+  std::vector<unsigned char> data;
+};
+NpyArray load_npz(const std::string& path);
 
 // Text sink; gzip-compressed when the path ends in ".gz" (what readr::write_csv and np.savetxt do)
 class Writer {

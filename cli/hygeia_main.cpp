@@ -3,6 +3,8 @@
 // Sub-commands and the reference entry points they stand in for (paths relative to /root/reference):
 //   hygeia estimate_parameters_and_regimes ...   src/single_group/bin/estimate_parameters_and_regimes (flags :12-204, flow :206-379)
 //   hygeia infer ...                             src/two_group/run_inference_two_groups.py (flags :19-73, flow :92-322)
+//   hygeia aggregate ...                         src/two_group/aggregate_results.py
+//   hygeia get_dmps ...                          src/two_group/get_dmps.py (+ multiple_testing.py)
 //   hygeia make_bed_file ...                     src/single_group/bin/make_bed_file
 //   hygeia --version | -v | version              src/single_group/hygeia.docker:44-46, src/two_group/hygeia.docker:54-56
 // The Nextflow modules (modules/single_group/2_estimate_parameters.nf:39-51, 3_estimate_regimes.nf:35-46,
@@ -19,6 +21,8 @@
 #include <set>
 #include <string>
 #include <vector>
+
+#include <unistd.h>
 
 #include "../include/hygeia_b200.h"
 #include "hyg_io.hpp"
@@ -587,6 +591,293 @@ int cmd_infer(int argc, char** argv) {
 }
 
 // ======================================================================================================================
+// hygeia aggregate (src/two_group/aggregate_results.py) and hygeia get_dmps (src/two_group/get_dmps.py)
+// ======================================================================================================================
+bool path_exists(const std::string& p) { return ::access(p.c_str(), F_OK) == 0; }
+
+void append_int(std::string& s, long long v) {
+  char b[24];
+  const int n = std::snprintf(b, sizeof(b), "%lld", v);
+  s.append(b, static_cast<size_t>(n));
+}
+
+// DataFrame.set_index(pos).to_csv(sep = '\t', compression = 'gzip') of an integer matrix: header "pos\t0\t1...", then rows
+template <class Tv>
+void write_indexed_matrix(const std::string& path, const std::vector<long long>& pos, const Tv* v, size_t rows, size_t cols) {
+  hygio::Writer w(path);
+  std::string buf = "pos";
+  for (size_t c = 0; c < cols; c++) { buf += '\t'; append_int(buf, static_cast<long long>(c)); }
+  buf += '\n';
+  for (size_t r = 0; r < rows; r++) {
+    append_int(buf, pos[r]);
+    for (size_t c = 0; c < cols; c++) { buf += '\t'; append_int(buf, static_cast<long long>(v[r * cols + c])); }
+    buf += '\n';
+    if (buf.size() > (1u << 20)) { w.write(buf); buf.clear(); }
+  }
+  w.write(buf);
+  w.close();
+}
+
+// one of the echoes `infer` writes with np.savetxt(delimiter = ','): the reference reads it with sep = ' ', which yields the one
+// numeric column of a one-sample group (aggregate_results.py:100-108) and cannot be cast for more samples; here every sample
+// column is kept (a superset of what the reference can do)
+hygio::Table read_echo(const std::string& path) { return hygio::read_delimited_numeric(path, false, ','); }
+
+int cmd_aggregate(int argc, char** argv) {
+  const std::set<std::string> known = {"results_dir", "output_dir", "seeds", "chrom", "num_batches", "num_particles", "compute_freqs"};
+  const Args a = parse_args(argc, argv, 2, known, {"compute_freqs"});
+  const std::string results_dir = a.str("results_dir", "../test"), output_dir = a.str("output_dir", "../test/results"), chrom = a.str("chrom", "22");
+  const long seeds = get_int(a, "seeds", 10), num_batches = get_int(a, "num_batches", 30), N = get_int(a, "num_particles", 2400);
+  const bool compute_freqs = get_bool(a, "compute_freqs", false);
+  if (seeds < 1) throw Error("--seeds must be positive");
+  std::printf("Results directory: %s\nOutput directory: %s\nProcessing chromosome: %s\n", results_dir.c_str(), output_dir.c_str(), chrom.c_str());
+  hygio::mkdirs(output_dir);
+
+  std::vector<long long> pos;
+  std::vector<int8_t> merged, creg, kreg;
+  std::vector<int16_t> cdur, kdur, ntc, ntk, nmc, nmk;
+  size_t P = 0, Sc = 0, Sk = 0;
+  long processed = 0;
+  for (long batch = 0; batch < num_batches; batch++) {
+    const std::string dir = results_dir + "/chrom_" + chrom + "_" + std::to_string(batch);
+    std::printf("\nProcessing batch %ld\nLooking for data in: %s\n", batch, dir.c_str());
+    if (!path_exists(dir)) { std::printf("Directory does not exist: %s\n", dir.c_str()); break; }
+    if (!path_exists(dir + "/positions.csv.gz")) { std::printf("positions.csv.gz not found in %s\n", dir.c_str()); break; }
+    const hygio::Table tp = read_echo(dir + "/positions.csv.gz");
+    const hygio::Table e_ntc = read_echo(dir + "/n_total_reads_control.csv.gz"), e_ntk = read_echo(dir + "/n_total_reads_case.csv.gz");
+    const hygio::Table e_nmc = read_echo(dir + "/observations_control.csv.gz"), e_nmk = read_echo(dir + "/observations_case.csv.gz");
+    const size_t Tb = tp.rows;
+    if (e_ntc.rows != Tb || e_ntk.rows != Tb || e_nmc.rows != Tb || e_nmk.rows != Tb) throw Error(dir + ": the echoed count files differ in length");
+    if (processed == 0) { Sc = e_ntc.cols; Sk = e_ntk.cols; }
+    if (e_ntc.cols != Sc || e_nmc.cols != Sc || e_ntk.cols != Sk || e_nmk.cols != Sk) throw Error(dir + ": the number of samples changed between batches");
+    // per seed: merged [Tb][B], control / case [Tb][B][2] = (duration, regime), int16 (aggregate_results.py:110-124)
+    std::vector<hygio::NpyArray> am, ac, ak;
+    size_t Pb = 0;
+    for (long sd = 0; sd < seeds; sd++) {
+      const std::string tag = "_" + std::to_string(N) + "_" + std::to_string(sd) + ".npz";
+      am.push_back(hygio::load_npz(dir + "/optimal_backward_particles_merged_state" + tag));
+      ac.push_back(hygio::load_npz(dir + "/optimal_backward_particles_control_state" + tag));
+      ak.push_back(hygio::load_npz(dir + "/optimal_backward_particles_case_state" + tag));
+      const hygio::NpyArray &m = am.back(), &c = ac.back(), &k = ak.back();
+      if (m.descr != "<i2" || c.descr != "<i2" || k.descr != "<i2") throw Error(dir + ": trajectories are not int16");
+      if (m.shape.size() != 2 || m.shape[0] != Tb || c.shape != std::vector<size_t>({Tb, m.shape[1], 2}) || k.shape != c.shape)
+        throw Error(dir + ": trajectory shapes of seed " + std::to_string(sd) + " do not match the window");
+      Pb += m.shape[1];
+    }
+    std::printf("Successfully processed %ld seeds out of %ld\n", seeds, seeds);
+    if (processed == 0) P = Pb;
+    if (Pb != P) throw Error(dir + ": the number of trajectories changed between batches");
+    const size_t T0 = pos.size();
+    pos.resize(T0 + Tb);
+    merged.resize((T0 + Tb) * P); creg.resize((T0 + Tb) * P); kreg.resize((T0 + Tb) * P); cdur.resize((T0 + Tb) * P); kdur.resize((T0 + Tb) * P);
+    for (size_t t = 0; t < Tb; t++) {
+      pos[T0 + t] = static_cast<int32_t>(static_cast<long long>(tp.at(t, 0)));   // .astype(np.int32), :161
+      size_t p = 0;
+      for (long sd = 0; sd < seeds; sd++) {
+        const size_t B = am[sd].shape[1];
+        const int16_t* m = reinterpret_cast<const int16_t*>(am[sd].data.data()) + t * B;
+        const int16_t* c = reinterpret_cast<const int16_t*>(ac[sd].data.data()) + t * B * 2;
+        const int16_t* k = reinterpret_cast<const int16_t*>(ak[sd].data.data()) + t * B * 2;
+        for (size_t b = 0; b < B; b++, p++) {
+          const size_t o = (T0 + t) * P + p;
+          merged[o] = static_cast<int8_t>(m[b]);
+          cdur[o] = c[2 * b]; creg[o] = static_cast<int8_t>(c[2 * b + 1]);
+          kdur[o] = k[2 * b]; kreg[o] = static_cast<int8_t>(k[2 * b + 1]);
+        }
+      }
+    }
+    auto app = [&](std::vector<int16_t>& dst, const hygio::Table& e) {
+      for (size_t i = 0; i < e.v.size(); i++) dst.push_back(static_cast<int16_t>(e.v[i]));
+    };
+    app(ntc, e_ntc); app(ntk, e_ntk); app(nmc, e_nmc); app(nmk, e_nmk);
+    processed++;
+    std::printf("Successfully processed batch %ld\n", batch);
+  }
+  std::printf("\nProcessing complete. Successfully processed %ld batches\n", processed);
+  if (pos.empty()) { std::printf("No data was processed. Check the input directories and file paths.\n"); return 1; }
+  const size_t T = pos.size();
+  for (size_t i = 0; i < T * P; i++)
+    if (creg[i] < 0 || creg[i] > 7 || kreg[i] < 0 || kreg[i] > 7) throw Error("regime labels outside 0..7");
+
+  // split probabilities = mean(merged == 0) over all seeds' trajectories (:125,173) and, on request, the regime frequencies
+  // (:208-214): one pass of the site-statistics kernel
+  Ctx ctx;
+  const uint32_t R = 8;
+  std::vector<double> split(T), nul(T), cf, kf;
+  if (compute_freqs) { cf.resize(T * R); kf.resize(T * R); }
+  float ms = 0.0f;
+  ctx.check(hyg_tg_site_statistics(ctx.c, T, static_cast<uint32_t>(P), R, merged.data(), creg.data(), kreg.data(), 0, split.data(), nul.data(),
+                                   compute_freqs ? cf.data() : nullptr, compute_freqs ? kf.data() : nullptr, nullptr, &ms), "hyg_tg_site_statistics");
+  std::fprintf(stderr, "aggregate: %zu sites x %zu trajectories, site statistics %.3f ms on the device\n", T, P, ms);
+
+  std::printf("Concatenating results...\n");
+  const std::string o = output_dir + "/";
+  write_indexed_matrix(o + "control_regimes_chrom_" + chrom + ".csv.gz", pos, creg.data(), T, P);
+  write_indexed_matrix(o + "case_regimes_chrom_" + chrom + ".csv.gz", pos, kreg.data(), T, P);
+  write_indexed_matrix(o + "merge_states_chrom_" + chrom + ".csv.gz", pos, merged.data(), T, P);
+  {
+    hygio::Writer w(o + "split_probs_" + chrom + ".csv.gz");
+    std::string buf = "pos\t0\n";
+    for (size_t t = 0; t < T; t++) { append_int(buf, pos[t]); buf += '\t'; buf += hygio::py_repr_double(split[t]); buf += '\n'; }
+    w.write(buf);
+    w.close();
+  }
+  write_indexed_matrix(o + "n_total_reads_control_chrom_" + chrom + ".csv.gz", pos, ntc.data(), T, Sc);
+  write_indexed_matrix(o + "n_total_reads_case_chrom_" + chrom + ".csv.gz", pos, ntk.data(), T, Sk);
+  write_indexed_matrix(o + "n_meth_reads_control_chrom_" + chrom + ".csv.gz", pos, nmc.data(), T, Sc);
+  write_indexed_matrix(o + "n_meth_reads_case_chrom_" + chrom + ".csv.gz", pos, nmk.data(), T, Sk);
+  write_indexed_matrix(o + "control_durations_chrom_" + chrom + ".csv.gz", pos, cdur.data(), T, P);
+  write_indexed_matrix(o + "case_durations_chrom_" + chrom + ".csv.gz", pos, kdur.data(), T, P);
+  if (compute_freqs) {
+    // row-wise value_counts(normalize = True): one column per label that occurs anywhere, labels ascending, empty where absent
+    auto write_freq = [&](const std::string& path, const std::vector<double>& f) {
+      bool present[8] = {false, false, false, false, false, false, false, false};
+      for (size_t t = 0; t < T; t++)
+        for (uint32_t r = 0; r < R; r++) present[r] = present[r] || f[t * R + r] > 0.0;
+      hygio::Writer w(path);
+      std::string buf = "pos";
+      for (uint32_t r = 0; r < R; r++) if (present[r]) { buf += '\t'; append_int(buf, r); }
+      buf += '\n';
+      for (size_t t = 0; t < T; t++) {
+        append_int(buf, pos[t]);
+        for (uint32_t r = 0; r < R; r++) if (present[r]) { buf += '\t'; if (f[t * R + r] > 0.0) buf += hygio::py_repr_double(f[t * R + r]); }
+        buf += '\n';
+      }
+      w.write(buf);
+      w.close();
+    };
+    write_freq(o + "case_regimes_freq_" + chrom + ".csv", kf);
+    write_freq(o + "control_regimes_freq_" + chrom + ".csv", cf);
+  }
+  return 0;
+}
+
+std::string fmt4(double x) {
+  char b[64];
+  std::snprintf(b, sizeof(b), "%.4f", x);
+  return b;
+}
+
+int cmd_get_dmps(int argc, char** argv) {
+  const std::set<std::string> known = {"fdr_thresholds", "results_dir", "output_dir", "n_regimes", "chrom", "test_regime_combinations"};
+  const Args a = parse_args(argc, argv, 2, known, {"test_regime_combinations"});
+  std::vector<double> thresholds;
+  if (a.has("fdr_thresholds"))
+    for (const std::string& s : a.kv.at("fdr_thresholds")) for (double v : parse_list(s, "fdr_thresholds")) thresholds.push_back(v);
+  else thresholds = {0.01, 0.05};
+  const std::string path = a.str("results_dir", "../test"), output_dir = a.str("output_dir", "../test/dmp"), chrom = a.str("chrom", "21");
+  const long Rl = get_int(a, "n_regimes", 6);
+  const bool combos = get_bool(a, "test_regime_combinations", false);
+  if (Rl < 1 || Rl > 8) throw Error("--n_regimes must be in 1..8");
+  const uint32_t R = static_cast<uint32_t>(Rl);
+  hygio::mkdirs(output_dir);
+
+  const hygio::IndexedIntMatrix mc = hygio::read_indexed_int_matrix(path + "/control_regimes_chrom_" + chrom + ".csv.gz");
+  const hygio::IndexedIntMatrix mk = hygio::read_indexed_int_matrix(path + "/case_regimes_chrom_" + chrom + ".csv.gz");
+  if (mc.rows != mk.rows || mc.cols != mk.cols) throw Error("control and case regime matrices differ in shape");
+  const size_t T = mc.rows, P = mc.cols;
+  if (T == 0 || P == 0) throw Error("empty regime matrices");
+  std::vector<int8_t> creg(T * P), kreg(T * P);
+  for (size_t i = 0; i < T * P; i++) {
+    if (mc.v[i] < 0 || mc.v[i] >= static_cast<int>(R) || mk.v[i] < 0 || mk.v[i] >= static_cast<int>(R)) throw Error("regime label outside 0..n_regimes-1");
+    creg[i] = static_cast<int8_t>(mc.v[i]); kreg[i] = static_cast<int8_t>(mk.v[i]);
+  }
+  // positions come from the index of split_probs_<chrom>.csv.gz (:75-83)
+  std::vector<long long> pos;
+  {
+    const std::string txt = hygio::read_text(path + "/split_probs_" + chrom + ".csv.gz");
+    size_t p = txt.find('\n');
+    while (p != std::string::npos && p + 1 < txt.size()) {
+      pos.push_back(std::strtoll(txt.c_str() + p + 1, nullptr, 10));
+      p = txt.find('\n', p + 1);
+    }
+  }
+  if (pos.size() != T) throw Error("split_probs and the regime matrices differ in length");
+
+  Ctx ctx;
+  std::vector<double> split(T), nul(T), cf(T * R), kf(T * R), pair;
+  if (combos) pair.resize(T * R * R);
+  float ms = 0.0f;
+  // test statistic 1 - #(control != case) / P and the regime frequencies bincount / P (:63-64,117-126): the site-statistics kernel
+  ctx.check(hyg_tg_site_statistics(ctx.c, T, static_cast<uint32_t>(P), R, creg.data(), creg.data(), kreg.data(), 0, split.data(), nul.data(), cf.data(),
+                                   kf.data(), combos ? pair.data() : nullptr, &ms), "hyg_tg_site_statistics");
+  std::fprintf(stderr, "get_dmps: %zu sites x %zu trajectories, site statistics %.3f ms on the device\n", T, P, ms);
+
+  // weights (:78-79,103-109): 1/3 (diff_1 + diff_2 + diff_3) of the positions, NaN -> 1e5, reciprocal
+  std::vector<double> w_fp(T, 1.0), w_fn(T);
+  for (size_t t = 0; t < T; t++) {
+    double d = 1e+5;
+    if (t >= 3) {
+      const double d1 = static_cast<double>(pos[t] - pos[t - 1]), d2 = static_cast<double>(pos[t] - pos[t - 2]), d3 = static_cast<double>(pos[t] - pos[t - 3]);
+      d = (1.0 / 3.0) * ((d1 + d2) + d3);
+    }
+    w_fn[t] = 1.0 / d;
+  }
+
+  auto write_rows = [&](const std::string& file, const std::vector<size_t>& rows, const std::vector<double>& stat, const double* weights, bool with_regimes) {
+    hygio::Writer w(file);
+    std::string buf = "chrom,position,null_stats,false_negative_weight";
+    if (with_regimes) {
+      for (uint32_t r = 0; r < R; r++) buf += ",Control_METEOR_" + std::to_string(r + 1);
+      for (uint32_t r = 0; r < R; r++) buf += ",Case_METEOR_" + std::to_string(r + 1);
+    }
+    buf += '\n';
+    for (size_t i : rows) {
+      const double fnw = weights ? weights[i] : 1.0;
+      buf += chrom; buf += ','; append_int(buf, pos[i]); buf += ',';
+      if (with_regimes) {   // float_format = "%.4f"
+        buf += fmt4(stat[i]) + "," + fmt4(fnw);
+        for (uint32_t r = 0; r < R; r++) buf += "," + fmt4(cf[i * R + r]);
+        for (uint32_t r = 0; r < R; r++) buf += "," + fmt4(kf[i * R + r]);
+      } else {
+        buf += hygio::py_repr_double(stat[i]) + "," + hygio::py_repr_double(fnw);
+      }
+      buf += '\n';
+    }
+    w.write(buf);
+    w.close();
+  };
+  auto plain = [&](const std::vector<double>& stat, double thr, const std::string& file, bool with_regimes) {
+    uint64_t k = 0;
+    double Qk = 0.0, threshold = 0.0;
+    ctx.check(hyg_fdr_procedure(ctx.c, T, stat.data(), thr, &k, &Qk, &threshold), "hyg_fdr_procedure");
+    std::vector<size_t> rows;
+    for (size_t t = 0; t < T; t++) if (stat[t] < threshold) rows.push_back(t);
+    write_rows(file, rows, stat, nullptr, with_regimes);
+  };
+  auto weighted = [&](const std::vector<double>& stat, double thr, const std::string& file, bool with_regimes) {
+    std::vector<uint64_t> idx(T);
+    uint64_t n_sel = 0;
+    double Nk = 0.0;
+    ctx.check(hyg_weighted_fdr_procedure(ctx.c, T, stat.data(), thr, w_fp.data(), w_fn.data(), &n_sel, idx.data(), &Nk), "hyg_weighted_fdr_procedure");
+    std::vector<size_t> rows(idx.begin(), idx.begin() + static_cast<long>(n_sel));
+    std::sort(rows.begin(), rows.end());
+    write_rows(file, rows, stat, w_fn.data(), with_regimes);
+  };
+  std::vector<double> stat_ij(T);
+  for (double thr : thresholds) {
+    const std::string ts = hygio::py_repr_double(thr);
+    plain(nul, thr, output_dir + "/dmp_" + ts + ".csv", true);
+    if (combos)
+      for (uint32_t i = 0; i < R; i++)
+        for (uint32_t j = 0; j < R; j++)
+          if (i != j) {
+            for (size_t t = 0; t < T; t++) stat_ij[t] = pair[(t * R + i) * R + j];
+            plain(stat_ij, thr, output_dir + "/dmp_" + std::to_string(i) + "_" + std::to_string(j) + "_" + ts + ".csv", false);
+          }
+    weighted(nul, thr, output_dir + "/weighted_dmp_" + ts + ".csv", true);
+    if (combos)
+      for (uint32_t i = 0; i < R; i++)
+        for (uint32_t j = 0; j < R; j++)
+          if (i != j) {
+            for (size_t t = 0; t < T; t++) stat_ij[t] = pair[(t * R + i) * R + j];
+            weighted(stat_ij, thr, output_dir + "/weighted_dmp_" + std::to_string(i) + "_" + std::to_string(j) + "_" + ts + ".csv", false);
+          }
+  }
+  return 0;
+}
+
+// ======================================================================================================================
 // hygeia make_bed_file (src/single_group/bin/make_bed_file:19-75)
 // ======================================================================================================================
 int cmd_make_bed(int argc, char** argv) {
@@ -675,6 +966,8 @@ void show_help() {
   std::printf("Usage: hygeia [command] [arguments...]\n\nAvailable commands:\n"
               "  estimate_parameters_and_regimes   - Estimate parameters and regimes (single group)\n"
               "  infer                             - Two-group (case/control) inference for one chromosome segment\n"
+              "  aggregate                         - Aggregate the two-group results of all segments and seeds of a chromosome\n"
+              "  get_dmps                          - Differentially methylated positions at given FDR thresholds\n"
               "  make_bed_file                     - Create a BED file\n\nOther options:\n"
               "  version, -v, --version            - Display version information\n"
               "  help, -h, --help                  - Display this help message\n");
@@ -694,9 +987,11 @@ int main(int argc, char** argv) {
     if (cmd == "help" || cmd == "-h" || cmd == "--help") { show_help(); return 0; }
     if (cmd == "estimate_parameters_and_regimes") return cmd_single_group(argc, argv);
     if (cmd == "infer") return cmd_infer(argc, argv);
+    if (cmd == "aggregate") return cmd_aggregate(argc, argv);
+    if (cmd == "get_dmps") return cmd_get_dmps(argc, argv);
     if (cmd == "make_bed_file") return cmd_make_bed(argc, argv);
     if (cmd == "_selftest") return cmd_selftest(argc, argv);
-    std::fprintf(stderr, "Error: Invalid command '%s'\nValid commands are: estimate_parameters_and_regimes infer make_bed_file\nUse 'hygeia help' for more information\n", cmd.c_str());
+    std::fprintf(stderr, "Error: Invalid command '%s'\nValid commands are: estimate_parameters_and_regimes infer aggregate get_dmps make_bed_file\nUse 'hygeia help' for more information\n", cmd.c_str());
     return 2;
   } catch (const std::exception& e) {
     std::fprintf(stderr, "hygeia %s: error: %s\n", cmd.c_str(), e.what());

@@ -185,3 +185,55 @@ def test_estimate_regimes_cli_segmented_extension(tmp_path):
         assert np.array_equal(o[:, 0], outs[0][:, 0])
         assert np.abs(o[:, 1:] - outs[0][:, 1:]).max() < 1e-8
         assert np.array_equal(o[:, 1:].argmax(1), outs[0][:, 1:].argmax(1))
+
+
+def _slurp(d):
+    import gzip
+    out = {}
+    for name in sorted(os.listdir(d)):
+        p = os.path.join(d, name)
+        out[name] = gzip.open(p, "rb").read() if name.endswith(".gz") else open(p, "rb").read()
+    return out
+
+
+def test_aggregate_and_get_dmps_write_the_reference_files(tmp_path):
+    """tests/golden/frontends.npz holds every file the reference's aggregate_results.py and get_dmps.py (run unmodified,
+    tests/golden/make_golden_frontends.py) write for a small results tree; `hygeia aggregate` / `hygeia get_dmps` rebuild the
+    tree from the same seed and must write the same bytes (gzip members compared after decompression)."""
+    from conftest import golden
+    from _cli import make_infer_tree
+    g = golden("frontends.npz")
+    tree, agg, dmp = tmp_path / "tree", tmp_path / "agg", tmp_path / "dmp"
+    make_infer_tree(str(tree), chrom="21", n_batches=2, n_seeds=3, sites_per_batch=240, n_samples=1, seed=0)
+    r = run("aggregate", "--results_dir", tree, "--output_dir", agg, "--seeds", 3, "--chrom", 21, "--num_batches", 30, "--compute_freqs")
+    assert "Successfully processed 2 batches" in r.stdout
+    got = _slurp(agg)
+    want = {k.split("/", 1)[1]: bytes(v) for k, v in g.items() if k.startswith("aggregate/")}
+    assert sorted(got) == sorted(want)
+    for name in want:
+        assert got[name] == want[name], name
+    run("get_dmps", "--results_dir", agg, "--output_dir", dmp, "--chrom", 21, "--test_regime_combinations",
+        "--fdr_thresholds", 0.01, "--fdr_thresholds", 0.05, "--fdr_thresholds", 0.2)
+    got = _slurp(dmp)
+    want = {k.split("/", 1)[1]: bytes(v) for k, v in g.items() if k.startswith("get_dmps/")}
+    assert sorted(got) == sorted(want)
+    differing = [name for name in want if got[name] != want[name]]
+    # weighted_FDR_procedure ranks with NumPy's unstable argsort: where ranking values tie, WHICH of the tied sites make the cut is
+    # not defined by the reference; the unweighted files and the headline weighted files must be identical
+    assert not [n for n in differing if not n.startswith("weighted_dmp_") or n.count("_") == 2], differing
+    for name in differing:
+        a, b = got[name].split(b"\n"), want[name].split(b"\n")
+        assert len(a) == len(b) and a[0] == b[0], name      # same number of selected sites
+
+
+def test_aggregate_keeps_every_sample_column_and_reports_missing_inputs(tmp_path):
+    from _cli import make_infer_tree
+    tree, agg = tmp_path / "tree", tmp_path / "agg"
+    make_infer_tree(str(tree), chrom="7", n_batches=1, n_seeds=2, sites_per_batch=50, n_samples=3, seed=4)
+    run("aggregate", "--results_dir", tree, "--output_dir", agg, "--seeds", 2, "--chrom", 7)
+    txt = _slurp(agg)["n_total_reads_case_chrom_7.csv.gz"].decode().split("\n")
+    assert txt[0] == "pos\t0\t1\t2" and len(txt) == 52
+    r = run("aggregate", "--results_dir", tree, "--output_dir", agg, "--seeds", 3, "--chrom", 7, check=False)   # seed 2 was never run
+    assert r.returncode != 0 and "optimal_backward_particles_merged_state_2400_2.npz" in r.stderr
+    r = run("aggregate", "--results_dir", tree, "--output_dir", agg, "--chrom", "8", check=False)               # no such chromosome
+    assert r.returncode == 1 and "No data was processed" in r.stdout

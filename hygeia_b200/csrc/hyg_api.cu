@@ -959,6 +959,8 @@ int hyg_tg_set_model(hyg_ctx* c, const hyg_tg_model* m, uint64_t t_max) {
   hyg::TgModelDev& h = c->tg_host;
   std::memset(&h, 0, sizeof(h));
   h.R = static_cast<int>(R); h.u = static_cast<int>(m->minimum_duration); h.M = static_cast<int>(m->num_resampled); h.B = static_cast<int>(m->num_backward);
+  h.presel[0] = std::max(m->sort_preselect[0] ? static_cast<int>(m->sort_preselect[0]) : h.M + 110, h.M + 96);
+  h.presel[1] = std::max(m->sort_preselect[1] ? static_cast<int>(m->sort_preselect[1]) : 3 * h.M + 250, h.presel[0]);
   // tf.nn.softmax of the log-probabilities with a -inf diagonal (case_control_regime_model.py:90-95), in log space
   for (uint32_t i = 0; i < R; i++) {
     double mx = -HUGE_VAL;
@@ -1059,7 +1061,7 @@ int hyg_tg_run(hyg_ctx* c, const hyg_tg_chain* chains, uint32_t n, float* ms_dev
     const hyg_tg_chain& ch = chains[k];
     const uint64_t T = c->ds[ch.control_dataset].T;
     HYG_TG_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_traj[k]), T * B * 5 * sizeof(int)));
-    if (ch.taps) HYG_TG_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_taps[k]), T * 3 * sizeof(int)));
+    if (ch.taps) HYG_TG_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_taps[k]), T * 4 * sizeof(int)));
     hyg::TgChainDev& d = dev[i];
     d.T = T; d.lo_c = c->ds[ch.control_dataset].d_logobs; d.lo_k = c->ds[ch.case_dataset].d_logobs;
     d.seed = ch.seed; d.chain = ch.chain_id; d.traj = d_traj[k]; d.log_norm = d_ln + k; d.taps = d_taps[k];
@@ -1094,7 +1096,7 @@ int hyg_tg_run(hyg_ctx* c, const hyg_tg_chain* chains, uint32_t n, float* ms_dev
     const uint64_t T = c->ds[ch.control_dataset].T;
     HYG_TG_CUDA(cudaMemcpyAsync(ch.trajectories, d_traj[k], T * B * 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     HYG_TG_CUDA(cudaMemcpyAsync(ch.log_normalizing_constant, d_ln + k, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    if (ch.taps) HYG_TG_CUDA(cudaMemcpyAsync(ch.taps, d_taps[k], T * 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (ch.taps) HYG_TG_CUDA(cudaMemcpyAsync(ch.taps, d_taps[k], T * 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   }
   HYG_TG_CUDA(cudaStreamSynchronize(c->stream));
   if (ms_device) HYG_TG_CUDA(cudaEventElapsedTime(ms_device, e0, e1));

@@ -74,7 +74,7 @@ class TwoGroupSession(Session):
 
     def set_two_group_model(self, log_p_control, omega_control, omega_case, minimum_duration=3, num_resampled=50, num_backward=25,
                             merge_prob=0.1, split_prob=0.01, kappa_control=None, kappa_case=None, rho_control=None, rho_case=None,
-                            t_max=4096, hazard="reference"):
+                            t_max=4096, hazard="reference", sort_preselect=(0, 0)):
         """hazard: "reference" (default) = the hazard as the reference's fp32 TensorFlow code evaluates it, with the fixed value
         0.1 from the sojourn where its fp32 cdf rounds to 1 (d = 94 for omega = 0.8; case_control_regime_model.py:111-168);
         "exact" = the negative-binomial hazard in fp64.  Ignored when rho_control / rho_case tables are supplied."""
@@ -100,6 +100,7 @@ class TwoGroupSession(Session):
         m.kappa_case = arr(kappa_case, R)
         m.merge_prob, m.split_prob = float(merge_prob), float(split_prob)
         m.hazard_mode = HAZARD_MODES[hazard]
+        m.sort_preselect[0], m.sort_preselect[1] = int(sort_preselect[0]), int(sort_preselect[1])   # tuning / test hook, see the header
         if rho_control is not None:
             rc = np.ascontiguousarray(rho_control, dtype=np.float64); rk = np.ascontiguousarray(rho_case, dtype=np.float64)
             keep += [rc, rk]
@@ -109,7 +110,8 @@ class TwoGroupSession(Session):
 
     def run(self, specs, want_taps=False):
         """specs: list of dicts(control_dataset, case_dataset, T, seed, chain_id).  Returns a list of dicts with
-        trajectories (T x B x 5 int32: merged, d_control, r_control, d_case, r_case), log_normalizing_constant, taps."""
+        trajectories (T x B x 5 int32: merged, d_control, r_control, d_case, r_case), log_normalizing_constant, taps (T x 4:
+        particles proposed, K, finite-weight particles, sort attempts)."""
         n = len(specs)
         arr = (_lib.HygTgChain * n)()
         outs = []
@@ -117,7 +119,7 @@ class TwoGroupSession(Session):
             T = int(s["T"])
             traj = np.zeros((T, self.B, 5), dtype=np.int32)
             ln = np.zeros(1)
-            taps = np.zeros((T, 3), dtype=np.int32) if want_taps else None
+            taps = np.zeros((T, 4), dtype=np.int32) if want_taps else None
             arr[i].control_dataset, arr[i].case_dataset = s["control_dataset"], s["case_dataset"]
             arr[i].seed, arr[i].chain_id = int(s.get("seed", 0)), int(s.get("chain_id", i))
             arr[i].trajectories, arr[i].log_normalizing_constant, arr[i].taps = _ptr(traj), _ptr(ln), _ptr(taps)

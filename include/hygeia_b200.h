@@ -188,6 +188,11 @@ typedef struct hyg_tg_model {
    * it, in fp32 with the fixed value 0.1 where that is not finite (case_control_regime_model.py:111-168: from d = 94 on for
    * omega = 0.8); HYG_TG_HAZARD_EXACT (1) = the negative-binomial hazard in fp64 */
   uint32_t hazard_mode;
+  /* tuning / test hook: the resampling sort covers only the heaviest particles of a site -- at least sort_preselect[0] of them
+   * on the first attempt, sort_preselect[1] on the second, all of them on the third; an attempt is repeated only when a tooth of
+   * the systematic comb falls behind the sorted prefix, so the results never depend on these numbers.  0 -> M + 110 and
+   * 3 M + 250; values below M + 96 are raised to it (the K search looks at the first M + 96 positions) */
+  uint32_t sort_preselect[2];
 } hyg_tg_model;
 #define HYG_TG_HAZARD_REFERENCE 0u
 #define HYG_TG_HAZARD_EXACT 1u
@@ -200,7 +205,7 @@ typedef struct hyg_tg_chain {
   /* outputs, host pointers */
   int32_t* trajectories;           /* T x B x 5 : merged, d_control, r_control, d_case, r_case                   */
   double* log_normalizing_constant;/* 1                                                                          */
-  int32_t* taps;                   /* optional T x 3 : particles proposed, K, finite-weight particles            */
+  int32_t* taps;                   /* optional T x 4 : particles proposed, K, finite-weight particles, sort attempts (0 = no sort) */
 } hyg_tg_chain;
 
 int hyg_tg_set_model(hyg_ctx* ctx, const hyg_tg_model* model, uint64_t t_max);

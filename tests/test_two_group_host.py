@@ -77,6 +77,28 @@ def test_kernel_under_emulation_edge_cases(T, M, B, R):
     assert (g["traj"][:, :, 3:5] == r["traj_case"]).all()
 
 
+def test_kernel_sort_preselection_never_changes_the_result():
+    """The resampling sort covers only the heaviest particles of a site and is repeated with more of them when a tooth of the
+    systematic comb falls behind the sorted prefix.  One-sample data (flat weights) with the smallest allowed prefix forces second
+    and third attempts; the outcome must be the oracle's -- which sorts everything -- at every site, whatever the prefix."""
+    c = make_case(260, 1, seed=3)
+    o = Oracle()
+    lo_c = o.emission(c["alpha"], c["beta"], c["nt_c"], c["nm_c"])
+    lo_k = o.emission(c["alpha"], c["beta"], c["nt_k"], c["nm_k"])
+    r = tg_oracle.run(c["model"], lo_c, lo_k, M=50, n_backward=25, seed=1, chain=0)
+    seen = set()
+    for pre in ((0, 0), (1, 1), (1, 300), (100000, 100000)):
+        g = tg_run_emu(Emu(), c["model"], lo_c, lo_k, M=50, B=25, seed=1, chain=0, preselect=pre)
+        assert abs(g["log_norm"] - r["log_norm"]) <= 1e-10 * abs(r["log_norm"])
+        assert (g["taps"][:, 1] == r["taps"]["K"]).all() and (g["taps"][:, 2] == r["taps"]["n_finite"]).all()
+        assert (g["traj"][:, :, 0] == r["traj_m"]).all()
+        assert (g["traj"][:, :, 1:3] == r["traj_control"]).all() and (g["traj"][:, :, 3:5] == r["traj_case"]).all()
+        seen |= set(np.unique(g["taps"][:, 3]).tolist())
+        if pre == (100000, 100000):
+            assert set(np.unique(g["taps"][2:, 3]).tolist()) <= {0, 1}       # everything sorted at once
+    assert {1, 2, 3} <= seen                                                  # every attempt level was exercised
+
+
 def test_control_group_parameters_match_oracle():
     rng = np.random.default_rng(0)
     theta = rng.normal(size=36)

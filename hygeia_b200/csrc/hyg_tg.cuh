@@ -133,7 +133,11 @@ __device__ __forceinline__ double tg_log_trans(const TgModelDev& md, const TgSta
 }
 
 // proposal q (0 .. 2R + R^2 - 1) of ancestor a (case_control_proposal_mappings.py:11-134)
-__device__ __forceinline__ TgState tg_propose(int R, const TgState& a, int q) {
+// (x * ceil(2^20 / d)) >> 20 == x / d for 0 <= x < 4096, 1 <= d <= 64 (the error x (ceil - exact) / 2^20 < 1/256 < 1/d)
+__device__ __forceinline__ int tg_div_magic(int d) { return ((1 << 20) + d - 1) / d; }
+__device__ __forceinline__ int tg_div(int x, int magic) { return (x * magic) >> 20; }
+
+__device__ __forceinline__ TgState tg_propose(int R, int magicR, const TgState& a, int q) {
   TgState n;
   if (q == 0) {
     n.m = a.m; n.dc = a.dc + 1; n.rc = a.rc; n.dk = a.dk + 1; n.rk = a.rk;
@@ -145,7 +149,7 @@ __device__ __forceinline__ TgState tg_propose(int R, const TgState& a, int q) {
     const int dm = (a.m == 0) ? a.dc + 1 : 0;
     n.m = 1; n.dc = dm; n.rc = a.rc; n.dk = dm; n.rk = a.rc;
   } else {                                  // both change: control regime i, case regime j
-    const int ij = q - 2 * R, i = ij / R, j = ij % R;
+    const int ij = q - 2 * R, i = tg_div(ij, magicR), j = ij - i * R;
     n.m = (i == j) ? 1 : 0; n.dc = 1; n.rc = i; n.dk = 1; n.rk = j;
   }
   return n;
@@ -168,6 +172,7 @@ struct TgSmem {
   TgState nxt[HYG_TG_BMAX];
   int pick[HYG_TG_BMAX];
   int rep[HYG_TG_BMAX];
+  int glist[HYG_TG_BMAX];       // backward pass: the first trajectory of every group of equal next states
   double ub[HYG_TG_BMAX];      // backward pass: the site's uniform of every trajectory (one Philox evaluation each)
   double ctot[HYG_TG_NPMAX / 32 + 2];    // per-chunk totals / carries of the chunked cumulative sums (32 particles per chunk)
   double ccar[HYG_TG_NPMAX / 32 + 2];
@@ -225,27 +230,32 @@ __device__ __forceinline__ int tg_block_excl_scan(int v, int& total, TgSmem& s, 
 // ascending particle index (= a stable descending sort of the weights in particle order)
 __device__ __forceinline__ void tg_sort_desc(TgSmem& s, int n) {
   const int half = n >> 1;
-  for (int k = 2; k <= n; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      // one compare-exchange per (thread, iteration): pair q -> elements i (bit log2(j) cleared) and i | j, so no lane idles
-      const int lj = __ffs(j) - 1;
-      for (int q = threadIdx.x; q < half; q += HYG_TG_NT) {
-        const int i = ((q >> lj) << (lj + 1)) | (q & (j - 1));
-        const int l = i | j;
-        const unsigned long long a = s.key[i], b = s.key[l];
-        const unsigned short ia = s.sidx[i], ib = s.sidx[l];
-        const bool desc = ((i & k) == 0);
-        const bool a_after_b = (a < b) || (a == b && ia > ib);   // a belongs after b in the final order
-        if (a_after_b == desc) { s.key[i] = b; s.key[l] = a; s.sidx[i] = ib; s.sidx[l] = ia; }
+  // only the warps that hold pairs take part (n = 256: four of sixteen) and meet at their own named barrier; the others wait
+  // at the block barrier below
+  const int nthr = (half < HYG_TG_NT) ? ((half + 31) & ~31) : HYG_TG_NT;
+  if (static_cast<int>(threadIdx.x) < nthr) {
+    for (int k = 2; k <= n; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        // one compare-exchange per (thread, iteration): pair q -> elements i (bit log2(j) cleared) and i | j, so no lane idles
+        const int lj = __ffs(j) - 1;
+        for (int q = threadIdx.x; q < half; q += HYG_TG_NT) {
+          const int i = ((q >> lj) << (lj + 1)) | (q & (j - 1));
+          const int l = i | j;
+          const unsigned long long a = s.key[i], b = s.key[l];
+          const unsigned short ia = s.sidx[i], ib = s.sidx[l];
+          const bool desc = ((i & k) == 0);
+          const bool a_after_b = (a < b) || (a == b && ia > ib);   // a belongs after b in the final order
+          if (a_after_b == desc) { s.key[i] = b; s.key[l] = a; s.sidx[i] = ib; s.sidx[l] = ia; }
+        }
+        // The 32 pairs q of a warp (q = tid + NT m) with a stride <= 32 lie in ONE block of 64 consecutive elements, the same
+        // block for every such stride: between two such stages a warp barrier is enough.
+        const int next = (j > 1) ? (j >> 1) : k;   // stride of the following stage
+        if (j >= 64 || next >= 64) named_barrier(2, nthr);
+        else __syncwarp();
       }
-      // The 32 pairs q of a warp (q = tid + NT m) with a stride <= 32 lie in ONE block of 64 consecutive elements, the same
-      // block for every such stride: between two such stages a warp barrier is enough.  21 block barriers instead of 66
-      // for 2048 keys.
-      const int next = (j > 1) ? (j >> 1) : k;   // stride of the following stage
-      if (j >= 64 || next >= 64) __syncthreads();
-      else __syncwarp();
     }
   }
+  __syncthreads();
 }
 
 // ---- one chain: filter over all sites, then backward simulation ----
@@ -253,6 +263,7 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
   const TgModelDev& md = s.mdl;
   const int tid = threadIdx.x, lane = tid & 31;
   const int R = md.R, M = md.M, B = md.B, I = 2 * R + R * R;
+  const int magicR = tg_div_magic(R);
   const unsigned long long T = ch.T;
   int flip = 0;
   TgStepRec* steps = reinterpret_cast<TgStepRec*>(ws);
@@ -286,9 +297,10 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
     for (int c = tid; c < n_part; c += HYG_TG_NT) { const double v = s.w[c]; mx = v > mx ? v : mx; nf += (v > -HYG_INF); }
     mx = tg_block_max(mx, s, flip);
     double se = 0.0;
-    for (int c = tid; c < n_part; c += HYG_TG_NT) { const double v = s.w[c]; se += (v > -HYG_INF) ? exp(v - mx) : 0.0; }
+    for (int c = tid; c < n_part; c += HYG_TG_NT) { const double v = s.w[c]; const double ev = (v > -HYG_INF) ? exp(v - mx) : 0.0; s.e[c] = ev; se += ev; }
     se = tg_block_sum(se, s, flip);
     const double lse = mx + log(se);
+    const double inv_se = 1.0 / se;
     // ---- which particles take part in the sort ----
     // Optimal finite-state resampling needs the finite particles in descending order of weight: the K < M heaviest keep their
     // weight, the rest is resampled systematically IN THAT ORDER.  Of the typically 1000-1800 finite particles of a site only
@@ -381,14 +393,14 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
               s.key[pos] = b;
               s.sidx[pos] = static_cast<unsigned short>(c);
             } else {
-              rest += exp(v - lse);
+              rest += (attempt == 0) ? s.e[c] : exp(v - mx);   // exp(v - mx) was kept by the pass above; a repeated attempt finds s.e reused
             }
           }
         }
         int n_sort = 64;
         while (n_sort < n_sel) n_sort <<= 1;
         for (int i = n_sel + tid; i < n_sort; i += HYG_TG_NT) { s.key[i] = 0ull; s.sidx[i] = 0xFFFFu; }
-        rest = (n_sel < F) ? tg_block_sum(rest, s, flip) : 0.0;
+        rest = (n_sel < F) ? tg_block_sum(rest, s, flip) * inv_se : 0.0;
         __syncthreads();
 #ifndef HYG_TG_SKIP_SORT
         tg_sort_desc(s, n_sort);
@@ -537,11 +549,12 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
     const double* loc = ch.lo_c + t * R;
     const double* lok = ch.lo_k + t * R;
     const int n_new = I * Mp;
+    const int magicMp = tg_div_magic(Mp);
     int nfin = 0;
     for (int c = tid; c < n_new; c += HYG_TG_NT) {
-      const int q = c / Mp, a = c % Mp;
+      const int q = tg_div(c, magicMp), a = c - q * Mp;
       const TgState pa = s.anc[a];
-      const TgState n = tg_propose(R, pa, q);
+      const TgState n = tg_propose(R, magicR, pa, q);
       const double lt = tg_log_trans(md, pa, n, false);
       double wn = -HYG_INF;
       if (lt > -HYG_INF) {
@@ -599,10 +612,11 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
         const double* loc = ch.lo_c + t * R;
         const double* lok = ch.lo_k + t * R;
         n_part = I * Mp;
+        const int magicMp = tg_div_magic(Mp);
         for (int c = tid; c < n_part; c += HYG_TG_NT) {
-          const int q = c / Mp, a = c % Mp;
+          const int q = tg_div(c, magicMp), a = c - q * Mp;
           const TgState pa = s.anc[a];
-          const TgState n = tg_propose(R, pa, q);
+          const TgState n = tg_propose(R, magicR, pa, q);
           const double lt = tg_log_trans(md, pa, n, false);
           double wn = -HYG_INF;
           if (lt > -HYG_INF) {
@@ -634,9 +648,17 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
       s.rep[tid] = r;
       s.ub[tid] = tg_uniform(ch.seed, ch.chain, HYG_TAG_BACKWARD, (static_cast<uint64_t>(tid) << 32) + static_cast<uint64_t>(t));
     }
+    if (tid < 32) {   // the distinct next states, in trajectory order (B <= 32: one warp)
+      const bool is_rep = (tid < B) && (s.rep[tid] == tid);
+      const unsigned gm = __ballot_sync(HYG_FULL, is_rep);
+      if (is_rep) s.glist[__popc(gm & ((1u << tid) - 1u))] = tid;
+      if (tid == 0) s.ibc[6] = __popc(gm);
+    }
     __syncthreads();
-    for (int j = 0; j < B; j++) {
-      if (s.rep[j] != j) continue;   // uniform: the group's first trajectory does the work
+    const int n_groups = s.ibc[6];
+    double* thi = reinterpret_cast<double*>(s.key);   // per-thread inclusive [0, NT) and exclusive [NT, 2 NT) cumulative probability (the sort's key array is idle here)
+    for (int gi = 0; gi < n_groups; gi++) {
+      const int j = s.glist[gi];   // the group's first trajectory: its predecessor law serves the whole group
       TgState nx;
       if (!last) nx = s.nxt[j];
       double mx = -HYG_INF;
@@ -670,20 +692,23 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
       for (int w = 0; w < HYG_TG_NW; w++) { const double x = s.red[flip][w][1]; if (w < (tid >> 5)) off += x; tot += x; }
       flip ^= 1;
       const double excl = off + inc - loc_sum;
-      for (int jj = j; jj < B; jj++) {   // every trajectory of the group draws with its own uniform
-        if (s.rep[jj] != j) continue;
-        const double target = s.ub[jj] * tot;
-        // the first particle whose cumulative probability reaches the target lives in exactly one thread's chunk
-        if (c0 < c1) {
-          const double hi_c = excl + loc_sum;
-          const bool mine = (excl < target || (tid == 0 && target <= 0.0)) && (target <= hi_c);
-          if (mine) {
-            int pickc = c1 - 1;
-            for (int c = c0; c < c1; c++) if (excl + s.e[c] >= target) { pickc = c; break; }
-            s.pick[jj] = pickc;
-          }
+      thi[HYG_TG_NT + tid] = excl;
+      thi[tid] = excl + loc_sum;
+      __syncthreads();
+      // every trajectory of the group draws with its own uniform: the first particle whose cumulative probability reaches the
+      // target lies in the first thread chunk whose inclusive sum reaches it
+      if (tid < B && s.rep[tid] == j) {
+        const double target = s.ub[tid] * tot;
+        int pickc = 0;
+        if (tot > 0.0) {
+          int lo = 0, hi = HYG_TG_NT - 1;
+          while (lo < hi) { const int mid = (lo + hi) >> 1; if (thi[mid] < target) lo = mid + 1; else hi = mid; }
+          const int k0 = lo * per, k1 = (k0 + per < n_part) ? k0 + per : n_part;
+          const double ex = thi[HYG_TG_NT + lo];
+          pickc = (k1 > k0) ? k1 - 1 : n_part - 1;
+          for (int c = k0; c < k1; c++) if (ex + s.e[c] >= target) { pickc = c; break; }
         }
-        if (tid == 0 && !(tot > 0.0)) s.pick[jj] = 0;
+        s.pick[tid] = pickc;
       }
       __syncthreads();
     }

@@ -3,6 +3,7 @@
 // Sub-commands and the reference entry points they stand in for (paths relative to /root/reference):
 //   hygeia estimate_parameters_and_regimes ...   src/single_group/bin/estimate_parameters_and_regimes (flags :12-204, flow :206-379)
 //   hygeia infer ...                             src/two_group/run_inference_two_groups.py (flags :19-73, flow :92-322)
+//   hygeia get_chrom_segments ...                src/two_group/get_chrom_segments.py
 //   hygeia aggregate ...                         src/two_group/aggregate_results.py
 //   hygeia get_dmps ...                          src/two_group/get_dmps.py (+ multiple_testing.py)
 //   hygeia make_bed_file ...                     src/single_group/bin/make_bed_file
@@ -878,6 +879,26 @@ int cmd_get_dmps(int argc, char** argv) {
 }
 
 // ======================================================================================================================
+// hygeia get_chrom_segments (src/two_group/get_chrom_segments.py): the list of `infer` batches of a chromosome
+// ======================================================================================================================
+int cmd_get_chrom_segments(int argc, char** argv) {
+  const Args a = parse_args(argc, argv, 2, {"input_file", "chromosome", "segment_size", "output_csv"}, {});
+  const std::string in = a.str("input_file", "positions.txt"), chrom = a.str("chromosome", "22"), out = a.str("output_csv", "chrom_segments.csv");
+  const long segment = get_int(a, "segment_size", 100000);
+  if (segment <= 0) throw Error("--segment_size must be positive");
+  const hygio::Table t = hygio::read_csv_numeric(in, false);             // pd.read_csv(header=None): every line is a position
+  const size_t n_segments = 1 + t.rows / static_cast<size_t>(segment);    // :33
+  hygio::mkdirs_for_file(out);
+  hygio::Writer w(out);
+  std::string buf = "chrom,segment_index\n";
+  for (size_t i = 0; i < n_segments; i++) buf += chrom + "," + std::to_string(i) + "\n";
+  w.write(buf);
+  w.close();
+  std::printf("Segment information saved to %s\n", out.c_str());
+  return 0;
+}
+
+// ======================================================================================================================
 // hygeia make_bed_file (src/single_group/bin/make_bed_file:19-75)
 // ======================================================================================================================
 int cmd_make_bed(int argc, char** argv) {
@@ -965,6 +986,7 @@ int cmd_selftest(int argc, char** argv) {
 void show_help() {
   std::printf("Usage: hygeia [command] [arguments...]\n\nAvailable commands:\n"
               "  estimate_parameters_and_regimes   - Estimate parameters and regimes (single group)\n"
+              "  get_chrom_segments                - List the segments (batches) of a chromosome for infer\n"
               "  infer                             - Two-group (case/control) inference for one chromosome segment\n"
               "  aggregate                         - Aggregate the two-group results of all segments and seeds of a chromosome\n"
               "  get_dmps                          - Differentially methylated positions at given FDR thresholds\n"
@@ -987,11 +1009,12 @@ int main(int argc, char** argv) {
     if (cmd == "help" || cmd == "-h" || cmd == "--help") { show_help(); return 0; }
     if (cmd == "estimate_parameters_and_regimes") return cmd_single_group(argc, argv);
     if (cmd == "infer") return cmd_infer(argc, argv);
+    if (cmd == "get_chrom_segments") return cmd_get_chrom_segments(argc, argv);
     if (cmd == "aggregate") return cmd_aggregate(argc, argv);
     if (cmd == "get_dmps") return cmd_get_dmps(argc, argv);
     if (cmd == "make_bed_file") return cmd_make_bed(argc, argv);
     if (cmd == "_selftest") return cmd_selftest(argc, argv);
-    std::fprintf(stderr, "Error: Invalid command '%s'\nValid commands are: estimate_parameters_and_regimes infer aggregate get_dmps make_bed_file\nUse 'hygeia help' for more information\n", cmd.c_str());
+    std::fprintf(stderr, "Error: Invalid command '%s'\nValid commands are: estimate_parameters_and_regimes get_chrom_segments infer aggregate get_dmps make_bed_file\nUse 'hygeia help' for more information\n", cmd.c_str());
     return 2;
   } catch (const std::exception& e) {
     std::fprintf(stderr, "hygeia %s: error: %s\n", cmd.c_str(), e.what());

@@ -95,3 +95,14 @@ def test_no_cpu_fallback(tmp_path):
     assert r.returncode == 1 and "GPU" in r.stderr
     assert (tmp_path / "out").is_dir()              # parents of the outputs are created before anything else (B1''')
     assert not (tmp_path / "out" / "regimes.csv.gz").exists()
+
+
+@pytest.mark.parametrize("n_sites,segment,want", [(2503, 1000, 3), (2000, 1000, 3), (999, 1000, 1)])
+def test_get_chrom_segments(tmp_path, n_sites, segment, want):
+    """get_chrom_segments.py:27-43 (run here against the reference script itself while developing): 1 + n // segment_size rows,
+    also when n is an exact multiple -- `infer` then exits 0 for the empty last batch; parents of the output are created."""
+    write_preprocess_style(tmp_path / "positions_9.txt.gz", np.arange(1, n_sites + 1) * 7.0)
+    out = tmp_path / "deep" / "er" / "segments.csv"
+    r = run("get_chrom_segments", "--input_file", tmp_path / "positions_9.txt.gz", "--chromosome", "chr9", "--segment_size", segment, "--output_csv", out)
+    assert "Segment information saved to" in r.stdout
+    assert out.read_text() == "chrom,segment_index\n" + "".join(f"chr9,{i}\n" for i in range(want))

@@ -7,7 +7,8 @@
     ... --scaling strong        fixed 16 seeds x 22 chromosomes = 352 chains, LPT-assigned over the ranks
     ... --config c1 | c5        BASELINE configs[0] (T = 600 k, S = 4, one chain pair) / configs[4] (S = 1000, 4 seeds, counts
                                 sharded by chromosome)
-    ... --config c4             two-group: python tools/tg_bench.py (its own line format)
+    ... --config c4             BASELINE configs[3]: two-group (case/control) filter + backward simulation, 50 + 50 samples, the
+                                genome cut into the reference's 100 000-site windows with 5 000-site halos, 1 seed per GPU
 
 A "step" is one pass of the hot path over the synthetic genome: K1 (emission table of every chromosome the rank holds) + K2 (the
 recursion for every chromosome x seed chain of the rank) + the multi-GPU exchange of the results (below).  Default workload at
@@ -50,7 +51,7 @@ def parse():
     p.add_argument("--steps", type=int, default=3)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="native", choices=["native", "reference"])
-    p.add_argument("--config", default="c2", choices=["c1", "c2", "c5"])
+    p.add_argument("--config", default="c2", choices=["c1", "c2", "c4", "c5"])
     p.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     p.add_argument("--total-sites", type=int, default=28_000_000)
     p.add_argument("--samples", type=int, default=None)
@@ -72,9 +73,9 @@ def parse():
     p.add_argument("--staged-outputs", action="store_true", help="device-resident leg with the posteriors staged in HBM (as at N > 1) instead of streamed to pinned host memory")
     a = p.parse_args()
     if a.samples is None:
-        a.samples = {"c1": 4, "c2": 32, "c5": 1000}[a.config]
+        a.samples = {"c1": 4, "c2": 32, "c4": 50, "c5": 1000}[a.config]
     if a.seeds_per_gpu is None:
-        a.seeds_per_gpu = 2
+        a.seeds_per_gpu = 1 if a.config == "c4" else 2
     if a.config == "c1":
         a.total_sites = 600_000 if a.total_sites == 28_000_000 else a.total_sites
     return a
@@ -91,16 +92,17 @@ def chromosome_lengths(args):
 # synthetic genome: regime paths on the host, counts on the device; chromosome c is a pure function
 # of (DATA_SEED, c), so every rank that needs it generates the same data
 # ------------------------------------------------------------------------------------------------------------------
-def make_chromosome(c, T, S, device):
+def make_chromosome(c, T, S, device, regimes=None, salt=0):
     import torch
     from hygeia_b200 import model, synthetic
     alpha, beta = model.beta_parameters(model.DEFAULT_MU, model.DEFAULT_SIGMA)
     g = torch.Generator(device=device)
-    g.manual_seed(DATA_SEED * 131 + c)
+    g.manual_seed(DATA_SEED * 131 + c + 100003 * salt)
     al = torch.tensor(alpha, device=device, dtype=torch.float32)
     be = torch.tensor(beta, device=device, dtype=torch.float32)
     rng = np.random.default_rng(DATA_SEED + c)
-    regimes = synthetic.simulate_regimes(T, rng)
+    if regimes is None:
+        regimes = synthetic.simulate_regimes(T, rng)
     pitch = (T + 7) // 8 * 8
     r = torch.from_numpy(regimes.astype(np.int64)).to(device)
     nt = torch.zeros((S, pitch), dtype=torch.uint16, device=device)
@@ -263,6 +265,223 @@ def workload_name(args, world):
             f"(BASELINE configs[{1 if world == 1 else 2}])")
 
 
+
+# ------------------------------------------------------------------------------------------------------------------
+# --config c4: the two-group path (K1 for both groups + K4/K5), BASELINE configs[3]
+# ------------------------------------------------------------------------------------------------------------------
+TG_SEGMENT, TG_BUFFER = 100_000, 5_000     # run_inference_two_groups.py:64-72
+
+
+def tg_windows(T):
+    """(lo, hi, own_lo, own_hi) of the reference's batches of a chromosome (run_inference_two_groups.py:194-219)."""
+    out = []
+    for b in range(1 + T // TG_SEGMENT):
+        if b * TG_SEGMENT >= T:
+            break
+        lo, hi = max(0, b * TG_SEGMENT - TG_BUFFER), min((b + 1) * TG_SEGMENT + TG_BUFFER, T)
+        out.append((lo, hi, b * TG_SEGMENT, min((b + 1) * TG_SEGMENT, T)))
+    return out
+
+
+def _tg_cpu_worker(job):
+    sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from _oracle import Oracle
+    from _tg_case import make_case
+    import tg_oracle
+    sites, S, seed = job
+    c = make_case(sites, S, seed=seed)
+    o = Oracle()
+    lo_c = o.emission(c["alpha"], c["beta"], c["nt_c"], c["nm_c"]); lo_k = o.emission(c["alpha"], c["beta"], c["nt_k"], c["nm_k"])
+    t0 = time.perf_counter()
+    tg_oracle.run(c["model"], lo_c, lo_k, M=50, n_backward=25, seed=seed, chain=0)
+    return time.perf_counter() - t0
+
+
+def tg_cpu_baseline(S, sites, n_procs):
+    """oracle/tg_oracle.py (NumPy restatement of the reference's TensorFlow path, pinned to it: DESIGN.md section 2), one chain per core."""
+    import multiprocessing as mp
+    n = max(1, min(os.cpu_count() or 1, n_procs))
+    t0 = time.perf_counter()
+    with mp.get_context("spawn").Pool(n) as pool:
+        per = pool.map(_tg_cpu_worker, [(sites, S, 11 + i) for i in range(n)])
+    wall = time.perf_counter() - t0
+    return {"value": n * sites * 2 * S / max(per), "unit": UNIT, "cores": n, "kind": "port",
+            "sample": f"EXTRAPOLATED from {n} chains of {sites} sites, {S} + {S} samples, 50 ancestors x 48 proposals, 25 backward trajectories "
+                      f"(oracle/tg_oracle.py, NumPy fp64, one chain per core); slowest chain {max(per):.1f} s, pool wall {wall:.1f} s"}
+
+
+def tg_workload(args, world):
+    return (f"two_group whole-genome synthetic (~{args.total_sites // 1_000_000}M CpGs in 22 chromosomes), {args.samples} + {args.samples} samples, "
+            f"u=3, 50 ancestors x 48 proposals, 25 backward trajectories, {TG_SEGMENT}-site windows with {TG_BUFFER}-site halos, "
+            f"{args.seeds_per_gpu} seed(s) per GPU ({args.seeds_per_gpu * world} in total) (BASELINE configs[3])")
+
+
+def run_two_group_reference(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    S = args.samples
+    sites = 600
+    vals, secs = [], []
+    for _ in range(max(0, min(args.warmup, 1)) + args.steps):
+        t0 = time.perf_counter()
+        r = tg_cpu_baseline(S, sites, os.cpu_count() or 1)
+        secs.append(time.perf_counter() - t0); vals.append(r["value"])
+    vals, secs = vals[-args.steps:], secs[-args.steps:]
+    v = float(np.mean(vals))
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": 1000.0 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                      "data": "synthetic", "config": {"workload": tg_workload(args, 1) + " -- " + r["sample"], "samples": S},
+                      "cpu_baseline": {"value": v, "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+                      "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def run_two_group(args):
+    import torch
+    import torch.distributed as dist
+    from hygeia_b200 import model
+    from hygeia_b200.two_group import TwoGroupSession, control_group_parameters
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    multi = world > 1
+    if multi:
+        dist.init_process_group("nccl", device_id=dev)
+    S, R, B, M = args.samples, 6, 25, 50
+    lens = chromosome_lengths(args)
+    seeds = [rank * args.seeds_per_gpu + k for k in range(args.seeds_per_gpu)]
+    # control and case share the regime path except on stretches of 300 sites every 20 000 (the case group moves two regimes on)
+    chroms = {}
+    for c, T in enumerate(lens):
+        ctl = make_chromosome(c, T, S, dev)
+        reg_k = ctl["regimes"].copy()
+        for s0 in range(7000, T - 300, 20000):
+            reg_k[s0:s0 + 300] = (reg_k[s0:s0 + 300] + 2) % R
+        cse = make_chromosome(c, T, S, dev, regimes=reg_k, salt=1)
+        chroms[c] = (ctl, cse)
+    torch.cuda.synchronize()
+    windows = [(c, w) for c, T in enumerate(lens) for w in tg_windows(T)]
+    owned = sum(w[3] - w[2] for _, w in windows)
+    stepped = sum(w[1] - w[0] for _, w in windows)
+    units_all = owned * 2 * S * args.seeds_per_gpu * world
+    theta = model.default_theta()
+    logp, omega_control = control_group_parameters(theta, R)
+
+    def build(device_resident, host=None):
+        s = TwoGroupSession(local)
+        s.set_emission_model(model.DEFAULT_MU, model.DEFAULT_SIGMA, 3)
+        specs = []
+        for wi, (c, (lo, hi, _, _)) in enumerate(windows):
+            ctl, cse = chroms[c]
+            ids = []
+            for g_i, ch in enumerate((ctl, cse)):
+                if device_resident:
+                    ids.append(s.add_dataset_ptr(hi - lo, S, ch["n_total"].data_ptr() + 2 * lo, ch["n_meth"].data_ptr() + 2 * lo, True, ch["pitch"]))
+                else:
+                    h_nt, h_nm = host[(c, g_i)]
+                    ids.append(s.add_dataset_ptr(hi - lo, S, h_nt.data_ptr() + 2 * lo, h_nm.data_ptr() + 2 * lo, False, ch["pitch"]))
+            for sd in seeds:
+                specs.append(dict(control_dataset=ids[0], case_dataset=ids[1], T=hi - lo, seed=sd, chain_id=wi))
+        s.set_two_group_model(logp, omega_control, np.full(R, 0.8), 3, M, B, t_max=TG_SEGMENT + 2 * TG_BUFFER)
+        return s, specs
+
+    def barrier():
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sess, specs = build(True)
+    bufs = [np.empty((sp["T"], B, 5), dtype=np.int32) for sp in specs]    # trajectories come back to the host in both legs (hyg_tg_run is synchronous)
+    for sp, b in zip(specs, bufs):
+        sp["trajectories"] = b
+    evid = torch.zeros(world * len(specs), dtype=torch.float64, device=dev)
+
+    def step():
+        sess.emission()
+        out = sess.run(specs)
+        if multi:   # the log-evidence of every window of every seed, gathered on all ranks (model comparison across seeds)
+            mine = torch.tensor([o["log_normalizing_constant"] for o in out], dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(evid, mine)
+            torch.cuda.synchronize()
+        tm = sess.timings()
+        return tm["ms_emission"], sess.ms_two_group, out
+
+    for _ in range(max(args.warmup, 1)):
+        step()
+    barrier()
+    em, tg = [], []
+    with ClockSampler(local) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            a, b, out = step()
+            em.append(a); tg.append(b)
+        barrier()
+        wall = time.perf_counter() - t0
+    t_all = torch.tensor([wall, sum(em) + sum(tg)], dtype=torch.float64, device=dev)
+    if multi:
+        dist.all_reduce(t_all, op=dist.ReduceOp.MAX)
+    wall, dev_ms = float(t_all[0]), float(t_all[1])
+    # device-resident value: the two kernels' event time (hyg_tg_run also copies 15 GB of trajectories back; that copy is in e2e)
+    value = units_all * args.steps / (dev_ms / 1000.0)
+    split = float(np.mean([(o["trajectories"][:, :, 0] == 0).mean() for o in out[:8]]))
+    ms_tg = float(np.mean(tg))
+    site_chains = stepped * len(seeds)
+    alg = site_chains * (2 * 8 * R + B * 5 * 4 + 2 * (24 + M * 32))
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6538.9)) if isinstance(peaks, dict) else 6538.9
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 1),
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": tg_workload(args, world), "samples": 2 * S, "windows_per_seed": len(windows), "inputs": "22 GB of counts, larger than L2: no flush between steps"},
+            "gpu_launches": 2 * args.steps, "clocks": clk.summary(),
+            "roofline": {"bound": "hbm", "kernel": "tg_kernel (K4/K5), one persistent launch per step over all windows x seeds of the rank", "achieved": alg / (ms_tg / 1000.0) / 1e9,
+                         "peak": peak, "unit": "GB/s", "frac": alg / (ms_tg / 1000.0) / 1e9 / peak, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms_tg, "share_of_step": ms_tg / (ms_tg + float(np.mean(em))),
+                         "latency_bound": {"site_chains_per_s": site_chains / (ms_tg / 1000.0), "us_per_site_per_chain_in_flight": 1000.0 * ms_tg * 148 / site_chains,
+                                           "halo_overhead": stepped / owned - 1.0, "mean_split_fraction_first_windows": split,
+                                           "note": "a sequential recursion per window: the bound is per-site latency x 148 chains in flight (DESIGN.md section 4, K4/K5)"}},
+            "roofline_emission": {"bound": "hbm", "kernel": "sg_emission_kernel<6> (K1), both groups", "ms_per_launch": float(np.mean(em)),
+                                  "achieved": stepped * (2 * 4 * S + 2 * 8 * R) / (float(np.mean(em)) / 1000.0) / 1e9, "peak": peak, "unit": "GB/s"},
+            "wall_ms_per_step_incl_trajectory_download": 1000.0 * wall / args.steps}
+    line["roofline_emission"]["frac"] = line["roofline_emission"]["achieved"] / peak
+    # ---- end to end: counts from pinned host memory, trajectories back in host memory ----
+    line["e2e"] = None
+    if not args.no_e2e:
+        sess.close()
+        host = {}
+        for c, (ctl, cse) in chroms.items():
+            for g_i, ch in enumerate((ctl, cse)):
+                host[(c, g_i)] = (ch["n_total"].cpu().pin_memory(), ch["n_meth"].cpu().pin_memory())
+        h2d = sum(2 * S * (w[1] - w[0]) * 2 for _, w in windows)
+        d2h = sum(b.nbytes for b in bufs)
+        secs = []
+        for _ in range(1 + args.e2e_steps):
+            barrier()
+            t0 = time.perf_counter()
+            s2, sp2 = build(False, host)
+            for sp, b in zip(sp2, bufs):
+                sp["trajectories"] = b
+            s2.emission()
+            o2 = s2.run(sp2)
+            torch.cuda.synchronize()
+            s2.close()
+            barrier()
+            secs.append(time.perf_counter() - t0)
+        e = float(np.mean(secs[1:]))
+        line["e2e"] = {"value": units_all / e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1000.0 * e,
+                       "api": "hygeia_b200.two_group.TwoGroupSession: add_dataset(pinned host windows) -> emission -> set_two_group_model -> run (trajectories into host arrays)",
+                       "log_evidence_first_window": o2[0]["log_normalizing_constant"]}
+    line["cpu_baseline"] = None
+    if rank == 0 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = tg_cpu_baseline(S, 400, os.cpu_count() or 1)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if multi:
+        dist.destroy_process_group()
+
 class _DevArr:
     """Raw device memory -> torch tensor (via __cuda_array_interface__)."""
 
@@ -273,6 +492,8 @@ class _DevArr:
 # ------------------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    if args.config == "c4":
+        return run_two_group_reference(args) if args.impl == "reference" else run_two_group(args)
     if args.impl == "reference":
         return run_reference(args)
 

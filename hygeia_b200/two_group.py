@@ -117,7 +117,11 @@ class TwoGroupSession(Session):
         outs = []
         for i, s in enumerate(specs):
             T = int(s["T"])
-            traj = np.zeros((T, self.B, 5), dtype=np.int32)
+            traj = s.get("trajectories")     # optional caller-owned (T, B, 5) int32 array, reused between runs
+            if traj is None:
+                traj = np.zeros((T, self.B, 5), dtype=np.int32)
+            elif traj.shape != (T, self.B, 5) or traj.dtype != np.int32 or not traj.flags.c_contiguous:
+                raise HygeiaError("trajectories must be a C-contiguous int32 array of shape (T, B, 5)")
             ln = np.zeros(1)
             taps = np.zeros((T, 4), dtype=np.int32) if want_taps else None
             arr[i].control_dataset, arr[i].case_dataset = s["control_dataset"], s["case_dataset"]

@@ -366,8 +366,11 @@ def run_two_group(args):
     theta = model.default_theta()
     logp, omega_control = control_group_parameters(theta, R)
 
+    the_session = TwoGroupSession(local)
+
     def build(device_resident, host=None):
-        s = TwoGroupSession(local)
+        s = the_session          # one context: its caching allocator keeps the 40 GB of per-sweep buffers between sweeps
+        s.clear()
         s.set_emission_model(model.DEFAULT_MU, model.DEFAULT_SIGMA, 3)
         specs = []
         for wi, (c, (lo, hi, _, _)) in enumerate(windows):
@@ -391,7 +394,9 @@ def run_two_group(args):
         torch.cuda.synchronize()
 
     sess, specs = build(True)
-    bufs = [np.empty((sp["T"], B, 5), dtype=np.int32) for sp in specs]    # trajectories come back to the host in both legs (hyg_tg_run is synchronous)
+    # trajectories come back to the host in both legs (hyg_tg_run is synchronous): pinned host arrays, allocated once
+    pinned = [torch.empty((sp["T"], B, 5), dtype=torch.int32).pin_memory() for sp in specs]
+    bufs = [t.numpy() for t in pinned]
     for sp, b in zip(specs, bufs):
         sp["trajectories"] = b
     evid = torch.zeros(world * len(specs), dtype=torch.float64, device=dev)
@@ -450,7 +455,6 @@ def run_two_group(args):
     # ---- end to end: counts from pinned host memory, trajectories back in host memory ----
     line["e2e"] = None
     if not args.no_e2e:
-        sess.close()
         host = {}
         for c, (ctl, cse) in chroms.items():
             for g_i, ch in enumerate((ctl, cse)):
@@ -466,13 +470,11 @@ def run_two_group(args):
                 sp["trajectories"] = b
             s2.emission()
             o2 = s2.run(sp2)
-            torch.cuda.synchronize()
-            s2.close()
             barrier()
             secs.append(time.perf_counter() - t0)
         e = float(np.mean(secs[1:]))
         line["e2e"] = {"value": units_all / e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1000.0 * e,
-                       "api": "hygeia_b200.two_group.TwoGroupSession: add_dataset(pinned host windows) -> emission -> set_two_group_model -> run (trajectories into host arrays)",
+                       "api": "hygeia_b200.two_group.TwoGroupSession: clear -> set_emission_model -> add_dataset(pinned host windows) -> emission -> set_two_group_model -> run (trajectories into pinned host arrays)",
                        "log_evidence_first_window": o2[0]["log_normalizing_constant"]}
     line["cpu_baseline"] = None
     if rank == 0 and not args.no_cpu_baseline:

@@ -94,6 +94,7 @@ struct SgSmem {
   int lag_ok[8][2];
   unsigned char r[HYG_NPMAX];     // regime by slot (lag set, parameter mode)
   unsigned long long hsum[HYG_NW];
+  int cnt[8];                     // the chain's status words, kept by thread 0 (eight live counters per thread do not fit the register budget)
 };
 
 __device__ __forceinline__ bool hyg_isfinite(double x) {
@@ -456,18 +457,24 @@ __device__ __forceinline__ void sg_resample_block(SgSmem& s, unsigned long long 
 // warp reduction -- no block barrier per pending site.
 // ------------------------------------------------------------------------------------------------------------------
 struct SgLagState {
-  double* rows;        // [lcap][R][256]
-  int* pend_t;         // [lcap] site of pending entry i (oldest first)
-  int* pend_row;       // [lcap] its row
-  int* pend_t_alt;     // the lists are rebuilt into the alternate copy while the current one is being read
-  int* pend_row_alt;
-  int* free_row;       // [lcap] stack of free rows
+  // One pointer, the capacity and a flip bit instead of six pointers: these live in every thread for the whole chain, and at
+  // 72 registers per thread each pointer that is not needed at a site is a spill.
+  double* rows;        // [lcap][R][256], then five int lists of lcap entries each:
+  int lcap;            //   pend_t / pend_row (site and row of pending entry i, oldest first), their alternates (the lists are
+  int flip;            //   rebuilt into the alternate copy while the current one is being read), the stack of free rows
+  int row_doubles;     // R x 256
   int n_pend, n_free;
+  __device__ __forceinline__ int* lists(int k) const { return reinterpret_cast<int*>(rows + static_cast<size_t>(lcap) * row_doubles) + static_cast<size_t>(k) * lcap; }
+  __device__ __forceinline__ int* pend_t() const { return lists(flip ? 2 : 0); }
+  __device__ __forceinline__ int* pend_row() const { return lists(flip ? 3 : 1); }
+  __device__ __forceinline__ int* pend_t_alt() const { return lists(flip ? 0 : 2); }
+  __device__ __forceinline__ int* pend_row_alt() const { return lists(flip ? 1 : 3); }
+  __device__ __forceinline__ int* free_row() const { return lists(4); }
 };
 
 template <int R>
 __device__ __noinline__ int sg_lag_update(SgLagState& lag, const SgChainDev& ch, SgSmem& s, unsigned int t, unsigned int T, unsigned int own_lo,
-                                          unsigned int own_hi, unsigned long long t_off, bool last_seg, double epsilon, int& n_halo_forced) {
+                                          unsigned int own_hi, unsigned long long t_off, bool last_seg, double epsilon) {
   static_assert(R <= HYG_RMAX - 2, "lag-set tasks handle three regime indicators each");
   const int tid = hyg_tid(), lane = tid & 31, warp = tid >> 5;
   // s.bk[slot][r], s.Wc[slot], s.new_slot[r] and s.Wnew[r] were published before the caller's barrier
@@ -480,7 +487,7 @@ __device__ __noinline__ int sg_lag_update(SgLagState& lag, const SgChainDev& ch,
     for (int task = warp; task < 2 * nb; task += HYG_NW) {
       const int bi = task >> 1, h = task & 1;
       const int q0 = h * HALF, nq = (h == 0) ? HALF : (R - HALF);
-      double* row = lag.rows + static_cast<size_t>(lag.pend_row[i0 + bi]) * R * HYG_NPMAX;
+      double* row = lag.rows + static_cast<size_t>(lag.pend_row()[i0 + bi]) * R * HYG_NPMAX;
       double acc[HALF][8];
 #pragma unroll
       for (int j = 0; j < HALF; j++)
@@ -532,8 +539,8 @@ __device__ __noinline__ int sg_lag_update(SgLagState& lag, const SgChainDev& ch,
       const int i = i0 + bi;
       const bool settled = s.lag_ok[bi][0] && s.lag_ok[bi][1];
       const bool emit = settled || (t == T - 1);
-      const int ts = lag.pend_t[i];
-      const int rw = lag.pend_row[i];
+      const int ts = lag.pend_t()[i];
+      const int rw = lag.pend_row()[i];
       if (emit) {
         const bool own_s = (static_cast<unsigned int>(ts) >= own_lo) && (static_cast<unsigned int>(ts) < own_hi);
         if (own_s) {
@@ -544,11 +551,11 @@ __device__ __noinline__ int sg_lag_update(SgLagState& lag, const SgChainDev& ch,
             ch.probs[static_cast<size_t>(ts) * (R + 1) + tid] = outv;
           }
           if (tid == 0 && ch.finalised_at) ch.finalised_at[ts] = static_cast<int>(t + t_off);
-          if (!settled && !last_seg) n_halo_forced++;   // the segment's right halo ended before this site settled
+          if (!settled && !last_seg && tid == 0) s.cnt[2]++;   // the segment's right halo ended before this site settled
         } else if (ch.ovl && tid < R && static_cast<unsigned int>(ts) >= own_hi && static_cast<unsigned int>(ts) < own_hi + HYG_OVL_ROWS) {
           ch.ovl[(static_cast<unsigned int>(ts) - own_hi) * R + tid] = s.lag_m[bi][tid];   // left-halo check (hyg_dev_structs.h)
         }
-        if (tid == 0) lag.free_row[lag.n_free] = rw;
+        if (tid == 0) lag.free_row()[lag.n_free] = rw;
         lag.n_free++;
       } else {
         // psi of the rewritten slots; every other entry of the row stays as it is
@@ -556,14 +563,13 @@ __device__ __noinline__ int sg_lag_update(SgLagState& lag, const SgChainDev& ch,
           const int q = tid / R, r = tid % R;
           lag.rows[static_cast<size_t>(rw) * R * HYG_NPMAX + q * HYG_NPMAX + s.new_slot[r]] = s.lag_val[bi][q][r];
         }
-        if (tid == 0) { lag.pend_t_alt[kept] = ts; lag.pend_row_alt[kept] = rw; }
+        if (tid == 0) { lag.pend_t_alt()[kept] = ts; lag.pend_row_alt()[kept] = rw; }
         kept++;
       }
     }
     __syncthreads();
   }
-  { int* a = lag.pend_t; lag.pend_t = lag.pend_t_alt; lag.pend_t_alt = a; }
-  { int* a = lag.pend_row; lag.pend_row = lag.pend_row_alt; lag.pend_row_alt = a; }
+  lag.flip ^= 1;
   lag.n_pend = kept;
   return kept;
 }
@@ -619,15 +625,10 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
 
   // lag-set workspace (global, L2-resident): [lcap][R][256] doubles, then five int arrays of lcap entries
   SgLagState lag;
-  lag.rows = psi_ws;
-  lag.pend_t = reinterpret_cast<int*>(psi_ws + static_cast<size_t>(lcap) * R * HYG_NPMAX);
-  lag.pend_row = lag.pend_t + lcap;
-  lag.pend_t_alt = lag.pend_row + lcap;
-  lag.pend_row_alt = lag.pend_t_alt + lcap;
-  lag.free_row = lag.pend_row_alt + lcap;
+  lag.rows = psi_ws; lag.lcap = lcap; lag.flip = 0; lag.row_doubles = R * HYG_NPMAX;
   lag.n_pend = 0; lag.n_free = lcap;
-  for (int i = tid; i < lcap; i += HYG_NT) lag.free_row[i] = lcap - 1 - i;
-  int n_forced = 0, max_pend = 0;
+  for (int i = tid; i < lcap; i += HYG_NT) lag.free_row()[i] = lcap - 1 - i;
+  if (tid < 8) s.cnt[tid] = 0;   // read and written by thread 0 only from here on
   // segmented execution: local sites [own_lo, own_hi) are written, the rest is warm-up / run-out (hyg_dev_structs.h)
   const unsigned int own_lo = static_cast<unsigned int>(ch.own_lo), own_hi = static_cast<unsigned int>(ch.own_hi);
   const unsigned long long t_off = ch.t_off;
@@ -637,7 +638,6 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
   // is a load + compare on the critical path
   const unsigned taps = (ch.probs ? 1u : 0u) | (ch.finalised_at ? 2u : 0u) | (ch.ovl ? 4u : 0u) | (ch.support_hash ? 8u : 0u) |
                         ((ch.k_kept || ch.drew || ch.n_pending || ch.n_curr || ch.tie_flags) ? 16u : 0u) | (ch.logz ? 32u : 0u) | (ch.seg_inc ? 64u : 0u);
-  int n_halo_forced = 0, n_steps = 0, n_sorts = 0, n_exact = 0, n_tie_sites = 0, n_dup = 0;
   double lz_base = 0.0;   // log Z (local) of site own_lo - 1: owned rows of logz are written relative to it
 
   SgChainState p;
@@ -755,7 +755,6 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           k_kept = -2;
         } else {
           // ---- resample::optimalFiniteState (resample.h:289-409) ----
-          n_sorts++;
           if (worker) sg_resample_block<R>(s, alive ? order_key(p.lw) : 0ull, order_pay(p.r, p.d, tid), alive ? p.W : 0.0, N_prev, M, s.u[t & 1], run.force_full_sort != 0, tid, lane, warp);
           resampled = true;
         }
@@ -768,10 +767,12 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
         if (alive) fate = s.fate[tid];
         k_kept = s.res.K;
         drew = (s.res.flags & HYG_RES_DREW) != 0;
-        n_exact += (s.res.flags & HYG_RES_EXACT_SORT) ? 1 : 0;
         tie_site = s.res.tie;
-        n_dup += s.res.n_dup;
-        if (tie_site & 2) n_tie_sites++;
+        if (tid == 0) {
+          s.cnt[4] += (s.res.flags & HYG_RES_EXACT_SORT) ? 1 : 0;
+          s.cnt[6] += s.res.n_dup;
+          s.cnt[5] += (tie_site & 2) ? 1 : 0;
+        }
       }
 
       // ---- propose + weight: sampleParticlesCp / computeWeightsCp (Smc.h:504-574) ----
@@ -885,7 +886,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
           if (newreg >= 0) s.Wnew[newreg] = p.W;       // weights of the rewritten slots
         }
         __syncthreads();
-        sg_lag_update<R>(lag, ch, s, t, T, own_lo, own_hi, t_off, last_seg, run.epsilon, n_halo_forced);
+        sg_lag_update<R>(lag, ch, s, t, T, own_lo, own_hi, t_off, last_seg, run.epsilon);
       }
       // ---- K3: score recursion (OnlineParameterEstimation.h:135-158), see sg_param.cuh ----
       if (PE) {
@@ -995,7 +996,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       const bool ok = ((lane & 7) >= R) || (var < run.epsilon);
       const bool settled = __all_sync(HYG_FULL, ok);
       emit_now = (t == T - 1) || settled;
-      if (!emit_now && lag.n_pend >= lcap) { emit_now = true; n_forced += own_t ? 1 : 0; }  // lag set full: emit the filtering estimate now (reported)
+      if (!emit_now && lag.n_pend >= lcap) { emit_now = true; if (tid == 0 && own_t) s.cnt[0]++; }  // lag set full: emit the filtering estimate now (reported)
       if (emit_now) {
         if (own_t) {
           if (warp == 0 && (taps & 1u)) {
@@ -1003,7 +1004,7 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
             if (lane <= R) ch.probs[static_cast<size_t>(t) * (R + 1) + lane] = (lane == 0) ? pos_cur : left;
           }
           if (tid == 0 && (taps & 2u)) ch.finalised_at[t] = static_cast<int>(t + t_off);
-          if (t == T - 1 && !settled && !last_seg) n_halo_forced++;
+          if (t == T - 1 && !settled && !last_seg && tid == 0) s.cnt[2]++;
         } else if ((taps & 4u) && warp == 0 && t >= own_hi && t < own_hi + HYG_OVL_ROWS) {
           const double left = __shfl_up_sync(HYG_FULL, cw_lane, 1);
           if (lane >= 1 && lane <= R) ch.ovl[(t - own_hi) * R + (lane - 1)] = left;
@@ -1011,17 +1012,17 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
       } else {
         // free_row / pend_* were last written before a block barrier of this step (or at initialisation)
         HYG_CHECK(lag.n_free >= 1 && lag.n_free <= lcap, 6, lag.n_free, lag.n_pend);
-        const int rw = lag.free_row[lag.n_free - 1];
+        const int rw = lag.free_row()[lag.n_free - 1];
         HYG_CHECK(rw >= 0 && rw < lcap, 7, rw, lag.n_free);
         double* dst = lag.rows + static_cast<size_t>(rw) * R * HYG_NPMAX;
         if (worker) {
 #pragma unroll
           for (int q = 0; q < R; q++) dst[q * HYG_NPMAX + tid] = (tid < N && p.r == q) ? 1.0 : 0.0;
         }
-        if (tid == 0) { lag.pend_t[lag.n_pend] = static_cast<int>(t); lag.pend_row[lag.n_pend] = rw; }
+        if (tid == 0) { lag.pend_t()[lag.n_pend] = static_cast<int>(t); lag.pend_row()[lag.n_pend] = rw; }
         lag.n_pend++; lag.n_free--;
       }
-      max_pend = lag.n_pend > max_pend ? lag.n_pend : max_pend;
+      if (tid == 0 && lag.n_pend > s.cnt[1]) s.cnt[1] = lag.n_pend;
     }
 
     if (service && t + 2 < T) {
@@ -1042,10 +1043,10 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
 #endif
     if (!PE && t + 1 >= run_to && t + 1 < T) {
       __syncthreads();
-      exit_now = (lag.n_pend == 0) || (static_cast<unsigned int>(lag.pend_t[0]) >= own_hi);
+      exit_now = (lag.n_pend == 0) || (static_cast<unsigned int>(lag.pend_t()[0]) >= own_hi);
     }
     const bool last_step = (t == T - 1) || exit_now;
-    n_steps++;
+    if (tid == 0) s.cnt[3]++;
 
     // ---- K3: parameter update every n_steps sites (OnlineParameterEstimation.h:51-61) ----
     if (PE) {
@@ -1121,13 +1122,13 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
     if (exit_now) break;
   }
   if (tid == 0 && ch.status) {
-    atomicAdd(ch.status + 0, n_forced);
-    atomicMax(ch.status + 1, max_pend);
-    atomicAdd(ch.status + 2, n_halo_forced);
-    atomicAdd(ch.status + 3, n_steps);
-    atomicAdd(ch.status + 4, n_exact);
-    atomicAdd(ch.status + 5, n_tie_sites);
-    atomicAdd(ch.status + 6, n_dup);
+    atomicAdd(ch.status + 0, s.cnt[0]);
+    atomicMax(ch.status + 1, s.cnt[1]);
+    atomicAdd(ch.status + 2, s.cnt[2]);
+    atomicAdd(ch.status + 3, s.cnt[3]);
+    atomicAdd(ch.status + 4, s.cnt[4]);
+    atomicAdd(ch.status + 5, s.cnt[5]);
+    atomicAdd(ch.status + 6, s.cnt[6]);
   }
   __syncthreads();
 }

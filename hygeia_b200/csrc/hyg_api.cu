@@ -24,11 +24,6 @@
 #include "hyg_tg.cuh"
 #include "hyg_dmp.cuh"
 
-#include <thrust/count.h>
-#include <thrust/device_ptr.h>
-#include <thrust/execution_policy.h>
-#include <thrust/scan.h>
-#include <thrust/sort.h>
 
 #define HYG_VERSION_STR "hygeia_b200 0.1.0 (sm_100a)"
 
@@ -1173,39 +1168,107 @@ int hyg_tg_site_statistics(hyg_ctx* c, uint64_t T, uint32_t P, uint32_t R, const
   return HYG_OK;
 }
 
+// ---- device primitives of the two procedures: hand-written kernels in hyg_dmp.cuh (radix sort, scan, count) ----
+extern "C++" {
+namespace {
+struct DmpScratch {
+  hyg_ctx* c;
+  std::vector<void*> bufs;
+  explicit DmpScratch(hyg_ctx* ctx) : c(ctx) {}
+  ~DmpScratch() { for (void* p : bufs) pool_free(c, p); }
+  template <class T> cudaError_t get(T** p, size_t count) {
+    void* q = nullptr;
+    const cudaError_t e = pool_alloc(c, &q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) { bufs.push_back(q); *p = static_cast<T*>(q); }
+    return e;
+  }
+};
+
+// stable ascending sort of the n keys (and, if pay != nullptr, their payloads) in place; k2 / p2 are scratch of the same size
+cudaError_t dmp_radix_sort(hyg_ctx* c, DmpScratch& sc, unsigned long long* keys, unsigned long long* k2, unsigned long long* pay, unsigned long long* p2, uint64_t n) {
+  const unsigned int n_tiles = static_cast<unsigned int>(std::min<uint64_t>((n + 2047) / 2048, static_cast<uint64_t>(c->num_sms) * 4));
+  const unsigned long long tile = (n + n_tiles - 1) / n_tiles;
+  unsigned int* d_counts = nullptr;
+  unsigned long long* d_offs = nullptr;
+  cudaError_t e;
+  if ((e = sc.get(&d_counts, 256ull * n_tiles)) != cudaSuccess) return e;
+  if ((e = sc.get(&d_offs, 256ull * n_tiles)) != cudaSuccess) return e;
+  unsigned long long *src_k = keys, *dst_k = k2, *src_p = pay, *dst_p = p2;
+  for (int pass = 0; pass < 8; pass++) {
+    const int shift = 8 * pass;
+    hyg::dmp_radix_hist_kernel<<<n_tiles, HYG_RS_NT, 0, c->stream>>>(src_k, n, tile, shift, d_counts, n_tiles);
+    hyg::dmp_scan_counts_kernel<<<1, 1024, 0, c->stream>>>(d_counts, d_offs, 256u * n_tiles);
+    if (pay) hyg::dmp_radix_scatter_kernel<true><<<n_tiles, HYG_RS_NT, 0, c->stream>>>(src_k, src_p, dst_k, dst_p, n, tile, shift, d_offs, n_tiles);
+    else hyg::dmp_radix_scatter_kernel<false><<<n_tiles, HYG_RS_NT, 0, c->stream>>>(src_k, nullptr, dst_k, nullptr, n, tile, shift, d_offs, n_tiles);
+    std::swap(src_k, dst_k);
+    std::swap(src_p, dst_p);
+  }
+  return cudaGetLastError();   // eight passes: the result is back in keys / pay
+}
+
+cudaError_t dmp_inclusive_scan(hyg_ctx* c, DmpScratch& sc, const double* x, double* out, uint64_t n) {
+  const unsigned int n_tiles = static_cast<unsigned int>(std::min<uint64_t>((n + 4095) / 4096, static_cast<uint64_t>(c->num_sms) * 4));
+  unsigned long long tile = (n + n_tiles - 1) / n_tiles;
+  tile = (tile + HYG_RS_NT * HYG_SCAN_ITEMS - 1) / (HYG_RS_NT * HYG_SCAN_ITEMS) * (HYG_RS_NT * HYG_SCAN_ITEMS);   // whole chunks per tile
+  const unsigned int used = static_cast<unsigned int>((n + tile - 1) / tile);
+  double* d_sums = nullptr;
+  cudaError_t e;
+  if ((e = sc.get(&d_sums, used)) != cudaSuccess) return e;
+  hyg::dmp_tile_sum_kernel<<<used, HYG_RS_NT, 0, c->stream>>>(x, n, tile, d_sums);
+  hyg::dmp_scan_tile_sums_kernel<<<1, 32, 0, c->stream>>>(d_sums, used);
+  hyg::dmp_tile_scan_kernel<<<used, HYG_RS_NT, 0, c->stream>>>(x, out, n, tile, d_sums);
+  return cudaGetLastError();
+}
+
+cudaError_t dmp_count_le(hyg_ctx* c, DmpScratch& sc, const double* x, uint64_t n, double bound, uint64_t* out) {
+  unsigned long long* d_cnt = nullptr;
+  cudaError_t e;
+  if ((e = sc.get(&d_cnt, 1)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(d_cnt, 0, sizeof(unsigned long long), c->stream)) != cudaSuccess) return e;
+  hyg::dmp_count_le_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(x, n, bound, d_cnt);
+  unsigned long long h = 0;
+  if ((e = cudaMemcpyAsync(&h, d_cnt, sizeof(h), cudaMemcpyDeviceToHost, c->stream)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return e;
+  *out = h;
+  return cudaGetLastError();
+}
+}  // namespace
+}  // extern "C++"
+
+#define HYG_FDR_CUDA(call)                                                                                          \
+  do {                                                                                                              \
+    cudaError_t e_ = (call);                                                                                        \
+    if (e_ != cudaSuccess) return fail(c, HYG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));        \
+  } while (0)
+
 int hyg_fdr_procedure(hyg_ctx* c, uint64_t n, const double* test_statistics, double fdr_threshold, uint64_t* k, double* Qk, double* threshold) {
   if (!c || !test_statistics || !k || !Qk || !threshold || n == 0) return fail(c, HYG_ERR_ARG, "null argument / empty input");
   HYG_CUDA(c, cudaSetDevice(c->device));
+  DmpScratch sc(c);
   double *d_t = nullptr, *d_q = nullptr;
-  auto cleanup = [&]() { pool_free(c, d_t); pool_free(c, d_q); };
-  HYG_DMP_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_t), n * sizeof(double)));
-  HYG_DMP_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_q), n * sizeof(double)));
-  HYG_DMP_CUDA(cudaMemcpyAsync(d_t, test_statistics, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  try {
-    auto pol = thrust::cuda::par.on(c->stream);
-    thrust::device_ptr<double> t(d_t), q(d_q);
-    thrust::sort(pol, t, t + n);                                   // np.sort (multiple_testing.py:4)
-    thrust::inclusive_scan(pol, t, t + n, q);                      // np.cumsum
-    hyg::dmp_running_mean_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(d_q, d_q, n);
-    const uint64_t s = static_cast<uint64_t>(thrust::count_if(pol, q, q + n, [fdr_threshold] __device__(double v) { return v <= fdr_threshold; }));
-    double first = 0.0;
-    HYG_DMP_CUDA(cudaMemcpyAsync(&first, d_t, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    HYG_DMP_CUDA(cudaStreamSynchronize(c->stream));
-    if (fdr_threshold < first) {                                   // :8-9
-      *k = 0; *Qk = 0.0; *threshold = 0.0;
-    } else {
-      // s >= 1 here (Qs[0] = sorted[0] <= fdr_threshold)
-      HYG_DMP_CUDA(cudaMemcpyAsync(Qk, d_q + (s - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-      if (s == n) *threshold = 1.01;                               // :10-11
-      else HYG_DMP_CUDA(cudaMemcpyAsync(threshold, d_t + s, sizeof(double), cudaMemcpyDeviceToHost, c->stream));   // :12
-      HYG_DMP_CUDA(cudaStreamSynchronize(c->stream));
-      *k = s;
-    }
-  } catch (const std::exception& e) {
-    cleanup();
-    return fail(c, HYG_ERR_CUDA, std::string("thrust: ") + e.what());
+  unsigned long long *d_k = nullptr, *d_k2 = nullptr;
+  HYG_FDR_CUDA(sc.get(&d_t, n)); HYG_FDR_CUDA(sc.get(&d_q, n)); HYG_FDR_CUDA(sc.get(&d_k, n)); HYG_FDR_CUDA(sc.get(&d_k2, n));
+  HYG_FDR_CUDA(cudaMemcpyAsync(d_t, test_statistics, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  hyg::dmp_make_keys_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(d_t, d_k, n);
+  HYG_FDR_CUDA(dmp_radix_sort(c, sc, d_k, d_k2, nullptr, nullptr, n));                       // np.sort (multiple_testing.py:4)
+  hyg::dmp_keys_to_doubles_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(d_k, d_t, n);
+  HYG_FDR_CUDA(dmp_inclusive_scan(c, sc, d_t, d_q, n));                                      // np.cumsum
+  hyg::dmp_running_mean_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(d_q, d_q, n);          // Qs (:5-6)
+  uint64_t s = 0;
+  HYG_FDR_CUDA(dmp_count_le(c, sc, d_q, n, fdr_threshold, &s));                              // :7
+  double first = 0.0;
+  HYG_FDR_CUDA(cudaMemcpyAsync(&first, d_t, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  HYG_FDR_CUDA(cudaStreamSynchronize(c->stream));
+  if (fdr_threshold < first) {                                   // :8-9
+    *k = 0; *Qk = 0.0; *threshold = 0.0;
+  } else {
+    // s >= 1 here (Qs[0] = sorted[0] <= fdr_threshold)
+    HYG_FDR_CUDA(cudaMemcpyAsync(Qk, d_q + (s - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (s == n) *threshold = 1.01;                               // :10-11
+    else HYG_FDR_CUDA(cudaMemcpyAsync(threshold, d_t + s, sizeof(double), cudaMemcpyDeviceToHost, c->stream));   // :12
+    HYG_FDR_CUDA(cudaStreamSynchronize(c->stream));
+    *k = s;
   }
-  cleanup();
   return HYG_OK;
 }
 
@@ -1214,35 +1277,30 @@ int hyg_weighted_fdr_procedure(hyg_ctx* c, uint64_t n, const double* test_statis
   if (!c || !test_statistics || !weights_false_positives || !weights_false_negatives || !n_selected || !indices || !Nk || n == 0)
     return fail(c, HYG_ERR_ARG, "null argument / empty input");
   HYG_CUDA(c, cudaSetDevice(c->device));
+  DmpScratch sc(c);
   double *d_t = nullptr, *d_fp = nullptr, *d_fn = nullptr, *d_rank = nullptr, *d_ex = nullptr, *d_sum = nullptr;
-  unsigned long long* d_idx = nullptr;
-  auto cleanup = [&]() { pool_free(c, d_t); pool_free(c, d_fp); pool_free(c, d_fn); pool_free(c, d_rank); pool_free(c, d_ex); pool_free(c, d_sum); pool_free(c, d_idx); };
-  for (double** p : {&d_t, &d_fp, &d_fn, &d_rank, &d_ex, &d_sum}) HYG_DMP_CUDA(pool_alloc(c, reinterpret_cast<void**>(p), n * sizeof(double)));
-  HYG_DMP_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_idx), n * sizeof(unsigned long long)));
-  HYG_DMP_CUDA(cudaMemcpyAsync(d_t, test_statistics, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  HYG_DMP_CUDA(cudaMemcpyAsync(d_fp, weights_false_positives, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  HYG_DMP_CUDA(cudaMemcpyAsync(d_fn, weights_false_negatives, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  try {
-    auto pol = thrust::cuda::par.on(c->stream);
-    hyg::dmp_weighted_rank_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(d_t, d_fp, d_fn, fdr_threshold, d_rank, d_ex, d_idx, n);
-    thrust::device_ptr<double> rank(d_rank), ex(d_ex), sum(d_sum);
-    thrust::device_ptr<unsigned long long> idx(d_idx);
-    // np.argsort(ranking) (:15); ties keep the smaller index first (numpy's default sort leaves tie order unspecified)
-    thrust::stable_sort_by_key(pol, rank, rank + n, thrust::make_zip_iterator(thrust::make_tuple(idx, ex)));
-    thrust::inclusive_scan(pol, ex, ex + n, sum);                  // Nsums (:18)
-    const uint64_t s = static_cast<uint64_t>(thrust::count_if(pol, sum, sum + n, [] __device__(double v) { return v <= 0.0; }));   // :19
-    *n_selected = s;
-    if (s > 0) HYG_DMP_CUDA(cudaMemcpyAsync(indices, d_idx, s * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-    // Nsums[s-1]; for s = 0 Python's index -1 is the last element (:20)
-    HYG_DMP_CUDA(cudaMemcpyAsync(Nk, d_sum + (s > 0 ? s - 1 : n - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    HYG_DMP_CUDA(cudaStreamSynchronize(c->stream));
-  } catch (const std::exception& e) {
-    cleanup();
-    return fail(c, HYG_ERR_CUDA, std::string("thrust: ") + e.what());
-  }
-  cleanup();
+  unsigned long long *d_idx = nullptr, *d_key = nullptr, *d_k2 = nullptr, *d_p2 = nullptr;
+  for (double** p : {&d_t, &d_fp, &d_fn, &d_rank, &d_ex, &d_sum}) HYG_FDR_CUDA(sc.get(p, n));
+  for (unsigned long long** p : {&d_idx, &d_key, &d_k2, &d_p2}) HYG_FDR_CUDA(sc.get(p, n));
+  HYG_FDR_CUDA(cudaMemcpyAsync(d_t, test_statistics, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  HYG_FDR_CUDA(cudaMemcpyAsync(d_fp, weights_false_positives, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  HYG_FDR_CUDA(cudaMemcpyAsync(d_fn, weights_false_negatives, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  hyg::dmp_weighted_rank_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(d_t, d_fp, d_fn, fdr_threshold, d_rank, d_ex, d_idx, n);
+  // np.argsort(ranking) (:15); ties keep the smaller index first (numpy's default sort leaves tie order unspecified)
+  hyg::dmp_make_keys_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(d_rank, d_key, n);
+  HYG_FDR_CUDA(dmp_radix_sort(c, sc, d_key, d_k2, d_idx, d_p2, n));
+  hyg::dmp_gather_kernel<<<c->num_sms * 4, 256, 0, c->stream>>>(d_ex, d_idx, d_rank, n);     // ranked excessive error rates (:17), d_rank reused
+  HYG_FDR_CUDA(dmp_inclusive_scan(c, sc, d_rank, d_sum, n));                                 // Nsums (:18)
+  uint64_t s = 0;
+  HYG_FDR_CUDA(dmp_count_le(c, sc, d_sum, n, 0.0, &s));                                      // :19
+  *n_selected = s;
+  if (s > 0) HYG_FDR_CUDA(cudaMemcpyAsync(indices, d_idx, s * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  // Nsums[s-1]; for s = 0 Python's index -1 is the last element (:20)
+  HYG_FDR_CUDA(cudaMemcpyAsync(Nk, d_sum + (s > 0 ? s - 1 : n - 1), sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  HYG_FDR_CUDA(cudaStreamSynchronize(c->stream));
   return HYG_OK;
 }
+#undef HYG_FDR_CUDA
 #undef HYG_DMP_CUDA
 
 int hyg_sg_sample_theta_prior(uint32_t dim, uint64_t seed, double* theta) {

@@ -267,7 +267,7 @@ __device__ __forceinline__ void dmp_site_stats_entry(const DmpArgs& a, unsigned 
 extern __shared__ __align__(16) unsigned char hyg_dmp_smem[];
 __global__ void __launch_bounds__(HYG_DMP_NT) dmp_site_stats_kernel(DmpArgs a) { dmp_site_stats_entry(a, hyg_dmp_smem); }
 
-// ---- FDR procedures (multiple_testing.py) : element-wise pieces; sorts and scans are thrust calls in hyg_api.cu ----
+// ---- FDR procedures (multiple_testing.py) : element-wise pieces; the sort, scan and count kernels follow ----
 // Qs[i] = 1 / (i + 1) * cumsum[i]   (multiple_testing.py:5-6: 1./np.linspace(1, n, n) * np.cumsum(sorted))
 __global__ void dmp_running_mean_kernel(const double* cumsum, double* qs, unsigned long long n) {
   for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < n;
@@ -286,6 +286,165 @@ __global__ void dmp_weighted_rank_kernel(const double* t, const double* wfp, con
     excess[i] = num;
     index[i] = i;
   }
+}
+
+// ---- device sort / scan / count for the two procedures (no library calls) -----------------------------------------------------
+// Stable LSD radix sort of (64-bit key, 64-bit payload) records, 8 bits per pass: per pass a histogram kernel (256 bins per tile),
+// one single-block exclusive scan over the bin-major (bin, tile) counts, and a scatter kernel that walks its tile IN ORDER, 256
+// records at a time, ranking equal digits with __match_any_sync inside a warp and a per-warp count table across warps -- so equal
+// keys keep their input order (np.sort / a stable argsort with ties by index).
+#define HYG_RS_NT 256
+#define HYG_RS_WARPS (HYG_RS_NT / 32)
+
+__device__ __forceinline__ unsigned long long dmp_key_of_double(double v) {
+  const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v));
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);   // ascending order of the doubles (-0 < +0; NaNs last)
+}
+__device__ __forceinline__ double dmp_double_of_key(unsigned long long k) {
+  const unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double(static_cast<long long>(b));
+}
+__global__ void dmp_make_keys_kernel(const double* v, unsigned long long* keys, unsigned long long n) {
+  for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
+    keys[i] = dmp_key_of_double(v[i]);
+}
+__global__ void dmp_keys_to_doubles_kernel(const unsigned long long* keys, double* v, unsigned long long n) {
+  for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
+    v[i] = dmp_double_of_key(keys[i]);
+}
+// counts[bin * n_tiles + tile]
+__global__ void __launch_bounds__(HYG_RS_NT) dmp_radix_hist_kernel(const unsigned long long* keys, unsigned long long n, unsigned long long tile, int shift,
+                                                                   unsigned int* counts, unsigned int n_tiles) {
+  __shared__ unsigned int h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const unsigned long long lo = blockIdx.x * tile, hi = (lo + tile < n) ? lo + tile : n;
+  for (unsigned long long i = lo + threadIdx.x; i < hi; i += HYG_RS_NT) atomicAdd(&h[(keys[i] >> shift) & 0xFFull], 1u);
+  __syncthreads();
+  counts[static_cast<size_t>(threadIdx.x) * n_tiles + blockIdx.x] = h[threadIdx.x];
+}
+// exclusive scan of m unsigned counts into 64-bit offsets, one block: per-thread contiguous chunks + a block scan of the chunk sums
+__global__ void __launch_bounds__(1024) dmp_scan_counts_kernel(const unsigned int* counts, unsigned long long* offsets, unsigned int m) {
+  __shared__ unsigned long long part[1024];
+  const unsigned int per = (m + 1023u) / 1024u;
+  const unsigned int lo = threadIdx.x * per, hi = (lo + per < m) ? lo + per : m;
+  unsigned long long sum = 0;
+  for (unsigned int i = lo; i < hi; i++) sum += counts[i];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long acc = 0;
+    for (int i = 0; i < 1024; i++) { const unsigned long long v = part[i]; part[i] = acc; acc += v; }
+  }
+  __syncthreads();
+  unsigned long long acc = part[threadIdx.x];
+  for (unsigned int i = lo; i < hi; i++) { offsets[i] = acc; acc += counts[i]; }
+}
+template <bool PAY>
+__global__ void __launch_bounds__(HYG_RS_NT) dmp_radix_scatter_kernel(const unsigned long long* keys, const unsigned long long* pay, unsigned long long* keys_out,
+                                                                      unsigned long long* pay_out, unsigned long long n, unsigned long long tile, int shift,
+                                                                      const unsigned long long* offsets, unsigned int n_tiles) {
+  __shared__ unsigned long long base[256];                 // next free output position per digit for this tile
+  __shared__ unsigned int wcnt[HYG_RS_WARPS][256];         // records of each digit in each warp of the current chunk
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  base[tid] = offsets[static_cast<size_t>(tid) * n_tiles + blockIdx.x];
+#pragma unroll
+  for (int w = 0; w < HYG_RS_WARPS; w++) wcnt[w][tid] = 0;
+  __syncthreads();
+  const unsigned long long lo = blockIdx.x * tile, hi = (lo + tile < n) ? lo + tile : n;
+  for (unsigned long long c0 = lo; c0 < hi; c0 += HYG_RS_NT) {
+    const unsigned long long i = c0 + tid;
+    const bool live = i < hi;
+    const unsigned long long k = live ? keys[i] : 0ull;
+    const unsigned int d = live ? static_cast<unsigned int>((k >> shift) & 0xFFull) : 0x100u;   // 0x100: no record
+    const unsigned int peers = __match_any_sync(0xFFFFFFFFu, d);
+    const unsigned int before = __popc(peers & ((1u << lane) - 1u));
+    if (live && before == 0) wcnt[warp][d] = __popc(peers);
+    __syncthreads();
+    if (live) {
+      unsigned long long pos = base[d] + before;
+#pragma unroll
+      for (int w = 0; w < HYG_RS_WARPS; w++) pos += (w < warp) ? wcnt[w][d] : 0u;
+      keys_out[pos] = k;
+      if (PAY) pay_out[pos] = pay[i];
+    }
+    __syncthreads();
+    {   // thread = digit: advance the base and clear the table for the next chunk
+      unsigned int tot = 0;
+#pragma unroll
+      for (int w = 0; w < HYG_RS_WARPS; w++) { tot += wcnt[w][tid]; wcnt[w][tid] = 0; }
+      base[tid] += tot;
+    }
+    __syncthreads();
+  }
+}
+
+// inclusive scan of doubles: (1) tile sums, (2) one-block exclusive scan of the tile sums, (3) in-tile scan + offset.  A tile is
+// walked in chunks of 256 x 4 elements: thread-sequential over its 4, shuffle scan over the warp, warp totals through shared memory.
+#define HYG_SCAN_ITEMS 4
+__device__ __forceinline__ double dmp_block_excl(double v, double* sh, double& total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const double t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) sh[warp] = inc;
+  __syncthreads();
+  double off = 0.0, tot = 0.0;
+#pragma unroll
+  for (int w = 0; w < HYG_RS_WARPS; w++) { const double x = sh[w]; if (w < warp) off += x; tot += x; }
+  __syncthreads();
+  total = tot;
+  return off + inc - v;
+}
+__global__ void __launch_bounds__(HYG_RS_NT) dmp_tile_sum_kernel(const double* x, unsigned long long n, unsigned long long tile, double* sums) {
+  __shared__ double sh[HYG_RS_WARPS];
+  const unsigned long long lo = blockIdx.x * tile, hi = (lo + tile < n) ? lo + tile : n;
+  double carry = 0.0;
+  for (unsigned long long c0 = lo; c0 < hi; c0 += HYG_RS_NT * HYG_SCAN_ITEMS) {
+    double v = 0.0;
+#pragma unroll
+    for (int j = 0; j < HYG_SCAN_ITEMS; j++) { const unsigned long long i = c0 + threadIdx.x * HYG_SCAN_ITEMS + j; if (i < hi) v += x[i]; }
+    double tot;
+    dmp_block_excl(v, sh, tot);
+    carry += tot;
+  }
+  if (threadIdx.x == 0) sums[blockIdx.x] = carry;
+}
+__global__ void dmp_scan_tile_sums_kernel(double* sums, unsigned int m) {   // one thread: m <= a few hundred
+  if (blockIdx.x == 0 && threadIdx.x == 0) { double acc = 0.0; for (unsigned int i = 0; i < m; i++) { const double v = sums[i]; sums[i] = acc; acc += v; } }
+}
+__global__ void __launch_bounds__(HYG_RS_NT) dmp_tile_scan_kernel(const double* x, double* out, unsigned long long n, unsigned long long tile, const double* offs) {
+  __shared__ double sh[HYG_RS_WARPS];
+  const unsigned long long lo = blockIdx.x * tile, hi = (lo + tile < n) ? lo + tile : n;
+  double carry = offs[blockIdx.x];
+  for (unsigned long long c0 = lo; c0 < hi; c0 += HYG_RS_NT * HYG_SCAN_ITEMS) {
+    double e[HYG_SCAN_ITEMS], v = 0.0;
+#pragma unroll
+    for (int j = 0; j < HYG_SCAN_ITEMS; j++) { const unsigned long long i = c0 + threadIdx.x * HYG_SCAN_ITEMS + j; e[j] = (i < hi) ? x[i] : 0.0; v += e[j]; }
+    double tot;
+    double run = carry + dmp_block_excl(v, sh, tot);
+#pragma unroll
+    for (int j = 0; j < HYG_SCAN_ITEMS; j++) { const unsigned long long i = c0 + threadIdx.x * HYG_SCAN_ITEMS + j; run += e[j]; if (i < hi) out[i] = run; }
+    carry += tot;
+  }
+}
+// #{i : x[i] <= bound}
+__global__ void dmp_count_le_kernel(const double* x, unsigned long long n, double bound, unsigned long long* count) {
+  unsigned long long c = 0;
+  for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
+    c += (x[i] <= bound) ? 1ull : 0ull;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(count, c);
+}
+// gather a double array through the sorted payload (index) array
+__global__ void dmp_gather_kernel(const double* src, const unsigned long long* idx, double* dst, unsigned long long n) {
+  for (unsigned long long i = blockIdx.x * static_cast<unsigned long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<unsigned long long>(gridDim.x) * blockDim.x)
+    dst[i] = src[idx[i]];
 }
 #endif
 

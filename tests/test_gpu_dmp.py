@@ -75,3 +75,31 @@ def test_fdr_edge_cases_vs_oracle(built):
     idx, Nk = dmp.weighted_FDR_procedure(np.array([0.9, 0.8]), 0.05, np.ones(2), np.ones(2))
     i2, N2 = dmp_oracle.weighted_FDR_procedure(np.array([0.9, 0.8]), 0.05, np.ones(2), np.ones(2))
     assert len(idx) == 0 and len(i2) == 0 and abs(Nk - N2) < 1e-12          # nothing selected: Nsums[-1], as the reference
+
+
+def test_device_sort_scan_count_at_size_with_ties_and_signs(built):
+    """The procedures' sort / scan / count are this repo's kernels (stable LSD radix sort on the order-preserving image of the
+    doubles, three-kernel scan): 300 000 statistics from a set of 76 values -- thousands of exact ties -- with ranking values of both
+    signs; the selected indices must be those of a STABLE argsort, in order."""
+    from hygeia_b200 import dmp
+    rng = np.random.default_rng(12)
+    n = 300_000
+    t = rng.integers(0, 76, size=n) / 75.0
+    wfn = rng.integers(1, 4, size=n).astype(np.float64)
+    wfp = np.ones(n)
+    a = 0.3
+    ranking = wfp * (t - a) / (wfn * (1 - t) + wfp * np.abs(t - a))
+    order = np.argsort(ranking, kind="stable")
+    nsums = np.cumsum((wfp * (t - a))[order])
+    s = int(np.sum(nsums <= 0))
+    idx, Nk = dmp.weighted_FDR_procedure(t, a, wfp, wfn)
+    assert (ranking < 0).any() and (ranking > 0).any() and s > 1000
+    assert len(idx) == s or abs(nsums[min(len(idx), n - 1)]) < 1e-6      # the count may differ only where a partial sum is 0 up to rounding
+    m = min(s, len(idx))
+    assert np.array_equal(idx[:m], order[:m])
+    assert abs(Nk - nsums[len(idx) - 1]) < 1e-7
+    k, Qk, thr = dmp.FDR_procedure(t, 0.2)
+    st = np.sort(t)
+    qs = np.cumsum(st) / np.arange(1, n + 1)
+    k2 = int(np.sum(qs <= 0.2))
+    assert abs(k - k2) <= 2 and abs(Qk - qs[k - 1]) < 1e-9 and thr == st[k]

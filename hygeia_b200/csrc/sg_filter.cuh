@@ -1038,9 +1038,6 @@ __device__ void sg_filter_chain(SgModelDev& mdl, const SgChainDev& ch, const SgR
     // (the lag set is ordered by site, oldest first); with the left-halo check on, a segment first steps through
     // HYG_OVL_ROWS sites of the next one.
     bool exit_now = false;
-#ifdef HYG_KEEP_B5
-    __syncthreads();
-#endif
     if (!PE && t + 1 >= run_to && t + 1 < T) {
       __syncthreads();
       exit_now = (lag.n_pend == 0) || (static_cast<unsigned int>(lag.pend_t()[0]) >= own_hi);

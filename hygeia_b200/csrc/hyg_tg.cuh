@@ -406,10 +406,12 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
         tg_sort_desc(s, n_sort);
 #endif
         // e[p] = exp(sorted normalised log-weight); reverse cumulative sums rcs[p] = sum_{i >= p} e[i]
+        double* slw = reinterpret_cast<double*>(s.key);   // sorted normalised log-weights (the keys are not needed after the sort)
         for (int p = tid; p < n_sort; p += HYG_TG_NT) {
-          double v = 0.0;
-          if (p < n_sel) v = exp(s.w[s.sidx[p]] - lse);
+          double v = 0.0, lwn = -HYG_INF;
+          if (p < n_sel) { lwn = s.w[s.sidx[p]] - lse; v = exp(lwn); }
           s.e[p] = v;
+          slw[p] = lwn;      // overwrites key[p]: the sort ended with a block barrier and nothing reads the keys after it
         }
         __syncthreads();
         // Reverse cumulative sums in chunks of 32, walked from the end: suf[p] = (shuffle-tree suffix inside the chunk) + carry,
@@ -455,11 +457,11 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
             const double lcn = s.lcn_tab[a];
             int cnt = 0;
             // counts beyond M do not change the outcome; a + 96 <= M + 95 < n_sel whenever n_sel < F
-            for (int base = a; base < n_sel && base < a + 96; base += 32) {
-              const int p = base + lane;
-              const bool gt = (p < n_sel) && (lcn + (s.w[s.sidx[p < n_sel ? p : 0]] - lse) > 0.0);
-              cnt += __popc(__ballot_sync(HYG_FULL, gt));
-            }
+            // three independent loads, then three ballots (slw is -inf beyond n_sel, up to n_sort >= 64; beyond that: no particle)
+            const int p0 = a + lane, p1 = p0 + 32, p2 = p0 + 64;
+            const double x0 = (p0 < n_sel) ? slw[p0] : -HYG_INF, x1 = (p1 < n_sel) ? slw[p1] : -HYG_INF, x2 = (p2 < n_sel) ? slw[p2] : -HYG_INF;
+            cnt = __popc(__ballot_sync(HYG_FULL, lcn + x0 > 0.0)) + __popc(__ballot_sync(HYG_FULL, lcn + x1 > 0.0)) +
+                  __popc(__ballot_sync(HYG_FULL, lcn + x2 > 0.0));
             b = a; a = a + cnt; lc = lcn;
           }
           int Kf = b;

@@ -352,6 +352,28 @@ inline int __reduce_min_sync(unsigned, int v) {
   });
   return static_cast<int>(static_cast<int64_t>(emu::my_warp().result[0]));
 }
+inline int __reduce_add_sync(unsigned, int v) {
+  emu::warp_rendezvous(static_cast<uint64_t>(static_cast<int64_t>(v)), [](emu::WarpState& w) {
+    int64_t b = 0;
+    unsigned n = emu::warp_width();
+    for (unsigned i = 0; i < n; i++) b += static_cast<int64_t>(w.slot[i]);
+    w.result[0] = static_cast<uint64_t>(b);
+  });
+  return static_cast<int>(static_cast<int64_t>(emu::my_warp().result[0]));
+}
+// mask of the lanes holding the same value as the caller (the last lane to arrive works out all the masks)
+inline unsigned __match_any_sync(unsigned, int v) {
+  unsigned lane = threadIdx.x % 32;
+  emu::warp_rendezvous(static_cast<uint64_t>(static_cast<int64_t>(v)), [](emu::WarpState& w) {
+    unsigned n = emu::warp_width();
+    for (unsigned i = 0; i < n; i++) {
+      unsigned b = 0;
+      for (unsigned j = 0; j < n; j++) if (w.slot[j] == w.slot[i]) b |= (1u << j);
+      w.result[i] = b;
+    }
+  });
+  return static_cast<unsigned>(emu::my_warp().result[lane]);
+}
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }
 inline int __all_sync(unsigned m, int pred) {
   unsigned n = emu::warp_width();

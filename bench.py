@@ -445,9 +445,9 @@ def run_two_group(args):
             "roofline": {"bound": "hbm", "kernel": "tg_kernel (K4/K5), one persistent launch per step over all windows x seeds of the rank", "achieved": alg / (ms_tg / 1000.0) / 1e9,
                          "peak": peak, "unit": "GB/s", "frac": alg / (ms_tg / 1000.0) / 1e9 / peak, "traffic": None,
                          "algorithmic_bytes_per_launch": alg, "ms_per_launch": ms_tg, "share_of_step": ms_tg / (ms_tg + float(np.mean(em))),
-                         "latency_bound": {"site_chains_per_s": site_chains / (ms_tg / 1000.0), "us_per_site_per_chain_in_flight": 1000.0 * ms_tg * 148 / site_chains,
+                         "latency_bound": {"site_chains_per_s": site_chains / (ms_tg / 1000.0), "us_per_site_per_chain_in_flight": 1000.0 * ms_tg * 296 / site_chains, "us_per_site_per_sm": 1000.0 * ms_tg * 148 / site_chains,
                                            "halo_overhead": stepped / owned - 1.0, "mean_split_fraction_first_windows": split,
-                                           "note": "a sequential recursion per window: the bound is per-site latency x 148 chains in flight (DESIGN.md section 4, K4/K5)"}},
+                                           "note": "a sequential recursion per window: the bound is per-site latency x 296 chains in flight (two resident CTAs per SM) (DESIGN.md section 4, K4/K5)"}},
             "roofline_emission": {"bound": "hbm", "kernel": "sg_emission_kernel<6> (K1), both groups", "ms_per_launch": float(np.mean(em)),
                                   "achieved": stepped * (2 * 4 * S + 2 * 8 * R) / (float(np.mean(em)) / 1000.0) / 1e9, "peak": peak, "unit": "GB/s"},
             "wall_ms_per_step_incl_trajectory_download": 1000.0 * wall / args.steps}

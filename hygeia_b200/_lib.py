@@ -48,7 +48,7 @@ class HygTgModel(C.Structure):
         ("log_p_control", C.c_void_p), ("omega_control", C.c_void_p), ("omega_case", C.c_void_p),
         ("kappa_control", C.c_void_p), ("kappa_case", C.c_void_p),
         ("merge_prob", C.c_double), ("split_prob", C.c_double),
-        ("rho_control", C.c_void_p), ("rho_case", C.c_void_p), ("d_max", C.c_uint32), ("hazard_mode", C.c_uint32), ("sort_preselect", C.c_uint32 * 2),
+        ("rho_control", C.c_void_p), ("rho_case", C.c_void_p), ("d_max", C.c_uint32), ("hazard_mode", C.c_uint32), ("sort_preselect", C.c_uint32 * 2), ("sort_scratch_from", C.c_uint32),
     ]
 
 

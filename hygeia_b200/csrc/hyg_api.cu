@@ -956,6 +956,7 @@ int hyg_tg_set_model(hyg_ctx* c, const hyg_tg_model* m, uint64_t t_max) {
   h.R = static_cast<int>(R); h.u = static_cast<int>(m->minimum_duration); h.M = static_cast<int>(m->num_resampled); h.B = static_cast<int>(m->num_backward);
   h.presel[0] = std::max(m->sort_preselect[0] ? static_cast<int>(m->sort_preselect[0]) : h.M + 110, h.M + 96);
   h.presel[1] = std::max(m->sort_preselect[1] ? static_cast<int>(m->sort_preselect[1]) : 3 * h.M + 250, h.presel[0]);
+  h.big_from = m->sort_scratch_from ? static_cast<int>(std::min<uint32_t>(m->sort_scratch_from - 1, HYG_TG_SORTMAX)) : HYG_TG_SORTMAX;
   // tf.nn.softmax of the log-probabilities with a -inf diagonal (case_control_regime_model.py:90-95), in log space
   for (uint32_t i = 0; i < R; i++) {
     double mx = -HUGE_VAL;
@@ -1064,13 +1065,14 @@ int hyg_tg_run(hyg_ctx* c, const hyg_tg_chain* chains, uint32_t n, float* ms_dev
   hyg::TgRunDev run;
   run.t_max = t_max;
   run.anc_pitch = static_cast<unsigned long long>(std::max(M, R * R));
-  run.ws_stride = (sizeof(hyg::TgStepRec) * t_max + sizeof(hyg::TgAncRec) * t_max * run.anc_pitch + 255) & ~static_cast<size_t>(255);
+  run.scratch_off = (sizeof(hyg::TgStepRec) * t_max + sizeof(hyg::TgAncRec) * t_max * run.anc_pitch + 255) & ~static_cast<size_t>(255);
+  run.ws_stride = (run.scratch_off + static_cast<size_t>(HYG_TG_BIGMAX) * 18 + 255) & ~static_cast<size_t>(255);
   run.n_chains = static_cast<int>(n);
   run.queue = c->d_queue;
-  // one CTA per SM; fewer when the per-CTA ancestor history would not fit in what is free
+  // HYG_TG_CTAS CTAs per SM; fewer when the per-CTA ancestor history would not fit in what is free
   size_t free_b = 0, total_b = 0;
   HYG_TG_CUDA(cudaMemGetInfo(&free_b, &total_b));
-  int grid = static_cast<int>(std::min<uint32_t>(n, static_cast<uint32_t>(c->num_sms)));
+  int grid = static_cast<int>(std::min<uint32_t>(n, static_cast<uint32_t>(c->num_sms) * HYG_TG_CTAS));
   const size_t fit = static_cast<size_t>(0.8 * static_cast<double>(free_b)) / run.ws_stride;
   if (fit < 1) { cleanup(); return fail(c, HYG_ERR_CUDA, "two-group: not enough device memory for one chain's ancestor history"); }
   grid = static_cast<int>(std::min<size_t>(static_cast<size_t>(grid), fit));

@@ -22,14 +22,25 @@
 
 #include "hyg_common.cuh"
 
+// Threads per CTA x resident CTAs per SM, measured on B200 (us per site and chain slot -> site-chains/s per GPU):
+//   round 1, one CTA per SM: 256 -> 173, 512 -> 133, 768 -> 153, 1024 -> 168 us
+//   round 2: 512 x 1: 25.7 us, 5.8e6/s;  256 x 2: 35.9 us per chain but two chains per SM, 8.2e6/s  <- the kernel is latency-bound
+//   (IPC 1.3 with one CTA per SM), so a second resident chain fills the idle issue slots
 #ifndef HYG_TG_NT
-#define HYG_TG_NT 512   // measured on B200: 256 -> 173, 512 -> 133, 768 -> 153, 1024 -> 168 us per site and chain
+#define HYG_TG_NT 256
 #endif
 #define HYG_TG_NW (HYG_TG_NT / 32)
 #define HYG_TG_NPMAX 2432     // >= M * (2R + R^2) for M = 50, R = 6, multiple of 256... (2400)
 #define HYG_TG_MMAX 64        // max resampled ancestors
 #define HYG_TG_BMAX 32        // max backward trajectories
-#define HYG_TG_SORTMAX 4096
+#ifndef HYG_TG_SORTMAX
+#define HYG_TG_SORTMAX 2048   // records the shared-memory sort arrays hold (two CTAs of 92 KB fit an SM); more -> global scratch
+#endif
+#ifndef HYG_TG_CTAS
+#define HYG_TG_CTAS 2         // resident CTAs per SM the kernel is compiled and launched for
+#endif
+#define HYG_TG_EMAX (HYG_TG_SORTMAX > HYG_TG_NPMAX ? HYG_TG_SORTMAX : HYG_TG_NPMAX)
+#define HYG_TG_BIGMAX 4096    // the global scratch of a CTA holds this many (key, value, index) records: >= the next power of two of NPMAX
 #define HYG_TG_BINS 256       // 1-nat bins of the normalised log-weight for the pre-selection of the sort
 #define HYG_TG_SELMAX 512     // pre-selection: at most this many of the heaviest particles are sorted on the first attempt
 #define HYG_TAG_FILTER 0x46494C54u
@@ -48,6 +59,7 @@ struct TgModelDev {
   const double2* lrho_k;
   double nl_rm1, nl_rm2;         // -log(R - 1), -log(R - 2)
   int presel[2];                 // the sort covers the heaviest particles only: at least this many on the 1st / 2nd attempt
+  int big_from;                  // more selected particles than this: the sort runs in the CTA's global scratch (<= HYG_TG_SORTMAX)
 };
 
 struct TgState {   // one particle
@@ -84,6 +96,7 @@ struct TgRunDev {
   unsigned long long ws_stride;    // bytes per CTA
   unsigned long long t_max;
   unsigned long long anc_pitch;    // ancestor records per site (>= M and >= the R^2 particles of the first site)
+  unsigned long long scratch_off;  // byte offset of the CTA's sort scratch inside its workspace (HYG_TG_BIGMAX x 18 bytes)
   unsigned int* queue;
   int n_chains;
 };
@@ -163,7 +176,7 @@ struct TgSmem {
   // sorting / resampling scratch
   unsigned long long key[HYG_TG_SORTMAX];   // exact order-preserving image of the normalised log-weight
   unsigned short sidx[HYG_TG_SORTMAX];      // particle index travelling with the key
-  double e[HYG_TG_SORTMAX];        // exp(normalised log-weight) in sorted order, then cumulative sums
+  double e[HYG_TG_EMAX];           // exp(normalised log-weight) by particle, then in sorted order, then cumulative sums
   // ancestors
   TgState anc[HYG_TG_MMAX];
   double anc_w[HYG_TG_MMAX], anc_logW[HYG_TG_MMAX];
@@ -228,7 +241,8 @@ __device__ __forceinline__ int tg_block_excl_scan(int v, int& total, TgSmem& s, 
 
 // in-place bitonic sort of (s.key, s.sidx)[0..n), n a power of two, all threads of the CTA: descending in the key, ties by
 // ascending particle index (= a stable descending sort of the weights in particle order)
-__device__ __forceinline__ void tg_sort_desc(TgSmem& s, int n) {
+template <class KP, class SP>
+__device__ __forceinline__ void tg_sort_desc(KP key, SP sidx, int n) {
   const int half = n >> 1;
   // only the warps that hold pairs take part (n = 256: four of sixteen) and meet at their own named barrier; the others wait
   // at the block barrier below
@@ -241,11 +255,11 @@ __device__ __forceinline__ void tg_sort_desc(TgSmem& s, int n) {
         for (int q = threadIdx.x; q < half; q += HYG_TG_NT) {
           const int i = ((q >> lj) << (lj + 1)) | (q & (j - 1));
           const int l = i | j;
-          const unsigned long long a = s.key[i], b = s.key[l];
-          const unsigned short ia = s.sidx[i], ib = s.sidx[l];
+          const unsigned long long a = key[i], b = key[l];
+          const unsigned short ia = sidx[i], ib = sidx[l];
           const bool desc = ((i & k) == 0);
           const bool a_after_b = (a < b) || (a == b && ia > ib);   // a belongs after b in the final order
-          if (a_after_b == desc) { s.key[i] = b; s.key[l] = a; s.sidx[i] = ib; s.sidx[l] = ia; }
+          if (a_after_b == desc) { key[i] = b; key[l] = a; sidx[i] = ib; sidx[l] = ia; }
         }
         // The 32 pairs q of a warp (q = tid + NT m) with a stride <= 32 lie in ONE block of 64 consecutive elements, the same
         // block for every such stride: between two such stages a warp barrier is enough.
@@ -256,6 +270,179 @@ __device__ __forceinline__ void tg_sort_desc(TgSmem& s, int n) {
     }
   }
   __syncthreads();
+}
+
+// One attempt of OptimalFiniteState (resampling_functions.py:7-52) on the particles of the histogram bins <= selbin: compaction,
+// sort, suffix sums, the K search, the systematic resampling of the residual.  Returns 1 when a tooth of the comb fell behind
+// the sorted prefix (the caller repeats with more particles), else 0 with s.parents / K / log_c / mode set.
+// BIG = false: the sort's arrays are the shared-memory ones (<= HYG_TG_SORTMAX particles); BIG = true: more particles than
+// that were selected (only possible when > 2048 of a site's 2400 particles are finite AND a tooth reached the lightest of them),
+// and the same code runs on a global scratch area of the CTA.
+template <bool BIG>
+__device__ __noinline__ int tg_ofs_attempt(TgSmem& s, const TgChainDev& ch, unsigned char* scratch, int attempt, int selbin, int n_sel, int F, int M,
+                                           unsigned long long t, double lse, double mx, double inv_se, int n_part, int c0, int c1, int& flip,
+                                           int& K, double& log_c, int& mode) {
+  const TgModelDev& md = s.mdl;
+  (void)md;
+  const int tid = threadIdx.x, lane = tid & 31;
+  unsigned long long* key = BIG ? reinterpret_cast<unsigned long long*>(scratch) : s.key;
+  double* ev = BIG ? reinterpret_cast<double*>(scratch + sizeof(unsigned long long) * HYG_TG_BIGMAX) : s.e;
+  unsigned short* sidx = BIG ? reinterpret_cast<unsigned short*>(scratch + (sizeof(unsigned long long) + sizeof(double)) * HYG_TG_BIGMAX) : s.sidx;
+  if (tid == 0) { s.ibc[4] = 0; s.ibc[5] = 0; }
+  __syncthreads();
+  // the selected particles' keys (any order: the sort's order is total, ties by particle index) and the others' total weight
+  double rest = 0.0;
+  for (int c = c0; c < c1; c++) {
+    const double v = s.w[c];
+    if (v > -HYG_INF) {
+      const double dn = lse - v;
+      const int bin = (dn < static_cast<double>(HYG_TG_BINS - 1)) ? static_cast<int>(dn < 0.0 ? 0.0 : dn) : HYG_TG_BINS - 1;
+      if (bin <= selbin) {
+        // order-preserving key of the normalised log-weight; the particle index travels beside it (stable ties)
+        unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v - lse));
+        b = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+        const int pos = atomicAdd(&s.ibc[4], 1);
+        key[pos] = b;
+        sidx[pos] = static_cast<unsigned short>(c);
+      } else {
+        rest += (attempt == 0) ? s.e[c] : exp(v - mx);   // exp(v - mx) was kept by the pass above; a repeated attempt finds s.e reused
+      }
+    }
+  }
+  int n_sort = 64;
+  while (n_sort < n_sel) n_sort <<= 1;
+  for (int i = n_sel + tid; i < n_sort; i += HYG_TG_NT) { key[i] = 0ull; sidx[i] = 0xFFFFu; }
+  rest = (n_sel < F) ? tg_block_sum(rest, s, flip) * inv_se : 0.0;
+  __syncthreads();
+#ifndef HYG_TG_SKIP_SORT
+  tg_sort_desc(key, sidx, n_sort);
+#endif
+  // e[p] = exp(sorted normalised log-weight); reverse cumulative sums rcs[p] = sum_{i >= p} e[i]
+  double* slw = reinterpret_cast<double*>(key);   // sorted normalised log-weights (the keys are not needed after the sort)
+  for (int p = tid; p < n_sort; p += HYG_TG_NT) {
+    double v = 0.0, lwn = -HYG_INF;
+    if (p < n_sel) { lwn = s.w[sidx[p]] - lse; v = exp(lwn); }
+    ev[p] = v;
+    slw[p] = lwn;      // overwrites key[p]: the sort ended with a block barrier and nothing reads the keys after it
+  }
+  __syncthreads();
+  // Reverse cumulative sums in chunks of 32, walked from the end: suf[p] = (shuffle-tree suffix inside the chunk) + carry,
+  // carry = the unsorted particles' total, then the later chunks' totals added one after the other.  The trees are
+  // independent, so every warp takes the chunks c = warp, warp + NW, ...; only the carry additions stay sequential.
+  // The sums are only needed at positions <= M (K < M): anc_w doubles as rcs[0..M].
+  const int n_chunks = (n_sel + 31) / 32;
+  for (int cidx = (tid >> 5); cidx < n_chunks; cidx += HYG_TG_NW) {
+    const int p = cidx * 32 + lane;
+    double inc = (p < n_sel) ? ev[p] : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double tt = __shfl_down_sync(HYG_FULL, inc, o);
+      if (lane + o < 32) inc += tt;
+    }
+    if (lane == 0) s.ctot[cidx] = inc;
+  }
+  __syncthreads();
+  if (tid < 32) {
+    double carry = rest;
+    for (int cidx = n_chunks - 1; cidx >= 0; cidx--) {
+      if (cidx * 32 <= M) {   // a chunk that holds positions <= M: its in-chunk suffix sums are needed too
+        const int p = cidx * 32 + lane;
+        double inc = (p < n_sel) ? ev[p] : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double tt = __shfl_down_sync(HYG_FULL, inc, o);
+          if (lane + o < 32) inc += tt;
+        }
+        if (p <= M && p < n_sel) s.anc_w[p] = inc + carry;
+      }
+      carry += s.ctot[cidx];
+    }
+    __syncwarp();   // anc_w[0..M] written above is read by every lane below
+    // fixed point with the reference's loop structure: (a, b, log_c) <- (k_new, a, log_c(a)) while a != b, a < n, a < M
+    // the loop below needs log(M - a) - log(rcs[a]) at a data-dependent sequence of a < M: all M values are taken now, by
+    // the lanes in parallel, so that no logarithm sits on the loop's dependency chain
+    for (int a0 = lane; a0 < M && a0 < n_sel; a0 += 32) s.lcn_tab[a0] = log(static_cast<double>(M - a0)) - log(s.anc_w[a0]);
+    __syncwarp();
+    int a = 0, b = -1;
+    double lc = -1.0;
+    while (a != b && a < F && a < M) {
+      const double lcn = s.lcn_tab[a];
+      int cnt = 0;
+      // counts beyond M do not change the outcome; a + 96 <= M + 95 < n_sel whenever n_sel < F
+      // three independent loads, then three ballots (slw is -inf beyond n_sel, up to n_sort >= 64; beyond that: no particle)
+      const int p0 = a + lane, p1 = p0 + 32, p2 = p0 + 64;
+      const double x0 = (p0 < n_sel) ? slw[p0] : -HYG_INF, x1 = (p1 < n_sel) ? slw[p1] : -HYG_INF, x2 = (p2 < n_sel) ? slw[p2] : -HYG_INF;
+      cnt = __popc(__ballot_sync(HYG_FULL, lcn + x0 > 0.0)) + __popc(__ballot_sync(HYG_FULL, lcn + x1 > 0.0)) +
+            __popc(__ballot_sync(HYG_FULL, lcn + x2 > 0.0));
+      b = a; a = a + cnt; lc = lcn;
+    }
+    int Kf = b;
+    if (!(Kf < F)) { Kf = F; lc = -HYG_INF; }
+    if (lane == 0) { s.ibc[0] = Kf; s.bc[0] = lc; }
+  }
+  __syncthreads();
+  K = s.ibc[0];
+  log_c = s.bc[0];
+  if (log_c - log_c != 0.0) {
+    // log c infinite: multinomial ancestors by inverse CDF over the particle-order weights, unbiased weights
+    mode = 2;
+    // cumulative sums over the particles in index order (s.e reused)
+    for (int c = tid; c < n_part; c += HYG_TG_NT) s.e[c] = (s.w[c] > -HYG_INF) ? exp(s.w[c] - lse) : 0.0;
+    __syncthreads();
+    if (tid == 0) { double acc = 0.0; for (int c = 0; c < n_part; c++) { acc += s.e[c]; s.e[c] = acc; } }
+    __syncthreads();
+    for (int a = tid; a < M; a += HYG_TG_NT) {
+      const double uu = tg_uniform(ch.seed, ch.chain, HYG_TAG_FILTER, (static_cast<uint64_t>(a + 1) << 32) + t) * s.e[n_part - 1];
+      int lo = 0, hi = n_part - 1;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.e[mid] < uu) lo = mid + 1; else hi = mid; }
+      s.parents[a] = lo;
+    }
+    log_c = 0.0;
+    __syncthreads();
+    return 0;
+  }
+  mode = 1;
+  const int L = M - K;
+  // kept particles
+  for (int a = tid; a < K; a += HYG_TG_NT) s.parents[a] = static_cast<int>(sidx[a]);
+  // residual: cumulative sums of e[K..n_sel) in sorted order, in chunks of 32 from K: shuffle-tree prefix inside a chunk (all
+  // warps, chunk c = warp, warp + NW, ...) + the earlier chunks' totals added one after the other (one thread)
+  const int r_chunks = (L > 0) ? (n_sel - K + 31) / 32 : 0;
+  for (int cidx = (tid >> 5); cidx < r_chunks; cidx += HYG_TG_NW) {
+    const int p = K + cidx * 32 + lane;
+    double inc = (p < n_sel) ? ev[p] : 0.0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double tt = __shfl_up_sync(HYG_FULL, inc, o);
+      if (lane >= o) inc += tt;
+    }
+    if (p < n_sel) ev[p] = inc;
+    if (lane == 31) s.ctot[cidx] = inc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double carry = 0.0;
+    for (int cidx = 0; cidx < r_chunks; cidx++) { s.ccar[cidx] = carry; carry += s.ctot[cidx]; }
+  }
+  if (tid == 32) s.ub[0] = tg_uniform(ch.seed, ch.chain, HYG_TAG_FILTER, t);   // the site's resampling uniform, evaluated once
+  __syncthreads();
+  for (int p = K + tid; p < n_sel && L > 0; p += HYG_TG_NT) ev[p] = ev[p] + s.ccar[(p - K) >> 5];
+  __syncthreads();
+  if (L > 0) {
+    const double tot = ev[n_sel - 1] + rest;   // the whole residual, sorted or not
+    const double u = s.ub[0];
+    for (int j = tid; j < L; j += HYG_TG_NT) {
+      // first residual position i with T_j <= Q_i, T_j = (j + u) / L  (resampling_functions.py:56-69); 0 if none
+      const double Tj = (static_cast<double>(j) + u) / static_cast<double>(L) * tot;
+      int lo = K, hi = n_sel;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (ev[mid] < Tj) lo = mid + 1; else hi = mid; }
+      if (lo >= n_sel && n_sel < F) s.ibc[5] = 1;   // the tooth lies among the unsorted particles: sort them all
+      const int ps = (lo < n_sel) ? lo : K;
+      s.parents[K + j] = static_cast<int>(sidx[ps]);
+    }
+  }
+  __syncthreads();
+  return s.ibc[5] ? 1 : 0;
 }
 
 // ---- one chain: filter over all sites, then backward simulation ----
@@ -376,161 +563,12 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
         const int n_sel = (attempt == 2) ? F : s.ibc[3 + 4 * attempt];
         n_attempts = attempt + 1;
         if (attempt == 1 && n_sel == s.ibc[3]) continue;   // the second selection is the first one: go straight to the full sort
-        if (tid == 0) { s.ibc[4] = 0; s.ibc[5] = 0; }
-        __syncthreads();
-        // the selected particles' keys (any order: the sort's order is total, ties by particle index) and the others' total weight
-        double rest = 0.0;
-        for (int c = c0; c < c1; c++) {
-          const double v = s.w[c];
-          if (v > -HYG_INF) {
-            const double dn = lse - v;
-            const int bin = (dn < static_cast<double>(HYG_TG_BINS - 1)) ? static_cast<int>(dn < 0.0 ? 0.0 : dn) : HYG_TG_BINS - 1;
-            if (bin <= selbin) {
-              // order-preserving key of the normalised log-weight; the particle index travels beside it (stable ties)
-              unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(v - lse));
-              b = (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
-              const int pos = atomicAdd(&s.ibc[4], 1);
-              s.key[pos] = b;
-              s.sidx[pos] = static_cast<unsigned short>(c);
-            } else {
-              rest += (attempt == 0) ? s.e[c] : exp(v - mx);   // exp(v - mx) was kept by the pass above; a repeated attempt finds s.e reused
-            }
-          }
+        {
+          const bool big = n_sel > md.big_from;
+          const int redo = big ? tg_ofs_attempt<true>(s, ch, ws + run.scratch_off, attempt, selbin, n_sel, F, M, t, lse, mx, inv_se, n_part, c0, c1, flip, K, log_c, mode)
+                               : tg_ofs_attempt<false>(s, ch, ws + run.scratch_off, attempt, selbin, n_sel, F, M, t, lse, mx, inv_se, n_part, c0, c1, flip, K, log_c, mode);
+          if (!redo) break;
         }
-        int n_sort = 64;
-        while (n_sort < n_sel) n_sort <<= 1;
-        for (int i = n_sel + tid; i < n_sort; i += HYG_TG_NT) { s.key[i] = 0ull; s.sidx[i] = 0xFFFFu; }
-        rest = (n_sel < F) ? tg_block_sum(rest, s, flip) * inv_se : 0.0;
-        __syncthreads();
-#ifndef HYG_TG_SKIP_SORT
-        tg_sort_desc(s, n_sort);
-#endif
-        // e[p] = exp(sorted normalised log-weight); reverse cumulative sums rcs[p] = sum_{i >= p} e[i]
-        double* slw = reinterpret_cast<double*>(s.key);   // sorted normalised log-weights (the keys are not needed after the sort)
-        for (int p = tid; p < n_sort; p += HYG_TG_NT) {
-          double v = 0.0, lwn = -HYG_INF;
-          if (p < n_sel) { lwn = s.w[s.sidx[p]] - lse; v = exp(lwn); }
-          s.e[p] = v;
-          slw[p] = lwn;      // overwrites key[p]: the sort ended with a block barrier and nothing reads the keys after it
-        }
-        __syncthreads();
-        // Reverse cumulative sums in chunks of 32, walked from the end: suf[p] = (shuffle-tree suffix inside the chunk) + carry,
-        // carry = the unsorted particles' total, then the later chunks' totals added one after the other.  The trees are
-        // independent, so every warp takes the chunks c = warp, warp + NW, ...; only the carry additions stay sequential.
-        // The sums are only needed at positions <= M (K < M): anc_w doubles as rcs[0..M].
-        const int n_chunks = (n_sel + 31) / 32;
-        for (int cidx = (tid >> 5); cidx < n_chunks; cidx += HYG_TG_NW) {
-          const int p = cidx * 32 + lane;
-          double inc = (p < n_sel) ? s.e[p] : 0.0;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const double tt = __shfl_down_sync(HYG_FULL, inc, o);
-            if (lane + o < 32) inc += tt;
-          }
-          if (lane == 0) s.ctot[cidx] = inc;
-        }
-        __syncthreads();
-        if (tid < 32) {
-          double carry = rest;
-          for (int cidx = n_chunks - 1; cidx >= 0; cidx--) {
-            if (cidx * 32 <= M) {   // a chunk that holds positions <= M: its in-chunk suffix sums are needed too
-              const int p = cidx * 32 + lane;
-              double inc = (p < n_sel) ? s.e[p] : 0.0;
-#pragma unroll
-              for (int o = 1; o < 32; o <<= 1) {
-                const double tt = __shfl_down_sync(HYG_FULL, inc, o);
-                if (lane + o < 32) inc += tt;
-              }
-              if (p <= M && p < n_sel) s.anc_w[p] = inc + carry;
-            }
-            carry += s.ctot[cidx];
-          }
-          __syncwarp();   // anc_w[0..M] written above is read by every lane below
-          // fixed point with the reference's loop structure: (a, b, log_c) <- (k_new, a, log_c(a)) while a != b, a < n, a < M
-          // the loop below needs log(M - a) - log(rcs[a]) at a data-dependent sequence of a < M: all M values are taken now, by
-          // the lanes in parallel, so that no logarithm sits on the loop's dependency chain
-          for (int a0 = lane; a0 < M && a0 < n_sel; a0 += 32) s.lcn_tab[a0] = log(static_cast<double>(M - a0)) - log(s.anc_w[a0]);
-          __syncwarp();
-          int a = 0, b = -1;
-          double lc = -1.0;
-          while (a != b && a < F && a < M) {
-            const double lcn = s.lcn_tab[a];
-            int cnt = 0;
-            // counts beyond M do not change the outcome; a + 96 <= M + 95 < n_sel whenever n_sel < F
-            // three independent loads, then three ballots (slw is -inf beyond n_sel, up to n_sort >= 64; beyond that: no particle)
-            const int p0 = a + lane, p1 = p0 + 32, p2 = p0 + 64;
-            const double x0 = (p0 < n_sel) ? slw[p0] : -HYG_INF, x1 = (p1 < n_sel) ? slw[p1] : -HYG_INF, x2 = (p2 < n_sel) ? slw[p2] : -HYG_INF;
-            cnt = __popc(__ballot_sync(HYG_FULL, lcn + x0 > 0.0)) + __popc(__ballot_sync(HYG_FULL, lcn + x1 > 0.0)) +
-                  __popc(__ballot_sync(HYG_FULL, lcn + x2 > 0.0));
-            b = a; a = a + cnt; lc = lcn;
-          }
-          int Kf = b;
-          if (!(Kf < F)) { Kf = F; lc = -HYG_INF; }
-          if (lane == 0) { s.ibc[0] = Kf; s.bc[0] = lc; }
-        }
-        __syncthreads();
-        K = s.ibc[0];
-        log_c = s.bc[0];
-        if (log_c - log_c != 0.0) {
-          // log c infinite: multinomial ancestors by inverse CDF over the particle-order weights, unbiased weights
-          mode = 2;
-          // cumulative sums over the particles in index order (s.e reused)
-          for (int c = tid; c < n_part; c += HYG_TG_NT) s.e[c] = (s.w[c] > -HYG_INF) ? exp(s.w[c] - lse) : 0.0;
-          __syncthreads();
-          if (tid == 0) { double acc = 0.0; for (int c = 0; c < n_part; c++) { acc += s.e[c]; s.e[c] = acc; } }
-          __syncthreads();
-          for (int a = tid; a < M; a += HYG_TG_NT) {
-            const double uu = tg_uniform(ch.seed, ch.chain, HYG_TAG_FILTER, (static_cast<uint64_t>(a + 1) << 32) + t) * s.e[n_part - 1];
-            int lo = 0, hi = n_part - 1;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.e[mid] < uu) lo = mid + 1; else hi = mid; }
-            s.parents[a] = lo;
-          }
-          log_c = 0.0;
-          __syncthreads();
-          break;
-        }
-        mode = 1;
-        const int L = M - K;
-        // kept particles
-        for (int a = tid; a < K; a += HYG_TG_NT) s.parents[a] = static_cast<int>(s.sidx[a]);
-        // residual: cumulative sums of e[K..n_sel) in sorted order, in chunks of 32 from K: shuffle-tree prefix inside a chunk (all
-        // warps, chunk c = warp, warp + NW, ...) + the earlier chunks' totals added one after the other (one thread)
-        const int r_chunks = (L > 0) ? (n_sel - K + 31) / 32 : 0;
-        for (int cidx = (tid >> 5); cidx < r_chunks; cidx += HYG_TG_NW) {
-          const int p = K + cidx * 32 + lane;
-          double inc = (p < n_sel) ? s.e[p] : 0.0;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const double tt = __shfl_up_sync(HYG_FULL, inc, o);
-            if (lane >= o) inc += tt;
-          }
-          if (p < n_sel) s.e[p] = inc;
-          if (lane == 31) s.ctot[cidx] = inc;
-        }
-        __syncthreads();
-        if (tid == 0) {
-          double carry = 0.0;
-          for (int cidx = 0; cidx < r_chunks; cidx++) { s.ccar[cidx] = carry; carry += s.ctot[cidx]; }
-        }
-        if (tid == 32) s.ub[0] = tg_uniform(ch.seed, ch.chain, HYG_TAG_FILTER, t);   // the site's resampling uniform, evaluated once
-        __syncthreads();
-        for (int p = K + tid; p < n_sel && L > 0; p += HYG_TG_NT) s.e[p] = s.e[p] + s.ccar[(p - K) >> 5];
-        __syncthreads();
-        if (L > 0) {
-          const double tot = s.e[n_sel - 1] + rest;   // the whole residual, sorted or not
-          const double u = s.ub[0];
-          for (int j = tid; j < L; j += HYG_TG_NT) {
-            // first residual position i with T_j <= Q_i, T_j = (j + u) / L  (resampling_functions.py:56-69); 0 if none
-            const double Tj = (static_cast<double>(j) + u) / static_cast<double>(L) * tot;
-            int lo = K, hi = n_sel;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (s.e[mid] < Tj) lo = mid + 1; else hi = mid; }
-            if (lo >= n_sel && n_sel < F) s.ibc[5] = 1;   // the tooth lies among the unsorted particles: sort them all
-            const int ps = (lo < n_sel) ? lo : K;
-            s.parents[K + j] = static_cast<int>(s.sidx[ps]);
-          }
-        }
-        __syncthreads();
-        if (!s.ibc[5]) break;
         __syncthreads();   // everyone has read the flag before the next attempt clears it
       }
     }
@@ -751,7 +789,7 @@ __device__ __forceinline__ void tg_entry(const TgModelDev* mdl, const TgChainDev
 }
 
 #ifndef HYG_EMU
-__global__ void __launch_bounds__(HYG_TG_NT, 1) tg_kernel(const TgModelDev* mdl, const TgChainDev* chains, TgRunDev run) {
+__global__ void __launch_bounds__(HYG_TG_NT, HYG_TG_CTAS) tg_kernel(const TgModelDev* mdl, const TgChainDev* chains, TgRunDev run) {
   tg_entry(mdl, chains, run);
 }
 #endif

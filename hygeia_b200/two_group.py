@@ -74,7 +74,7 @@ class TwoGroupSession(Session):
 
     def set_two_group_model(self, log_p_control, omega_control, omega_case, minimum_duration=3, num_resampled=50, num_backward=25,
                             merge_prob=0.1, split_prob=0.01, kappa_control=None, kappa_case=None, rho_control=None, rho_case=None,
-                            t_max=4096, hazard="reference", sort_preselect=(0, 0)):
+                            t_max=4096, hazard="reference", sort_preselect=(0, 0), sort_scratch_from=0):
         """hazard: "reference" (default) = the hazard as the reference's fp32 TensorFlow code evaluates it, with the fixed value
         0.1 from the sojourn where its fp32 cdf rounds to 1 (d = 94 for omega = 0.8; case_control_regime_model.py:111-168);
         "exact" = the negative-binomial hazard in fp64.  Ignored when rho_control / rho_case tables are supplied."""
@@ -101,6 +101,7 @@ class TwoGroupSession(Session):
         m.merge_prob, m.split_prob = float(merge_prob), float(split_prob)
         m.hazard_mode = HAZARD_MODES[hazard]
         m.sort_preselect[0], m.sort_preselect[1] = int(sort_preselect[0]), int(sort_preselect[1])   # tuning / test hook, see the header
+        m.sort_scratch_from = int(sort_scratch_from)                                                # test hook, see the header
         if rho_control is not None:
             rc = np.ascontiguousarray(rho_control, dtype=np.float64); rk = np.ascontiguousarray(rho_case, dtype=np.float64)
             keep += [rc, rk]

@@ -193,6 +193,9 @@ typedef struct hyg_tg_model {
    * the systematic comb falls behind the sorted prefix, so the results never depend on these numbers.  0 -> M + 110 and
    * 3 M + 250; values below M + 96 are raised to it (the K search looks at the first M + 96 positions) */
   uint32_t sort_preselect[2];
+  /* test hook: when at least this many particles are selected for the sort, it runs in the CTA's global scratch area instead of
+   * shared memory (the path that more than 2048 finite particles of a site would take); 0 -> only then */
+  uint32_t sort_scratch_from;
 } hyg_tg_model;
 #define HYG_TG_HAZARD_REFERENCE 0u
 #define HYG_TG_HAZARD_EXACT 1u

@@ -75,7 +75,7 @@ class Emu:
         return out
 
 
-def tg_run_emu(emu, model, lo_c, lo_k, M=50, B=25, seed=0, chain=0, preselect=(0, 0)):
+def tg_run_emu(emu, model, lo_c, lo_k, M=50, B=25, seed=0, chain=0, preselect=(0, 0), scratch_from=0):
     """Two-group filter + backward simulation under emulation; `model` is an oracle/tg_oracle.TwoGroupModel."""
     lo_c = np.ascontiguousarray(lo_c, dtype=np.float64); lo_k = np.ascontiguousarray(lo_k, dtype=np.float64)
     T, R = lo_c.shape
@@ -84,6 +84,6 @@ def tg_run_emu(emu, model, lo_c, lo_k, M=50, B=25, seed=0, chain=0, preselect=(0
     traj = np.zeros((T, B, 5), np.int32); ln = np.zeros(1); taps = np.zeros((T, 4), np.int32)
     rc = emu.lib.hygemu_tg_run(C.c_int(R), C.c_int(model.u), C.c_int(M), C.c_int(B), _p(logP), _p(logPm), _p(rho_c), _p(rho_k),
                                C.c_uint32(model.d_max), C.c_uint64(T), _p(lo_c), _p(lo_k), C.c_uint64(seed), C.c_uint32(chain),
-                               _p(traj), _p(ln), _p(taps), C.c_int(preselect[0]), C.c_int(preselect[1]))
+                               _p(traj), _p(ln), _p(taps), C.c_int(preselect[0]), C.c_int(preselect[1]), C.c_int(scratch_from))
     assert rc == 0
     return dict(traj=traj, log_norm=float(ln[0]), taps=taps)

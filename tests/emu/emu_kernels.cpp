@@ -91,7 +91,7 @@ int hygemu_sg_emission(const double* alpha, const double* beta, int R, uint64_t 
 // K4/K5 under emulation: two-group filter + backward simulation of one chain.
 int hygemu_tg_run(int R, int u, int M, int B, const double* logP /*R x R*/, const double* logPm /*2 x 2*/, const double* rho_c,
                   const double* rho_k, uint32_t dmax, uint64_t T, const double* lo_c, const double* lo_k, uint64_t seed, uint32_t chain,
-                  int* traj, double* log_norm, int* taps, int presel0, int presel1) {
+                  int* traj, double* log_norm, int* taps, int presel0, int presel1, int scratch_from) {
   hyg::TgModelDev mdl;
   std::memset(&mdl, 0, sizeof(mdl));
   mdl.R = R; mdl.u = u; mdl.M = M; mdl.B = B; mdl.dmax = dmax;
@@ -106,12 +106,14 @@ int hygemu_tg_run(int R, int u, int M, int B, const double* logP /*R x R*/, cons
   mdl.lrho_c = lrc.data(); mdl.lrho_k = lrk.data();
   mdl.nl_rm1 = -std::log(static_cast<double>(R) - 1.0); mdl.nl_rm2 = -std::log(static_cast<double>(R) - 2.0);
   mdl.presel[0] = std::max(presel0 ? presel0 : M + 110, M + 96); mdl.presel[1] = std::max(presel1 ? presel1 : 3 * M + 250, mdl.presel[0]);
+  mdl.big_from = scratch_from ? std::min(scratch_from - 1, HYG_TG_SORTMAX) : HYG_TG_SORTMAX;
   hyg::TgChainDev ch;
   ch.T = T; ch.lo_c = lo_c; ch.lo_k = lo_k; ch.seed = seed; ch.chain = chain; ch.traj = traj; ch.log_norm = log_norm; ch.taps = taps;
   hyg::TgRunDev run;
   run.t_max = T;
   run.anc_pitch = std::max(M, R * R);
-  run.ws_stride = sizeof(hyg::TgStepRec) * T + sizeof(hyg::TgAncRec) * T * run.anc_pitch;
+  run.scratch_off = (sizeof(hyg::TgStepRec) * T + sizeof(hyg::TgAncRec) * T * run.anc_pitch + 255) & ~static_cast<size_t>(255);
+  run.ws_stride = run.scratch_off + static_cast<size_t>(HYG_TG_BIGMAX) * 18 + 256;
   std::vector<unsigned char> ws(run.ws_stride);
   unsigned int queue = 0;
   run.ws = ws.data(); run.queue = &queue; run.n_chains = 1;

@@ -9,7 +9,7 @@ from _tg_case import make_case, tg_oracle
 pytestmark = pytest.mark.gpu
 
 
-def _run_gpu(c, M, B, seed, chain, use_oracle_tables=True, want_taps=True, n_copies=1, hazard="exact", sort_preselect=(0, 0)):
+def _run_gpu(c, M, B, seed, chain, use_oracle_tables=True, want_taps=True, n_copies=1, hazard="exact", sort_preselect=(0, 0), sort_scratch_from=0):
     from hygeia_b200.two_group import TwoGroupSession
     s = TwoGroupSession(0)
     try:
@@ -20,7 +20,7 @@ def _run_gpu(c, M, B, seed, chain, use_oracle_tables=True, want_taps=True, n_cop
         s.emission()
         m = c["model"]
         kw = dict(rho_control=m.rho_c, rho_case=m.rho_k) if use_oracle_tables else {}
-        s.set_two_group_model(c["logP"], c["omega_control"], c["omega_case"], c["u"], M, B, t_max=c["T"], hazard=hazard, sort_preselect=sort_preselect, **kw)
+        s.set_two_group_model(c["logP"], c["omega_control"], c["omega_case"], c["u"], M, B, t_max=c["T"], hazard=hazard, sort_preselect=sort_preselect, sort_scratch_from=sort_scratch_from, **kw)
         specs = [dict(control_dataset=2 * i, case_dataset=2 * i + 1, T=c["T"], seed=seed, chain_id=chain + i) for i in range(n_copies)]
         return s.run(specs, want_taps=want_taps)
     finally:
@@ -125,6 +125,11 @@ def test_two_group_sort_preselection_never_changes_the_result():
         seen |= set(np.unique(g["taps"][:, 3]).tolist())
     assert {1, 2, 3} <= seen
     _compare(base, _oracle(c, 50, 25, seed=1, chain=0), frac=0.95)
+    # the sort in the global scratch area (what more than 2048 selected particles would take), forced for every site
+    for pre in ((0, 0), (100000, 100000)):
+        g = _run_gpu(c, 50, 25, seed=1, chain=0, sort_preselect=pre, sort_scratch_from=1)[0]
+        assert g["log_normalizing_constant"] == base["log_normalizing_constant"]
+        assert np.array_equal(g["trajectories"], base["trajectories"]) and np.array_equal(g["taps"][:, :3], base["taps"][:, :3])
 
 
 def test_two_group_many_chains_are_independent():

@@ -99,6 +99,22 @@ def test_kernel_sort_preselection_never_changes_the_result():
     assert {1, 2, 3} <= seen                                                  # every attempt level was exercised
 
 
+def test_kernel_sort_in_global_scratch_is_the_same_sort():
+    """More than 2048 selected particles do not fit the shared-memory sort arrays; the same code then runs on a global scratch
+    area.  Forced here for every site (scratch_from = 1), with and without the pre-selection: identical to the oracle."""
+    c = make_case(120, 1, seed=3)
+    o = Oracle()
+    lo_c = o.emission(c["alpha"], c["beta"], c["nt_c"], c["nm_c"])
+    lo_k = o.emission(c["alpha"], c["beta"], c["nt_k"], c["nm_k"])
+    r = tg_oracle.run(c["model"], lo_c, lo_k, M=50, n_backward=25, seed=1, chain=0)
+    for pre in ((0, 0), (100000, 100000)):
+        g = tg_run_emu(Emu(), c["model"], lo_c, lo_k, M=50, B=25, seed=1, chain=0, preselect=pre, scratch_from=1)
+        assert abs(g["log_norm"] - r["log_norm"]) <= 1e-10 * abs(r["log_norm"])
+        assert (g["taps"][:, 1] == r["taps"]["K"]).all()
+        assert (g["traj"][:, :, 0] == r["traj_m"]).all()
+        assert (g["traj"][:, :, 1:3] == r["traj_control"]).all() and (g["traj"][:, :, 3:5] == r["traj_case"]).all()
+
+
 def test_control_group_parameters_match_oracle():
     rng = np.random.default_rng(0)
     theta = rng.normal(size=36)

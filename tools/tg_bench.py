@@ -1,4 +1,4 @@
-"""K4/K5 (two-group filter + backward simulation): microseconds per site and chain with every SM busy.
+"""K4/K5 (two-group filter + backward simulation): microseconds per site and chain with every SM busy (two resident CTAs per SM).
 
     python tools/tg_bench.py [--sites 4000] [--chains 148] [--samples 8]
 """
@@ -17,7 +17,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--sites", type=int, default=4000)
-    ap.add_argument("--chains", type=int, default=148)
+    ap.add_argument("--chains", type=int, default=296, help="default: two resident CTAs on each of the 148 SMs")
     ap.add_argument("--samples", type=int, default=8)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--backward", type=int, default=25)
@@ -41,7 +41,8 @@ def main():
     ms = ms[1:]
     avg = float(np.mean(ms))
     print(json.dumps({"kernel": "tg_kernel (K4/K5)", "sites": T, "chains": a.chains, "ms": ms,
-                      "us_per_site_per_chain": 1000.0 * avg / T / max(1, -(-a.chains // 148)),
+                      "us_per_site_per_chain": 1000.0 * avg / T / max(1, -(-a.chains // 296)),
+                      "us_per_site_per_sm": 1000.0 * avg * 148 / (T * a.chains),
                       "site_chains_per_s": T * a.chains / avg * 1e3,
                       "log_norm_chain0": float(out[0]["log_normalizing_constant"])}))
 

@@ -1033,7 +1033,7 @@ int hyg_tg_run(hyg_ctx* c, const hyg_tg_chain* chains, uint32_t n, float* ms_dev
   std::iota(order.begin(), order.end(), 0u);
   std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) { return c->ds[chains[x].control_dataset].T > c->ds[chains[y].control_dataset].T; });
   std::vector<hyg::TgChainDev> dev(n);
-  std::vector<int*> d_traj(n, nullptr), d_taps(n, nullptr);
+  std::vector<int*> d_traj(n, nullptr), d_taps(n, nullptr), traj_mapped(n, nullptr);
   double* d_ln = nullptr;
   hyg::TgChainDev* d_chains = nullptr;
   unsigned char* d_ws = nullptr;
@@ -1056,11 +1056,22 @@ int hyg_tg_run(hyg_ctx* c, const hyg_tg_chain* chains, uint32_t n, float* ms_dev
     const uint32_t k = order[i];
     const hyg_tg_chain& ch = chains[k];
     const uint64_t T = c->ds[ch.control_dataset].T;
-    HYG_TG_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_traj[k]), T * B * 5 * sizeof(int)));
+    // pinned (page-locked) caller memory is addressable from the device: the backward pass then writes every site's 500 bytes
+    // of trajectories straight into it (posted writes over PCIe, ~4 GB/s of the link) and there is no staging copy afterwards
+    {
+      cudaPointerAttributes pa;
+      std::memset(&pa, 0, sizeof(pa));
+      if (c->zero_copy_out && cudaPointerGetAttributes(&pa, ch.trajectories) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer) {
+        traj_mapped[k] = static_cast<int*>(pa.devicePointer);
+      } else {
+        cudaGetLastError();
+        HYG_TG_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_traj[k]), T * B * 5 * sizeof(int)));
+      }
+    }
     if (ch.taps) HYG_TG_CUDA(pool_alloc(c, reinterpret_cast<void**>(&d_taps[k]), T * 4 * sizeof(int)));
     hyg::TgChainDev& d = dev[i];
     d.T = T; d.lo_c = c->ds[ch.control_dataset].d_logobs; d.lo_k = c->ds[ch.case_dataset].d_logobs;
-    d.seed = ch.seed; d.chain = ch.chain_id; d.traj = d_traj[k]; d.log_norm = d_ln + k; d.taps = d_taps[k];
+    d.seed = ch.seed; d.chain = ch.chain_id; d.traj = traj_mapped[k] ? traj_mapped[k] : d_traj[k]; d.log_norm = d_ln + k; d.taps = d_taps[k];
   }
   hyg::TgRunDev run;
   run.t_max = t_max;
@@ -1091,7 +1102,7 @@ int hyg_tg_run(hyg_ctx* c, const hyg_tg_chain* chains, uint32_t n, float* ms_dev
   for (uint32_t k = 0; k < n; k++) {
     const hyg_tg_chain& ch = chains[k];
     const uint64_t T = c->ds[ch.control_dataset].T;
-    HYG_TG_CUDA(cudaMemcpyAsync(ch.trajectories, d_traj[k], T * B * 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (!traj_mapped[k]) HYG_TG_CUDA(cudaMemcpyAsync(ch.trajectories, d_traj[k], T * B * 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     HYG_TG_CUDA(cudaMemcpyAsync(ch.log_normalizing_constant, d_ln + k, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     if (ch.taps) HYG_TG_CUDA(cudaMemcpyAsync(ch.taps, d_taps[k], T * 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   }

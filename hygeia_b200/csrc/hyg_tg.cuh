@@ -185,6 +185,7 @@ struct TgSmem {
   TgState nxt[HYG_TG_BMAX];
   int pick[HYG_TG_BMAX];
   int rep[HYG_TG_BMAX];
+  int trj[HYG_TG_BMAX * 5];      // backward pass: the site's sampled states, staged for one coalesced write
   int glist[HYG_TG_BMAX];       // backward pass: the first trajectory of every group of equal next states
   double ub[HYG_TG_BMAX];      // backward pass: the site's uniform of every trajectory (one Philox evaluation each)
   double ctot[HYG_TG_NPMAX / 32 + 2];    // per-chunk totals / carries of the chunked cumulative sums (32 particles per chunk)
@@ -757,10 +758,12 @@ __device__ void tg_chain(const TgChainDev& ch, const TgRunDev& run, TgSmem& s, u
       const int c = s.pick[j];
       TgState st; st.m = s.m[c]; st.dc = s.dc[c]; st.rc = s.rc[c]; st.dk = s.dk[c]; st.rk = s.rk[c];
       s.nxt[j] = st;
-      int* o = ch.traj + (static_cast<size_t>(t) * B + j) * 5;
+      int* o = s.trj + j * 5;
       o[0] = st.m; o[1] = st.dc; o[2] = st.rc; o[3] = st.dk; o[4] = st.rk;
     }
     __syncthreads();
+    // the site's B x 5 integers leave as one run of consecutive words (they may go straight to pinned host memory over PCIe)
+    for (int i = tid; i < B * 5; i += HYG_TG_NT) ch.traj[static_cast<size_t>(t) * B * 5 + i] = s.trj[i];
   }
 }
 

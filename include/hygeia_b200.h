@@ -206,7 +206,8 @@ typedef struct hyg_tg_chain {
   uint64_t seed;
   uint32_t chain_id;
   /* outputs, host pointers */
-  int32_t* trajectories;           /* T x B x 5 : merged, d_control, r_control, d_case, r_case                   */
+  int32_t* trajectories;           /* T x B x 5 : merged, d_control, r_control, d_case, r_case.  Pinned (page-locked) host
+                                      memory is written by the kernel directly (no staging copy), pageable memory by a copy */
   double* log_normalizing_constant;/* 1                                                                          */
   int32_t* taps;                   /* optional T x 4 : particles proposed, K, finite-weight particles, sort attempts (0 = no sort) */
 } hyg_tg_chain;

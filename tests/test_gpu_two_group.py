@@ -132,6 +132,31 @@ def test_two_group_sort_preselection_never_changes_the_result():
         assert np.array_equal(g["trajectories"], base["trajectories"]) and np.array_equal(g["taps"][:, :3], base["taps"][:, :3])
 
 
+def test_two_group_trajectories_into_pinned_host_memory():
+    """Caller-owned trajectory arrays: pageable ones are filled by a copy after the launch, page-locked ones are written by the
+    backward pass itself (no staging copy).  Same numbers either way."""
+    import torch
+    from hygeia_b200.two_group import TwoGroupSession
+    c = make_case(300, 2, seed=6)
+    s = TwoGroupSession(0)
+    try:
+        s.set_emission_model(c["mu"], c["sigma"], c["u"])
+        s.add_dataset(c["nt_c"], c["nm_c"]); s.add_dataset(c["nt_k"], c["nm_k"])
+        s.emission()
+        s.set_two_group_model(c["logP"], c["omega_control"], c["omega_case"], c["u"], 50, 25, t_max=c["T"])
+        spec = dict(control_dataset=0, case_dataset=1, T=c["T"], seed=3, chain_id=0)
+        a = s.run([dict(spec)])[0]
+        pinned = torch.full((c["T"], 25, 5), -7, dtype=torch.int32).pin_memory()
+        b = s.run([dict(spec, trajectories=pinned.numpy())])[0]
+        pageable = np.full((c["T"], 25, 5), -7, dtype=np.int32)
+        d = s.run([dict(spec, trajectories=pageable)])[0]
+    finally:
+        s.close()
+    assert b["trajectories"] is not None and np.array_equal(pinned.numpy(), a["trajectories"]) and np.array_equal(pageable, a["trajectories"])
+    assert a["log_normalizing_constant"] == b["log_normalizing_constant"] == d["log_normalizing_constant"]
+    assert (a["trajectories"][:, :, 0] >= 0).all()
+
+
 def test_two_group_many_chains_are_independent():
     # 3 chains (same data, different chain ids) in one launch: each equals its own oracle run
     c = make_case(120, 2, seed=8)

@@ -3,6 +3,7 @@
 // Sub-commands and the reference entry points they stand in for (paths relative to /root/reference):
 //   hygeia estimate_parameters_and_regimes ...   src/single_group/bin/estimate_parameters_and_regimes (flags :12-204, flow :206-379)
 //   hygeia infer ...                             src/two_group/run_inference_two_groups.py (flags :19-73, flow :92-322)
+//   hygeia preprocess ...                        src/two_group/preprocess_bed.py (host-side ETL; parity unpinned, see there)
 //   hygeia get_chrom_segments ...                src/two_group/get_chrom_segments.py
 //   hygeia aggregate ...                         src/two_group/aggregate_results.py
 //   hygeia get_dmps ...                          src/two_group/get_dmps.py (+ multiple_testing.py)
@@ -879,6 +880,186 @@ int cmd_get_dmps(int argc, char** argv) {
 }
 
 // ======================================================================================================================
+// hygeia preprocess (src/two_group/preprocess_bed.py; polars 1.8.2, src/two_group/requirements.txt:49): BED-format methylation
+// calls -> the per-chromosome count matrices `infer` and `estimate_parameters_and_regimes` read.  Host-side ETL, no GPU.
+// PARITY UNPINNED: polars is not installable in the build image, so this is a restatement of the script's data flow as read
+// (full joins without key coalescing, nulls -> 0, f64::round = half away from zero), checked against an independent pandas
+// restatement (oracle/preprocess_oracle.py) and hand-made cases, not against the script itself.
+// ======================================================================================================================
+std::vector<std::string> split_tab(const char* b, const char* e) {
+  std::vector<std::string> out;
+  const char* c = b;
+  while (c <= e) {
+    const char* q = static_cast<const char*>(std::memchr(c, '\t', static_cast<size_t>(e - c)));
+    if (!q) q = e;
+    out.emplace_back(c, q);
+    c = q + 1;
+  }
+  return out;
+}
+
+struct CollapsedSite { long long start; double total, avg; };
+
+// read_bed_file + collapse_strands (:124-263): rows of this chromosome with ref_genotype CG, the two strands of a CpG joined on
+// (+).end == (-).start, coverage summed, methylation percentage coverage-weighted, position = (+).start or (-).start - 1
+std::vector<CollapsedSite> read_bed_collapsed(const std::string& path, const std::string& chrom) {
+  const std::string txt = hygio::read_text(path);
+  struct Row { long long start, end; double cov, pm; };
+  std::vector<Row> pos, neg;
+  size_t p = txt.find('\n');                       // skip_rows = 1: the header line
+  p = (p == std::string::npos) ? txt.size() : p + 1;
+  size_t line = 1;
+  while (p < txt.size()) {
+    size_t eol = txt.find('\n', p);
+    if (eol == std::string::npos) eol = txt.size();
+    const char* b = txt.data() + p;
+    const char* e = txt.data() + eol;
+    p = eol + 1;
+    line++;
+    if (e > b && e[-1] == '\r') e--;
+    if (b == e) continue;
+    const std::vector<std::string> f = split_tab(b, e);
+    if (f.size() < 12) throw Error(path + ": line " + std::to_string(line) + " has fewer than 12 tab-separated fields");
+    if (f[0] != chrom || f[11] != "CG") continue;
+    Row r;
+    r.start = std::strtoll(f[1].c_str(), nullptr, 10); r.end = std::strtoll(f[2].c_str(), nullptr, 10);
+    r.cov = std::strtod(f[9].c_str(), nullptr); r.pm = std::strtod(f[10].c_str(), nullptr);
+    if (f[5] == "+") pos.push_back(r);
+    else if (f[5] == "-") neg.push_back(r);
+  }
+  std::map<long long, size_t> neg_by_start;
+  for (size_t i = 0; i < neg.size(); i++) neg_by_start.emplace(neg[i].start, i);   // first occurrence wins; CpG calls are unique per strand
+  std::vector<char> used(neg.size(), 0);
+  std::vector<CollapsedSite> out;
+  auto emit = [&](bool has_pos, const Row* a, const Row* b2) {
+    const double cp = has_pos ? a->cov : 0.0, pp = has_pos ? a->pm : 0.0;
+    const double cn = b2 ? b2->cov : 0.0, pn = b2 ? b2->pm : 0.0;
+    const double tot = cp + cn;
+    if (!(tot > 0.0)) return;                                             // sites without coverage are dropped
+    CollapsedSite c;
+    c.start = has_pos ? a->start : b2->start - 1;
+    c.total = tot;
+    c.avg = ((cp * pp) + (cn * pn)) / tot;
+    out.push_back(c);
+  };
+  for (const Row& r : pos) {
+    auto it = neg_by_start.find(r.end);
+    if (it != neg_by_start.end()) { used[it->second] = 1; emit(true, &r, &neg[it->second]); }
+    else emit(true, &r, nullptr);
+  }
+  for (size_t i = 0; i < neg.size(); i++) if (!used[i]) emit(false, nullptr, &neg[i]);
+  std::stable_sort(out.begin(), out.end(), [](const CollapsedSite& x, const CollapsedSite& y) { return x.start < y.start; });
+  return out;
+}
+
+int cmd_preprocess(int argc, char** argv) {
+  const std::set<std::string> known = {"cpg_file_path", "output_path", "case_data_path", "case_id_names", "control_data_path", "control_id_names", "chromosome", "verbose"};
+  const Args a = parse_args(argc, argv, 2, known, {"verbose"});
+  if (!a.has("cpg_file_path")) throw Error("Required flag --cpg_file_path not provided");
+  const std::string cpg_path = a.str("cpg_file_path", ""), out_dir = a.str("output_path", "../test"), chrom = a.str("chromosome", "22");
+  auto multi = [&](const char* k) { return a.has(k) ? a.kv.at(k) : std::vector<std::string>(); };
+  const std::vector<std::string> case_paths = multi("case_data_path"), control_paths = multi("control_data_path");
+  std::vector<std::string> case_ids = multi("case_id_names"), control_ids = multi("control_id_names");
+  if (case_paths.empty() && control_paths.empty()) throw Error("Must provide either case samples, control samples, or both");
+  if (!case_ids.empty() && case_ids.size() != case_paths.size()) throw Error("Number of case data paths must match number of case ID names");
+  if (!control_ids.empty() && control_ids.size() != control_paths.size()) throw Error("Number of control data paths must match number of control ID names");
+  if (!path_exists(cpg_path)) throw Error("CpG file not found: " + cpg_path);
+  hygio::mkdirs(out_dir);
+
+  // load_cpg_sites (:97-122): tab-separated with a header; rows whose seqID equals the chromosome; Pos0 = start - 1
+  std::vector<long long> pos0;
+  {
+    const std::string txt = hygio::read_text(cpg_path);
+    size_t eol = txt.find('\n');
+    if (eol == std::string::npos) throw Error(cpg_path + ": empty file");
+    const char* hb = txt.data();
+    const char* he = txt.data() + eol;
+    if (he > hb && he[-1] == '\r') he--;
+    const std::vector<std::string> hdr = split_tab(hb, he);
+    size_t c_seq = SIZE_MAX, c_start = SIZE_MAX;
+    for (size_t i = 0; i < hdr.size(); i++) { if (hdr[i] == "seqID") c_seq = i; if (hdr[i] == "start") c_start = i; }
+    if (c_seq == SIZE_MAX || c_start == SIZE_MAX) throw Error(cpg_path + ": columns seqID and start are required");
+    size_t p = eol + 1;
+    while (p < txt.size()) {
+      size_t e2 = txt.find('\n', p);
+      if (e2 == std::string::npos) e2 = txt.size();
+      const char* b = txt.data() + p;
+      const char* e = txt.data() + e2;
+      p = e2 + 1;
+      if (e > b && e[-1] == '\r') e--;
+      if (b == e) continue;
+      const std::vector<std::string> f = split_tab(b, e);
+      if (f.size() <= std::max(c_seq, c_start)) continue;
+      if (f[c_seq] == chrom) pos0.push_back(std::strtoll(f[c_start].c_str(), nullptr, 10) - 1);
+    }
+  }
+  if (pos0.empty()) throw Error("No CpG sites found for chromosome " + chrom);
+  std::stable_sort(pos0.begin(), pos0.end());
+  const size_t T = pos0.size();
+  std::map<long long, size_t> row_of;
+  for (size_t i = 0; i < T; i++) row_of.emplace(pos0[i], i);
+
+  // process_sample_data (:265-358): per sample, methylated = round(coverage x pct / 100), unmethylated = round(coverage x (100 -
+  // pct) / 100), joined onto the CpG list; a call at a position that is not in the list ends up with a null position and is dropped
+  // (:379-383); a listed site without a call is null -> 0 (:402).  NaN marks "null" until then.
+  const double NaN = std::nan("");
+  bool any_null = false;
+  auto group = [&](const std::vector<std::string>& paths, std::vector<double>& meth, std::vector<double>& unmeth) {
+    const size_t S = paths.size();
+    meth.assign(T * S, NaN); unmeth.assign(T * S, NaN);
+    for (size_t s = 0; s < S; s++) {
+      if (!path_exists(paths[s])) { std::fprintf(stderr, "File not found: %s\n", paths[s].c_str()); continue; }
+      for (const CollapsedSite& c : read_bed_collapsed(paths[s], chrom)) {
+        auto it = row_of.find(c.start);
+        if (it == row_of.end()) continue;
+        meth[it->second * S + s] = std::round(c.total * c.avg / 100.0);
+        unmeth[it->second * S + s] = std::round(c.total * (100.0 - c.avg) / 100.0);
+      }
+    }
+    for (double v : meth) any_null = any_null || std::isnan(v);
+  };
+  std::vector<double> mc, uc, mk, uk;
+  group(control_paths, mc, uc);
+  group(case_paths, mk, uk);
+
+  // save_results (:430-470): np.savetxt(fmt = '%s', delimiter = ','); a frame with nulls went through float64 ("12.0"), one without
+  // stays integer ("12")
+  auto cell = [&](double v) {
+    if (std::isnan(v)) v = 0.0;
+    std::string t = std::to_string(static_cast<long long>(v));
+    return any_null ? t + ".0" : t;
+  };
+  auto save = [&](const std::string& name, const std::vector<double>& x, const std::vector<double>* y, size_t S) {
+    hygio::Writer w(out_dir + "/" + name + "_" + chrom + ".txt.gz");
+    std::string buf;
+    for (size_t t = 0; t < T; t++) {
+      for (size_t s = 0; s < S; s++) {
+        double v = std::isnan(x[t * S + s]) ? 0.0 : x[t * S + s];
+        if (y) v += std::isnan((*y)[t * S + s]) ? 0.0 : (*y)[t * S + s];
+        if (s) buf += ',';
+        buf += cell(v);
+      }
+      buf += '\n';
+      if (buf.size() > (1u << 20)) { w.write(buf); buf.clear(); }
+    }
+    w.write(buf);
+    w.close();
+  };
+  {
+    hygio::Writer w(out_dir + "/positions_" + chrom + ".txt.gz");
+    std::string buf;
+    for (size_t t = 0; t < T; t++) { append_int(buf, pos0[t]); buf += '\n'; }
+    w.write(buf);
+    w.close();
+  }
+  { hygio::Writer w(out_dir + "/cpg_sites_merged_" + chrom + ".txt.gz"); w.write(std::to_string(T) + "\n"); w.close(); }
+  if (!control_paths.empty()) { save("n_methylated_reads_control", mc, nullptr, control_paths.size()); save("n_total_reads_control", mc, &uc, control_paths.size()); }
+  if (!case_paths.empty()) { save("n_methylated_reads_case", mk, nullptr, case_paths.size()); save("n_total_reads_case", mk, &uk, case_paths.size()); }
+  std::printf("Successfully processed %zu CpG sites for chromosome %s\n", T, chrom.c_str());
+  return 0;
+}
+
+// ======================================================================================================================
 // hygeia get_chrom_segments (src/two_group/get_chrom_segments.py): the list of `infer` batches of a chromosome
 // ======================================================================================================================
 int cmd_get_chrom_segments(int argc, char** argv) {
@@ -986,6 +1167,7 @@ int cmd_selftest(int argc, char** argv) {
 void show_help() {
   std::printf("Usage: hygeia [command] [arguments...]\n\nAvailable commands:\n"
               "  estimate_parameters_and_regimes   - Estimate parameters and regimes (single group)\n"
+              "  preprocess                        - BED-format methylation calls -> per-chromosome count matrices\n"
               "  get_chrom_segments                - List the segments (batches) of a chromosome for infer\n"
               "  infer                             - Two-group (case/control) inference for one chromosome segment\n"
               "  aggregate                         - Aggregate the two-group results of all segments and seeds of a chromosome\n"
@@ -1009,12 +1191,13 @@ int main(int argc, char** argv) {
     if (cmd == "help" || cmd == "-h" || cmd == "--help") { show_help(); return 0; }
     if (cmd == "estimate_parameters_and_regimes") return cmd_single_group(argc, argv);
     if (cmd == "infer") return cmd_infer(argc, argv);
+    if (cmd == "preprocess") return cmd_preprocess(argc, argv);
     if (cmd == "get_chrom_segments") return cmd_get_chrom_segments(argc, argv);
     if (cmd == "aggregate") return cmd_aggregate(argc, argv);
     if (cmd == "get_dmps") return cmd_get_dmps(argc, argv);
     if (cmd == "make_bed_file") return cmd_make_bed(argc, argv);
     if (cmd == "_selftest") return cmd_selftest(argc, argv);
-    std::fprintf(stderr, "Error: Invalid command '%s'\nValid commands are: estimate_parameters_and_regimes get_chrom_segments infer aggregate get_dmps make_bed_file\nUse 'hygeia help' for more information\n", cmd.c_str());
+    std::fprintf(stderr, "Error: Invalid command '%s'\nValid commands are: estimate_parameters_and_regimes preprocess get_chrom_segments infer aggregate get_dmps make_bed_file\nUse 'hygeia help' for more information\n", cmd.c_str());
     return 2;
   } catch (const std::exception& e) {
     std::fprintf(stderr, "hygeia %s: error: %s\n", cmd.c_str(), e.what());

@@ -1161,6 +1161,29 @@ int cmd_selftest(int argc, char** argv) {
     hygio::savetxt_e18(std::string(argv[3]) + "_txt.csv.gz", c, 2, 2);
     return 0;
   }
+  if (what == "loadnpz" && argc > 3) {   // hygeia _selftest loadnpz <file>  -> descr, shape, sum of the (int16 / int32 / float32 / float64) payload
+    const hygio::NpyArray a = hygio::load_npz(argv[3]);
+    std::string shape;
+    size_t n = 1;
+    for (size_t d : a.shape) { shape += (shape.empty() ? "" : "x") + std::to_string(d); n *= d; }
+    double sum = 0.0;
+    for (size_t i = 0; i < n; i++) {
+      if (a.descr == "<i2") sum += reinterpret_cast<const int16_t*>(a.data.data())[i];
+      else if (a.descr == "<i4") sum += reinterpret_cast<const int32_t*>(a.data.data())[i];
+      else if (a.descr == "<f4") sum += reinterpret_cast<const float*>(a.data.data())[i];
+      else if (a.descr == "<f8") sum += reinterpret_cast<const double*>(a.data.data())[i];
+    }
+    std::printf("%s %s %.17g\n", a.descr.c_str(), shape.c_str(), sum);
+    return 0;
+  }
+  if (what == "readmatrix" && argc > 3) {   // hygeia _selftest readmatrix <file.tsv[.gz]>  -> rows, cols, index name, sums
+    const hygio::IndexedIntMatrix m = hygio::read_indexed_int_matrix(argv[3]);
+    long long si = 0, sv = 0;
+    for (long long v : m.index) si += v;
+    for (int16_t v : m.v) sv += v;
+    std::printf("%zu %zu %s %lld %lld\n", m.rows, m.cols, m.index_name.c_str(), si, sv);
+    return 0;
+  }
   throw Error("unknown self test");
 }
 

@@ -106,3 +106,26 @@ def test_get_chrom_segments(tmp_path, n_sites, segment, want):
     r = run("get_chrom_segments", "--input_file", tmp_path / "positions_9.txt.gz", "--chromosome", "chr9", "--segment_size", segment, "--output_csv", out)
     assert "Segment information saved to" in r.stdout
     assert out.read_text() == "chrom,segment_index\n" + "".join(f"chr9,{i}\n" for i in range(want))
+
+
+def test_npz_and_matrix_readers_take_what_numpy_and_pandas_write(tmp_path):
+    """`hygeia aggregate` reads the trajectories np.savez_compressed wrote (zip64 local headers, deflate) and `hygeia get_dmps` the
+    tab-separated matrices pandas wrote: the readers against files written by NumPy / pandas themselves."""
+    import pandas as pd
+    rng = np.random.default_rng(3)
+    a = rng.integers(-300, 300, size=(40, 25, 2)).astype(np.int16)
+    np.savez_compressed(tmp_path / "c.npz", a)
+    np.savez(tmp_path / "u.npz", a)
+    for name in ("c.npz", "u.npz"):
+        descr, shape, total = run("_selftest", "loadnpz", tmp_path / name).stdout.split()
+        assert (descr, shape, float(total)) == ("<i2", "40x25x2", float(a.sum()))
+    f = rng.random(17).astype(np.float32)
+    np.savez_compressed(tmp_path / "f.npz", f)
+    descr, shape, total = run("_selftest", "loadnpz", tmp_path / "f.npz").stdout.split()
+    assert (descr, shape) == ("<f4", "17") and abs(float(total) - float(f.astype(np.float64).sum())) < 1e-6
+    assert run("_selftest", "loadnpz", tmp_path / "missing.npz", check=False).returncode == 1
+    m = pd.DataFrame(rng.integers(0, 6, size=(30, 12)).astype(np.int8))
+    pos = pd.Series(np.cumsum(rng.integers(1, 900, size=30)), name="pos")
+    m.set_index(pos).to_csv(tmp_path / "m.csv.gz", sep="\t", compression="gzip")
+    rows, cols, name, si, sv = run("_selftest", "readmatrix", tmp_path / "m.csv.gz").stdout.split()
+    assert (int(rows), int(cols), name, int(si), int(sv)) == (30, 12, "pos", int(pos.sum()), int(m.to_numpy().sum()))

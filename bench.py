@@ -679,6 +679,12 @@ def main():
 
     # the gathered evidences: rank 0 holds log Z_T of every chain of the job -- sanity: finite, and this rank's slice is its own
     gather_check = None
+    if not multi:
+        # one GPU: the same sum over this job's chains, from the host copies -- comparable with the gathered sum of a multi-GPU run of
+        # the same job (--scaling strong: 352 chains whatever N is)
+        lz = [float(outs[(c, sd)]["logz"][-1]) for c, sd in my_chains]
+        gather_check = {"chains_gathered": len(lz), "all_finite": bool(np.isfinite(lz).all()), "collective_bytes_per_step": 0,
+                        "sum_log_evidence": float(np.sum(lz))}
     if multi and rank == 0:
         ea = evid_all.cpu().numpy().reshape(world, -1)
         gather_check = {"chains_gathered": int((ea != 0).sum()), "all_finite": bool(np.isfinite(ea).all()),

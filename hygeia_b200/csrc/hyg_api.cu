@@ -983,8 +983,9 @@ int hyg_tg_set_model(hyg_ctx* c, const hyg_tg_model* m, uint64_t t_max) {
       if (!(m->omega_control[r] > 0.0 && m->omega_control[r] < 1.0 && m->omega_case[r] > 0.0 && m->omega_case[r] < 1.0))
         return fail(c, HYG_ERR_ARG, "two-group: omega must be in (0,1)");
     const double two[HYG_RMAX] = {2, 2, 2, 2, 2, 2, 2, 2};
-    // sojourn times beyond d_max reuse the last entry (the hazard of a negative binomial is flat by then)
-    dmax = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(t_max, m->minimum_duration + 1), 4096));
+    // sojourn times beyond d_max reuse the last entry: the exact hazard of a negative binomial is flat by then, and the reference-mode
+    // hazard is the constant 0.1 from the sojourn where the fp32 cdf rounds to 1 (4071 for omega = 0.995; 262144 covers omega up to 0.9999)
+    dmax = static_cast<uint32_t>(std::min<uint64_t>(std::max<uint64_t>(t_max, m->minimum_duration + 1), 262144));
     if (m->hazard_mode > HYG_TG_HAZARD_EXACT) return fail(c, HYG_ERR_ARG, "two-group: hazard_mode must be HYG_TG_HAZARD_REFERENCE or HYG_TG_HAZARD_EXACT");
     auto* build = (m->hazard_mode == HYG_TG_HAZARD_EXACT) ? hyg::build_hazard_table : hyg::build_reference_hazard_table;
     build(m->omega_control, m->kappa_control ? m->kappa_control : two, h.R, h.u, dmax, rho_c);

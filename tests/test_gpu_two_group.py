@@ -157,6 +157,19 @@ def test_two_group_trajectories_into_pinned_host_memory():
     assert (a["trajectories"][:, :, 0] >= 0).all()
 
 
+def test_two_group_at_the_shape_of_baseline_config_3():
+    """50 + 50 samples (emission differences of hundreds of nats between regimes) and a window long enough for sojourns beyond the
+    sojourns where the reference-mode hazard of the control regimes turns into the constant 0.1 (197 ... 808)."""
+    c = make_case(1500, 50, seed=13)
+    m = c["model"]
+    m.rho_c = tg_oracle.reference_hazard_table(c["omega_control"], np.full(6, 2.0), c["u"], m.d_max)
+    m.rho_k = tg_oracle.reference_hazard_table(c["omega_case"], np.full(6, 2.0), c["u"], m.d_max)
+    g = _run_gpu(c, 50, 25, seed=2, chain=5, use_oracle_tables=False, hazard="reference")[0]
+    r = _oracle(c, 50, 25, seed=2, chain=5)
+    _compare(g, r, frac=0.95)
+    assert g["trajectories"][:, :, 1].max() > 200       # control sojourns past the first switch-over
+
+
 def test_two_group_many_chains_are_independent():
     # 3 chains (same data, different chain ids) in one launch: each equals its own oracle run
     c = make_case(120, 2, seed=8)

@@ -26,7 +26,7 @@ int hygemu_sg_filter(const double* vartheta, uint32_t n_vartheta, const double* 
   hyg::SgHostModel hm;
   if (hm.set_known(vartheta, n_vartheta)) return -1;
   if (hm.set_theta(theta, dim_theta, T)) return -2;
-  if (hm.R != 6) return -3;
+  if (hm.R < 2 || hm.R > 6) return -3;
   hyg::SgModelDev mdl;
   mdl.R = hm.R; mdl.u = hm.u; mdl.n_particles = static_cast<int>(n_particles); mdl.dcap = hm.dcap;
   for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) { mdl.P[i][j] = hm.P[i][j]; mdl.logP[i][j] = hm.logP[i][j]; }
@@ -55,8 +55,20 @@ int hygemu_sg_filter(const double* vartheta, uint32_t n_vartheta, const double* 
   ch.theta0 = theta; ch.theta_trace = theta_trace;
   const hyg::SgModelDev* pm = &mdl;
   const hyg::SgChainDev* pc = &ch;
-  if (use_param_est) emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<6, true>(pm, pc, run); });
-  else emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<6, false>(pm, pc, run); });
+  // one instantiation per number of regimes, as the library dispatches them (parameter mode: R = 6 only under emulation)
+  if (use_param_est) {
+    if (hm.R != 6) return -2;
+    emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<6, true>(pm, pc, run); });
+    return 0;
+  }
+  switch (hm.R) {
+    case 2: emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<2, false>(pm, pc, run); }); break;
+    case 3: emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<3, false>(pm, pc, run); }); break;
+    case 4: emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<4, false>(pm, pc, run); }); break;
+    case 5: emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<5, false>(pm, pc, run); }); break;
+    case 6: emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<6, false>(pm, pc, run); }); break;
+    default: return -2;
+  }
   return 0;
 }
 

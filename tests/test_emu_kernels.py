@@ -188,3 +188,29 @@ def test_filter_segment_right_halo_forced_is_counted(emu, oracle, default_model)
     assert r["status"][2] == pend[t] and r["status"][3] == t + 1
     r = emu.sg_filter(g["vartheta"], g["theta"], lo[:t + 1], uniforms=g["uniforms"][:t + 1])
     assert r["status"][2] == 0
+
+
+@pytest.mark.parametrize("mu,sigma,omega,u,n_particles", [
+    ((0.9, 0.1, 0.5, 0.5), (0.05, 0.05, 0.1, 0.2886751), (0.99, 0.97, 0.95, 0.9), 5, 250),
+    ((0.85, 0.15), (0.08, 0.08), (0.98, 0.98), 2, 40),
+    ((0.8, 0.2, 0.5), (0.1, 0.1, 0.2), (0.97, 0.97, 0.9), 4, 64),
+])
+def test_filter_other_numbers_of_regimes_and_minimum_durations(emu, oracle, mu, sigma, omega, u, n_particles):
+    """The recursion kernel is instantiated for R = 2 .. 6 (hyg_api.cu dispatches on R); every instantiation against the oracle."""
+    from hygeia_b200 import model, philox, synthetic
+    R = len(mu)
+    vartheta, dim = model.get_known_parameters(mu, sigma, u=u)
+    theta = model.default_theta(R, omega=omega)
+    T = 1200
+    rng = np.random.default_rng(40 + R)
+    reg = synthetic.simulate_regimes(T, rng) % R
+    nt, nm = synthetic.simulate_counts(reg, 2, rng, mu=mu, sigma=sigma)
+    un = philox.uniforms_by_site(5, 0, T)
+    want = oracle.run(vartheta, theta, un, nt, nm, None, tie_order="canonical", n_particles=n_particles)
+    al, be = model.beta_parameters(mu, sigma)
+    got = emu.sg_filter(vartheta, theta, oracle.emission(al, be, nt, nm), uniforms=un, n_particles=n_particles)
+    for k in ("drew_uniform", "n_pending", "n_curr", "finalised_at", "support_hash"):
+        assert np.array_equal(got[k], want[k]), k
+    assert (got["k_kept"] != want["k_kept"]).sum() <= 1
+    assert np.allclose(got["logz"], want["logz"], rtol=1e-10, atol=0)
+    assert np.allclose(got["probs"], want["regime_probs"][:, 1:], rtol=1e-6, atol=1e-12)

@@ -56,9 +56,15 @@ int hygemu_sg_filter(const double* vartheta, uint32_t n_vartheta, const double* 
   const hyg::SgModelDev* pm = &mdl;
   const hyg::SgChainDev* pc = &ch;
   // one instantiation per number of regimes, as the library dispatches them (parameter mode: R = 6 only under emulation)
-  if (use_param_est) {
-    if (hm.R != 6) return -2;
-    emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<6, true>(pm, pc, run); });
+  if (use_param_est) {   // (the static stand-in for the dynamic shared memory is sized for R = 6, the largest)
+    switch (hm.R) {
+      case 2: emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<2, true>(pm, pc, run); }); break;
+      case 3: emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<3, true>(pm, pc, run); }); break;
+      case 4: emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<4, true>(pm, pc, run); }); break;
+      case 5: emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<5, true>(pm, pc, run); }); break;
+      case 6: emu::launch(dim3(1), dim3(HYG_NT), [=]() { hyg::sg_filter_entry<6, true>(pm, pc, run); }); break;
+      default: return -2;
+    }
     return 0;
   }
   switch (hm.R) {

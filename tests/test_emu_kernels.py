@@ -214,3 +214,24 @@ def test_filter_other_numbers_of_regimes_and_minimum_durations(emu, oracle, mu, 
     assert (got["k_kept"] != want["k_kept"]).sum() <= 1
     assert np.allclose(got["logz"], want["logz"], rtol=1e-10, atol=0)
     assert np.allclose(got["probs"], want["regime_probs"][:, 1:], rtol=1e-6, atol=1e-12)
+
+
+@pytest.mark.parametrize("mu,sigma,omega,u", [((0.9, 0.1, 0.5, 0.5), (0.05, 0.05, 0.1, 0.2886751), (0.99, 0.97, 0.95, 0.9), 3),
+                                              ((0.85, 0.15, 0.5), (0.08, 0.08, 0.2), (0.98, 0.98, 0.9), 2)])
+def test_parameter_estimation_other_numbers_of_regimes(emu, oracle, mu, sigma, omega, u):
+    """K3 (score recursion + ADAM + table rebuild on the device) is instantiated per R as well: theta traces against the oracle."""
+    from hygeia_b200 import model, philox, synthetic
+    R = len(mu)
+    vartheta, dim = model.get_known_parameters(mu, sigma, u=u)
+    theta0 = model.default_theta(R, omega=omega) + 0.3 * np.random.default_rng(1).standard_normal(dim)
+    T = 900
+    rng = np.random.default_rng(50 + R)
+    reg = synthetic.simulate_regimes(T, rng) % R
+    nt, nm = synthetic.simulate_counts(reg, 2, rng, mu=mu, sigma=sigma)
+    un = philox.uniforms_by_site(5, 0, T)
+    want = oracle.run(vartheta, theta0, un, nt, nm, None, tie_order="canonical", param_est=True, n_steps_without_update=50)
+    al, be = model.beta_parameters(mu, sigma)
+    got = emu.sg_filter(vartheta, theta0, oracle.emission(al, be, nt, nm), uniforms=un, param_est=True, n_steps_without_update=50)
+    assert np.abs(want["theta_trace"][-1] - theta0).max() > 1e-2          # theta moved
+    assert np.allclose(got["theta_trace"], want["theta_trace"], rtol=0, atol=1e-9)
+    assert np.allclose(got["logz"], want["logz"], rtol=1e-10, atol=0)

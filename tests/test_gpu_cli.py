@@ -237,3 +237,37 @@ def test_aggregate_keeps_every_sample_column_and_reports_missing_inputs(tmp_path
     assert r.returncode != 0 and "optimal_backward_particles_merged_state_2400_2.npz" in r.stderr
     r = run("aggregate", "--results_dir", tree, "--output_dir", agg, "--chrom", "8", check=False)               # no such chromosome
     assert r.returncode == 1 and "No data was processed" in r.stdout
+
+
+def test_estimate_regimes_cli_with_four_regimes(tmp_path):
+    """--mu / --sigma of length 4 and --u 5: the front end, the tables and the kernels are generic in R and u."""
+    from hygeia_b200 import model, synthetic
+    from hygeia_b200.single_group import run_online_combined_inference
+    mu, sigma, omega = (0.9, 0.1, 0.5, 0.5), (0.05, 0.05, 0.1, 0.2886751), (0.99, 0.97, 0.95, 0.9)
+    R, T, S = 4, 1200, 2
+    rng = np.random.default_rng(8)
+    reg = synthetic.simulate_regimes(T, rng) % R
+    nt, nm = synthetic.simulate_counts(reg, S, rng, mu=mu, sigma=sigma)
+    ch = dict(positions=synthetic.simulate_positions(T, rng), n_total=nt, n_meth=nm)
+    _write_single_group_inputs(tmp_path, ch)
+    p = rng.random((R, R)); np.fill_diagonal(p, 0.0); p /= p.sum(1, keepdims=True)
+    with open(tmp_path / "p.csv", "w") as f:
+        f.write(",".join(f"regime_{i}" for i in range(1, R + 1)) + "\n")
+        for row in p:
+            f.write(",".join(repr(float(v)) for v in row) + "\n")
+    (tmp_path / "kappa.csv").write_text("kappa\n" + "\n".join(["2"] * R) + "\n")
+    (tmp_path / "omega.csv").write_text("omega\n" + "\n".join(repr(float(v)) for v in omega) + "\n")
+    out = tmp_path / "o" / "regimes.csv.gz"
+    run("estimate_parameters_and_regimes", "--mu", ",".join(map(str, mu)), "--sigma", ",".join(map(str, sigma)), "--u", 5,
+        "--p_input_csv_file", tmp_path / "p.csv", "--kappa_input_csv_file", tmp_path / "kappa.csv", "--omega_input_csv_file", tmp_path / "omega.csv",
+        "--n_methylated_reads_csv_file", tmp_path / "n_methylated_reads_1.txt.gz", "--genomic_positions_csv_file", tmp_path / "positions_1.txt.gz",
+        "--n_total_reads_csv_file", tmp_path / "n_total_reads_1.txt.gz", "--regime_probabilities_csv_file", out,
+        "--estimate_regime_probabilities", "--randomise_rng_seed", "FALSE", "--rng_seed", 5)
+    header, rows = read_csv(out)
+    assert header == ["genomic_position"] + [f"regime_{i}" for i in range(1, R + 1)] and len(rows) == T - 1
+    got = np.array([[float(x) for x in r] for r in rows])
+    vartheta, _ = model.get_known_parameters(mu, sigma, u=5)
+    theta = model.convert_model_parameters_to_theta(p, np.array(omega))
+    want = run_online_combined_inference(vartheta, theta, ch["positions"][1:], nt[:, 1:], nm[:, 1:], rng_seed=5)["regimeProbabilityEstimates"]
+    assert np.array_equal(got[:, 0], want[:, 0]) and np.allclose(got[:, 1:], want[:, 1:], rtol=1e-6, atol=1e-12)
+    assert (got[:, 1:].argmax(1) == reg[1:]).mean() > 0.9

@@ -473,7 +473,9 @@ def run_two_group(args):
             barrier()
             secs.append(time.perf_counter() - t0)
         e = float(np.mean(secs[1:]))
+        same = bool(all(a["log_normalizing_constant"] == b["log_normalizing_constant"] for a, b in zip(out, o2)))
         line["e2e"] = {"value": units_all / e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1000.0 * e,
+                       "log_evidences_equal_to_device_resident_leg": same,
                        "api": "hygeia_b200.two_group.TwoGroupSession: clear -> set_emission_model -> add_dataset(pinned host windows) -> emission -> set_two_group_model -> run (trajectories into pinned host arrays)",
                        "log_evidence_first_window": o2[0]["log_normalizing_constant"]}
     line["cpu_baseline"] = None

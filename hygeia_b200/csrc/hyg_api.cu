@@ -463,8 +463,11 @@ int hyg_sg_add_dataset(hyg_ctx* c, uint64_t T, uint32_t S, const uint16_t* n_tot
       HYG_CUDA(c, cudaMemset2DAsync(a + T, d.pitch * 2, 0, (d.pitch - T) * 2, S, c->stream));
       HYG_CUDA(c, cudaMemset2DAsync(b + T, d.pitch * 2, 0, (d.pitch - T) * 2, S, c->stream));
     }
-    HYG_CUDA(c, cudaMemcpy2DAsync(a, d.pitch * 2, n_total, T * 2, T * 2, S, cudaMemcpyHostToDevice, c->stream));
-    HYG_CUDA(c, cudaMemcpy2DAsync(b, d.pitch * 2, n_meth, T * 2, T * 2, S, cudaMemcpyHostToDevice, c->stream));
+    // host rows may be longer than T (a window of a chromosome-wide matrix): `pitch` is then the host row pitch in elements
+    if (pitch != 0 && pitch < T) return fail(c, HYG_ERR_ARG, "host pitch must be >= T (or 0 = T)");
+    const size_t spitch = (pitch ? pitch : T) * sizeof(uint16_t);
+    HYG_CUDA(c, cudaMemcpy2DAsync(a, d.pitch * 2, n_total, spitch, T * 2, S, cudaMemcpyHostToDevice, c->stream));
+    HYG_CUDA(c, cudaMemcpy2DAsync(b, d.pitch * 2, n_meth, spitch, T * 2, S, cudaMemcpyHostToDevice, c->stream));
     d.d_nt = a; d.d_nm = b; d.owned = true;
   }
   HYG_CUDA(c, pool_alloc(c, reinterpret_cast<void**>(&d.d_logobs), static_cast<size_t>(T) * c->hm.R * sizeof(double)));

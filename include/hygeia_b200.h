@@ -50,8 +50,9 @@ int hyg_sg_get_tables(hyg_ctx* ctx, double* P, double* omega, uint32_t d_max, do
 /* ---- data sets: one per chromosome / count matrix ----------------------------------------------------------------
  * Counts are uint16 (the reference itself narrows to int16: src/two_group/run_inference_two_groups.py:246-253), layout
  * [S][T] with the SITE index fastest.  `on_device` != 0: the pointers are device pointers with row pitch `pitch`
- * elements (pitch even, >= T, the pad readable) and are used in place; otherwise they are host pointers (pitch = T)
- * and are copied host -> device by this call. */
+ * elements (pitch even, >= T, the pad readable) and are used in place; otherwise they are host pointers with row pitch
+ * `pitch` elements (>= T; 0 = T -- a window of a wider host matrix can be staged without repacking) and are copied
+ * host -> device by this call. */
 int hyg_sg_add_dataset(hyg_ctx* ctx, uint64_t T, uint32_t S, const uint16_t* n_total, const uint16_t* n_meth, int on_device, uint64_t pitch);
 int hyg_sg_clear(hyg_ctx* ctx);           /* drop all data sets and chains */
 

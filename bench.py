@@ -619,19 +619,8 @@ def main():
     def exchange():
         """NCCL: all-gather of log Z_T of every chain; reduce(sum) to rank 0 of the posteriors summed over this rank's seeds."""
         v = exch
-        for ps in v["psum"].values():
-            ps.zero_()
-        v["evid_mine"].zero_()
-        for i, (c, sd, pv, zv) in enumerate(v["views"]):
-            v["psum"][c] += pv[:, 1:]
-            v["evid_mine"][i] = zv[-1]
-        dist.all_gather_into_tensor(evid_all, v["evid_mine"])
-        nb = evid_all.numel() * 8
-        if args.config != "c5":   # c5: chromosomes are disjoint across ranks, their seed sums are complete where they are
-            for c in range(n_chrom):
-                dist.reduce(v["psum"][c], dst=0, op=dist.ReduceOp.SUM)
-                nb += v["psum"][c].numel() * 8
-        coll_bytes[0] = nb
+        # c5: chromosomes are disjoint across ranks, their seed sums are complete where they are
+        coll_bytes[0] = sharding.exchange_results(dist, v["views"], v["psum"], v["evid_mine"], evid_all, range(n_chrom) if args.config != "c5" else [])
 
     def step_device():
         sess.emission()

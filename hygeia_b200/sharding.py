@@ -36,3 +36,26 @@ def chains_for_rank(chrom_lengths: Sequence[int], n_seeds: int, rank: int, world
     chains = [(c, s) for c in range(len(chrom_lengths)) for s in range(n_seeds)]
     bins = lpt_assign([chrom_lengths[c] for c, _ in chains], world)
     return [chains[i] for i in bins[rank]]
+
+
+def exchange_results(dist, views, psum, evid_mine, evid_all, reduce_chromosomes):
+    """The multi-GPU exchange of a sweep's RESULTS (the chains themselves never exchange anything): an all-gather of every chain's
+    final log-evidence and a reduce (sum) to rank 0 of the posterior rows summed over this rank's seeds, per chromosome -- what the
+    reference obtains by concatenating per-seed files (src/two_group/aggregate_results.py:125-147).
+
+    dist: torch.distributed (NCCL on the GPUs, gloo in the CPU tests); views: [(chromosome, seed, posteriors [T, 1 + R], logz [T])]
+    of this rank's chains (device views of the library's buffers in bench.py); psum: {chromosome: [T, R] accumulator} holding every
+    chromosome in `reduce_chromosomes` on every rank (each rank must issue the same sequence of collectives); evid_mine: [slots]
+    with slots >= len(views) equal on all ranks; evid_all: [world * slots].  Returns the bytes each rank put into collectives."""
+    for ps in psum.values():
+        ps.zero_()
+    evid_mine.zero_()
+    for i, (c, _sd, pv, zv) in enumerate(views):
+        psum[c] += pv[:, 1:]
+        evid_mine[i] = zv[-1]
+    dist.all_gather_into_tensor(evid_all, evid_mine)
+    nbytes = evid_all.numel() * evid_all.element_size()
+    for c in reduce_chromosomes:
+        dist.reduce(psum[c], dst=0, op=dist.ReduceOp.SUM)
+        nbytes += psum[c].numel() * psum[c].element_size()
+    return nbytes

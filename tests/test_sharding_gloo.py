@@ -79,3 +79,57 @@ def test_two_rank_gloo_matches_single_process():
     p.join(timeout=60)
     assert np.allclose(one, two, rtol=1e-12)
     assert np.all(one < 0)
+
+
+def _posterior(c, sd, T, R=6):
+    rng = np.random.default_rng(1000 * c + sd)
+    p = rng.random((T, 1 + R))
+    p[:, 0] = np.arange(T)
+    return p, np.cumsum(-rng.random(T))
+
+
+def _exchange_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lens, n_seeds, R = [50, 40, 30, 20], 4, 6
+    mine = sharding.chains_for_rank(lens, n_seeds, rank, world, by="chain")
+    views = []
+    for c, sd in mine:
+        p, z = _posterior(c, sd, lens[c])
+        views.append((c, sd, torch.from_numpy(p), torch.from_numpy(z)))
+    slots = -(-len(lens) * n_seeds // world) + 2                       # every rank uses the same number of slots
+    psum = {c: torch.zeros((lens[c], R), dtype=torch.float64) for c in range(len(lens))}
+    evid_mine = torch.zeros(slots, dtype=torch.float64)
+    evid_all = torch.zeros(world * slots, dtype=torch.float64)
+    nbytes = sharding.exchange_results(dist, views, psum, evid_mine, evid_all, range(len(lens)))
+    if rank == 0:
+        q.put((dict((c, psum[c].numpy().copy()) for c in psum), evid_all.numpy().copy(), nbytes))
+    dist.destroy_process_group()
+
+
+def test_result_exchange_on_two_ranks():
+    """bench.py's multi-GPU exchange (sharding.exchange_results) on gloo: rank 0 ends with the posteriors summed over ALL seeds of
+    every chromosome and every rank with the log-evidence of every chain of the job."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    psum, evid_all, nbytes = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    lens, n_seeds = [50, 40, 30, 20], 4
+    for c, T in enumerate(lens):
+        want = sum(_posterior(c, sd, T)[0][:, 1:] for sd in range(n_seeds))
+        assert np.allclose(psum[c], want, rtol=1e-13)
+    want_evid = sorted(_posterior(c, sd, T)[1][-1] for c, T in enumerate(lens) for sd in range(n_seeds))
+    got_evid = sorted(v for v in evid_all if v != 0.0)
+    assert np.allclose(got_evid, want_evid, rtol=1e-15) and len(got_evid) == 16
+    assert nbytes == evid_all.size * 8 + sum(T * 6 * 8 for T in lens)

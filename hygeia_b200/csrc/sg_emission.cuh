@@ -25,8 +25,10 @@
 
 #include "hyg_common.cuh"
 
+#ifndef HYG_EM_NT
 #define HYG_EM_NT 1024
-#define HYG_EM_TILE 1024           // site pairs per tile (= one pair per thread)
+#endif
+#define HYG_EM_TILE HYG_EM_NT      // site pairs per tile (= one pair per thread)
 #define HYG_EM_SMEM_DOUBLES 29040  // 232320 B of table rows; + 16 B mbarrier slot <= the 227 KB opt-in limit of sm_100
 
 namespace hyg {
